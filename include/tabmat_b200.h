@@ -1,0 +1,257 @@
+/*
+ * tabmat_b200 — C-ABI of the B200 (sm_100a) sandwich / matvec / transpose_matvec path.
+ *
+ * This header is the drop-in boundary.  Every entry point replaces one Python-callable
+ * function of the reference's four Cython extension modules (the "plugin boundary",
+ * SURVEY.md §8b); the reference function it stands in for is cited as file:line relative
+ * to the reference tree (Quantco/tabmat @ 7af8b2c, src/tabmat/ext/...).
+ *
+ * Conventions (all entry points):
+ *   - every data pointer is a DEVICE pointer on the current CUDA device, borrowed for
+ *     the duration of the call; nothing is retained;
+ *   - outputs are caller-allocated; "overwrites" means the function fully defines the
+ *     output (no zero-initialisation needed), "accumulates" means `out +=`;
+ *   - `rows` / `cols` are int32 index lists; NULL means "all rows/cols" (the reference
+ *     materialises np.arange instead, util.py:6-24).  Lists must be sorted and unique
+ *     (the reference silently assumes this);
+ *   - `c_order` = 1 for row-major (C-contiguous), 0 for column-major (F-contiguous);
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous on it;
+ *   - return value 0 = ok, non-zero = error; tm_last_error() gives the message
+ *     (the reference's native code has no error return; validation lives in Python);
+ *   - scratch memory is taken from the stream-ordered device pool
+ *     (cudaMallocAsync/cudaFreeAsync) — the B200 stand-in for alloc.h:35-54;
+ *   - sparse index arrays are int32 (n, p, nnz < 2^31 per GPU shard).
+ *   - `_f32` / `_f64` suffixes select the arithmetic type, mirroring the reference's
+ *     Cython fused type `floating`.
+ */
+#ifndef TABMAT_B200_H
+#define TABMAT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* tm_stream_t;
+
+/* ---- library ---------------------------------------------------------------------- */
+int tm_version(void);
+const char* tm_last_error(void);
+/* Number of kernel launches issued by this library since the last reset (bench.py's
+ * `gpu_launches`). */
+int64_t tm_launch_count(void);
+void tm_reset_launch_count(void);
+/* 1 if the tcgen05 (TMEM/TMA) dense path can run on the current device (cc 10.x). */
+int tm_has_tcgen05(void);
+/* Select the dense f32 sandwich implementation: 0 = auto (tcgen05 when eligible),
+ * 1 = force the CUDA-core kernel, 2 = force tcgen05 (error when not eligible). */
+void tm_set_dense_f32_mode(int mode);
+
+/* ---- dense block (reference: ext/dense.pyx) --------------------------------------- */
+/* dense_sandwich, dense.pyx:19-44 -> _dense{C,F}_sandwich, dense_helpers-tmpl.cpp:266-308.
+ * out[a*n_cols+b] = sum_t X[rows[t], cols[a]] * d[rows[t]] * X[rows[t], cols[b]].
+ * Overwrites out (n_cols x n_cols, row-major, exactly symmetric). */
+int tm_dense_sandwich_f32(const float* X, int64_t n, int64_t p, int c_order, const float* d,
+                          const int32_t* rows, int64_t n_rows, const int32_t* cols,
+                          int64_t n_cols, float* out, tm_stream_t stream);
+int tm_dense_sandwich_f64(const double* X, int64_t n, int64_t p, int c_order, const double* d,
+                          const int32_t* rows, int64_t n_rows, const int32_t* cols,
+                          int64_t n_cols, double* out, tm_stream_t stream);
+
+/* dense_matvec, dense.pyx:76-101 -> _dense{C,F}_matvec, dense_helpers-tmpl.cpp:385-417.
+ * res[r] = sum_c X[rows[r], cols[c]] * v[cols[c]]   (v indexed by absolute column).
+ * accumulate=0: out[r] = res[r]; accumulate=1: out[r] += res[r]. */
+int tm_dense_matvec_f32(const float* X, int64_t n, int64_t p, int c_order, const float* v,
+                        const int32_t* rows, int64_t n_rows, const int32_t* cols,
+                        int64_t n_cols, float* out, int accumulate, tm_stream_t stream);
+int tm_dense_matvec_f64(const double* X, int64_t n, int64_t p, int c_order, const double* v,
+                        const int32_t* rows, int64_t n_rows, const int32_t* cols,
+                        int64_t n_cols, double* out, int accumulate, tm_stream_t stream);
+
+/* dense_rmatvec, dense.pyx:48-73 -> _dense{C,F}_rmatvec, dense_helpers-tmpl.cpp:314-383.
+ * out[c] = sum_t X[rows[t], cols[c]] * v[rows[t]].  Overwrites out (n_cols). */
+int tm_dense_rmatvec_f32(const float* X, int64_t n, int64_t p, int c_order, const float* v,
+                         const int32_t* rows, int64_t n_rows, const int32_t* cols,
+                         int64_t n_cols, float* out, tm_stream_t stream);
+int tm_dense_rmatvec_f64(const double* X, int64_t n, int64_t p, int c_order, const double* v,
+                         const int32_t* rows, int64_t n_rows, const int32_t* cols,
+                         int64_t n_cols, double* out, tm_stream_t stream);
+
+/* transpose_square_dot_weights (dense), dense.pyx:103-122.
+ * out[j] = sum_i w[i] * (X[i,j] - shift[j])^2.  Overwrites out (p). */
+int tm_dense_sq_dot_weights_f32(const float* X, int64_t n, int64_t p, int c_order,
+                                const float* w, const float* shift, float* out,
+                                tm_stream_t stream);
+int tm_dense_sq_dot_weights_f64(const double* X, int64_t n, int64_t p, int c_order,
+                                const double* w, const double* shift, double* out,
+                                tm_stream_t stream);
+
+/* ---- sparse block (reference: ext/sparse.pyx) -------------------------------------- */
+/* Device layout of a sparse block: CSR (data, indices, indptr[n+1]) with column indices
+ * sorted inside each row, plus `csr_row` = the row id of every CSR non-zero (COO row
+ * array, nnz entries); and CSC (data, indices, indptr[p+1]).  The reference keeps CSC
+ * plus a lazily cached CSR (sparse_matrix.py:133-143). */
+
+/* sparse_sandwich, sparse.pyx:17-77.  out = A[rows,cols]^T diag(d[rows]) A[rows,cols].
+ * Overwrites out (n_cols x n_cols, exactly symmetric). */
+int tm_sparse_sandwich_f32(const float* csr_data, const int32_t* csr_indices,
+                           const int32_t* csr_indptr, const int32_t* csr_row, int64_t n,
+                           int64_t p, int64_t nnz, const float* d, const int32_t* rows,
+                           int64_t n_rows, const int32_t* cols, int64_t n_cols, float* out,
+                           tm_stream_t stream);
+int tm_sparse_sandwich_f64(const double* csr_data, const int32_t* csr_indices,
+                           const int32_t* csr_indptr, const int32_t* csr_row, int64_t n,
+                           int64_t p, int64_t nnz, const double* d, const int32_t* rows,
+                           int64_t n_rows, const int32_t* cols, int64_t n_cols, double* out,
+                           tm_stream_t stream);
+
+/* csr_dense_sandwich, sparse.pyx:211-260 -> _csr_dense{C,F}_sandwich,
+ * sparse_helpers-tmpl.cpp:23-143.
+ * out[a*nB+b] = sum_t A[rows[t], A_cols[a]] * d[rows[t]] * B[rows[t], B_cols[b]].
+ * Overwrites out (nA x nB). */
+int tm_csr_dense_sandwich_f32(const float* csr_data, const int32_t* csr_indices,
+                              const int32_t* csr_indptr, int64_t n, int64_t p_sparse,
+                              const float* B, int64_t q, int b_c_order, const float* d,
+                              const int32_t* rows, int64_t n_rows, const int32_t* A_cols,
+                              int64_t nA, const int32_t* B_cols, int64_t nB, float* out,
+                              tm_stream_t stream);
+int tm_csr_dense_sandwich_f64(const double* csr_data, const int32_t* csr_indices,
+                              const int32_t* csr_indptr, int64_t n, int64_t p_sparse,
+                              const double* B, int64_t q, int b_c_order, const double* d,
+                              const int32_t* rows, int64_t n_rows, const int32_t* A_cols,
+                              int64_t nA, const int32_t* B_cols, int64_t nB, double* out,
+                              tm_stream_t stream);
+
+/* csr_matvec_unrestricted / csr_matvec, sparse.pyx:79-140.
+ * res[t] = sum_{j in cols} X[rows[t], j] * v[j].  accumulate: out[t] (+)= res[t]. */
+int tm_csr_matvec_f32(const float* csr_data, const int32_t* csr_indices,
+                      const int32_t* csr_indptr, int64_t n, int64_t p, const float* v,
+                      const int32_t* rows, int64_t n_rows, const int32_t* cols, int64_t n_cols,
+                      float* out, int accumulate, tm_stream_t stream);
+int tm_csr_matvec_f64(const double* csr_data, const int32_t* csr_indices,
+                      const int32_t* csr_indptr, int64_t n, int64_t p, const double* v,
+                      const int32_t* rows, int64_t n_rows, const int32_t* cols, int64_t n_cols,
+                      double* out, int accumulate, tm_stream_t stream);
+
+/* csc_rmatvec_unrestricted / csc_rmatvec, sparse.pyx:142-199.
+ * res[c] = sum_{i in rows} X[i, cols[c]] * v[i].  accumulate: out[c] (+)= res[c]. */
+int tm_csc_rmatvec_f32(const float* csc_data, const int32_t* csc_indices,
+                       const int32_t* csc_indptr, int64_t n, int64_t p, const float* v,
+                       const int32_t* rows, int64_t n_rows, const int32_t* cols, int64_t n_cols,
+                       float* out, int accumulate, tm_stream_t stream);
+int tm_csc_rmatvec_f64(const double* csc_data, const int32_t* csc_indices,
+                       const int32_t* csc_indptr, int64_t n, int64_t p, const double* v,
+                       const int32_t* rows, int64_t n_rows, const int32_t* cols, int64_t n_cols,
+                       double* out, int accumulate, tm_stream_t stream);
+
+/* transpose_square_dot_weights (sparse), sparse.pyx:262-282.
+ * out[j] = sum_{nz (i,j)} w[i] * X[i,j]^2.  Overwrites out (p). */
+int tm_csc_sq_dot_weights_f32(const float* csc_data, const int32_t* csc_indices,
+                              const int32_t* csc_indptr, int64_t n, int64_t p, const float* w,
+                              float* out, tm_stream_t stream);
+int tm_csc_sq_dot_weights_f64(const double* csc_data, const int32_t* csc_indices,
+                              const int32_t* csc_indptr, int64_t n, int64_t p, const double* w,
+                              double* out, tm_stream_t stream);
+
+/* ---- categorical block (reference: ext/categorical.pyx, ext/split.pyx) -------------- */
+/* `codes` is the int32 category index per row (read-only; -1 = missing);
+ * `n_cat_cols` = number of matrix columns = #categories - drop_first; column of row k is
+ * codes[k] - drop_first, rows with a negative column contribute nothing. */
+
+/* sandwich_categorical_{fast,complex}, categorical.pyx:183-218.
+ * out[codes[k]-drop_first] += d[k] for k in rows.  Overwrites out (n_cat_cols). */
+int tm_cat_sandwich_f32(const int32_t* codes, int64_t n, const float* d, const int32_t* rows,
+                        int64_t n_rows, int64_t n_cat_cols, int drop_first, float* out,
+                        tm_stream_t stream);
+int tm_cat_sandwich_f64(const int32_t* codes, int64_t n, const double* d, const int32_t* rows,
+                        int64_t n_rows, int64_t n_cat_cols, int drop_first, double* out,
+                        tm_stream_t stream);
+
+/* transpose_matvec_{fast,complex}, categorical.pyx:23-117 ->
+ * _transpose_matvec_all_rows_*, cat_split_helpers-tmpl.cpp:4-41.
+ * out[c] += v[k] for k in rows, c = codes[k]-drop_first, c in cols.  ACCUMULATES into out
+ * (length n_cat_cols) at the ABSOLUTE column index, like the reference. */
+int tm_cat_transpose_matvec_f32(const int32_t* codes, int64_t n, const float* v,
+                                const int32_t* rows, int64_t n_rows, const int32_t* cols,
+                                int64_t n_cols, int64_t n_cat_cols, int drop_first, float* out,
+                                tm_stream_t stream);
+int tm_cat_transpose_matvec_f64(const int32_t* codes, int64_t n, const double* v,
+                                const int32_t* rows, int64_t n_rows, const int32_t* cols,
+                                int64_t n_cols, int64_t n_cat_cols, int drop_first, double* out,
+                                tm_stream_t stream);
+
+/* matvec_{fast,complex}, categorical.pyx:128-180.
+ * out[i] += v[c], c = codes[i]-drop_first, c >= 0 and c in cols.  ACCUMULATES (length n). */
+int tm_cat_matvec_f32(const int32_t* codes, int64_t n, const float* v, const int32_t* cols,
+                      int64_t n_cols, int64_t n_cat_cols, int drop_first, float* out,
+                      tm_stream_t stream);
+int tm_cat_matvec_f64(const int32_t* codes, int64_t n, const double* v, const int32_t* cols,
+                      int64_t n_cols, int64_t n_cat_cols, int drop_first, double* out,
+                      tm_stream_t stream);
+
+/* sandwich_cat_dense, split.pyx:32-80 -> _sandwich_cat_dense{C,F}_{fast,complex},
+ * cat_split_helpers-tmpl.cpp:97-151.
+ * out[(codes[k]-drop_first)*nJ + b] += d[k] * Y[k, j_cols[b]] for k in rows.
+ * Overwrites out (n_cat_cols x nJ). */
+int tm_cat_dense_sandwich_f32(const int32_t* codes, int64_t n, int64_t n_cat_cols,
+                              int drop_first, const float* d, const float* Y, int64_t q,
+                              int y_c_order, const int32_t* rows, int64_t n_rows,
+                              const int32_t* j_cols, int64_t nJ, float* out,
+                              tm_stream_t stream);
+int tm_cat_dense_sandwich_f64(const int32_t* codes, int64_t n, int64_t n_cat_cols,
+                              int drop_first, const double* d, const double* Y, int64_t q,
+                              int y_c_order, const int32_t* rows, int64_t n_rows,
+                              const int32_t* j_cols, int64_t nJ, double* out,
+                              tm_stream_t stream);
+
+/* sandwich_cat_cat, split.pyx:83-111 -> _sandwich_cat_cat_{fast,complex},
+ * cat_split_helpers-tmpl.cpp:44-94.
+ * out[(ci[k]-dfi)*Kj + (cj[k]-dfj)] += d[k] for k in rows.  Overwrites out (Ki x Kj). */
+int tm_cat_cat_sandwich_f32(const int32_t* i_codes, const int32_t* j_codes, int64_t n,
+                            int64_t Ki, int64_t Kj, int i_drop_first, int j_drop_first,
+                            const float* d, const int32_t* rows, int64_t n_rows, float* out,
+                            tm_stream_t stream);
+int tm_cat_cat_sandwich_f64(const int32_t* i_codes, const int32_t* j_codes, int64_t n,
+                            int64_t Ki, int64_t Kj, int i_drop_first, int j_drop_first,
+                            const double* d, const int32_t* rows, int64_t n_rows, double* out,
+                            tm_stream_t stream);
+
+/* CategoricalMatrix._cross_sparse, categorical_matrix.py:825-838 (the reference runs this
+ * block through scipy's csr_matmat; there is no reference native function).
+ * out[(codes[k]-drop_first)*nS + s] += d[k] * A[k, s_cols[s]] for k in rows.
+ * Overwrites out (n_cat_cols x nS). */
+int tm_cat_sparse_sandwich_f32(const int32_t* codes, int64_t n, int64_t n_cat_cols,
+                               int drop_first, const float* d, const float* csr_data,
+                               const int32_t* csr_indices, const int32_t* csr_indptr,
+                               const int32_t* csr_row, int64_t p_sparse, int64_t nnz,
+                               const int32_t* rows, int64_t n_rows, const int32_t* s_cols,
+                               int64_t nS, float* out, tm_stream_t stream);
+int tm_cat_sparse_sandwich_f64(const int32_t* codes, int64_t n, int64_t n_cat_cols,
+                               int drop_first, const double* d, const double* csr_data,
+                               const int32_t* csr_indices, const int32_t* csr_indptr,
+                               const int32_t* csr_row, int64_t p_sparse, int64_t nnz,
+                               const int32_t* rows, int64_t n_rows, const int32_t* s_cols,
+                               int64_t nS, double* out, tm_stream_t stream);
+
+/* ---- SplitMatrix assembly (reference: split_matrix.py:336-354, the numpy scatter) ---- */
+/* out[ri[a]*ld + ci[b]] = blk[a*nb + b]  (and, when mirror != 0, out[ci[b]*ld + ri[a]] too).
+ * ri / ci NULL = identity.  `out` is float64 (SplitMatrix.sandwich always returns float64,
+ * split_matrix.py:336). */
+int tm_scatter_block_f32(const float* blk, int64_t na, int64_t nb, const int64_t* ri,
+                         const int64_t* ci, double* out, int64_t ld, int mirror,
+                         tm_stream_t stream);
+int tm_scatter_block_f64(const double* blk, int64_t na, int64_t nb, const int64_t* ri,
+                         const int64_t* ci, double* out, int64_t ld, int mirror,
+                         tm_stream_t stream);
+/* Categorical self block: out[ri[a]*ld + ri[b]] = (a==b) ? diag[a] : 0. */
+int tm_scatter_diag_f32(const float* diag, int64_t na, const int64_t* ri, double* out,
+                        int64_t ld, tm_stream_t stream);
+int tm_scatter_diag_f64(const double* diag, int64_t na, const int64_t* ri, double* out,
+                        int64_t ld, tm_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TABMAT_B200_H */

@@ -1,0 +1,101 @@
+"""ctypes binding of ``libtabmat_b200.so`` (the C-ABI declared in ``include/tabmat_b200.h``).
+
+There is deliberately NO fallback: if the shared library is missing, importing this module
+raises; if no CUDA device is present, every compute entry point raises.  The product path
+never routes through ``oracle/`` or any CPU implementation.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "libtabmat_b200.so"
+
+c_f32p = C.c_void_p
+c_i32p = C.c_void_p
+c_i64 = C.c_int64
+c_int = C.c_int
+c_ptr = C.c_void_p
+
+
+def _load() -> C.CDLL:
+    if not LIB_PATH.exists():
+        if os.environ.get("TABMAT_B200_AUTOBUILD", "1") == "1":
+            from . import build as _build
+
+            _build.build()
+        if not LIB_PATH.exists():
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `python -m tabmat_b200.build` "
+                "(tabmat_b200 has no CPU fallback)"
+            )
+    return C.CDLL(str(LIB_PATH))
+
+
+lib = _load()
+
+# name -> argtypes (restype is int unless listed in _RESTYPES)
+P = c_ptr
+I = c_i64  # noqa: E741
+N = c_int
+_SIGS = {
+    "tm_dense_sandwich": [P, I, I, N, P, P, I, P, I, P, P],
+    "tm_dense_matvec": [P, I, I, N, P, P, I, P, I, P, N, P],
+    "tm_dense_rmatvec": [P, I, I, N, P, P, I, P, I, P, P],
+    "tm_dense_sq_dot_weights": [P, I, I, N, P, P, P, P],
+    "tm_sparse_sandwich": [P, P, P, P, I, I, I, P, P, I, P, I, P, P],
+    "tm_csr_dense_sandwich": [P, P, P, I, I, P, I, N, P, P, I, P, I, P, I, P, P],
+    "tm_csr_matvec": [P, P, P, I, I, P, P, I, P, I, P, N, P],
+    "tm_csc_rmatvec": [P, P, P, I, I, P, P, I, P, I, P, N, P],
+    "tm_csc_sq_dot_weights": [P, P, P, I, I, P, P, P],
+    "tm_cat_sandwich": [P, I, P, P, I, I, N, P, P],
+    "tm_cat_transpose_matvec": [P, I, P, P, I, P, I, I, N, P, P],
+    "tm_cat_matvec": [P, I, P, P, I, I, N, P, P],
+    "tm_cat_dense_sandwich": [P, I, I, N, P, P, I, N, P, I, P, I, P, P],
+    "tm_cat_cat_sandwich": [P, P, I, I, I, N, N, P, P, I, P, P],
+    "tm_cat_sparse_sandwich": [P, I, I, N, P, P, P, P, P, I, I, P, I, P, I, P, P],
+    "tm_scatter_block": [P, I, I, P, P, P, I, N, P],
+    "tm_scatter_diag": [P, I, P, P, I, P],
+}
+
+#: every symbol include/tabmat_b200.h declares (checked by tests/test_capi_symbols.py)
+EXPORTED = ["tm_version", "tm_last_error", "tm_launch_count", "tm_reset_launch_count",
+            "tm_has_tcgen05", "tm_set_dense_f32_mode"]
+for _name, _args in _SIGS.items():
+    for _suf in ("f32", "f64"):
+        _fn = getattr(lib, f"{_name}_{_suf}")
+        _fn.argtypes = _args
+        _fn.restype = c_int
+        EXPORTED.append(f"{_name}_{_suf}")
+
+lib.tm_version.restype = c_int
+lib.tm_last_error.restype = C.c_char_p
+lib.tm_launch_count.restype = c_i64
+lib.tm_reset_launch_count.restype = None
+lib.tm_has_tcgen05.restype = c_int
+lib.tm_set_dense_f32_mode.argtypes = [c_int]
+lib.tm_set_dense_f32_mode.restype = None
+
+
+class TabmatB200Error(RuntimeError):
+    pass
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise TabmatB200Error(lib.tm_last_error().decode("utf-8", "replace"))
+
+
+def fn(name: str, dtype_suffix: str):
+    return getattr(lib, f"{name}_{dtype_suffix}")
+
+
+def launch_count() -> int:
+    return int(lib.tm_launch_count())
+
+
+def reset_launch_count() -> None:
+    lib.tm_reset_launch_count()

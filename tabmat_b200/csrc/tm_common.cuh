@@ -1,0 +1,115 @@
+// Shared helpers for the tabmat_b200 CUDA library (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/tabmat_b200.h"
+
+namespace tmb {
+
+// ---- error plumbing -------------------------------------------------------------------
+extern thread_local char g_err[512];
+extern std::atomic<long long> g_launches;
+
+inline int fail(const char* msg) {
+    snprintf(g_err, sizeof(g_err), "%s", msg);
+    return 1;
+}
+inline int fail_cuda(cudaError_t e, const char* where) {
+    snprintf(g_err, sizeof(g_err), "%s: %s", where, cudaGetErrorString(e));
+    return 2;
+}
+
+#define TM_CUDA(call)                                             \
+    do {                                                          \
+        cudaError_t _e = (call);                                  \
+        if (_e != cudaSuccess) return tmb::fail_cuda(_e, #call);   \
+    } while (0)
+
+#define TM_LAUNCHED()                                                     \
+    do {                                                                  \
+        tmb::g_launches.fetch_add(1, std::memory_order_relaxed);           \
+        cudaError_t _e = cudaGetLastError();                              \
+        if (_e != cudaSuccess) return tmb::fail_cuda(_e, "kernel launch"); \
+    } while (0)
+
+inline cudaStream_t as_stream(tm_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+int sm_count();
+
+// ---- stream-ordered scratch (device workspace arena; replaces reference alloc.h) -------
+struct Scratch {
+    void* p = nullptr;
+    cudaStream_t s = nullptr;
+    cudaError_t err = cudaSuccess;
+    Scratch(size_t bytes, cudaStream_t st) : s(st) {
+        if (bytes == 0) bytes = 16;
+        err = cudaMallocAsync(&p, bytes, st);
+    }
+    ~Scratch() {
+        if (p) cudaFreeAsync(p, s);
+    }
+    template <typename T>
+    T* as() {
+        return reinterpret_cast<T*>(p);
+    }
+    Scratch(const Scratch&) = delete;
+    Scratch& operator=(const Scratch&) = delete;
+};
+
+// ---- device helpers -------------------------------------------------------------------
+template <typename F>
+__device__ __forceinline__ void red_add(F* addr, F v) {
+    atomicAdd(addr, v);  // result unused -> RED.E.ADD
+}
+
+__device__ __forceinline__ int64_t row_at(const int32_t* __restrict__ rows, int64_t t) {
+    return rows ? (int64_t)rows[t] : t;
+}
+
+constexpr int kMaxGridX = 2147483647;
+
+inline int grid_for(int64_t work_items, int block, int max_blocks) {
+    int64_t g = (work_items + block - 1) / block;
+    if (g < 1) g = 1;
+    if (g > max_blocks) g = max_blocks;
+    return (int)g;
+}
+
+// out[i] = 0 for i < n (tiny helper used where cudaMemsetAsync would also do)
+template <typename F>
+__global__ void k_fill_zero(F* __restrict__ out, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) out[i] = F(0);
+}
+
+// map[j] = position of j in list (or -1).  map has `p` entries, pre-filled with -1.
+__global__ void k_build_pos_map(const int32_t* __restrict__ list, int64_t m,
+                                int32_t* __restrict__ map);
+// mask[j] = 1 for j in list
+__global__ void k_build_mask(const int32_t* __restrict__ list, int64_t m,
+                             uint8_t* __restrict__ mask);
+
+// Build an int32 position map of length p on `stream`: identity when list == nullptr is NOT
+// materialised (callers test the pointer).  Returns 0 on success.
+int build_pos_map(const int32_t* list, int64_t m, int64_t p, int32_t* map, cudaStream_t st);
+int build_mask(const int32_t* list, int64_t m, int64_t p, uint8_t* mask, cudaStream_t st);
+
+// dmask[k] = d[k] if k in rows else 0   (row restriction folded into the weights)
+template <typename F>
+int masked_weights(const F* d, int64_t n, const int32_t* rows, int64_t n_rows, F* dmask,
+                   cudaStream_t st);
+
+// mirror the strict lower triangle of a square row-major matrix into the upper one
+template <typename F>
+int symmetrize_from_lower(F* out, int64_t m, cudaStream_t st);
+template <typename F>
+int symmetrize_from_upper(F* out, int64_t m, cudaStream_t st);
+
+}  // namespace tmb

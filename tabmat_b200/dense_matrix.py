@@ -1,0 +1,257 @@
+"""DenseMatrix on the device (reference: dense_matrix.py:24-347).
+
+The array lives in HBM as a C- or F-contiguous 2-D CUDA tensor.  ``sandwich`` runs the
+tcgen05 weighted-SYRK kernel (fp32, C order, p <= 256) or the CUDA-core kernel; ``matvec`` /
+``transpose_matvec`` run GEMV kernels with optional row/column restrictions."""
+
+from __future__ import annotations
+
+import warnings
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _dev
+from .ext.dense import (
+    dense_matvec,
+    dense_rmatvec,
+    dense_sandwich,
+    transpose_square_dot_weights,
+)
+from .matrix_base import MatrixBase, _names_with_default, _vec_in
+from .util import (
+    _check_indexer,
+    check_matvec_dimensions,
+    check_matvec_out_shape,
+    check_sandwich_compatible,
+    check_transpose_matvec_out_shape,
+    is_unrestricted,
+    setup_restrictions,
+)
+
+
+def _dense_to_dev(input_array) -> torch.Tensor:
+    if _dev.is_dev(input_array):
+        t = input_array
+        if t.dim() == 1:
+            t = t.reshape(-1, 1)
+        elif t.dim() > 2:
+            raise ValueError("Input array must be 1- or 2-dimensional")
+        if not (t.is_contiguous() or t.t().is_contiguous()):
+            warnings.warn("Input array is not contiguous; making a copy.", UserWarning,
+                          stacklevel=3)
+            t = t.t().contiguous().t()  # F order, like the reference (dense_matrix.py:49-58)
+        return t
+    a = np.asarray(input_array)
+    if a.ndim == 1:
+        a = a.reshape(-1, 1)
+    elif a.ndim > 2:
+        raise ValueError("Input array must be 1- or 2-dimensional")
+    if not a.flags["C_CONTIGUOUS"] and not a.flags["F_CONTIGUOUS"]:
+        warnings.warn("Input array is not contiguous; making a copy.", UserWarning, stacklevel=3)
+        a = np.asfortranarray(a)
+    dev = _dev.require_cuda()
+    if a.flags["C_CONTIGUOUS"]:
+        if not a.flags.writeable:
+            a = a.copy()
+        return torch.from_numpy(a).to(dev)
+    # F order: upload the transposed (C-contiguous) buffer and view it back
+    at = a.T
+    if not at.flags.writeable:
+        at = at.copy()
+    return torch.from_numpy(at).to(dev).t()
+
+
+class DenseMatrix(MatrixBase):
+    """Dense block backed by a CUDA tensor; same API as ``tabmat.DenseMatrix``."""
+
+    def __init__(self, input_array, column_names=None, term_names=None):
+        self._array = _dense_to_dev(input_array)
+        width = self._array.shape[1]
+        if column_names is not None:
+            if len(column_names) != width:
+                raise ValueError(f"Expected {width} column names, got {len(column_names)}")
+            self._colnames = column_names
+        else:
+            self._colnames = [None] * width
+        if term_names is not None:
+            if len(term_names) != width:
+                raise ValueError(f"Expected {width} term names, got {len(term_names)}")
+            self._terms = term_names
+        else:
+            self._terms = self._colnames
+
+    # ---- array-like surface ----------------------------------------------------------
+    def __getitem__(self, key):
+        row, col = _check_indexer(key)
+        colnames = np.array(self.column_names, dtype=object)[col].ravel().tolist()
+        terms = np.array(self.term_names, dtype=object)[col].ravel().tolist()
+        sub = self._array[_torch_index(row, self._array.device),
+                          _torch_index(col, self._array.device)]
+        if sub.dim() == 2 and not (sub.is_contiguous() or sub.t().is_contiguous()):
+            sub = sub.contiguous()
+        return type(self)(sub, column_names=colnames, term_names=terms)
+
+    def __str__(self):
+        return "{}x{} DenseMatrix:\n\n".format(*self.shape) + np.array_str(self.toarray())
+
+    def __repr__(self):
+        return f"{type(self).__name__}({np.array2string(self.toarray(), separator=', ')})"
+
+    @property
+    def shape(self):  # type: ignore
+        return tuple(self._array.shape)
+
+    @property
+    def ndim(self):  # type: ignore
+        return 2
+
+    @property
+    def dtype(self):  # type: ignore
+        return _dev.np_dtype(self._array.dtype)
+
+    def transpose(self):
+        return type(self)(self._array.t())
+
+    T = property(transpose)
+
+    def astype(self, dtype, order="K", casting="unsafe", copy=True):
+        return type(self)(self._array.to(_dev.torch_dtype(dtype)), column_names=self.column_names,
+                          term_names=self.term_names)
+
+    def getcol(self, i):
+        return type(self)(self._array[:, [i]].contiguous(), column_names=[self.column_names[i]],
+                          term_names=[self.term_names[i]])
+
+    def toarray(self):
+        a = self._array
+        if a.is_contiguous():
+            return _dev.to_host(a)
+        return _dev.to_host(a.t()).T  # keeps F order on the host
+
+    def unpack(self):
+        return self.toarray()
+
+    # ---- hot path --------------------------------------------------------------------
+    def sandwich(self, d, rows=None, cols=None):
+        """X[rows, cols].T @ diag(d[rows]) @ X[rows, cols] (dense_matrix.py:153-163)."""
+        if not _dev.is_dev(d):
+            d = np.asarray(d)
+        check_sandwich_compatible(self, d)
+        d_t, host = _vec_in(d)
+        rows_t, cols_t = setup_restrictions(self.shape, rows, cols)
+        return _dev.ret(dense_sandwich(self._array, d_t, rows_t, cols_t), host)
+
+    def _cross_sandwich(self, other, d, rows=None, L_cols=None, R_cols=None):
+        from .categorical_matrix import CategoricalMatrix
+        from .sparse_matrix import SparseMatrix
+
+        if isinstance(other, (SparseMatrix, CategoricalMatrix)):
+            res = other._cross_sandwich(self, d, rows, R_cols, L_cols)
+            return res.T if isinstance(res, np.ndarray) else res.t()
+        raise TypeError
+
+    def _get_col_stds(self, weights, col_means):
+        w_t, host = _vec_in(weights, self._array.dtype)
+        m_t, _ = _vec_in(col_means, self._array.dtype)
+        sqrt_arg = transpose_square_dot_weights(self._array, w_t, m_t)
+        return _dev.ret(torch.sqrt(torch.clamp_min(sqrt_arg, 0)), host)
+
+    def _matvec_helper(self, vec, rows, cols, out, transpose: bool):
+        if not _dev.is_dev(vec):
+            vec = np.asarray(vec)
+        check_matvec_dimensions(self, vec, transpose=transpose)
+        res_dtype = np.result_type(self.dtype, _np_dtype(vec))
+        vec_t, host = _vec_in(vec, self._array.dtype)
+        if is_unrestricted(rows, self.shape[0]):
+            rows = None
+        if is_unrestricted(cols, self.shape[1]):
+            cols = None
+        rows_t, cols_t = setup_restrictions(self.shape, rows, cols)
+        fast = dense_rmatvec if transpose else dense_matvec
+        if vec_t.dim() == 1:
+            res = fast(self._array, vec_t, rows_t, cols_t)
+        else:
+            flat = vec_t.reshape(vec_t.shape[0], -1)
+            cols_out = [fast(self._array, flat[:, j].contiguous(), rows_t, cols_t)
+                        for j in range(flat.shape[1])]
+            res = torch.stack(cols_out, dim=1).reshape((-1,) + tuple(vec_t.shape[1:]))
+        if res_dtype != self.dtype and np.issubdtype(res_dtype, np.floating):
+            res = res.to(_dev.torch_dtype(res_dtype))
+        if out is None:
+            return _dev.ret(res, host)
+        sel = cols_t if transpose else rows_t
+        return _accumulate_out(out, res, sel)
+
+    def transpose_matvec(self, vec, rows=None, cols=None, out=None):
+        """self[rows, cols].T @ vec[rows] (dense_matrix.py:238-247)."""
+        check_transpose_matvec_out_shape(self, out)
+        return self._matvec_helper(vec, rows, cols, out, True)
+
+    def matvec(self, vec, cols=None, out=None):
+        """self[:, cols] @ vec[cols] (dense_matrix.py:249-257)."""
+        check_matvec_out_shape(self, out)
+        return self._matvec_helper(vec, None, cols, out, False)
+
+    def multiply(self, other):
+        """Row-wise scaling by a vector (or element-wise by a matrix)."""
+        o, _ = _vec_in(other, self._array.dtype)
+        if o.dim() == 1:
+            o = o[:, None]
+        return type(self)((self._array * o), column_names=self.column_names,
+                          term_names=self.term_names)
+
+    # ---- names -----------------------------------------------------------------------
+    def get_names(self, type: str = "column", missing_prefix: Optional[str] = None,
+                  indices: Optional[list] = None) -> list:
+        if type == "column":
+            names = self._colnames
+        elif type == "term":
+            names = self._terms
+        else:
+            raise ValueError(f"Type must be 'column' or 'term', got {type}")
+        return _names_with_default(names, missing_prefix, indices)
+
+    def set_names(self, names, type: str = "column"):
+        if isinstance(names, str):
+            names = [names]
+        if len(names) != self.shape[1]:
+            raise ValueError(f"Length of names must be {self.shape[1]}")
+        if type == "column":
+            self._colnames = names
+        elif type == "term":
+            self._terms = names
+        else:
+            raise ValueError(f"Type must be 'column' or 'term', got {type}")
+
+
+def _np_dtype(x) -> np.dtype:
+    if isinstance(x, torch.Tensor):
+        return _dev.np_dtype(x.dtype)
+    return np.asarray(x).dtype
+
+
+def _torch_index(ix, device):
+    if isinstance(ix, slice):
+        return ix
+    a = np.asarray(ix)
+    if a.dtype == bool:
+        return torch.from_numpy(a).to(device)
+    return torch.from_numpy(a.astype(np.int64)).to(device)
+
+
+def _accumulate_out(out, res: torch.Tensor, sel: Optional[torch.Tensor]):
+    """out[sel] += res, in place, for a numpy or CUDA ``out``; returns ``out`` itself."""
+    if _dev.is_dev(out):
+        if sel is None:
+            out += res.to(out.dtype)
+        else:
+            out.index_add_(0, sel.to(torch.int64), res.to(out.dtype))
+        return out
+    res_h = _dev.to_host(res)
+    if sel is None:
+        out += res_h
+    else:
+        out[_dev.to_host(sel)] += res_h
+    return out

@@ -1,0 +1,418 @@
+"""SplitMatrix: column blocks of dense / sparse / categorical parts (reference:
+split_matrix.py:22-554).
+
+``sandwich`` computes every self block and every cross block on the device and places them
+straight into the p x p float64 output with scatter kernels (the reference assembles the
+output with numpy fancy indexing on the host, split_matrix.py:336-354).  Like the reference,
+all dense blocks are merged into one DenseMatrix and all sparse blocks into one SparseMatrix
+at construction (split_matrix.py:85-141)."""
+
+from __future__ import annotations
+
+import warnings
+from collections.abc import Sequence
+from typing import Optional, Union
+
+import numpy as np
+import torch
+from scipy import sparse as sps
+
+from . import _dev
+from ._lib import check, fn
+from .categorical_matrix import CategoricalMatrix
+from .dense_matrix import DenseMatrix, _accumulate_out
+from .ext.split import is_sorted, split_col_subsets
+from .matrix_base import MatrixBase, _vec_in
+from .sparse_matrix import SparseMatrix
+from .standardized_mat import StandardizedMatrix
+from .util import (
+    check_matvec_dimensions,
+    check_matvec_out_shape,
+    check_sandwich_compatible,
+    check_transpose_matvec_out_shape,
+)
+
+
+def as_tabmat(a):
+    """Convert an array to the corresponding MatrixBase type (split_matrix.py:22-38)."""
+    if isinstance(a, (MatrixBase, StandardizedMatrix)):
+        return a
+    elif sps.issparse(a):
+        return SparseMatrix(a.tocsc(copy=False))
+    elif isinstance(a, np.ndarray) or _dev.is_dev(a):
+        return DenseMatrix(a)
+    else:
+        raise ValueError(f"Cannot convert type {type(a)} to Matrix.")
+
+
+def hstack(tup: Sequence) -> MatrixBase:
+    """Stack matrices horizontally (split_matrix.py:41-63)."""
+    matrices = [as_tabmat(a) for a in tup]
+    if len(matrices) == 0:
+        raise ValueError("Need at least one array to concatenate.")
+    if all(isinstance(mat, SparseMatrix) for mat in matrices):
+        return _hstack_sparse(matrices)
+    elif all(isinstance(mat, DenseMatrix) for mat in matrices):
+        return _hstack_dense(matrices)
+    else:
+        return SplitMatrix(matrices)
+
+
+def _hstack_dense(mats) -> DenseMatrix:
+    arrs = [m._array for m in mats]
+    if all(a.t().is_contiguous() and not a.is_contiguous() for a in arrs):
+        # all F order: stack the transposes' rows, keep F order
+        return DenseMatrix(torch.cat([a.t() for a in arrs], dim=0).t())
+    return DenseMatrix(torch.cat(arrs, dim=1).contiguous())
+
+
+def _hstack_sparse(mats) -> SparseMatrix:
+    """Column-concatenate sparse blocks on the device (CSR entries interleaved per row)."""
+    n = mats[0].shape[0]
+    dev = mats[0]._csr.data.device
+    counts = [(m._csr.indptr[1:] - m._csr.indptr[:-1]).to(torch.int64) for m in mats]
+    total = torch.stack(counts, 0).sum(0)
+    new_indptr = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+    new_indptr[1:] = torch.cumsum(total, 0)
+    nnz = int(new_indptr[-1].item())
+    if nnz > np.iinfo(np.int32).max:
+        raise ValueError("merged sparse block exceeds int32 indexing")
+    data = torch.empty(nnz, dtype=mats[0]._csr.data.dtype, device=dev)
+    indices = torch.empty(nnz, dtype=torch.int32, device=dev)
+    prefix = torch.zeros(n, dtype=torch.int64, device=dev)
+    col_off = 0
+    for m, cnt in zip(mats, counts):
+        c = m._csr
+        row = c.row.to(torch.int64)
+        pos = torch.arange(c.nnz, device=dev, dtype=torch.int64) - c.indptr.to(torch.int64)[row]
+        dest = new_indptr[row] + prefix[row] + pos
+        data[dest] = c.data.to(data.dtype)
+        indices[dest] = c.indices + col_off
+        prefix += cnt
+        col_off += m.shape[1]
+    return SparseMatrix.from_device_csr(data, indices, new_indptr.to(torch.int32), (n, col_off))
+
+
+def _filter_out_empty(matrices, indices):
+    keep_idxs = [i for i, m in enumerate(matrices) if m.shape[1] > 0]
+    return [matrices[i] for i in keep_idxs], [indices[i] for i in keep_idxs]
+
+
+def _combine_matrices(matrices, indices):
+    """Merge all DenseMatrix blocks into one and all SparseMatrix blocks into one; categorical
+    blocks stay as they are (split_matrix.py:85-141)."""
+    n_row = matrices[0].shape[0]
+    for mat_type_, stack_fn in [(DenseMatrix, _hstack_dense), (SparseMatrix, _hstack_sparse)]:
+        this_type = [i for i, mat in enumerate(matrices) if isinstance(mat, mat_type_)]
+        if len(this_type) > 1:
+            new_matrix = stack_fn([matrices[i] for i in this_type])
+            new_indices = np.concatenate([indices[i] for i in this_type])
+            new_colnames = np.concatenate(
+                [np.array(matrices[i]._colnames, dtype=object) for i in this_type])
+            new_terms = np.concatenate(
+                [np.array(matrices[i]._terms, dtype=object) for i in this_type])
+            sorter = np.argsort(new_indices)
+            if np.array_equal(sorter, np.arange(len(sorter))):
+                sorted_matrix = new_matrix
+            else:
+                sorted_matrix = new_matrix[:, sorter]
+            sorted_matrix._colnames = new_colnames[sorter].tolist()
+            sorted_matrix._terms = new_terms[sorter].tolist()
+            assert sorted_matrix.shape[0] == n_row
+            matrices[this_type[0]] = sorted_matrix
+            indices[this_type[0]] = new_indices[sorter]
+            indices = [idx for i, idx in enumerate(indices) if i not in this_type[1:]]
+            matrices = [mat for i, mat in enumerate(matrices) if i not in this_type[1:]]
+    return matrices, indices
+
+
+class SplitMatrix(MatrixBase):
+    """Matrix with dense, sparse and categorical column blocks; same API as
+    ``tabmat.SplitMatrix``."""
+
+    def __init__(self, matrices: Sequence[MatrixBase], indices: Optional[list] = None):
+        flatten_matrices = []
+        index_corrections = []
+        for mat in matrices:
+            if not isinstance(mat, MatrixBase):
+                raise ValueError("Expected all elements of matrices to be subclasses of MatrixBase.")
+            if isinstance(mat, SplitMatrix):
+                current_idx = 0
+                for iind, imat in zip(mat.indices, mat.matrices):
+                    flatten_matrices.append(imat)
+                    index_corrections.append(
+                        iind - np.arange(len(iind), dtype=np.int64) - current_idx)
+                    current_idx += len(iind)
+            else:
+                flatten_matrices.append(mat)
+                index_corrections.append(np.zeros(mat.shape[1], dtype=np.int64))
+
+        self.dtype = flatten_matrices[0].dtype
+        n_row = flatten_matrices[0].shape[0]
+        for i, mat in enumerate(flatten_matrices):
+            if mat.dtype != self.dtype:
+                warnings.warn(
+                    "Matrices do not all have the same dtype. Dtypes are "
+                    f"{[elt.dtype for elt in flatten_matrices]}."
+                )
+            if not mat.shape[0] == n_row:
+                raise ValueError(
+                    "All matrices should have the same first dimension, "
+                    f"but the first matrix has first dimension {n_row} and matrix {i} "
+                    f"has first dimension {mat.shape[0]}."
+                )
+
+        if indices is None:
+            indices = []
+            current_idx = 0
+            for mat, ind_corr in zip(flatten_matrices, index_corrections):
+                indices.append(
+                    np.arange(current_idx, current_idx + mat.shape[1], dtype=np.int64) + ind_corr)
+                current_idx += mat.shape[1]
+            n_col = current_idx
+        else:
+            indices = list(indices)
+            all_indices = np.concatenate(indices)
+            n_col = len(all_indices)
+            if (np.arange(n_col, dtype=np.int64) != np.sort(all_indices)).any():
+                raise ValueError(
+                    "Indices should contain all integers from 0 to one less than the "
+                    "number of columns."
+                )
+            for i in range(len(indices)):
+                indices[i] = np.asarray(indices[i])
+                if not is_sorted(indices[i]):
+                    raise ValueError(
+                        f"Each index block should be sorted, but indices[{i}] was not sorted"
+                    )
+
+        for i, (mat, idx) in enumerate(zip(flatten_matrices, indices)):
+            if not mat.shape[1] == len(idx):
+                raise ValueError(
+                    f"Element {i} of indices should should have length {mat.shape[1]}, "
+                    f"but it has shape {idx.shape}"
+                )
+
+        filtered_mats, filtered_idxs = _filter_out_empty(flatten_matrices, indices)
+        combined_matrices, combined_indices = _combine_matrices(filtered_mats, filtered_idxs)
+
+        self.matrices = combined_matrices
+        self.indices = [np.asarray(elt, dtype=np.int64) for elt in combined_indices]
+        self.shape = (n_row, n_col)
+        self._indices_dev: Optional[list] = None
+        assert self.shape[1] > 0
+
+    # ---- helpers ---------------------------------------------------------------------
+    def _dev_indices(self):
+        if self._indices_dev is None:
+            self._indices_dev = [_dev.to_dev(idx) for idx in self.indices]
+        return self._indices_dev
+
+    def _split_col_subsets(self, cols):
+        """(positions of each block's columns in the output, block-local column ids, n_cols);
+        see split_matrix.py:269-291."""
+        if cols is None:
+            return self.indices, [None for _ in range(len(self.indices))], self.shape[1]
+        if _dev.is_dev(cols):
+            cols = _dev.to_host(cols)
+        cols = np.asarray(cols).astype(np.int32)
+        return split_col_subsets(self.indices, cols)
+
+    def astype(self, dtype, order="K", casting="unsafe", copy=True):
+        new_matrices = [mat.astype(dtype=dtype, order=order, casting=casting, copy=True)
+                        for mat in self.matrices]
+        return SplitMatrix(new_matrices, self.indices)
+
+    def toarray(self) -> np.ndarray:
+        out = np.empty(self.shape)
+        for mat, idx in zip(self.matrices, self.indices):
+            out[:, idx] = mat.toarray()
+        return out
+
+    def getcol(self, i: int):
+        i %= self.shape[1]
+        for mat, idx in zip(self.matrices, self.indices):
+            if i in idx:
+                loc = np.where(idx == i)[0][0]
+                return mat.getcol(loc)
+        raise RuntimeError(f"Column {i} was not found.")
+
+    # ---- hot path --------------------------------------------------------------------
+    def sandwich(self, d, rows=None, cols=None):
+        """X[rows, cols].T @ diag(d[rows]) @ X[rows, cols] as float64 (split_matrix.py:324-356)."""
+        if not _dev.is_dev(d):
+            d = np.asarray(d)
+        check_sandwich_compatible(self, d)
+        d_t, host = _vec_in(d)
+        out = self._sandwich_dev(d_t, _dev.idx32(rows), cols)
+        return _dev.ret(out, host)
+
+    def _sandwich_dev(self, d_t: torch.Tensor, rows_t, cols) -> torch.Tensor:
+        subset_cols_indices, subset_cols, n_cols = self._split_col_subsets(cols)
+        if cols is None:
+            pos_t = self._dev_indices()
+            sub_t = [None] * len(self.matrices)
+        else:
+            pos_t = [_dev.to_dev(np.asarray(p, dtype=np.int64)) for p in subset_cols_indices]
+            sub_t = [_dev.idx32(s) for s in subset_cols]
+        st = _dev.stream_ptr()
+        # every (i, j) entry is written by exactly one block (or its mirror): no zero-fill
+        out = torch.empty((n_cols, n_cols), dtype=torch.float64, device=d_t.device)
+        k = len(self.matrices)
+        for i in range(k):
+            mat_i = self.matrices[i]
+            mi = int(pos_t[i].numel())
+            if mi == 0:
+                continue
+            if isinstance(mat_i, CategoricalMatrix):
+                diag, _ = mat_i._sandwich_diag(d_t, rows_t, sub_t[i])
+                check(fn("tm_scatter_diag", _dev.suffix(diag.dtype))(
+                    _dev.ptr(diag), mi, _dev.ptr(pos_t[i]), _dev.ptr(out), n_cols, st))
+            else:
+                res = mat_i.sandwich(d_t, rows_t, sub_t[i])
+                check(fn("tm_scatter_block", _dev.suffix(res.dtype))(
+                    _dev.ptr(res), mi, mi, _dev.ptr(pos_t[i]), _dev.ptr(pos_t[i]), _dev.ptr(out),
+                    n_cols, 0, st))
+            for j in range(i + 1, k):
+                mj = int(pos_t[j].numel())
+                if mj == 0:
+                    continue
+                res = self.matrices[i]._cross_sandwich(self.matrices[j], d_t, rows_t, sub_t[i],
+                                                       sub_t[j])
+                res = res.contiguous()
+                check(fn("tm_scatter_block", _dev.suffix(res.dtype))(
+                    _dev.ptr(res), mi, mj, _dev.ptr(pos_t[i]), _dev.ptr(pos_t[j]), _dev.ptr(out),
+                    n_cols, 1, st))
+        return out
+
+    def _get_col_means(self, weights):
+        host = not _dev.is_dev(weights)
+        parts = [mat._get_col_means(weights) for mat in self.matrices]
+        return self._gather_cols(parts, host)
+
+    def _get_col_stds(self, weights, col_means):
+        host = not _dev.is_dev(weights)
+        parts = []
+        for idx, mat in zip(self.indices, self.matrices):
+            cm = col_means[idx] if host else col_means[_dev.to_dev(idx)]
+            parts.append(mat._get_col_stds(weights, cm))
+        return self._gather_cols(parts, host)
+
+    def _gather_cols(self, parts, host: bool):
+        if host:
+            out = np.empty(self.shape[1], dtype=self.dtype)
+            for idx, part in zip(self.indices, parts):
+                out[idx] = part
+            return out
+        out = torch.empty(self.shape[1], dtype=_dev.torch_dtype(self.dtype), device=parts[0].device)
+        for idx_t, part in zip(self._dev_indices(), parts):
+            out[idx_t] = part.to(out.dtype)
+        return out
+
+    def matvec(self, v, cols=None, out=None):
+        """self[:, cols] @ v[cols] (split_matrix.py:373-420)."""
+        assert not isinstance(v, sps.spmatrix)
+        if not _dev.is_dev(v):
+            v = np.asarray(v)
+        check_matvec_dimensions(self, v, transpose=False)
+        check_matvec_out_shape(self, out)
+        v_t, host = _vec_in(v)
+        _, subset_cols, n_cols = self._split_col_subsets(cols)
+        out_dtype = np.result_type(self.dtype, _dev.np_dtype(v_t.dtype)
+                                   if v_t.dtype in (torch.float32, torch.float64) else np.float64)
+        tdt = _dev.torch_dtype(out_dtype)
+        if v_t.dtype != tdt:
+            v_t = v_t.to(tdt)
+        out_shape = [self.shape[0]] + list(v_t.shape[1:])
+        if out is not None and _dev.is_dev(out):
+            if out.dtype != tdt:
+                raise ValueError(
+                    f"out array is required to have dtype {out_dtype} but hasdtype {out.dtype}")
+            acc = out
+        else:
+            acc = torch.zeros(out_shape, dtype=tdt, device=v_t.device)
+        sub_t = [None if s is None else _dev.idx32(s) for s in subset_cols]
+        for sub, idx_t, mat in zip(sub_t, self._dev_indices(), self.matrices):
+            if sub is not None and sub.numel() == 0:
+                continue
+            in_vec = v_t.index_select(0, idx_t)
+            if in_vec.dtype != _dev.torch_dtype(mat.dtype) and not isinstance(mat, CategoricalMatrix):
+                # mixed-dtype split: compute the block in its own dtype, add into acc
+                acc += mat.matvec(in_vec, sub).to(tdt)
+            elif acc.dim() == 1:
+                mat.matvec(in_vec, sub, out=acc)
+            else:
+                acc += mat.matvec(in_vec, sub).to(tdt)
+        if out is not None and not _dev.is_dev(out):
+            return _accumulate_out(out, acc, None)
+        if out is not None:
+            return out
+        return _dev.ret(acc, host)
+
+    def transpose_matvec(self, v, rows=None, cols=None, out=None):
+        """self[rows, cols].T @ v[rows] (split_matrix.py:422-460)."""
+        if not _dev.is_dev(v):
+            v = np.asarray(v)
+        check_matvec_dimensions(self, v, transpose=True)
+        check_transpose_matvec_out_shape(self, out)
+        v_t, host = _vec_in(v)
+        subset_cols_indices, subset_cols, n_cols = self._split_col_subsets(cols)
+        out_dtype = np.result_type(self.dtype, _dev.np_dtype(v_t.dtype)
+                                   if v_t.dtype in (torch.float32, torch.float64) else np.float64)
+        tdt = _dev.torch_dtype(out_dtype)
+        if v_t.dtype != tdt:
+            v_t = v_t.to(tdt)
+        rows_t = _dev.idx32(rows)
+        res = torch.zeros([n_cols] + list(v_t.shape[1:]), dtype=tdt, device=v_t.device)
+        if cols is None:
+            pos_t = self._dev_indices()
+            sub_t = [None] * len(self.matrices)
+        else:
+            pos_t = [_dev.to_dev(np.asarray(p, dtype=np.int64)) for p in subset_cols_indices]
+            sub_t = [_dev.idx32(s) for s in subset_cols]
+        for pos, sub, mat in zip(pos_t, sub_t, self.matrices):
+            if pos.numel() == 0:
+                continue
+            part = mat.transpose_matvec(v_t, rows=rows_t, cols=sub)
+            res.index_add_(0, pos, part.to(tdt))
+        if out is None:
+            return _dev.ret(res, host)
+        sel = None if cols is None else _dev.idx32(cols)
+        return _accumulate_out(out, res, sel)
+
+    def __getitem__(self, key):
+        if isinstance(key, tuple):
+            row, col = key
+        else:
+            row = key
+            col = slice(None, None, None)
+        if col == slice(None, None, None):
+            if isinstance(row, int):
+                row = [row]
+            return SplitMatrix([mat[row, :] for mat in self.matrices], self.indices)
+        raise NotImplementedError(f"Only row indexing is supported. Index passed was {key}.")
+
+    def multiply(self, other):
+        return SplitMatrix([mat.multiply(other) for mat in self.matrices], indices=self.indices)
+
+    def __repr__(self):
+        out = "SplitMatrix:"
+        for i, mat in enumerate(self.matrices):
+            out += f"\n\nComponent {i} with type {mat.__class__.__name__}\n" + mat.__repr__()
+        return out
+
+    __array_priority__ = 13
+
+    def get_names(self, type: str = "column", missing_prefix: Optional[str] = None,
+                  indices: Optional[list] = None) -> list:
+        names = np.empty(self.shape[1], dtype=object)
+        for idx, mat in zip(self.indices, self.matrices):
+            names[idx] = mat.get_names(type, missing_prefix, idx)
+        return names.tolist()
+
+    def set_names(self, names: Union[str, list], type: str = "column"):
+        names_array = np.array(names, dtype=object)
+        if len(names) != self.shape[1]:
+            raise ValueError(f"Length of names must be {self.shape[1]}")
+        for idx, mat in zip(self.indices, self.matrices):
+            mat.set_names(names_array[idx].tolist(), type)
