@@ -78,6 +78,9 @@ lib.tm_reset_launch_count.restype = None
 lib.tm_has_tcgen05.restype = c_int
 lib.tm_set_dense_f32_mode.argtypes = [c_int]
 lib.tm_set_dense_f32_mode.restype = None
+# TABMAT_B200_DENSE_F32_MODE: 0 auto (tcgen05 when eligible) | 1 CUDA-core only | 2 force tcgen05
+if os.environ.get("TABMAT_B200_DENSE_F32_MODE"):
+    lib.tm_set_dense_f32_mode(int(os.environ["TABMAT_B200_DENSE_F32_MODE"]))
 
 
 class TabmatB200Error(RuntimeError):

@@ -1,0 +1,78 @@
+"""GPU parity, boundary level: every C-ABI entry point against the oracle (C restatement)
+and against the golden vectors produced by the reference itself, on identical seeded inputs.
+
+Tolerance (north_star): normwise 1e-5 fp64 / 1e-3 fp32; categorical counts bit-exact."""
+
+import numpy as np
+import pytest
+
+from tests import cases
+
+pytestmark = pytest.mark.gpu
+
+ALL_CASES = list(cases.boundary_cases())
+
+
+@pytest.mark.parametrize("name,kind,args", ALL_CASES, ids=[c[0] for c in ALL_CASES])
+def test_cuda_matches_oracle_and_golden(name, kind, args, golden_boundary):
+    from tests.gpu_runner import run_cuda
+
+    got = run_cuda(kind, args)
+    orc = cases.run_oracle(kind, args)
+    assert got.dtype == orc.dtype
+    cases.assert_close(got, orc, got.dtype, name + " vs oracle")
+    cases.assert_close(got, golden_boundary[name], got.dtype, name + " vs reference golden")
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_cat_sandwich_counts_bit_exact(dt):
+    """d == 1: the segmented reduction is an exact count (north_star: bit-exact)."""
+    from tests.gpu_runner import run_cuda
+
+    rng = np.random.default_rng(5)
+    n, K = 1_000_003, 2000
+    codes = rng.integers(0, K, size=n).astype(np.int32)
+    got = run_cuda("cat_sandwich", dict(codes=codes, d=np.ones(n, dt), rows=None, K=K,
+                                        drop_first=False))
+    assert np.array_equal(got, np.bincount(codes, minlength=K).astype(dt))
+    ci = rng.integers(0, 50, size=n).astype(np.int32)
+    cj = rng.integers(0, 30, size=n).astype(np.int32)
+    got = run_cuda("cat_cat_sandwich", dict(ic=ci, jc=cj, Ki=50, Kj=30, d=np.ones(n, dt),
+                                            rows=None, i_drop_first=False, j_drop_first=False))
+    ref = np.zeros((50, 30))
+    np.add.at(ref, (ci, cj), 1)
+    assert np.array_equal(got, ref.astype(dt))
+
+
+@pytest.mark.parametrize("seed", range(3))
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_random_medium_shapes(seed, dt):
+    """Medium shapes (oracle still finishes in seconds): ragged n, many tiles."""
+    from tests.gpu_runner import run_cuda
+
+    rng = np.random.default_rng(100 + seed)
+    n = int(rng.integers(3000, 9000))
+    I = cases.make_inputs(200 + seed, n, dt, p_dense=int(rng.integers(65, 200)),  # noqa: E741
+                          p_sparse=int(rng.integers(100, 400)), Ki=int(rng.integers(20, 300)),
+                          Kj=17, density=0.02)
+    for kind, args in [
+        ("dense_sandwich", dict(X=I["X"], d=I["d"], rows=None, cols=None)),
+        ("dense_sandwich", dict(X=np.asfortranarray(I["X"]), d=I["d"], rows=I["rows"],
+                                cols=I["cols_dense"])),
+        ("sparse_sandwich", dict(A=I["A"], d=I["d"], rows=I["rows"], cols=None)),
+        ("csr_dense_sandwich", dict(A=I["A"], B=I["X"], d=I["d"], rows=None, A_cols=None,
+                                    B_cols=None)),
+        ("cat_dense_sandwich", dict(codes=I["ci_missing"], K=I["Ki"], d=I["d"], Y=I["X"],
+                                    rows=None, j_cols=None, drop_first=False)),
+        ("cat_cat_sandwich", dict(ic=I["ci_missing"], jc=I["cj"], Ki=I["Ki"], Kj=I["Kj"],
+                                  d=I["d"], rows=I["rows"], i_drop_first=False,
+                                  j_drop_first=False)),
+        ("cat_sparse_sandwich", dict(codes=I["ci"], K=I["Ki"], d=I["d"], A=I["A"], rows=None,
+                                     s_cols=None, drop_first=False)),
+        ("csr_matvec", dict(A=I["A"], v=I["v_sparse"], rows=None, cols=None)),
+        ("csc_rmatvec", dict(A=I["A"], v=I["v_n"], rows=None, cols=None)),
+        ("dense_rmatvec", dict(X=I["X"], v=I["v_n"], rows=None, cols=None)),
+        ("dense_matvec", dict(X=I["X"], v=I["v_dense"], rows=None, cols=None)),
+    ]:
+        got = run_cuda(kind, args)
+        cases.assert_close(got, cases.run_oracle(kind, args), dt, f"{kind} seed={seed}")
