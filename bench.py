@@ -315,7 +315,7 @@ def block_breakdown(Xs, d, reps=3):
         else:
             timed(f"{names[i]}.self", lambda mi=mi: mi.sandwich(d))
         for j in range(i + 1, len(mats)):
-            timed(f"{names[i]}x{names[j]}", lambda mi=mi, mj=mats[j]: mi._cross_sandwich(mj, d))
+            timed(f"{names[i]}x{names[j]}", lambda mi=mi, mj=mats[j]: mi._cross_sandwich(mj, d, None, None, None))
     return out
 
 

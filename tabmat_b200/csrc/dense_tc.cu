@@ -6,9 +6,9 @@
 // Data flow per CTA (one persistent CTA per SM, split-K over row tiles of BK=32 rows):
 //
 //   warp 0  (1 lane)  TMA producer: X[k0:k0+32, :] -> smem stage "R" as column groups of
-//                     32 floats (one 128B-swizzled box [32 rows][128 B] per group).  For
-//                     row-major X this is exactly the MN-major SWIZZLE_128B canonical UMMA
-//                     layout (8-row x 128 B atoms stacked along K), so no transpose is needed.
+//                     32 floats (one swizzled box [32 rows][128 B] per group).  For row-major
+//                     X this is exactly the MN-major SWIZZLE_128B_BASE32B canonical UMMA
+//                     layout (4-row x 128 B atoms stacked along K), so no transpose is needed.
 //   warps 2-9         scale warps: B[r][c] = rna_tf32(d[k0+r] * R[r][c]) into a second smem
 //                     buffer with the same (swizzled) addresses; R is rounded to tf32 in place
 //                     (round-to-nearest; raw fp32 bits would be truncated by the MMA, a biased
@@ -50,6 +50,8 @@ struct Params {
     long long num_row_tiles;
     int stages;
     int tmem_cols;
+    float* dbg;       // debug dump (tools/tc_debug.py); nullptr in production
+    int variant;      // bring-up switches (0 in production)
 };
 
 // ---- PTX wrappers ----------------------------------------------------------------------
@@ -125,7 +127,11 @@ __device__ __forceinline__ uint32_t to_tf32(float x) {
 
 // UMMA shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
 //   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 | [32,46) stride byte offset >> 4
-//   [46,48) version = 1 (Blackwell) | [61,64) layout type (2 = SWIZZLE_128B)
+//   [46,48) version = 1 (Blackwell) | [61,64) layout type (1 = SWIZZLE_128B_BASE32B)
+// MN-major 32-bit operands only exist in the 128B-swizzle-with-32B-atoms layout
+// (Swizzle<2,5,2>: 32-byte chunk index ^= row & 3; K atom = 4 rows of 128 B = 512 B), which is
+// what TMA writes with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.  One K=8 instruction therefore
+// spans two K atoms: SBO = 512 B; the next 32-column group is LBO = GROUP_BYTES away.
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes,
                                               uint32_t sbo_bytes) {
     uint64_t d = 0;
@@ -133,7 +139,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
     d |= (uint64_t)(lbo_bytes >> 4) << 16;
     d |= (uint64_t)(sbo_bytes >> 4) << 32;
     d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
+    d |= (uint64_t)1 << 61;  // SWIZZLE_128B_BASE32B: the only MN-major layout tf32 supports
     return d;
 }
 
@@ -248,11 +254,13 @@ k_dense_syrk_tc(const __grid_constant__ CUtensorMap tmap, const Params prm) {
                     uint32_t acc = (it > 0 || ks > 0) ? 1u : 0u;
                     int tile = 0;
                     for (int mt = 0; mt < prm.mtiles; ++mt) {
+                        const uint32_t lbo = (prm.variant & 1) ? 512u : (uint32_t)GROUP_BYTES;
+                        const uint32_t sbo = (prm.variant & 1) ? (uint32_t)GROUP_BYTES : 512u;
                         uint64_t da = make_desc(Ra + (uint32_t)(mt * 4) * GROUP_BYTES + ks * 1024,
-                                                GROUP_BYTES, 1024);
+                                                lbo, sbo);
                         for (int nt = 0; nt <= mt; ++nt, ++tile) {
                             uint64_t db = make_desc(
-                                Ba + (uint32_t)(nt * 4) * GROUP_BYTES + ks * 1024, GROUP_BYTES, 1024);
+                                Ba + (uint32_t)(nt * 4) * GROUP_BYTES + ks * 1024, lbo, sbo);
                             tcgen05_mma_tf32(tmem_base + (uint32_t)tile * 128, da, db, idesc, acc);
                         }
                     }
@@ -298,6 +306,11 @@ k_dense_syrk_tc(const __grid_constant__ CUtensorMap tmap, const Params prm) {
                 *reinterpret_cast<uint4*>(B + (size_t)g * GROUP_BYTES) = b;
             }
             fence_proxy_async();
+            if (prm.dbg && blockIdx.x == 0 && it == 0) {
+                // raw stage-0 smem (R half then B half) as floats
+                const float* sm = reinterpret_cast<const float*>(base);
+                for (uint32_t i = t; i < stage_bytes / 4; i += NUM_SCALE_THREADS) prm.dbg[i] = sm[i];
+            }
             mbar_arrive(&scaled[s]);
         }
 
@@ -320,6 +333,11 @@ k_dense_syrk_tc(const __grid_constant__ CUtensorMap tmap, const Params prm) {
                             tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(tile * 128 + n0);
                         TM_TMEM_LD_32x32B_X32(taddr, v);
                         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                        if (prm.dbg && blockIdx.x == 0) {
+                            float* T = prm.dbg + 65536 + (size_t)tile * 128 * 128;
+                            for (int j = 0; j < 32; ++j)
+                                T[(q * 32 + lane) * 128 + n0 + j] = __uint_as_float(v[j]);
+                        }
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             const int Rr = nt * 128 + n0 + j;  // output row (= X column of B)
@@ -385,6 +403,9 @@ bool dense_tc_eligible(int64_t n, int64_t p, int c_order, const void* X) {
     return tc::get_encode() != nullptr;
 }
 
+float* g_tc_dbg = nullptr;
+int g_tc_variant = 0;
+
 int dense_sandwich_tc_f32(const float* X, int64_t n, int64_t p, int c_order, const float* d,
                           float* out, cudaStream_t st) {
     using namespace tc;
@@ -399,7 +420,7 @@ int dense_sandwich_tc_f32(const float* X, int64_t n, int64_t p, int c_order, con
     cuuint32_t estr[2] = {1, 1};
     CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(X), gdim,
                       gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed");
 
@@ -411,6 +432,8 @@ int dense_sandwich_tc_f32(const float* X, int64_t n, int64_t p, int c_order, con
     prm.groups = (int)((p + 31) / 32);
     prm.mtiles = (int)((p + 127) / 128);
     prm.num_row_tiles = (n + BK - 1) / BK;
+    prm.dbg = g_tc_dbg;
+    prm.variant = g_tc_variant;
     int ntiles = prm.mtiles * (prm.mtiles + 1) / 2;
     prm.tmem_cols = ntiles == 1 ? 128 : 512;
     int stage_bytes = 2 * prm.mtiles * 4 * GROUP_BYTES;
@@ -441,5 +464,8 @@ int tm_has_tcgen05(void) {
     return tmb::tc::device_cc_major() == 10 && tmb::tc::get_encode() != nullptr ? 1 : 0;
 }
 void tm_set_dense_f32_mode(int mode) { tmb::g_dense_f32_mode = mode; }
+/* test hook (not part of the public header): device buffer of >= 65536 + 3*128*128 floats */
+void tm_debug_set_tc_buffer(float* buf) { tmb::g_tc_dbg = buf; }
+void tm_debug_set_tc_variant(int v) { tmb::g_tc_variant = v; }
 
 }  // extern "C"
