@@ -309,12 +309,17 @@ def block_breakdown(Xs, d, reps=3):
             ts.append(e0.elapsed_time(e1))
         out[label] = float(np.mean(ts))
 
+    fused_pairs = set(Xs._fused_dense_cross(d, None).keys())
+    if fused_pairs:
+        timed("dense.cross_fused", lambda: Xs._fused_dense_cross(d, None))
     for i, mi in enumerate(mats):
         if isinstance(mi, CategoricalMatrix):
             timed(f"{names[i]}.self", lambda mi=mi: mi._sandwich_diag(d))
         else:
             timed(f"{names[i]}.self", lambda mi=mi: mi.sandwich(d))
         for j in range(i + 1, len(mats)):
+            if (i, j) in fused_pairs or (j, i) in fused_pairs:
+                continue
             timed(f"{names[i]}x{names[j]}", lambda mi=mi, mj=mats[j]: mi._cross_sandwich(mj, d, None, None, None))
     return out
 
@@ -324,6 +329,10 @@ def block_bytes(label, n, nnz, fsize=4):
     def K_of(s):
         return int(s[3:])
     a, _, b = label.partition("x")
+    if label == "dense.cross_fused":
+        ps = SPARSE_BLOCKS * SPARSE_COLS
+        return (n * (P_DENSE * fsize + len(CAT_LEVELS) * 4 + fsize) + nnz * (fsize + 4)
+                + 4 * (n + 1) + (ps + sum(CAT_LEVELS)) * P_DENSE * fsize)
     if label == "dense.self":
         return n * P_DENSE * fsize + n * fsize + P_DENSE * P_DENSE * fsize
     if label == "sparse.self":

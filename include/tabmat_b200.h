@@ -235,6 +235,31 @@ int tm_cat_sparse_sandwich_f64(const int32_t* codes, int64_t n, int64_t n_cat_co
                                const int32_t* rows, int64_t n_rows, const int32_t* s_cols,
                                int64_t nS, double* out, tm_stream_t stream);
 
+/* ---- fused cross blocks of a SplitMatrix (reference: the Python block loop,
+ * split_matrix.py:346-354, which calls categorical_matrix.py:759-791 -> split.pyx:32-80 once per
+ * categorical block and sparse_matrix.py:206-229 -> sparse.pyx:211-260 for the sparse block,
+ * re-reading the dense block each time) ------------------------------------------------------ */
+/* One pass over the C-contiguous dense block X (n x p, p % 4 == 0 for f32 / p % 2 == 0 for
+ * f64, p <= 256 / 128):
+ *   out_cat[i][(codes[i][k]-drop_first[i])*p + b] += d[k] * X[k, b]        i < n_cat (<= 8)
+ *   out_sparse[j*p + b]                           += A[k, j] * d[k] * X[k, b]   (A in CSR)
+ * for k in rows.  `codes`, `K`, `drop_first`, `out_cat` are HOST arrays of length n_cat (of
+ * device pointers / values).  out_sparse may be NULL (no sparse block).  Overwrites outputs. */
+int tm_dense_cross_sandwich_f32(const float* X, int64_t n, int64_t p, const float* d,
+                                const int32_t* rows, int64_t n_rows, int n_cat,
+                                const int32_t* const* codes, const int64_t* K,
+                                const int32_t* drop_first, float* const* out_cat,
+                                const float* csr_data, const int32_t* csr_indices,
+                                const int32_t* csr_indptr, int64_t p_sparse, float* out_sparse,
+                                tm_stream_t stream);
+int tm_dense_cross_sandwich_f64(const double* X, int64_t n, int64_t p, const double* d,
+                                const int32_t* rows, int64_t n_rows, int n_cat,
+                                const int32_t* const* codes, const int64_t* K,
+                                const int32_t* drop_first, double* const* out_cat,
+                                const double* csr_data, const int32_t* csr_indices,
+                                const int32_t* csr_indptr, int64_t p_sparse, double* out_sparse,
+                                tm_stream_t stream);
+
 /* ---- SplitMatrix assembly (reference: split_matrix.py:336-354, the numpy scatter) ---- */
 /* out[ri[a]*ld + ci[b]] = blk[a*nb + b]  (and, when mirror != 0, out[ci[b]*ld + ri[a]] too).
  * ri / ci NULL = identity.  `out` is float64 (SplitMatrix.sandwich always returns float64,

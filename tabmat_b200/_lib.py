@@ -22,12 +22,18 @@ c_ptr = C.c_void_p
 
 
 def _load() -> C.CDLL:
-    if not LIB_PATH.exists():
-        if os.environ.get("TABMAT_B200_AUTOBUILD", "1") == "1":
-            from . import build as _build
+    if os.environ.get("TABMAT_B200_AUTOBUILD", "1") == "1":
+        # (re)build when the library is missing or older than its sources; a no-op otherwise
+        import importlib.util
+        import shutil
 
+        spec = importlib.util.spec_from_file_location("_tabmat_b200_build", _PKG / "build.py")
+        _build = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(_build)
+        if shutil.which(_build.NVCC) or os.path.exists(_build.NVCC):
             _build.build()
-        if not LIB_PATH.exists():
+    if not LIB_PATH.exists():
+        if True:
             raise ImportError(
                 f"{LIB_PATH} is missing: build it with `python -m tabmat_b200.build` "
                 "(tabmat_b200 has no CPU fallback)"
@@ -57,6 +63,7 @@ _SIGS = {
     "tm_cat_dense_sandwich": [P, I, I, N, P, P, I, N, P, I, P, I, P, P],
     "tm_cat_cat_sandwich": [P, P, I, I, I, N, N, P, P, I, P, P],
     "tm_cat_sparse_sandwich": [P, I, I, N, P, P, P, P, P, I, I, P, I, P, I, P, P],
+    "tm_dense_cross_sandwich": [P, I, I, P, P, I, N, P, P, P, P, P, P, P, I, P, P],
     "tm_scatter_block": [P, I, I, P, P, P, I, N, P],
     "tm_scatter_diag": [P, I, P, P, I, P],
 }

@@ -76,6 +76,38 @@ def sandwich_cat_sparse(i_indices: torch.Tensor, i_ncol: int, d: torch.Tensor, A
     return out
 
 
+def dense_cross_sandwich(X: torch.Tensor, d: torch.Tensor, rows: Optional[torch.Tensor], cats,
+                         A: Optional[DeviceCSR]):
+    """All cross blocks that share the dense operand in ONE pass over X (tm_dense_cross_sandwich).
+
+    ``cats`` is a list of ``(codes, n_cols, drop_first)``; returns ``(list of (n_cols_i, p)
+    tensors, (p_sparse, p) tensor or None)``.  Fused form of the reference's per-pair loop
+    (split_matrix.py:346-354 -> split.pyx:32-80 / sparse.pyx:211-260)."""
+    import ctypes as C
+
+    n, p, c_order = dense_layout(X)
+    if not c_order:
+        raise ValueError("dense_cross_sandwich needs a C-contiguous dense block")
+    nc = len(cats)
+    outs = [torch.empty((int(k), p), dtype=X.dtype, device=X.device) for (_, k, _) in cats]
+    out_s = None
+    if A is not None and A.shape[1] > 0:
+        out_s = torch.empty((A.shape[1], p), dtype=X.dtype, device=X.device)
+    codes_arr = (C.c_void_p * max(nc, 1))(*[c.data_ptr() for (c, _, _) in cats])
+    out_arr = (C.c_void_p * max(nc, 1))(*[o.data_ptr() for o in outs])
+    K_arr = (C.c_int64 * max(nc, 1))(*[int(k) for (_, k, _) in cats])
+    df_arr = (C.c_int32 * max(nc, 1))(*[int(bool(f)) for (_, _, f) in cats])
+    check(fn("tm_dense_cross_sandwich", _dev.suffix(X.dtype))(
+        _dev.ptr(X), n, p, _dev.ptr(d), _dev.ptr(rows), _dev.length(rows), nc,
+        C.cast(codes_arr, C.c_void_p), C.cast(K_arr, C.c_void_p), C.cast(df_arr, C.c_void_p),
+        C.cast(out_arr, C.c_void_p),
+        _dev.ptr(A.data) if out_s is not None else None,
+        _dev.ptr(A.indices) if out_s is not None else None,
+        _dev.ptr(A.indptr) if out_s is not None else None,
+        A.shape[1] if out_s is not None else 0, _dev.ptr(out_s), _dev.stream_ptr()))
+    return outs, out_s
+
+
 def split_col_subsets(indices: list, cols: np.ndarray):
     """For sorted ``cols``: per block, the positions inside ``cols`` that fall into the block
     and the block-local column ids (split_col_subsets, split.pyx:157-209).  Host side."""

@@ -21,7 +21,7 @@ from . import _dev
 from ._lib import check, fn
 from .categorical_matrix import CategoricalMatrix
 from .dense_matrix import DenseMatrix, _accumulate_out
-from .ext.split import is_sorted, split_col_subsets
+from .ext.split import dense_cross_sandwich, is_sorted, split_col_subsets
 from .matrix_base import MatrixBase, _vec_in
 from .sparse_matrix import SparseMatrix
 from .standardized_mat import StandardizedMatrix
@@ -259,6 +259,7 @@ class SplitMatrix(MatrixBase):
         # every (i, j) entry is written by exactly one block (or its mirror): no zero-fill
         out = torch.empty((n_cols, n_cols), dtype=torch.float64, device=d_t.device)
         k = len(self.matrices)
+        fused = self._fused_dense_cross(d_t, rows_t) if cols is None else {}
         for i in range(k):
             mat_i = self.matrices[i]
             mi = int(pos_t[i].numel())
@@ -277,13 +278,51 @@ class SplitMatrix(MatrixBase):
                 mj = int(pos_t[j].numel())
                 if mj == 0:
                     continue
-                res = self.matrices[i]._cross_sandwich(self.matrices[j], d_t, rows_t, sub_t[i],
-                                                       sub_t[j])
-                res = res.contiguous()
+                if (j, i) in fused:  # computed as (block j rows) x (block i cols)
+                    res = fused[(j, i)]
+                    check(fn("tm_scatter_block", _dev.suffix(res.dtype))(
+                        _dev.ptr(res), mj, mi, _dev.ptr(pos_t[j]), _dev.ptr(pos_t[i]),
+                        _dev.ptr(out), n_cols, 1, st))
+                    continue
+                if (i, j) in fused:
+                    res = fused[(i, j)]
+                else:
+                    res = self.matrices[i]._cross_sandwich(self.matrices[j], d_t, rows_t,
+                                                           sub_t[i], sub_t[j])
+                    res = res.contiguous()
                 check(fn("tm_scatter_block", _dev.suffix(res.dtype))(
                     _dev.ptr(res), mi, mj, _dev.ptr(pos_t[i]), _dev.ptr(pos_t[j]), _dev.ptr(out),
                     n_cols, 1, st))
         return out
+
+    def _fused_dense_cross(self, d_t: torch.Tensor, rows_t) -> dict:
+        """{(a, b): block a rows x dense-block b cols} for every categorical / sparse block a,
+        from ONE pass over the dense block (ext.split.dense_cross_sandwich), when the layout
+        allows it; {} otherwise (the per-pair kernels are used then)."""
+        dense = [i for i, m in enumerate(self.matrices) if isinstance(m, DenseMatrix)]
+        if len(dense) != 1:
+            return {}
+        b = dense[0]
+        X = self.matrices[b]._array
+        width = 4 if X.dtype == torch.float32 else 2
+        p = X.shape[1]
+        if (X.dtype != d_t.dtype or not X.is_contiguous() or p % width or p > 64 * width
+                or X.data_ptr() % 16):
+            return {}
+        cats = [(i, m) for i, m in enumerate(self.matrices)
+                if isinstance(m, CategoricalMatrix) and m.shape[1] > 0
+                and _dev.torch_dtype(m.dtype) == X.dtype]
+        sparse = [(i, m) for i, m in enumerate(self.matrices)
+                  if isinstance(m, SparseMatrix) and m._csr.data.dtype == X.dtype and m._csr.nnz]
+        if len(cats) > 8 or len(sparse) > 1 or not (cats or sparse):
+            return {}
+        outs, out_s = dense_cross_sandwich(
+            X, d_t, rows_t, [(m._codes, m.shape[1], m.drop_first) for _, m in cats],
+            sparse[0][1]._csr if sparse else None)
+        fused = {(i, b): o for (i, _), o in zip(cats, outs)}
+        if sparse and out_s is not None:
+            fused[(sparse[0][0], b)] = out_s
+        return fused
 
     def _get_col_means(self, weights):
         host = not _dev.is_dev(weights)

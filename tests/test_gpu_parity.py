@@ -76,3 +76,39 @@ def test_random_medium_shapes(seed, dt):
     ]:
         got = run_cuda(kind, args)
         cases.assert_close(got, cases.run_oracle(kind, args), dt, f"{kind} seed={seed}")
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("p", [8, 64, 128, 200])
+@pytest.mark.parametrize("with_rows", [False, True])
+def test_fused_dense_cross(dt, p, with_rows):
+    """tm_dense_cross_sandwich (one pass over the dense block) == the per-pair oracle results,
+    incl. replicated small tables, drop_first, missing codes and a row restriction."""
+    import torch
+
+    from oracle import c_oracle as orc
+    from tabmat_b200.ext.split import dense_cross_sandwich
+    from tests.gpu_runner import _csr, _dev, _i32
+
+    if dt == np.float64 and p > 128:
+        pytest.skip("f64 fused path is limited to 128 columns")
+    rng = np.random.default_rng(p)
+    n = 5003
+    X = rng.standard_normal((n, p)).astype(dt)
+    import scipy.sparse as sps
+
+    A = sps.random(n, 300, density=0.01, random_state=rng, format="csr").astype(dt)
+    d = rng.standard_normal(n).astype(dt)
+    d[rng.random(n) < 0.1] = 0
+    Ks = [3, 40, 1500]
+    dfs = [False, True, False]
+    codes = [rng.integers(-1, K + int(df), size=n).astype(np.int32) for K, df in zip(Ks, dfs)]
+    rows = np.sort(rng.choice(n, size=n // 2, replace=False)).astype(np.int32) if with_rows else None
+    outs, out_s = dense_cross_sandwich(
+        _dev(X), _dev(d), _i32(rows), [(_i32(c), K, df) for c, K, df in zip(codes, Ks, dfs)],
+        _csr(A))
+    torch.cuda.synchronize()
+    for o, c, K, df in zip(outs, codes, Ks, dfs):
+        ref = orc.cat_dense_sandwich(c, K, d, X, rows, None, df)
+        cases.assert_close(o.cpu().numpy(), ref, dt, f"fused cat K={K}")
+    cases.assert_close(out_s.cpu().numpy(), orc.csr_dense_sandwich(A, X, d, rows), dt, "fused sparse")
