@@ -453,7 +453,7 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD % args.n, "rows_per_gpu": n_local, "p": p,
                        "nnz_sparse_total": nnz, "l2": "inputs (>20 GB per step) exceed the 126 MB L2",
-                       "parallelism": f"row-shard x{world} + allreduce(packed lower triangle, f32)",
+                       "parallelism": f"row-shard x{world} + NCCL allreduce of the flat block workspace (f32, 90 MB)",
                        "algorithmic_flop_per_step": flops,
                        "whole_step_hbm_gbs": whole_bytes / (ms_step * 1e-3) / 1e9,
                        "whole_step_hbm_frac": whole_bytes / (ms_step * 1e-3) / 1e9 / hbm_peak},

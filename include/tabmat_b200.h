@@ -260,6 +260,47 @@ int tm_dense_cross_sandwich_f64(const double* X, int64_t n, int64_t p, const dou
                                 const int32_t* csr_indptr, int64_t p_sparse, double* out_sparse,
                                 tm_stream_t stream);
 
+/* ---- SplitMatrix.sandwich as one native call (reference: split_matrix.py:324-356) ---------- */
+/* One column block of a SplitMatrix (device pointers; `col_index` = positions of the block's
+ * columns in the p x p result, split_matrix.py:232-247 `indices`). */
+typedef struct tm_block_desc {
+    int32_t kind;       /* 0 dense, 1 sparse (CSR + row ids), 2 categorical */
+    int32_t c_order;    /* dense: 1 row-major, 0 column-major */
+    int32_t drop_first; /* categorical */
+    int32_t reserved;
+    int64_t ncols;      /* block width (categorical: #categories - drop_first) */
+    const void* data;   /* dense: X (n x ncols); sparse: CSR data; categorical: int32 codes */
+    const int32_t* csr_indices;
+    const int32_t* csr_indptr;
+    const int32_t* csr_row;
+    int64_t nnz;
+    const int64_t* col_index;
+} tm_block_desc;
+
+/* Elements (of the block dtype) of the flat workspace that holds every self block and every
+ * cross block: for i: self_i (dense/sparse ncols_i^2, categorical ncols_i = the diagonal), then
+ * for j > i: cross_ij (ncols_i * ncols_j). */
+int64_t tm_split_workspace_elems(const tm_block_desc* blocks, int n_blocks);
+/* Every block of X[rows,:]^T diag(d[rows]) X[rows,:] into `workspace` (overwrites).  All blocks
+ * share the dtype of the entry point; dense and sparse blocks must already be merged
+ * (split_matrix.py:85-141).  Cross blocks that share the dense operand are computed in one
+ * pass (tm_dense_cross_sandwich) when the dense block is row-major. */
+int tm_split_sandwich_blocks_f32(const tm_block_desc* blocks, int n_blocks, int64_t n,
+                                 const float* d, const int32_t* rows, int64_t n_rows,
+                                 float* workspace, tm_stream_t stream);
+int tm_split_sandwich_blocks_f64(const tm_block_desc* blocks, int n_blocks, int64_t n,
+                                 const double* d, const int32_t* rows, int64_t n_rows,
+                                 double* workspace, tm_stream_t stream);
+/* Place the workspace into the p x p float64 result (split_matrix.py:336-354); `ld` = p.
+ * Separate from the block computation so that a row-sharded caller can allreduce the flat
+ * workspace in between. */
+int tm_split_sandwich_assemble_f32(const tm_block_desc* blocks, int n_blocks,
+                                   const float* workspace, double* out, int64_t ld,
+                                   tm_stream_t stream);
+int tm_split_sandwich_assemble_f64(const tm_block_desc* blocks, int n_blocks,
+                                   const double* workspace, double* out, int64_t ld,
+                                   tm_stream_t stream);
+
 /* ---- SplitMatrix assembly (reference: split_matrix.py:336-354, the numpy scatter) ---- */
 /* out[ri[a]*ld + ci[b]] = blk[a*nb + b]  (and, when mirror != 0, out[ci[b]*ld + ri[a]] too).
  * ri / ci NULL = identity.  `out` is float64 (SplitMatrix.sandwich always returns float64,

@@ -64,13 +64,15 @@ _SIGS = {
     "tm_cat_cat_sandwich": [P, P, I, I, I, N, N, P, P, I, P, P],
     "tm_cat_sparse_sandwich": [P, I, I, N, P, P, P, P, P, I, I, P, I, P, I, P, P],
     "tm_dense_cross_sandwich": [P, I, I, P, P, I, N, P, P, P, P, P, P, P, I, P, P],
+    "tm_split_sandwich_blocks": [P, N, I, P, P, I, P, P],
+    "tm_split_sandwich_assemble": [P, N, P, P, I, P],
     "tm_scatter_block": [P, I, I, P, P, P, I, N, P],
     "tm_scatter_diag": [P, I, P, P, I, P],
 }
 
 #: every symbol include/tabmat_b200.h declares (checked by tests/test_capi_symbols.py)
 EXPORTED = ["tm_version", "tm_last_error", "tm_launch_count", "tm_reset_launch_count",
-            "tm_has_tcgen05", "tm_set_dense_f32_mode"]
+            "tm_has_tcgen05", "tm_set_dense_f32_mode", "tm_split_workspace_elems"]
 for _name, _args in _SIGS.items():
     for _suf in ("f32", "f64"):
         _fn = getattr(lib, f"{_name}_{_suf}")
@@ -78,6 +80,19 @@ for _name, _args in _SIGS.items():
         _fn.restype = c_int
         EXPORTED.append(f"{_name}_{_suf}")
 
+
+
+class BlockDesc(C.Structure):
+    """ctypes mirror of ``tm_block_desc`` (include/tabmat_b200.h)."""
+
+    _fields_ = [("kind", C.c_int32), ("c_order", C.c_int32), ("drop_first", C.c_int32),
+                ("reserved", C.c_int32), ("ncols", C.c_int64), ("data", C.c_void_p),
+                ("csr_indices", C.c_void_p), ("csr_indptr", C.c_void_p), ("csr_row", C.c_void_p),
+                ("nnz", C.c_int64), ("col_index", C.c_void_p)]
+
+
+lib.tm_split_workspace_elems.argtypes = [C.c_void_p, c_int]
+lib.tm_split_workspace_elems.restype = c_i64
 lib.tm_version.restype = c_int
 lib.tm_last_error.restype = C.c_char_p
 lib.tm_launch_count.restype = c_i64

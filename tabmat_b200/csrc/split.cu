@@ -1,0 +1,256 @@
+// SplitMatrix.sandwich as ONE native call (reference: the Python block loop of
+// split_matrix.py:324-356, which makes one native call per self block and per cross pair and
+// assembles the result with numpy fancy indexing).
+//
+//   tm_split_sandwich_blocks_*   computes every self block and every cross block of the column
+//                                blocks into one flat workspace (layout below);
+//   tm_split_sandwich_assemble_* places the workspace into the p x p float64 result
+//                                (split_matrix.py:336-354) — kept separate so that a row-sharded
+//                                multi-GPU caller can allreduce the flat workspace in between.
+//
+// Workspace layout (elements of the block dtype), blocks in the given order:
+//   for i in 0..nb-1:  self_i   dense / sparse: ncols_i x ncols_i (row-major, symmetric)
+//                               categorical:    ncols_i           (the diagonal)
+//     for j in i+1..nb-1: cross_ij, stored as (rows of block a) x (cols of block b), row-major,
+//                         where (a, b) is the kernel's native orientation:
+//                           categorical x dense / sparse x dense / categorical x sparse /
+//                           categorical_i x categorical_j (i < j)
+#include <vector>
+
+#include "tm_common.cuh"
+
+namespace tmb {
+
+enum { KIND_DENSE = 0, KIND_SPARSE = 1, KIND_CAT = 2 };
+
+static inline int64_t self_elems(const tm_block_desc& b) {
+    return b.kind == KIND_CAT ? b.ncols : b.ncols * b.ncols;
+}
+
+// orientation of the stored cross block of blocks (i, j), i < j: returns true when the stored
+// rows belong to block j (i.e. the kernel's native orientation is (j, i))
+static inline bool cross_rows_are_j(const tm_block_desc& bi, const tm_block_desc& bj) {
+    if (bi.kind == KIND_DENSE) return true;                           // (sparse|cat) x dense
+    if (bi.kind == KIND_SPARSE && bj.kind == KIND_CAT) return true;   // cat x sparse
+    return false;  // sparse x dense (i sparse, j dense), cat x dense, cat x sparse, cat_i x cat_j
+}
+
+// overload shims over the extern "C" entry points
+#define TM_SHIM(name, F, SUF)                                                     \
+    template <typename... A>                                                      \
+    static inline int name(F*, A... a) {                                          \
+        return tm_##name##_##SUF(a...);                                           \
+    }
+TM_SHIM(dense_sandwich, float, f32)
+TM_SHIM(dense_sandwich, double, f64)
+TM_SHIM(sparse_sandwich, float, f32)
+TM_SHIM(sparse_sandwich, double, f64)
+TM_SHIM(csr_dense_sandwich, float, f32)
+TM_SHIM(csr_dense_sandwich, double, f64)
+TM_SHIM(cat_sandwich, float, f32)
+TM_SHIM(cat_sandwich, double, f64)
+TM_SHIM(cat_dense_sandwich, float, f32)
+TM_SHIM(cat_dense_sandwich, double, f64)
+TM_SHIM(cat_cat_sandwich, float, f32)
+TM_SHIM(cat_cat_sandwich, double, f64)
+TM_SHIM(cat_sparse_sandwich, float, f32)
+TM_SHIM(cat_sparse_sandwich, double, f64)
+TM_SHIM(dense_cross_sandwich, float, f32)
+TM_SHIM(dense_cross_sandwich, double, f64)
+TM_SHIM(scatter_block, float, f32)
+TM_SHIM(scatter_block, double, f64)
+TM_SHIM(scatter_diag, float, f32)
+TM_SHIM(scatter_diag, double, f64)
+
+template <typename F>
+int split_blocks(const tm_block_desc* blk, int nb, int64_t n, const F* d, const int32_t* rows,
+                 int64_t n_rows, F* ws, tm_stream_t stream) {
+    F* tag = nullptr;
+    if (nb <= 0) return 0;
+    if (nb > 64) return fail("tm_split_sandwich: more than 64 blocks");
+    // offsets
+    std::vector<int64_t> self_off(nb);
+    std::vector<std::vector<int64_t>> cross_off(nb, std::vector<int64_t>(nb, -1));
+    int64_t off = 0;
+    for (int i = 0; i < nb; ++i) {
+        self_off[i] = off;
+        off += self_elems(blk[i]);
+        for (int j = i + 1; j < nb; ++j) {
+            cross_off[i][j] = off;
+            off += blk[i].ncols * blk[j].ncols;
+        }
+    }
+    // can the dense-operand cross blocks be fused into one pass?
+    int dense_idx = -1, n_dense = 0, n_sparse = 0, n_cat = 0, sparse_idx = -1;
+    for (int i = 0; i < nb; ++i) {
+        if (blk[i].kind == KIND_DENSE) { dense_idx = i; ++n_dense; }
+        else if (blk[i].kind == KIND_SPARSE) { sparse_idx = i; ++n_sparse; }
+        else if (blk[i].kind == KIND_CAT) ++n_cat;
+        else return fail("tm_split_sandwich: unknown block kind");
+    }
+    constexpr int W = sizeof(F) == 4 ? 4 : 2;
+    bool fuse = n_dense == 1 && n_sparse <= 1 && n_cat <= 8 && (n_cat + n_sparse) > 0;
+    if (fuse) {
+        const tm_block_desc& D = blk[dense_idx];
+        fuse = D.c_order && D.ncols % W == 0 && D.ncols <= 64 * W &&
+               (reinterpret_cast<uintptr_t>(D.data) & 15) == 0;
+    }
+    if (fuse) {
+        const tm_block_desc& D = blk[dense_idx];
+        const int32_t* codes[8];
+        int64_t K[8];
+        int32_t df[8];
+        F* outs[8];
+        int c = 0;
+        for (int i = 0; i < nb; ++i) {
+            if (blk[i].kind != KIND_CAT) continue;
+            codes[c] = static_cast<const int32_t*>(blk[i].data);
+            K[c] = blk[i].ncols;
+            df[c] = blk[i].drop_first;
+            int a = i < dense_idx ? i : dense_idx, b = i < dense_idx ? dense_idx : i;
+            outs[c] = ws + cross_off[a][b];
+            ++c;
+        }
+        const F* sdata = nullptr;
+        const int32_t *sind = nullptr, *sptr = nullptr;
+        int64_t ps = 0;
+        F* out_s = nullptr;
+        if (sparse_idx >= 0 && blk[sparse_idx].nnz > 0) {
+            const tm_block_desc& S = blk[sparse_idx];
+            sdata = static_cast<const F*>(S.data);
+            sind = S.csr_indices;
+            sptr = S.csr_indptr;
+            ps = S.ncols;
+            int a = sparse_idx < dense_idx ? sparse_idx : dense_idx;
+            int b = sparse_idx < dense_idx ? dense_idx : sparse_idx;
+            out_s = ws + cross_off[a][b];
+        } else if (sparse_idx >= 0) {
+            int a = sparse_idx < dense_idx ? sparse_idx : dense_idx;
+            int b = sparse_idx < dense_idx ? dense_idx : sparse_idx;
+            TM_CUDA(cudaMemsetAsync(ws + cross_off[a][b], 0,
+                                    sizeof(F) * (size_t)(blk[a].ncols * blk[b].ncols),
+                                    as_stream(stream)));
+        }
+        int rc = dense_cross_sandwich(tag, static_cast<const F*>(D.data), n, D.ncols, d, rows,
+                                      n_rows, c, codes, K, df, outs, sdata, sind, sptr, ps, out_s,
+                                      stream);
+        if (rc) return rc;
+    }
+
+    for (int i = 0; i < nb; ++i) {
+        const tm_block_desc& bi = blk[i];
+        F* so = ws + self_off[i];
+        int rc = 0;
+        if (bi.kind == KIND_DENSE)
+            rc = dense_sandwich(tag, static_cast<const F*>(bi.data), n, bi.ncols, bi.c_order, d,
+                                rows, n_rows, (const int32_t*)nullptr, (int64_t)0, so, stream);
+        else if (bi.kind == KIND_SPARSE)
+            rc = sparse_sandwich(tag, static_cast<const F*>(bi.data), bi.csr_indices, bi.csr_indptr,
+                                 bi.csr_row, n, bi.ncols, bi.nnz, d, rows, n_rows,
+                                 (const int32_t*)nullptr, (int64_t)0, so, stream);
+        else
+            rc = cat_sandwich(tag, static_cast<const int32_t*>(bi.data), n, d, rows, n_rows,
+                              bi.ncols, (int)bi.drop_first, so, stream);
+        if (rc) return rc;
+        for (int j = i + 1; j < nb; ++j) {
+            const tm_block_desc& bj = blk[j];
+            F* co = ws + cross_off[i][j];
+            const bool has_dense = bi.kind == KIND_DENSE || bj.kind == KIND_DENSE;
+            if (fuse && has_dense) continue;
+            // normalise to (a, b) = the kernel's native (rows, cols) orientation
+            const tm_block_desc& a = cross_rows_are_j(bi, bj) ? bj : bi;
+            const tm_block_desc& b = cross_rows_are_j(bi, bj) ? bi : bj;
+            if (a.kind == KIND_SPARSE && b.kind == KIND_DENSE)
+                rc = csr_dense_sandwich(tag, static_cast<const F*>(a.data), a.csr_indices,
+                                        a.csr_indptr, n, a.ncols, static_cast<const F*>(b.data),
+                                        b.ncols, (int)b.c_order, d, rows, n_rows,
+                                        (const int32_t*)nullptr, (int64_t)0,
+                                        (const int32_t*)nullptr, (int64_t)0, co, stream);
+            else if (a.kind == KIND_CAT && b.kind == KIND_DENSE)
+                rc = cat_dense_sandwich(tag, static_cast<const int32_t*>(a.data), n, a.ncols,
+                                        (int)a.drop_first, d, static_cast<const F*>(b.data),
+                                        b.ncols, (int)b.c_order, rows, n_rows,
+                                        (const int32_t*)nullptr, (int64_t)0, co, stream);
+            else if (a.kind == KIND_CAT && b.kind == KIND_SPARSE)
+                rc = cat_sparse_sandwich(tag, static_cast<const int32_t*>(a.data), n, a.ncols,
+                                         (int)a.drop_first, d, static_cast<const F*>(b.data),
+                                         b.csr_indices, b.csr_indptr, b.csr_row, b.ncols, b.nnz,
+                                         rows, n_rows, (const int32_t*)nullptr, (int64_t)0, co,
+                                         stream);
+            else if (a.kind == KIND_CAT && b.kind == KIND_CAT)
+                rc = cat_cat_sandwich(tag, static_cast<const int32_t*>(a.data),
+                                      static_cast<const int32_t*>(b.data), n, a.ncols, b.ncols,
+                                      (int)a.drop_first, (int)b.drop_first, d, rows, n_rows, co,
+                                      stream);
+            else
+                return fail("tm_split_sandwich: unsupported block pair (two dense or two sparse "
+                            "blocks must be merged first, split_matrix.py:85-141)");
+            if (rc) return rc;
+        }
+    }
+    return 0;
+}
+
+template <typename F>
+int split_assemble(const tm_block_desc* blk, int nb, const F* ws, double* out, int64_t ld,
+                   tm_stream_t stream) {
+    F* tag = nullptr;
+    int64_t off = 0;
+    for (int i = 0; i < nb; ++i) {
+        const tm_block_desc& bi = blk[i];
+        int rc;
+        if (bi.kind == KIND_CAT)
+            rc = scatter_diag(tag, ws + off, bi.ncols, bi.col_index, out, ld, stream);
+        else
+            rc = scatter_block(tag, ws + off, bi.ncols, bi.ncols, bi.col_index, bi.col_index, out,
+                               ld, 0, stream);
+        if (rc) return rc;
+        off += self_elems(bi);
+        for (int j = i + 1; j < nb; ++j) {
+            const tm_block_desc& bj = blk[j];
+            const tm_block_desc& a = cross_rows_are_j(bi, bj) ? bj : bi;
+            const tm_block_desc& b = cross_rows_are_j(bi, bj) ? bi : bj;
+            rc = scatter_block(tag, ws + off, a.ncols, b.ncols, a.col_index, b.col_index, out, ld,
+                               1, stream);
+            if (rc) return rc;
+            off += bi.ncols * bj.ncols;
+        }
+    }
+    return 0;
+}
+
+}  // namespace tmb
+
+extern "C" {
+
+int64_t tm_split_workspace_elems(const tm_block_desc* blocks, int n_blocks) {
+    int64_t off = 0;
+    for (int i = 0; i < n_blocks; ++i) {
+        off += tmb::self_elems(blocks[i]);
+        for (int j = i + 1; j < n_blocks; ++j) off += blocks[i].ncols * blocks[j].ncols;
+    }
+    return off;
+}
+
+int tm_split_sandwich_blocks_f32(const tm_block_desc* blocks, int n_blocks, int64_t n,
+                                 const float* d, const int32_t* rows, int64_t n_rows,
+                                 float* workspace, tm_stream_t stream) {
+    return tmb::split_blocks<float>(blocks, n_blocks, n, d, rows, n_rows, workspace, stream);
+}
+int tm_split_sandwich_blocks_f64(const tm_block_desc* blocks, int n_blocks, int64_t n,
+                                 const double* d, const int32_t* rows, int64_t n_rows,
+                                 double* workspace, tm_stream_t stream) {
+    return tmb::split_blocks<double>(blocks, n_blocks, n, d, rows, n_rows, workspace, stream);
+}
+int tm_split_sandwich_assemble_f32(const tm_block_desc* blocks, int n_blocks,
+                                   const float* workspace, double* out, int64_t ld,
+                                   tm_stream_t stream) {
+    return tmb::split_assemble<float>(blocks, n_blocks, workspace, out, ld, stream);
+}
+int tm_split_sandwich_assemble_f64(const tm_block_desc* blocks, int n_blocks,
+                                   const double* workspace, double* out, int64_t ld,
+                                   tm_stream_t stream) {
+    return tmb::split_assemble<double>(blocks, n_blocks, workspace, out, ld, stream);
+}
+
+}  // extern "C"

@@ -7,9 +7,11 @@ sum-allreduce produces the replicated result.  ``transpose_matvec`` / column mea
 length-p vector the same way; ``matvec`` needs no collective (the output rows are sharded like
 the input rows).  The reference has no multi-process code at all; this layer is new.
 
-The payload of the sandwich allreduce is the PACKED lower triangle (p(p+1)/2 elements in the
-block dtype) rather than the full float64 square: at the 4e7-row SplitMatrix benchmark
-(p = 6388, f32) that is 81.6 MB instead of 326 MB.
+For a SplitMatrix the payload of the sandwich allreduce is the flat block workspace of
+``tm_split_sandwich_blocks`` (every cross block once, categorical self blocks as diagonals,
+block dtype): 98 MB f32 at the 4e7-row benchmark (p = 6388) instead of the 326 MB float64
+square; the p x p float64 is assembled after the collective.  Other matrices reduce the packed
+lower triangle (p(p+1)/2 elements).
 """
 
 from __future__ import annotations
@@ -101,7 +103,17 @@ class RowShardedMatrix:
     def sandwich(self, d_local, rows=None, cols=None) -> torch.Tensor:
         """Replicated (X[rows, cols].T * d[rows]) @ X[rows, cols]; ``d_local`` is this rank's
         slice of d, ``rows`` a sorted GLOBAL restriction (or None)."""
-        part = self.local.sandwich(d_local, shard_rows(rows, self.lo, self.hi), cols)
+        local_rows = shard_rows(rows, self.lo, self.hi)
+        if cols is None and hasattr(self.local, "_sandwich_blocks_dev"):
+            # SplitMatrix: allreduce the flat block workspace (every structurally distinct
+            # entry once, block dtype) and assemble the p x p float64 after the collective
+            from . import _dev
+
+            ws = self.local._sandwich_blocks_dev(d_local, _dev.idx32(local_rows))
+            if ws is not None:
+                self._allreduce(ws)
+                return self.local._assemble_dev(ws)
+        part = self.local.sandwich(d_local, local_rows, cols)
         if self.world_size == 1:
             return part
         p = part.shape[0]

@@ -18,7 +18,7 @@ import torch
 from scipy import sparse as sps
 
 from . import _dev
-from ._lib import check, fn
+from ._lib import BlockDesc, check, fn, lib
 from .categorical_matrix import CategoricalMatrix
 from .dense_matrix import DenseMatrix, _accumulate_out
 from .ext.split import dense_cross_sandwich, is_sorted, split_col_subsets
@@ -247,7 +247,68 @@ class SplitMatrix(MatrixBase):
         out = self._sandwich_dev(d_t, _dev.idx32(rows), cols)
         return _dev.ret(out, host)
 
+    # ---- whole-matrix native path (cols=None): two C calls instead of a Python block loop --
+    def _native_plan(self, tdtype: torch.dtype):
+        """(ctypes array of tm_block_desc, workspace elements) or None when the blocks cannot go
+        through tm_split_sandwich_* (mixed dtypes)."""
+        key = ("plan", tdtype)
+        cache = self.__dict__.setdefault("_plan_cache", {})
+        if key in cache:
+            return cache[key]
+        plan = None
+        ok = tdtype in (torch.float32, torch.float64)
+        descs = (BlockDesc * len(self.matrices))()
+        for b, (mat, idx_t) in enumerate(zip(self.matrices, self._dev_indices())):
+            if not ok:
+                break
+            dsc = descs[b]
+            dsc.ncols = mat.shape[1]
+            dsc.col_index = idx_t.data_ptr()
+            if isinstance(mat, DenseMatrix):
+                X = mat._array
+                ok = X.dtype == tdtype
+                dsc.kind, dsc.c_order, dsc.data = 0, int(X.is_contiguous()), X.data_ptr()
+            elif isinstance(mat, SparseMatrix):
+                c = mat._csr
+                ok = c.data.dtype == tdtype
+                dsc.kind, dsc.data, dsc.nnz = 1, c.data.data_ptr(), c.nnz
+                dsc.csr_indices, dsc.csr_indptr = c.indices.data_ptr(), c.indptr.data_ptr()
+                dsc.csr_row = c.row.data_ptr()
+            elif isinstance(mat, CategoricalMatrix):
+                ok = _dev.torch_dtype(mat.dtype) == tdtype
+                dsc.kind, dsc.data, dsc.drop_first = 2, mat._codes.data_ptr(), int(mat.drop_first)
+            else:
+                ok = False
+        if ok:
+            plan = (descs, int(lib.tm_split_workspace_elems(descs, len(self.matrices))))
+        cache[key] = plan
+        return plan
+
+    def _sandwich_blocks_dev(self, d_t: torch.Tensor, rows_t) -> Optional[torch.Tensor]:
+        """Flat workspace with every self / cross block (layout: csrc/split.cu), or None."""
+        plan = self._native_plan(d_t.dtype)
+        if plan is None:
+            return None
+        descs, elems = plan
+        ws = torch.empty(elems, dtype=d_t.dtype, device=d_t.device)
+        check(fn("tm_split_sandwich_blocks", _dev.suffix(d_t.dtype))(
+            descs, len(self.matrices), self.shape[0], _dev.ptr(d_t), _dev.ptr(rows_t),
+            _dev.length(rows_t), _dev.ptr(ws), _dev.stream_ptr()))
+        return ws
+
+    def _assemble_dev(self, ws: torch.Tensor) -> torch.Tensor:
+        descs, _ = self._native_plan(ws.dtype)
+        p = self.shape[1]
+        out = torch.empty((p, p), dtype=torch.float64, device=ws.device)
+        check(fn("tm_split_sandwich_assemble", _dev.suffix(ws.dtype))(
+            descs, len(self.matrices), _dev.ptr(ws), _dev.ptr(out), p, _dev.stream_ptr()))
+        return out
+
     def _sandwich_dev(self, d_t: torch.Tensor, rows_t, cols) -> torch.Tensor:
+        if cols is None:
+            ws = self._sandwich_blocks_dev(d_t, rows_t)
+            if ws is not None:
+                return self._assemble_dev(ws)
         subset_cols_indices, subset_cols, n_cols = self._split_col_subsets(cols)
         if cols is None:
             pos_t = self._dev_indices()
