@@ -260,6 +260,20 @@ int tm_dense_cross_sandwich_f64(const double* X, int64_t n, int64_t p, const dou
                                 const int32_t* csr_indptr, int64_t p_sparse, double* out_sparse,
                                 tm_stream_t stream);
 
+/* Dense self block AND the dense x categorical cross blocks of categoricals with few levels in
+ * one pass on the tensor cores (fp32, row-major X, p % 4 == 0, p <= 128, sum of K <= 384):
+ * the weighted SYRK of tm_dense_sandwich_f32 plus one-hot MMAs
+ *   out_cat[(off_i + codes[i][k] - drop_first[i]) * p + b] += d[k] * X[k, b],  off_i = sum_{c<i} K[c]
+ * (reference: dense.pyx:19-44 + split.pyx:32-80 called per pair from split_matrix.py:337-354).
+ * `codes`, `K`, `drop_first` are HOST arrays of length n_cat (<= 8).  out_dense (p x p) and
+ * out_cat (sum K x p) are overwritten.  Inputs are rounded to TF32 (10-bit mantissa), sums are
+ * accumulated in fp32. */
+int tm_dense_onehot_sandwich_f32(const float* X, int64_t n, int64_t p, const float* d,
+                                 const int32_t* rows, int64_t n_rows, int n_cat,
+                                 const int32_t* const* codes, const int64_t* K,
+                                 const int32_t* drop_first, float* out_dense, float* out_cat,
+                                 tm_stream_t stream);
+
 /* ---- SplitMatrix.sandwich as one native call (reference: split_matrix.py:324-356) ---------- */
 /* One column block of a SplitMatrix (device pointers; `col_index` = positions of the block's
  * columns in the p x p result, split_matrix.py:232-247 `indices`). */

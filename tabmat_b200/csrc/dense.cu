@@ -304,11 +304,6 @@ int dense_colreduce(const F* X, int64_t n, int64_t p, int c_order, const F* w, c
     return 0;
 }
 
-// implemented in dense_tc.cu
-int dense_sandwich_tc_f32(const float* X, int64_t n, int64_t p, int c_order, const float* d,
-                          float* out, cudaStream_t st);
-bool dense_tc_eligible(int64_t n, int64_t p, int c_order, const void* X);
-extern int g_dense_f32_mode;
 
 }  // namespace tmb
 

@@ -1,23 +1,28 @@
 // Dense fp32 weighted SYRK  out = X^T diag(d) X  on the 5th-gen tensor cores (sm_100a):
 // tcgen05.mma kind::tf32 with accumulators in TMEM, X tiles staged by TMA, d folded in
 // between the HBM->smem stage and the MMA (the reference folds d while packing its R
-// panel, dense_helpers-tmpl.cpp:224,229).
+// panel, dense_helpers-tmpl.cpp:224,229).  Categorical blocks with few levels ride along
+// as one-hot MMAs against the same d-scaled tile (the reference makes one
+// sandwich_cat_dense call per block, split.pyx:32-80).
 //
 // Data flow per CTA (one persistent CTA per SM, split-K over row tiles of BK=32 rows):
 //
-//   warp 0  (1 lane)  TMA producer: X[k0:k0+32, :] -> smem stage "R" as column groups of
-//                     32 floats (one swizzled box [32 rows][128 B] per group).  For row-major
-//                     X this is exactly the MN-major SWIZZLE_128B_BASE32B canonical UMMA
-//                     layout (4-row x 128 B atoms stacked along K), so no transpose is needed.
-//   warps 2-9         scale warps: B[r][c] = rna_tf32(d[k0+r] * R[r][c]) into a second smem
-//                     buffer with the same (swizzled) addresses; R is rounded to tf32 in place
-//                     (round-to-nearest; raw fp32 bits would be truncated by the MMA, a biased
-//                     error).  fence.proxy.async, then arrive on the stage's "scaled" barrier.
-//   warp 1  (1 lane)  MMA issuer: for each 8-row K step and each lower-triangular 128x128
-//                     output tile (mt >= nt):  D[mt,nt] += R[:,mt]^T * B[:,nt]
-//                     (A = R, B = scaled, both MN-major); tcgen05.commit frees the stage.
+//   warp 0  (1 lane)  TMA producer: one box X[k0:k0+32, 0:P] per stage -> ring "R"
+//                     (row-major, no swizzle; only the scale warps read it).
+//   warps 2-9         scale warps: transpose + round + scale each stage into the K-major
+//                     SWIZZLE_128B UMMA layout (one 128-byte row of 32 k-values per X column):
+//                       A'[c][k] = rna_tf32(X[k0+k, c])         B'[c][k] = rna_tf32(d[k0+k] * X[k0+k, c])
+//                     and set the one-hot operand  O[slot][k] = 1  (slot = off_i + code_i[k0+k]);
+//                     reads are conflict-free LDS.32 (lanes along c), writes are STS.128 of
+//                     4 consecutive k.  (MN-major tf32 operands straight from the TMA tile work
+//                     too - SWIZZLE_128B_BASE32B - but issue 4-6x slower than the 64-cycle MMA
+//                     floor on B200, measured; K-major runs at the floor.)
+//   warp 1  (1 lane)  MMA issuer, per 8-row K step:
+//                       D[mt,nt]   += A'[mt] * B'[nt]^T   for the lower-triangular 128x128 tiles
+//                       D'[c,slot] += B'[0]  * O^T        one-hot blocks (N up to 256 per MMA)
+//                     tcgen05.commit releases the R stage and the A'/B'/O slot.
 //   warps 2-9         epilogue: tcgen05.ld the accumulators and RED.ADD them into `out`
-//                     transposed (upper triangle, coalesced across the warp's lanes).
+//                     (transposed: lanes = output columns, coalesced) / into the one-hot result.
 //
 // A small second kernel mirrors the upper triangle into the lower one.
 // Only the C-order, P <= 256 case is handled here; everything else is served by the
@@ -32,24 +37,38 @@ int g_dense_f32_mode = 0;
 
 namespace tc {
 
-constexpr int BK = 32;                     // rows per pipeline stage
-constexpr int GROUP_BYTES = BK * 128;      // one 32-column group of a stage: [BK][128 B]
+constexpr int BK = 32;                     // rows per pipeline stage (= one 128 B K-major row)
+constexpr int TILE_BYTES = 128 * 128;      // one K-major operand tile: 128 X-columns x 32 k x 4 B
+constexpr int GROUP_BYTES = 32 * 128;      // 32 one-hot slots x 128 B
 constexpr int NUM_SCALE_WARPS = 8;
 constexpr int NUM_SCALE_THREADS = NUM_SCALE_WARPS * 32;
 constexpr int NUM_THREADS = 64 + NUM_SCALE_THREADS;  // producer warp + mma warp + scale warps
-constexpr int MAX_STAGES = 8;
-constexpr int SMEM_BUDGET = 200 * 1024;
+constexpr int MAX_STAGES = 16;
+constexpr int SB = 2;                      // depth of the operand (A'/B'/one-hot) ring
+constexpr int SMEM_BUDGET = 220 * 1024;
 
 struct Params {
     const float* d;
     float* out;
     long long n;
     int P;            // number of columns (<= 256)
-    int groups;       // ceil(P/32): column groups actually loaded by TMA
+    int groups;       // ceil(P/32)
     int mtiles;       // ceil(P/128): 128-wide output tile rows (1 or 2)
     long long num_row_tiles;
-    int stages;
+    int stagesR;      // depth of the TMA ring (raw X tiles)
+    int r_bytes;      // bytes of one raw stage: X tile | d (128 B) | one-hot codes (8 x 128 B)
+    int aux_off;      // offset of d inside a stage (BK * P * 4 rounded up to 128)
     int tmem_cols;
+    // one-hot extension (P <= 128 only): categorical blocks with few levels ride along as
+    // extra MMAs  D'[dense col, slot] += (d*X)^T OneHot,  slot = oh_off[c] + code - oh_df[c]
+    int oh_groups;    // ceil(oh_slots / 32); 0 = no one-hot blocks
+    int oh_slots;
+    int oh_ncat;
+    const int32_t* oh_codes[8];
+    int oh_off[8];
+    int oh_K[8];
+    int oh_df[8];
+    float* oh_out;    // [oh_slots][P], accumulated with RED
     float* dbg;       // debug dump (tools/tc_debug.py); nullptr in production
     int variant;      // bring-up switches (0 in production)
 };
@@ -119,6 +138,19 @@ __device__ __forceinline__ void tcgen05_mma_tf32(uint32_t tmem_d, uint64_t desc_
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// one elected lane of a converged warp (the compiler then emits the tcgen05 instructions
+// straight-line instead of a per-active-lane serialisation loop)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ uint32_t to_tf32(float x) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -127,27 +159,28 @@ __device__ __forceinline__ uint32_t to_tf32(float x) {
 
 // UMMA shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
 //   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 | [32,46) stride byte offset >> 4
-//   [46,48) version = 1 (Blackwell) | [61,64) layout type (1 = SWIZZLE_128B_BASE32B)
-// MN-major 32-bit operands only exist in the 128B-swizzle-with-32B-atoms layout
-// (Swizzle<2,5,2>: 32-byte chunk index ^= row & 3; K atom = 4 rows of 128 B = 512 B), which is
-// what TMA writes with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.  One K=8 instruction therefore
-// spans two K atoms: SBO = 512 B; the next 32-column group is LBO = GROUP_BYTES away.
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes,
-                                              uint32_t sbo_bytes) {
+//   [46,48) version = 1 (Blackwell) | [61,64) layout type (2 = SWIZZLE_128B)
+// K-major SWIZZLE_128B: one operand row (an X column / a one-hot slot) = 128 B = 32 k-values,
+// 16-byte chunk index ^= row & 7; 8-row groups are SBO = 1024 B apart; LBO is unused.  A K=8
+// instruction reads 32 B of every row: the k-step advances the start address by 32 B.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
-    d |= (uint64_t)(lbo_bytes >> 4) << 16;
-    d |= (uint64_t)(sbo_bytes >> 4) << 32;
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
     d |= (uint64_t)1 << 46;
-    d |= (uint64_t)1 << 61;  // SWIZZLE_128B_BASE32B: the only MN-major layout tf32 supports
+    d |= (uint64_t)2 << 61;
     return d;
 }
+// byte offset of element (row, k) inside a K-major SWIZZLE_128B tile; k4 = k / 4 (16 B chunk)
+__device__ __forceinline__ uint32_t kmajor_chunk_off(uint32_t row, uint32_t k4) {
+    return row * 128u + ((k4 ^ (row & 7u)) << 4);
+}
 
-// tcgen05 instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=tf32,
-// both operands MN-major, M=128, N=128.
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) |
-           ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// tcgen05 instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=tf32, K-major.
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) |
+           ((uint32_t)(M >> 4) << 24);
 }
 
 #define TM_TMEM_LD_32x32B_X32(taddr, v)                                                            \
@@ -162,6 +195,46 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, 
           "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])             \
         : "r"(taddr))
 
+// Transpose + round + scale 4 row-chunks (k4 = kb, kb+ks, kb+2ks, kb+3ks; 4 rows each) of X
+// column c of a raw stage into the K-major operand tiles: all 16 loads first, then the math.
+__device__ __forceinline__ void scale_col4(const float* __restrict__ R, int P,
+                                           const float* __restrict__ dsm, uint8_t* Ap, uint8_t* Bp,
+                                           int c, int kb, int ks) {
+    float x[4][4];
+    const float* r0 = R + c;
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) x[u][i] = r0[(size_t)(4 * (kb + u * ks) + i) * P];
+    const uint32_t tile_off = (uint32_t)(c >> 7) * TILE_BYTES;
+    const uint32_t row = (uint32_t)c & 127u;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int k4 = kb + u * ks;
+        const float4 dv = *reinterpret_cast<const float4*>(dsm + 4 * k4);
+        uint4 a, bb;
+        a.x = to_tf32(x[u][0]);
+        a.y = to_tf32(x[u][1]);
+        a.z = to_tf32(x[u][2]);
+        a.w = to_tf32(x[u][3]);
+        bb.x = to_tf32(dv.x * x[u][0]);
+        bb.y = to_tf32(dv.y * x[u][1]);
+        bb.z = to_tf32(dv.z * x[u][2]);
+        bb.w = to_tf32(dv.w * x[u][3]);
+        const uint32_t off = tile_off + kmajor_chunk_off(row, (uint32_t)k4);
+        *reinterpret_cast<uint4*>(Ap + off) = a;
+        *reinterpret_cast<uint4*>(Bp + off) = bb;
+    }
+}
+
+// bring-up timeline: cycle stamps of CTA 0's first TL_ITERS iterations (prm.dbg only)
+constexpr int TL_ITERS = 1024;
+constexpr int TL_OFF = 65536 + 3 * 128 * 128;  // float offset of the int64 timeline in dbg
+__device__ __forceinline__ void tl_stamp(const Params& prm, int it, int e) {
+    if (prm.dbg && blockIdx.x == 0 && it < TL_ITERS)
+        reinterpret_cast<long long*>(prm.dbg + TL_OFF)[(size_t)it * 8 + e] = clock64();
+}
+
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 k_dense_syrk_tc(const __grid_constant__ CUtensorMap tmap, const Params prm) {
@@ -169,39 +242,43 @@ k_dense_syrk_tc(const __grid_constant__ CUtensorMap tmap, const Params prm) {
     uint8_t* base = reinterpret_cast<uint8_t*>(
         (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
 
-    const int S = prm.stages;
-    const int G = prm.mtiles * 4;  // column groups allocated per stage (multiple of 4)
-    const uint32_t half_bytes = (uint32_t)G * GROUP_BYTES;
-    const uint32_t stage_bytes = 2 * half_bytes;
+    const int SR = prm.stagesR;
+    const int P = prm.P;
+    const uint32_t half_bytes = (uint32_t)prm.mtiles * TILE_BYTES;   // A' (or B') of one slot
+    const uint32_t oh_bytes = (uint32_t)prm.oh_groups * GROUP_BYTES;
+    const uint32_t slot_bytes = 2 * half_bytes + oh_bytes;
 
-    uint64_t* bars = reinterpret_cast<uint64_t*>(base + (size_t)S * stage_bytes);
-    uint64_t* full = bars;
-    uint64_t* scaled = bars + MAX_STAGES;
-    uint64_t* empty = bars + 2 * MAX_STAGES;
-    uint64_t* done = bars + 3 * MAX_STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * MAX_STAGES + 1);
+    // smem: [operand ring: SB x (A' | B' | one-hot)] [R ring: SR x r_bytes] [barriers]
+    uint8_t* Oper = base;
+    uint8_t* Rring = Oper + (size_t)SB * slot_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(Rring + (size_t)SR * prm.r_bytes);
+    uint64_t* full = bars;                          // [MAX_STAGES] TMA -> scale warps
+    uint64_t* emptyR = bars + MAX_STAGES;           // [MAX_STAGES] scale warps -> producer
+    uint64_t* scaled = bars + 2 * MAX_STAGES;       // [SB] scale warps -> MMA
+    uint64_t* emptyB = bars + 2 * MAX_STAGES + SB;  // [SB] MMA -> scale warps
+    uint64_t* done = bars + 2 * MAX_STAGES + 2 * SB;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
 
-    // Column groups that TMA never writes (P not a multiple of 128) must read as zeros.
-    if (prm.groups < G) {
-        for (int s = 0; s < S; ++s) {
-            for (int h = 0; h < 2; ++h) {
-                uint4* z = reinterpret_cast<uint4*>(base + (size_t)s * stage_bytes + h * half_bytes +
-                                                    (size_t)prm.groups * GROUP_BYTES);
-                int cnt = (G - prm.groups) * GROUP_BYTES / 16;
-                for (int i = threadIdx.x; i < cnt; i += NUM_THREADS) z[i] = make_uint4(0, 0, 0, 0);
-            }
-        }
+    // operand ring starts as zeros: X columns >= P of a tile are never written, and the
+    // one-hot tiles are all-zero except for the ones set (and cleared again) per stage
+    {
+        uint4* z = reinterpret_cast<uint4*>(Oper);
+        for (uint32_t i = threadIdx.x; i < SB * slot_bytes / 16; i += NUM_THREADS)
+            z[i] = make_uint4(0, 0, 0, 0);
         fence_proxy_async();
     }
 
     if (warp == 0 && lane == 0) {
-        for (int s = 0; s < S; ++s) {
-            mbar_init(&full[s], 1);
-            mbar_init(&scaled[s], NUM_SCALE_THREADS);
-            mbar_init(&empty[s], 1);
+        for (int s = 0; s < SR; ++s) {
+            mbar_init(&full[s], 2);  // TMA expect_tx arrive + the producer warp's d/codes stores
+            mbar_init(&emptyR[s], NUM_SCALE_WARPS);
+        }
+        for (int b = 0; b < SB; ++b) {
+            mbar_init(&scaled[b], NUM_SCALE_WARPS);  // one arrive per scale warp
+            mbar_init(&emptyB[b], 1);
         }
         mbar_init(done, 1);
         fence_barrier_init();
@@ -218,108 +295,220 @@ k_dense_syrk_tc(const __grid_constant__ CUtensorMap tmap, const Params prm) {
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    const int syrk_tiles = prm.mtiles * (prm.mtiles + 1) / 2;
+    const uint32_t oh_col0 = (uint32_t)syrk_tiles * 128;  // first TMEM column of the one-hot block
 
     // row tiles of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...
-    long long my_count = 0;
+    int my_count = 0;
     if ((long long)blockIdx.x < prm.num_row_tiles)
-        my_count = (prm.num_row_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+        my_count = (int)((prm.num_row_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
 
     if (warp == 0) {
-        // ===== TMA producer =====
-        if (lane == 0) {
-            for (long long it = 0; it < my_count; ++it) {
-                int s = (int)(it % S);
-                uint32_t ph = (uint32_t)((it / S) & 1);
-                mbar_wait(&empty[s], ph ^ 1);
-                long long k0 = ((long long)blockIdx.x + it * gridDim.x) * BK;
-                uint8_t* R = base + (size_t)s * stage_bytes;
-                mbar_expect_tx(&full[s], (uint32_t)prm.groups * GROUP_BYTES);
-                for (int g = 0; g < prm.groups; ++g)
-                    tma_load_2d(R + (size_t)g * GROUP_BYTES, &tmap, &full[s], g * 32, (int)k0);
+        // ===== producer warp: TMA for the X tile; d and the one-hot codes of the stage's 32
+        // rows go through registers into the stage's aux area (prefetched one stage ahead, so
+        // the scale warps never have a global load in flight when they fence) =====
+        float dreg = 0.f;
+        int creg[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) creg[c] = -1;
+        auto prefetch = [&](int it) {
+            const long long k = ((long long)blockIdx.x + (long long)it * gridDim.x) * BK + lane;
+            const bool ok = k < prm.n;
+            dreg = ok ? prm.d[k] : 0.f;
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                if (c < prm.oh_ncat) creg[c] = ok ? prm.oh_codes[c][k] - prm.oh_df[c] : -1;
+        };
+        if (my_count > 0) prefetch(0);
+        int s = 0;
+        uint32_t ph = 0;
+        for (int it = 0; it < my_count; ++it, ++s) {
+            if (s == SR) {
+                s = 0;
+                ph ^= 1;
             }
+            if (lane == 0) mbar_wait(&emptyR[s], ph ^ 1);
+            __syncwarp();
+            uint8_t* stage = Rring + (size_t)s * prm.r_bytes;
+            if (lane == 0) {
+                tl_stamp(prm, it, 0);
+                const long long k0 = ((long long)blockIdx.x + (long long)it * gridDim.x) * BK;
+                mbar_expect_tx(&full[s], (uint32_t)(BK * P * 4));
+                tma_load_2d(stage, &tmap, &full[s], 0, (int)k0);
+            }
+            float* dsm = reinterpret_cast<float*>(stage + prm.aux_off);
+            int* csm = reinterpret_cast<int*>(stage + prm.aux_off + 128);
+            dsm[lane] = dreg;
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                if (c < prm.oh_ncat) csm[c * 32 + lane] = creg[c];
+            if (it + 1 < my_count) prefetch(it + 1);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full[s]);
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
-        const uint32_t idesc = make_idesc(128, 128, 1, 1);
-        for (long long it = 0; it < my_count; ++it) {
-            int s = (int)(it % S);
-            uint32_t ph = (uint32_t)((it / S) & 1);
-            mbar_wait(&scaled[s], ph);
+        const uint32_t idesc = make_idesc(128, 128);
+        for (int it = 0; it < my_count; ++it) {
+            const int b = it & (SB - 1);
+            const uint32_t phb = (uint32_t)((it / SB) & 1);
+            mbar_wait(&scaled[b], phb);
             tcgen05_fence_after();
-            if (lane == 0) {
-                uint32_t Ra = smem_u32(base + (size_t)s * stage_bytes);
-                uint32_t Ba = Ra + half_bytes;
+            if (elect_one()) {
+                tl_stamp(prm, it, 4);
+                const uint32_t Aa = smem_u32(Oper + (size_t)b * slot_bytes);
+                const uint32_t Ba = Aa + half_bytes;
+                const uint32_t Oa = Ba + half_bytes;
 #pragma unroll
                 for (int ks = 0; ks < BK / 8; ++ks) {
-                    uint32_t acc = (it > 0 || ks > 0) ? 1u : 0u;
+                    const uint32_t acc = (it > 0 || ks > 0) ? 1u : 0u;
                     int tile = 0;
                     for (int mt = 0; mt < prm.mtiles; ++mt) {
-                        const uint32_t lbo = (prm.variant & 1) ? 512u : (uint32_t)GROUP_BYTES;
-                        const uint32_t sbo = (prm.variant & 1) ? (uint32_t)GROUP_BYTES : 512u;
-                        uint64_t da = make_desc(Ra + (uint32_t)(mt * 4) * GROUP_BYTES + ks * 1024,
-                                                lbo, sbo);
+                        const uint64_t da = make_desc(Aa + (uint32_t)mt * TILE_BYTES + ks * 32);
                         for (int nt = 0; nt <= mt; ++nt, ++tile) {
-                            uint64_t db = make_desc(
-                                Ba + (uint32_t)(nt * 4) * GROUP_BYTES + ks * 1024, lbo, sbo);
+                            const uint64_t db = make_desc(Ba + (uint32_t)nt * TILE_BYTES + ks * 32);
                             tcgen05_mma_tf32(tmem_base + (uint32_t)tile * 128, da, db, idesc, acc);
                         }
                     }
+                    // one-hot blocks: D'[dense col, slot] += (d*X)[:, col]^T * OneHot[:, slot]
+                    if (prm.oh_groups) {
+                        const uint64_t da = make_desc(Ba + ks * 32);
+                        for (int g0 = 0; g0 < prm.oh_groups; g0 += 8) {
+                            const int ng = prm.oh_groups - g0 < 8 ? prm.oh_groups - g0 : 8;
+                            const uint64_t db = make_desc(Oa + (uint32_t)g0 * GROUP_BYTES + ks * 32);
+                            tcgen05_mma_tf32(tmem_base + oh_col0 + (uint32_t)g0 * 32, da, db,
+                                             make_idesc(128, ng * 32), acc);
+                        }
+                    }
                 }
-                tcgen05_commit(&empty[s]);
+                tcgen05_commit(&emptyB[b]);
+                tl_stamp(prm, it, 5);
             }
             __syncwarp();
         }
-        if (lane == 0) tcgen05_commit(done);
+        if (elect_one()) tcgen05_commit(done);
         __syncwarp();
     } else {
         // ===== scale warps, then epilogue =====
-        const int t = (int)threadIdx.x - 64;  // 0..255
-        const int r = t >> 3;                 // row of this thread's 16-byte chunk inside a stage
-        float d_next = 0.f;
-        if (my_count > 0) {
-            long long k = (long long)blockIdx.x * BK + r;
-            d_next = (k < prm.n) ? prm.d[k] : 0.f;
-        }
-        for (long long it = 0; it < my_count; ++it) {
-            int s = (int)(it % S);
-            uint32_t ph = (uint32_t)((it / S) & 1);
-            float dk = d_next;
-            if (it + 1 < my_count) {
-                long long k = ((long long)blockIdx.x + (it + 1) * gridDim.x) * BK + r;
-                d_next = (k < prm.n) ? prm.d[k] : 0.f;
+        const int w = warp - 2;                // 0..7
+        const int t = (int)threadIdx.x - 64;   // 0..255
+        // one-hot: thread t encodes row (t >> 3) of categorical block (t & 7)
+        const int oh_r = t >> 3;
+        const int oh_c = t & 7;
+        const bool oh_thread = oh_c < prm.oh_ncat;
+        const int my_off = oh_thread ? prm.oh_off[oh_c] : 0;
+        const int my_K = oh_thread ? prm.oh_K[oh_c] : 0;
+        uint32_t prev0 = 0xffffffffu, prev1 = 0xffffffffu;  // one set in operand slot 0 / 1
+        const int items = prm.groups * 8;     // (column group, 4-row k chunk) pairs per stage
+        const int g_start = w % prm.groups, k4_start = w / prm.groups;
+        const int g_inc = NUM_SCALE_WARPS % prm.groups, k4_inc = NUM_SCALE_WARPS / prm.groups;
+        int s = 0;
+        uint32_t ph = 0;
+        for (int it = 0; it < my_count; ++it, ++s) {
+            if (s == SR) {
+                s = 0;
+                ph ^= 1;
             }
-            mbar_wait(&full[s], ph);
-            uint8_t* R = base + (size_t)s * stage_bytes + (size_t)t * 16;
-            uint8_t* B = R + half_bytes;
-            for (int g = 0; g < prm.groups; ++g) {
-                float4 x = *reinterpret_cast<const float4*>(R + (size_t)g * GROUP_BYTES);
-                uint4 a, b;
-                a.x = to_tf32(x.x);
-                a.y = to_tf32(x.y);
-                a.z = to_tf32(x.z);
-                a.w = to_tf32(x.w);
-                b.x = to_tf32(dk * x.x);
-                b.y = to_tf32(dk * x.y);
-                b.z = to_tf32(dk * x.z);
-                b.w = to_tf32(dk * x.w);
-                *reinterpret_cast<uint4*>(R + (size_t)g * GROUP_BYTES) = a;
-                *reinterpret_cast<uint4*>(B + (size_t)g * GROUP_BYTES) = b;
+            const int b = it & (SB - 1);
+            const uint32_t phb = (uint32_t)((it / SB) & 1);
+            // one lane polls, the warp follows through __syncwarp
+            if (lane == 0) mbar_wait(&emptyB[b], phb ^ 1);  // MMAs of iteration it-SB left slot b
+            __syncwarp();
+            if (t == 0) tl_stamp(prm, it, 1);
+            uint8_t* Ap = Oper + (size_t)b * slot_bytes;
+            uint8_t* Bp = Ap + half_bytes;
+            if (lane == 0) mbar_wait(&full[s], ph);
+            __syncwarp();
+            if (t == 0) tl_stamp(prm, it, 2);
+            const uint8_t* stage = Rring + (size_t)s * prm.r_bytes;
+            const float* dsm = reinterpret_cast<const float*>(stage + prm.aux_off);
+            if (prm.oh_groups) {
+                uint8_t* O = Bp + half_bytes;
+                const uint32_t pa = b ? prev1 : prev0;
+                if (pa != 0xffffffffu) *reinterpret_cast<float*>(O + pa) = 0.f;
+                uint32_t na = 0xffffffffu;
+                if (oh_thread) {
+                    const int code =
+                        reinterpret_cast<const int*>(stage + prm.aux_off + 128)[oh_c * 32 + oh_r];
+                    if (code >= 0 && code < my_K && dsm[oh_r] != 0.f) {
+                        const uint32_t slot = (uint32_t)(my_off + code);
+                        na = kmajor_chunk_off(slot, (uint32_t)oh_r >> 2) +
+                             (((uint32_t)oh_r & 3u) << 2);
+                        *reinterpret_cast<float*>(O + na) = 1.0f;
+                    }
+                }
+                if (b) prev1 = na; else prev0 = na;
+            }
+            const float* R = reinterpret_cast<const float*>(Rring + (size_t)s * prm.r_bytes);
+            if (P == 128) {
+                // 4 column groups: warp w owns column group w & 3, row chunks (w >> 2) + {0,2,4,6}
+                scale_col4(R, 128, dsm, Ap, Bp, (w & 3) * 32 + lane, w >> 2, 2);
+            } else if (P == 256) {
+                // 8 column groups: warp w owns column group w, all 8 row chunks
+                scale_col4(R, 256, dsm, Ap, Bp, w * 32 + lane, 0, 1);
+                scale_col4(R, 256, dsm, Ap, Bp, w * 32 + lane, 4, 1);
+            } else {
+            // items (column group g, 4-row chunk k4): this warp takes item w, w+8, ... in batches
+            // of 4 with all 16 shared-memory loads of a batch in flight before the math
+            int g = g_start, k4 = k4_start;
+            for (int base_item = w; base_item < items; base_item += 4 * NUM_SCALE_WARPS) {
+                float x[4][4];
+                int gg[4], kk[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    gg[u] = g;
+                    kk[u] = k4;
+                    const int c = g * 32 + lane;
+                    const bool ok = (base_item + u * NUM_SCALE_WARPS < items) && c < P;
+                    const float* r0 = R + (size_t)(4 * k4) * P + c;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) x[u][i] = ok ? r0[(size_t)i * P] : 0.f;
+                    g += g_inc;
+                    k4 += k4_inc;
+                    if (g >= prm.groups) {
+                        g -= prm.groups;
+                        k4 += 1;
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int c = gg[u] * 32 + lane;
+                    const bool ok = (base_item + u * NUM_SCALE_WARPS < items) && c < P;
+                    const int kq = ok ? kk[u] : 0;
+                    if (ok) {
+                        const float4 dv = *reinterpret_cast<const float4*>(dsm + 4 * kq);
+                        const float d0 = dv.x, d1 = dv.y, d2 = dv.z, d3 = dv.w;
+                        uint4 a, bb;
+                        a.x = to_tf32(x[u][0]);
+                        a.y = to_tf32(x[u][1]);
+                        a.z = to_tf32(x[u][2]);
+                        a.w = to_tf32(x[u][3]);
+                        bb.x = to_tf32(d0 * x[u][0]);
+                        bb.y = to_tf32(d1 * x[u][1]);
+                        bb.z = to_tf32(d2 * x[u][2]);
+                        bb.w = to_tf32(d3 * x[u][3]);
+                        const uint32_t off = (uint32_t)(c >> 7) * TILE_BYTES +
+                                             kmajor_chunk_off((uint32_t)c & 127u, (uint32_t)kq);
+                        *reinterpret_cast<uint4*>(Ap + off) = a;
+                        *reinterpret_cast<uint4*>(Bp + off) = bb;
+                    }
+                }
+            }
             }
             fence_proxy_async();
-            if (prm.dbg && blockIdx.x == 0 && it == 0) {
-                // raw stage-0 smem (R half then B half) as floats
-                const float* sm = reinterpret_cast<const float*>(base);
-                for (uint32_t i = t; i < stage_bytes / 4; i += NUM_SCALE_THREADS) prm.dbg[i] = sm[i];
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&emptyR[s]);   // the raw stage can be refilled
+                mbar_arrive(&scaled[b]);   // the operands are ready for the MMA warp
             }
-            mbar_arrive(&scaled[s]);
+            if (t == 0) tl_stamp(prm, it, 3);
         }
 
-        // epilogue: TMEM -> registers -> RED into the upper triangle of `out` (transposed)
+        // epilogue: TMEM -> registers -> RED into `out` (transposed: lanes = output columns)
         mbar_wait(done, 0);
         tcgen05_fence_after();
         const int q = warp & 3;               // TMEM lane quarter this warp may access
-        const int chalf = (warp - 2) >> 2;    // which 64-column half of a tile this warp drains
-        const int P = prm.P;
+        const int chalf = (warp - 2) >> 2;    // which half of the column chunks this warp drains
         if (my_count > 0) {
             int tile = 0;
             for (int mt = 0; mt < prm.mtiles; ++mt) {
@@ -344,6 +533,23 @@ k_dense_syrk_tc(const __grid_constant__ CUtensorMap tmap, const Params prm) {
                             if (Rr < P && C < P && C >= Rr)
                                 atomicAdd(&prm.out[(size_t)Rr * P + C], __uint_as_float(v[j]));
                         }
+                    }
+                }
+            }
+            // one-hot block: D'[col = lane, slot] -> oh_out[slot, col]
+            const int C = q * 32 + lane;
+#pragma unroll 1
+            for (int ch = chalf; ch < prm.oh_groups; ch += 2) {
+                uint32_t v[32];
+                uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + oh_col0 + (uint32_t)ch * 32;
+                TM_TMEM_LD_32x32B_X32(taddr, v);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int slot = ch * 32 + j;
+                    if (slot < prm.oh_slots && C < P) {
+                        float val = __uint_as_float(v[j]);
+                        if (val != 0.f) atomicAdd(&prm.oh_out[(size_t)slot * P + C], val);
                     }
                 }
             }
@@ -407,7 +613,7 @@ float* g_tc_dbg = nullptr;
 int g_tc_variant = 0;
 
 int dense_sandwich_tc_f32(const float* X, int64_t n, int64_t p, int c_order, const float* d,
-                          float* out, cudaStream_t st) {
+                          float* out, cudaStream_t st, const TcOneHot* oh) {
     using namespace tc;
     (void)c_order;
     PFN_encodeTiled enc = get_encode();
@@ -416,15 +622,16 @@ int dense_sandwich_tc_f32(const float* X, int64_t n, int64_t p, int c_order, con
     CUtensorMap tmap;
     cuuint64_t gdim[2] = {(cuuint64_t)p, (cuuint64_t)n};
     cuuint64_t gstride[1] = {(cuuint64_t)p * sizeof(float)};
-    cuuint32_t box[2] = {32, (cuuint32_t)BK};
+    cuuint32_t box[2] = {(cuuint32_t)p, (cuuint32_t)BK};  // one box = the whole row tile
     cuuint32_t estr[2] = {1, 1};
     CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(X), gdim,
                       gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                      CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed");
 
     Params prm;
+    memset(&prm, 0, sizeof(prm));
     prm.d = d;
     prm.out = out;
     prm.n = n;
@@ -435,13 +642,35 @@ int dense_sandwich_tc_f32(const float* X, int64_t n, int64_t p, int c_order, con
     prm.dbg = g_tc_dbg;
     prm.variant = g_tc_variant;
     int ntiles = prm.mtiles * (prm.mtiles + 1) / 2;
-    prm.tmem_cols = ntiles == 1 ? 128 : 512;
-    int stage_bytes = 2 * prm.mtiles * 4 * GROUP_BYTES;
-    int stages = (SMEM_BUDGET - 1024) / stage_bytes;
-    if (stages > MAX_STAGES) stages = MAX_STAGES;
-    if (stages < 2) return fail("dense_tc: not enough shared memory for 2 stages");
-    prm.stages = stages;
-    size_t smem = (size_t)stages * stage_bytes + 1024 /*align slack*/ + 512 /*barriers*/;
+    if (oh && oh->ncat > 0) {
+        if (prm.mtiles != 1) return fail("dense_tc: one-hot blocks need p <= 128");
+        if (oh->ncat > 8) return fail("dense_tc: at most 8 one-hot blocks");
+        int slots = 0;
+        for (int c = 0; c < oh->ncat; ++c) {
+            prm.oh_codes[c] = oh->codes[c];
+            prm.oh_off[c] = slots;
+            prm.oh_K[c] = oh->K[c];
+            prm.oh_df[c] = oh->drop_first[c];
+            slots += oh->K[c];
+        }
+        if (slots > TC_ONEHOT_MAX_SLOTS) return fail("dense_tc: too many one-hot slots");
+        prm.oh_ncat = oh->ncat;
+        prm.oh_slots = slots;
+        prm.oh_groups = (slots + 31) / 32;
+        prm.oh_out = oh->out;
+        TM_CUDA(cudaMemsetAsync(oh->out, 0, sizeof(float) * (size_t)slots * (size_t)p, st));
+    }
+    int cols_needed = ntiles * 128 + prm.oh_groups * 32;
+    prm.tmem_cols = cols_needed <= 128 ? 128 : (cols_needed <= 256 ? 256 : 512);
+    const int half = prm.mtiles * TILE_BYTES;
+    prm.aux_off = (int)((BK * p * 4 + 127) / 128 * 128);
+    prm.r_bytes = prm.aux_off + 128 + 8 * 128;
+    const int fixed = SB * (2 * half + prm.oh_groups * GROUP_BYTES) + 1024 /*align*/ + 512 /*barriers*/;
+    int stagesR = (SMEM_BUDGET - fixed) / prm.r_bytes;
+    if (stagesR > MAX_STAGES) stagesR = MAX_STAGES;
+    if (stagesR < 2) return fail("dense_tc: not enough shared memory for 2 stages");
+    prm.stagesR = stagesR;
+    size_t smem = (size_t)stagesR * prm.r_bytes + fixed;
 
     static bool attr_set = false;
     if (!attr_set) {
@@ -459,6 +688,38 @@ int dense_sandwich_tc_f32(const float* X, int64_t n, int64_t p, int c_order, con
 }  // namespace tmb
 
 extern "C" {
+
+int tm_dense_onehot_sandwich_f32(const float* X, int64_t n, int64_t p, const float* d,
+                                 const int32_t* rows, int64_t n_rows, int n_cat,
+                                 const int32_t* const* codes, const int64_t* K,
+                                 const int32_t* drop_first, float* out_dense, float* out_cat,
+                                 tm_stream_t stream) {
+    using namespace tmb;
+    cudaStream_t st = as_stream(stream);
+    if (!dense_tc_eligible(n, p, 1, X) || p > 128)
+        return fail("tm_dense_onehot_sandwich_f32: needs sm_100, row-major X, p % 4 == 0, p <= 128");
+    if (n_cat < 0 || n_cat > 8) return fail("tm_dense_onehot_sandwich_f32: 0..8 categorical blocks");
+    TcOneHot oh;
+    oh.ncat = n_cat;
+    oh.out = out_cat;
+    int64_t slots = 0;
+    for (int c = 0; c < n_cat; ++c) {
+        oh.codes[c] = codes[c];
+        oh.K[c] = (int)K[c];
+        oh.drop_first[c] = drop_first[c];
+        slots += K[c];
+    }
+    if (slots > TC_ONEHOT_MAX_SLOTS)
+        return fail("tm_dense_onehot_sandwich_f32: more than 384 category columns in total");
+    if (rows) {
+        Scratch dm(sizeof(float) * (size_t)n, st);
+        if (dm.err != cudaSuccess) return fail_cuda(dm.err, "scratch");
+        int rc = masked_weights<float>(d, n, rows, n_rows, dm.as<float>(), st);
+        if (rc) return rc;
+        return dense_sandwich_tc_f32(X, n, p, 1, dm.as<float>(), out_dense, st, n_cat ? &oh : nullptr);
+    }
+    return dense_sandwich_tc_f32(X, n, p, 1, d, out_dense, st, n_cat ? &oh : nullptr);
+}
 
 int tm_has_tcgen05(void) {
     return tmb::tc::device_cc_major() == 10 && tmb::tc::get_encode() != nullptr ? 1 : 0;

@@ -15,6 +15,7 @@
 //                         where (a, b) is the kernel's native orientation:
 //                           categorical x dense / sparse x dense / categorical x sparse /
 //                           categorical_i x categorical_j (i < j)
+#include <cstdlib>
 #include <vector>
 
 #include "tm_common.cuh"
@@ -62,6 +63,28 @@ TM_SHIM(scatter_block, double, f64)
 TM_SHIM(scatter_diag, float, f32)
 TM_SHIM(scatter_diag, double, f64)
 
+// one non-blocking side stream + two events per thread (created lazily, never destroyed);
+// TABMAT_B200_SIDE_STREAM=0 keeps everything on the caller's stream
+static cudaStream_t side_stream() {
+    static thread_local cudaStream_t st = nullptr;
+    static thread_local bool tried = false;
+    if (!tried) {
+        tried = true;
+        const char* e = getenv("TABMAT_B200_SIDE_STREAM");
+        if (!(e && atoi(e) == 0)) cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+    }
+    return st;
+}
+static cudaEvent_t side_event(int i) {
+    static thread_local cudaEvent_t ev[2] = {nullptr, nullptr};
+    if (!ev[i]) cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming);
+    return ev[i];
+}
+
+static inline int64_t n_rows_or_all(const int32_t* rows, int64_t n_rows, int64_t n) {
+    return rows ? n_rows : n;
+}
+
 template <typename F>
 int split_blocks(const tm_block_desc* blk, int nb, int64_t n, const F* d, const int32_t* rows,
                  int64_t n_rows, F* ws, tm_stream_t stream) {
@@ -95,6 +118,65 @@ int split_blocks(const tm_block_desc* blk, int nb, int64_t n, const F* d, const 
         fuse = D.c_order && D.ncols % W == 0 && D.ncols <= 64 * W &&
                (reinterpret_cast<uintptr_t>(D.data) & 15) == 0;
     }
+    // categorical blocks with few levels ride along the fp32 tensor-core SYRK as one-hot MMAs
+    std::vector<char> on_tensor(nb, 0);
+    bool dense_self_done = false;
+    bool side_used = false;
+    if (fuse && sizeof(F) == 4) {
+        const tm_block_desc& D = blk[dense_idx];
+        static const bool onehot_off = getenv("TABMAT_B200_ONEHOT") && atoi(getenv("TABMAT_B200_ONEHOT")) == 0;
+        if (!onehot_off && g_dense_f32_mode != 1 && D.ncols <= 128 && n_rows_or_all(rows, n_rows, n) > 0 &&
+            dense_tc_eligible(n, D.ncols, 1, D.data)) {
+            TcOneHot oh;
+            oh.ncat = 0;
+            int64_t slots = 0;
+            int which[8];
+            for (int i = 0; i < nb && oh.ncat < 8; ++i) {
+                if (blk[i].kind != KIND_CAT || blk[i].ncols <= 0 || blk[i].ncols > 256) continue;
+                if (slots + blk[i].ncols > TC_ONEHOT_MAX_SLOTS) continue;
+                which[oh.ncat] = i;
+                oh.codes[oh.ncat] = static_cast<const int32_t*>(blk[i].data);
+                oh.K[oh.ncat] = (int)blk[i].ncols;
+                oh.drop_first[oh.ncat] = blk[i].drop_first;
+                slots += blk[i].ncols;
+                ++oh.ncat;
+            }
+            // The tensor-core pass is HBM / tensor bound while the scatter passes below are bound
+            // by the L2 atomic units: run it on a side stream so that the two overlap.
+            cudaStream_t st = side_stream() ? side_stream() : as_stream(stream);
+            side_used = st != as_stream(stream);
+            if (side_used) {
+                TM_CUDA(cudaEventRecord(side_event(0), as_stream(stream)));
+                TM_CUDA(cudaStreamWaitEvent(st, side_event(0), 0));
+            }
+            Scratch tmp(sizeof(float) * (size_t)(slots > 0 ? slots : 1) * (size_t)D.ncols, st);
+            Scratch dm(rows ? sizeof(float) * (size_t)n : 0, st);
+            if (tmp.err != cudaSuccess) return fail_cuda(tmp.err, "scratch");
+            if (dm.err != cudaSuccess) return fail_cuda(dm.err, "scratch");
+            const float* dd = reinterpret_cast<const float*>(d);
+            if (rows) {
+                int rc = masked_weights<float>(dd, n, rows, n_rows, dm.as<float>(), st);
+                if (rc) return rc;
+                dd = dm.as<float>();
+            }
+            oh.out = tmp.as<float>();
+            int rc = dense_sandwich_tc_f32(static_cast<const float*>(D.data), n, D.ncols, 1, dd,
+                                           reinterpret_cast<float*>(ws + self_off[dense_idx]), st,
+                                           oh.ncat ? &oh : nullptr);
+            if (rc) return rc;
+            dense_self_done = true;
+            int64_t o = 0;
+            for (int c = 0; c < oh.ncat; ++c) {
+                int i = which[c];
+                int a = i < dense_idx ? i : dense_idx, b = i < dense_idx ? dense_idx : i;
+                TM_CUDA(cudaMemcpyAsync(ws + cross_off[a][b], tmp.as<float>() + o * D.ncols,
+                                        sizeof(float) * (size_t)(blk[i].ncols * D.ncols),
+                                        cudaMemcpyDeviceToDevice, st));
+                o += blk[i].ncols;
+                on_tensor[i] = 1;
+            }
+        }
+    }
     if (fuse) {
         const tm_block_desc& D = blk[dense_idx];
         const int32_t* codes[8];
@@ -103,7 +185,7 @@ int split_blocks(const tm_block_desc* blk, int nb, int64_t n, const F* d, const 
         F* outs[8];
         int c = 0;
         for (int i = 0; i < nb; ++i) {
-            if (blk[i].kind != KIND_CAT) continue;
+            if (blk[i].kind != KIND_CAT || on_tensor[i]) continue;
             codes[c] = static_cast<const int32_t*>(blk[i].data);
             K[c] = blk[i].ncols;
             df[c] = blk[i].drop_first;
@@ -131,17 +213,21 @@ int split_blocks(const tm_block_desc* blk, int nb, int64_t n, const F* d, const 
                                     sizeof(F) * (size_t)(blk[a].ncols * blk[b].ncols),
                                     as_stream(stream)));
         }
-        int rc = dense_cross_sandwich(tag, static_cast<const F*>(D.data), n, D.ncols, d, rows,
-                                      n_rows, c, codes, K, df, outs, sdata, sind, sptr, ps, out_s,
-                                      stream);
-        if (rc) return rc;
+        if (c > 0 || out_s) {
+            int rc = dense_cross_sandwich(tag, static_cast<const F*>(D.data), n, D.ncols, d, rows,
+                                          n_rows, c, codes, K, df, outs, sdata, sind, sptr, ps,
+                                          out_s, stream);
+            if (rc) return rc;
+        }
     }
 
     for (int i = 0; i < nb; ++i) {
         const tm_block_desc& bi = blk[i];
         F* so = ws + self_off[i];
         int rc = 0;
-        if (bi.kind == KIND_DENSE)
+        if (bi.kind == KIND_DENSE && dense_self_done)
+            rc = 0;
+        else if (bi.kind == KIND_DENSE)
             rc = dense_sandwich(tag, static_cast<const F*>(bi.data), n, bi.ncols, bi.c_order, d,
                                 rows, n_rows, (const int32_t*)nullptr, (int64_t)0, so, stream);
         else if (bi.kind == KIND_SPARSE)
@@ -187,6 +273,10 @@ int split_blocks(const tm_block_desc* blk, int nb, int64_t n, const F* d, const 
                             "blocks must be merged first, split_matrix.py:85-141)");
             if (rc) return rc;
         }
+    }
+    if (side_used) {  // join the side stream
+        TM_CUDA(cudaEventRecord(side_event(1), side_stream()));
+        TM_CUDA(cudaStreamWaitEvent(as_stream(stream), side_event(1), 0));
     }
     return 0;
 }

@@ -112,4 +112,20 @@ int symmetrize_from_lower(F* out, int64_t m, cudaStream_t st);
 template <typename F>
 int symmetrize_from_upper(F* out, int64_t m, cudaStream_t st);
 
+// ---- tcgen05 dense kernel (dense_tc.cu) -----------------------------------------------
+// Categorical blocks with few levels that ride along the fp32 weighted SYRK as one-hot MMAs:
+// out[(off_c + codes_c[k] - drop_first_c) * p + b] += d[k] * X[k, b]   (off_c = sum of K before c)
+constexpr int TC_ONEHOT_MAX_SLOTS = 384;
+struct TcOneHot {
+    int ncat;
+    const int32_t* codes[8];
+    int K[8];
+    int drop_first[8];
+    float* out;  // [sum K][p], overwritten
+};
+int dense_sandwich_tc_f32(const float* X, int64_t n, int64_t p, int c_order, const float* d,
+                          float* out, cudaStream_t st, const TcOneHot* oh = nullptr);
+bool dense_tc_eligible(int64_t n, int64_t p, int c_order, const void* X);
+extern int g_dense_f32_mode;
+
 }  // namespace tmb

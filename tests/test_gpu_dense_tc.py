@@ -78,3 +78,46 @@ def test_tcgen05_linearity_at_scale(force_mode):
     assert (s1 + s2 - s12).abs().max().item() / scale < 1e-3
     diag = (d1[:, None].double() * X.double() ** 2).sum(0)
     assert ((s1.diagonal().double() - diag).abs().max() / diag.abs().max()).item() < 1e-3
+
+
+@pytest.mark.parametrize("n,p", [(5003, 128), (70_001, 64), (999, 8), (40_000, 100)])
+@pytest.mark.parametrize("with_rows", [False, True])
+def test_onehot_fused_dense_and_small_cats(n, p, with_rows):
+    """tm_dense_onehot_sandwich_f32: SYRK + one-hot MMAs for categoricals with few levels."""
+    import ctypes as C
+
+    import torch
+
+    from oracle import c_oracle as orc
+    from tabmat_b200._lib import check, lib
+
+    rng = np.random.default_rng(n + p)
+    X = rng.standard_normal((n, p)).astype(np.float32)
+    d = rng.standard_normal(n).astype(np.float32)
+    d[rng.random(n) < 0.05] = 0
+    Ks, dfs = [10, 50, 200, 1, 33], [False, True, False, False, True]
+    codes = [rng.integers(-1, K + int(df), size=n).astype(np.int32) for K, df in zip(Ks, dfs)]
+    rows = np.sort(rng.choice(n, size=n // 2, replace=False)).astype(np.int32) if with_rows else None
+    Xd, dd = torch.from_numpy(X).cuda(), torch.from_numpy(d).cuda()
+    cd = [torch.from_numpy(c).cuda() for c in codes]
+    rd = None if rows is None else torch.from_numpy(rows).cuda()
+    out_dense = torch.empty((p, p), dtype=torch.float32, device="cuda")
+    out_cat = torch.empty((sum(Ks), p), dtype=torch.float32, device="cuda")
+    nc = len(Ks)
+    codes_arr = (C.c_void_p * nc)(*[c.data_ptr() for c in cd])
+    K_arr = (C.c_int64 * nc)(*Ks)
+    df_arr = (C.c_int32 * nc)(*[int(f) for f in dfs])
+    check(lib.tm_dense_onehot_sandwich_f32(
+        Xd.data_ptr(), n, p, dd.data_ptr(), None if rd is None else rd.data_ptr(),
+        0 if rd is None else len(rows), nc, C.cast(codes_arr, C.c_void_p),
+        C.cast(K_arr, C.c_void_p), C.cast(df_arr, C.c_void_p), out_dense.data_ptr(),
+        out_cat.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    cases.assert_close(out_dense.cpu().numpy(), orc.dense_sandwich(X, d, rows, None), np.float32,
+                       "dense self")
+    got = out_cat.cpu().numpy()
+    o = 0
+    for c, K, df in zip(codes, Ks, dfs):
+        ref = orc.cat_dense_sandwich(c, K, d, X, rows, None, df)
+        cases.assert_close(got[o:o + K], ref, np.float32, f"one-hot cat K={K}")
+        o += K
