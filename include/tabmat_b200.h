@@ -261,7 +261,7 @@ int tm_dense_cross_sandwich_f64(const double* X, int64_t n, int64_t p, const dou
                                 tm_stream_t stream);
 
 /* Dense self block AND the dense x categorical cross blocks of categoricals with few levels in
- * one pass on the tensor cores (fp32, row-major X, p % 4 == 0, p <= 128, sum of K <= 384):
+ * one pass on the tensor cores (fp32, row-major X, p % 4 == 0, p <= 128, sum of K <= 320):
  * the weighted SYRK of tm_dense_sandwich_f32 plus one-hot MMAs
  *   out_cat[(off_i + codes[i][k] - drop_first[i]) * p + b] += d[k] * X[k, b],  off_i = sum_{c<i} K[c]
  * (reference: dense.pyx:19-44 + split.pyx:32-80 called per pair from split_matrix.py:337-354).

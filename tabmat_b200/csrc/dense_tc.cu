@@ -138,6 +138,26 @@ __device__ __forceinline__ void tcgen05_mma_tf32(uint32_t tmem_d, uint64_t desc_
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// A operand from TMEM (lanes = M rows, one 32-bit column per k), B from shared memory
+__device__ __forceinline__ void tcgen05_mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a,
+                                                    uint64_t desc_b, uint32_t idesc,
+                                                    uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u)
+        : "memory");
+}
+// each lane writes 4 consecutive TMEM columns of its own TMEM lane (warp's lane quarter)
+__device__ __forceinline__ void tmem_st_x4(uint32_t taddr, uint32_t v0, uint32_t v1, uint32_t v2,
+                                           uint32_t v3) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr),
+                 "r"(v0), "r"(v1), "r"(v2), "r"(v3)
+                 : "memory");
+}
 // one elected lane of a converged warp (the compiler then emits the tcgen05 instructions
 // straight-line instead of a per-active-lane serialisation loop)
 __device__ __forceinline__ bool elect_one() {
@@ -196,34 +216,34 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
         : "r"(taddr))
 
 // Transpose + round + scale 4 row-chunks (k4 = kb, kb+ks, kb+2ks, kb+3ks; 4 rows each) of X
-// column c of a raw stage into the K-major operand tiles: all 16 loads first, then the math.
+// column c of a raw stage: the rounded values go to the K-major shared-memory tile S (N side of
+// the MMAs), the d-scaled values to this lane's TMEM lane of the T operand (M side).  All 16
+// loads are issued before the math.  Lanes with c >= P write nothing to S (those rows stay
+// zero) and zeros to T (tcgen05.st is warp-collective).
 __device__ __forceinline__ void scale_col4(const float* __restrict__ R, int P,
-                                           const float* __restrict__ dsm, uint8_t* Ap, uint8_t* Bp,
-                                           int c, int kb, int ks) {
+                                           const float* __restrict__ dsm, uint8_t* Sp,
+                                           uint32_t t_addr, int c, int kb, int ks) {
     float x[4][4];
+    const bool ok = c < P;
     const float* r0 = R + c;
 #pragma unroll
     for (int u = 0; u < 4; ++u)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) x[u][i] = r0[(size_t)(4 * (kb + u * ks) + i) * P];
+        for (int i = 0; i < 4; ++i) x[u][i] = ok ? r0[(size_t)(4 * (kb + u * ks) + i) * P] : 0.f;
     const uint32_t tile_off = (uint32_t)(c >> 7) * TILE_BYTES;
     const uint32_t row = (uint32_t)c & 127u;
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
         const int k4 = kb + u * ks;
         const float4 dv = *reinterpret_cast<const float4*>(dsm + 4 * k4);
-        uint4 a, bb;
+        uint4 a;
         a.x = to_tf32(x[u][0]);
         a.y = to_tf32(x[u][1]);
         a.z = to_tf32(x[u][2]);
         a.w = to_tf32(x[u][3]);
-        bb.x = to_tf32(dv.x * x[u][0]);
-        bb.y = to_tf32(dv.y * x[u][1]);
-        bb.z = to_tf32(dv.z * x[u][2]);
-        bb.w = to_tf32(dv.w * x[u][3]);
-        const uint32_t off = tile_off + kmajor_chunk_off(row, (uint32_t)k4);
-        *reinterpret_cast<uint4*>(Ap + off) = a;
-        *reinterpret_cast<uint4*>(Bp + off) = bb;
+        if (ok) *reinterpret_cast<uint4*>(Sp + tile_off + kmajor_chunk_off(row, (uint32_t)k4)) = a;
+        tmem_st_x4(t_addr + (uint32_t)(4 * k4), to_tf32(dv.x * x[u][0]), to_tf32(dv.y * x[u][1]),
+                   to_tf32(dv.z * x[u][2]), to_tf32(dv.w * x[u][3]));
     }
 }
 
@@ -244,11 +264,11 @@ k_dense_syrk_tc(const __grid_constant__ CUtensorMap tmap, const Params prm) {
 
     const int SR = prm.stagesR;
     const int P = prm.P;
-    const uint32_t half_bytes = (uint32_t)prm.mtiles * TILE_BYTES;   // A' (or B') of one slot
+    const uint32_t half_bytes = (uint32_t)prm.mtiles * TILE_BYTES;   // S of one slot
     const uint32_t oh_bytes = (uint32_t)prm.oh_groups * GROUP_BYTES;
-    const uint32_t slot_bytes = 2 * half_bytes + oh_bytes;
+    const uint32_t slot_bytes = half_bytes + oh_bytes;
 
-    // smem: [operand ring: SB x (A' | B' | one-hot)] [R ring: SR x r_bytes] [barriers]
+    // smem: [operand ring: SB x (S | one-hot)] [R ring: SR x r_bytes] [barriers]
     uint8_t* Oper = base;
     uint8_t* Rring = Oper + (size_t)SB * slot_bytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(Rring + (size_t)SR * prm.r_bytes);
@@ -297,6 +317,7 @@ k_dense_syrk_tc(const __grid_constant__ CUtensorMap tmap, const Params prm) {
     const uint32_t tmem_base = *tmem_slot;
     const int syrk_tiles = prm.mtiles * (prm.mtiles + 1) / 2;
     const uint32_t oh_col0 = (uint32_t)syrk_tiles * 128;  // first TMEM column of the one-hot block
+    const uint32_t t_col0 = oh_col0 + (uint32_t)prm.oh_groups * 32;  // T operand ring (SB x mtiles x 32)
 
     // row tiles of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...
     int my_count = 0;
@@ -356,28 +377,28 @@ k_dense_syrk_tc(const __grid_constant__ CUtensorMap tmap, const Params prm) {
             tcgen05_fence_after();
             if (elect_one()) {
                 tl_stamp(prm, it, 4);
-                const uint32_t Aa = smem_u32(Oper + (size_t)b * slot_bytes);
-                const uint32_t Ba = Aa + half_bytes;
-                const uint32_t Oa = Ba + half_bytes;
+                const uint32_t Sa = smem_u32(Oper + (size_t)b * slot_bytes);
+                const uint32_t Oa = Sa + half_bytes;
+                const uint32_t Ta = tmem_base + t_col0 + (uint32_t)(b * prm.mtiles) * 32;
 #pragma unroll
                 for (int ks = 0; ks < BK / 8; ++ks) {
                     const uint32_t acc = (it > 0 || ks > 0) ? 1u : 0u;
                     int tile = 0;
                     for (int mt = 0; mt < prm.mtiles; ++mt) {
-                        const uint64_t da = make_desc(Aa + (uint32_t)mt * TILE_BYTES + ks * 32);
+                        const uint32_t ta = Ta + (uint32_t)mt * 32 + ks * 8;
                         for (int nt = 0; nt <= mt; ++nt, ++tile) {
-                            const uint64_t db = make_desc(Ba + (uint32_t)nt * TILE_BYTES + ks * 32);
-                            tcgen05_mma_tf32(tmem_base + (uint32_t)tile * 128, da, db, idesc, acc);
+                            const uint64_t db = make_desc(Sa + (uint32_t)nt * TILE_BYTES + ks * 32);
+                            tcgen05_mma_tf32_ts(tmem_base + (uint32_t)tile * 128, ta, db, idesc, acc);
                         }
                     }
                     // one-hot blocks: D'[dense col, slot] += (d*X)[:, col]^T * OneHot[:, slot]
                     if (prm.oh_groups) {
-                        const uint64_t da = make_desc(Ba + ks * 32);
+                        const uint32_t ta = Ta + ks * 8;
                         for (int g0 = 0; g0 < prm.oh_groups; g0 += 8) {
                             const int ng = prm.oh_groups - g0 < 8 ? prm.oh_groups - g0 : 8;
                             const uint64_t db = make_desc(Oa + (uint32_t)g0 * GROUP_BYTES + ks * 32);
-                            tcgen05_mma_tf32(tmem_base + oh_col0 + (uint32_t)g0 * 32, da, db,
-                                             make_idesc(128, ng * 32), acc);
+                            tcgen05_mma_tf32_ts(tmem_base + oh_col0 + (uint32_t)g0 * 32, ta, db,
+                                                make_idesc(128, ng * 32), acc);
                         }
                     }
                 }
@@ -399,9 +420,12 @@ k_dense_syrk_tc(const __grid_constant__ CUtensorMap tmap, const Params prm) {
         const int my_off = oh_thread ? prm.oh_off[oh_c] : 0;
         const int my_K = oh_thread ? prm.oh_K[oh_c] : 0;
         uint32_t prev0 = 0xffffffffu, prev1 = 0xffffffffu;  // one set in operand slot 0 / 1
-        const int items = prm.groups * 8;     // (column group, 4-row k chunk) pairs per stage
-        const int g_start = w % prm.groups, k4_start = w / prm.groups;
-        const int g_inc = NUM_SCALE_WARPS % prm.groups, k4_inc = NUM_SCALE_WARPS / prm.groups;
+        // X column of this thread: TMEM lane quarter q = warp & 3 (a warp can only touch its own
+        // quarter); the two warps of a quarter split the 8 row chunks (P <= 128) or the two
+        // 128-column tiles (P > 128)
+        const int q = warp & 3;
+        const int h = w >> 2;
+        const int my_col = (prm.mtiles == 2 ? h * 128 : 0) + q * 32 + lane;
         int s = 0;
         uint32_t ph = 0;
         for (int it = 0; it < my_count; ++it, ++s) {
@@ -415,15 +439,14 @@ k_dense_syrk_tc(const __grid_constant__ CUtensorMap tmap, const Params prm) {
             if (lane == 0) mbar_wait(&emptyB[b], phb ^ 1);  // MMAs of iteration it-SB left slot b
             __syncwarp();
             if (t == 0) tl_stamp(prm, it, 1);
-            uint8_t* Ap = Oper + (size_t)b * slot_bytes;
-            uint8_t* Bp = Ap + half_bytes;
+            uint8_t* Sp = Oper + (size_t)b * slot_bytes;
             if (lane == 0) mbar_wait(&full[s], ph);
             __syncwarp();
             if (t == 0) tl_stamp(prm, it, 2);
             const uint8_t* stage = Rring + (size_t)s * prm.r_bytes;
             const float* dsm = reinterpret_cast<const float*>(stage + prm.aux_off);
             if (prm.oh_groups) {
-                uint8_t* O = Bp + half_bytes;
+                uint8_t* O = Sp + half_bytes;
                 const uint32_t pa = b ? prev1 : prev0;
                 if (pa != 0xffffffffu) *reinterpret_cast<float*>(O + pa) = 0.f;
                 uint32_t na = 0xffffffffu;
@@ -440,61 +463,18 @@ k_dense_syrk_tc(const __grid_constant__ CUtensorMap tmap, const Params prm) {
                 if (b) prev1 = na; else prev0 = na;
             }
             const float* R = reinterpret_cast<const float*>(Rring + (size_t)s * prm.r_bytes);
-            if (P == 128) {
-                // 4 column groups: warp w owns column group w & 3, row chunks (w >> 2) + {0,2,4,6}
-                scale_col4(R, 128, dsm, Ap, Bp, (w & 3) * 32 + lane, w >> 2, 2);
-            } else if (P == 256) {
-                // 8 column groups: warp w owns column group w, all 8 row chunks
-                scale_col4(R, 256, dsm, Ap, Bp, w * 32 + lane, 0, 1);
-                scale_col4(R, 256, dsm, Ap, Bp, w * 32 + lane, 4, 1);
-            } else {
-            // items (column group g, 4-row chunk k4): this warp takes item w, w+8, ... in batches
-            // of 4 with all 16 shared-memory loads of a batch in flight before the math
-            int g = g_start, k4 = k4_start;
-            for (int base_item = w; base_item < items; base_item += 4 * NUM_SCALE_WARPS) {
-                float x[4][4];
-                int gg[4], kk[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    gg[u] = g;
-                    kk[u] = k4;
-                    const int c = g * 32 + lane;
-                    const bool ok = (base_item + u * NUM_SCALE_WARPS < items) && c < P;
-                    const float* r0 = R + (size_t)(4 * k4) * P + c;
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) x[u][i] = ok ? r0[(size_t)i * P] : 0.f;
-                    g += g_inc;
-                    k4 += k4_inc;
-                    if (g >= prm.groups) {
-                        g -= prm.groups;
-                        k4 += 1;
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int c = gg[u] * 32 + lane;
-                    const bool ok = (base_item + u * NUM_SCALE_WARPS < items) && c < P;
-                    const int kq = ok ? kk[u] : 0;
-                    if (ok) {
-                        const float4 dv = *reinterpret_cast<const float4*>(dsm + 4 * kq);
-                        const float d0 = dv.x, d1 = dv.y, d2 = dv.z, d3 = dv.w;
-                        uint4 a, bb;
-                        a.x = to_tf32(x[u][0]);
-                        a.y = to_tf32(x[u][1]);
-                        a.z = to_tf32(x[u][2]);
-                        a.w = to_tf32(x[u][3]);
-                        bb.x = to_tf32(d0 * x[u][0]);
-                        bb.y = to_tf32(d1 * x[u][1]);
-                        bb.z = to_tf32(d2 * x[u][2]);
-                        bb.w = to_tf32(d3 * x[u][3]);
-                        const uint32_t off = (uint32_t)(c >> 7) * TILE_BYTES +
-                                             kmajor_chunk_off((uint32_t)c & 127u, (uint32_t)kq);
-                        *reinterpret_cast<uint4*>(Ap + off) = a;
-                        *reinterpret_cast<uint4*>(Bp + off) = bb;
-                    }
+            {
+                const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + t_col0 +
+                                        (uint32_t)(b * prm.mtiles + (my_col >> 7)) * 32;
+                if (prm.mtiles == 1) {
+                    scale_col4(R, P, dsm, Sp, t_addr, my_col, h, 2);
+                } else {
+                    scale_col4(R, P, dsm, Sp, t_addr, my_col, 0, 1);
+                    scale_col4(R, P, dsm, Sp, t_addr, my_col, 4, 1);
                 }
             }
-            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tcgen05_fence_before();
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) {
@@ -507,7 +487,6 @@ k_dense_syrk_tc(const __grid_constant__ CUtensorMap tmap, const Params prm) {
         // epilogue: TMEM -> registers -> RED into `out` (transposed: lanes = output columns)
         mbar_wait(done, 0);
         tcgen05_fence_after();
-        const int q = warp & 3;               // TMEM lane quarter this warp may access
         const int chalf = (warp - 2) >> 2;    // which half of the column chunks this warp drains
         if (my_count > 0) {
             int tile = 0;
@@ -660,12 +639,12 @@ int dense_sandwich_tc_f32(const float* X, int64_t n, int64_t p, int c_order, con
         prm.oh_out = oh->out;
         TM_CUDA(cudaMemsetAsync(oh->out, 0, sizeof(float) * (size_t)slots * (size_t)p, st));
     }
-    int cols_needed = ntiles * 128 + prm.oh_groups * 32;
+    int cols_needed = ntiles * 128 + prm.oh_groups * 32 + SB * prm.mtiles * 32;
     prm.tmem_cols = cols_needed <= 128 ? 128 : (cols_needed <= 256 ? 256 : 512);
     const int half = prm.mtiles * TILE_BYTES;
     prm.aux_off = (int)((BK * p * 4 + 127) / 128 * 128);
     prm.r_bytes = prm.aux_off + 128 + 8 * 128;
-    const int fixed = SB * (2 * half + prm.oh_groups * GROUP_BYTES) + 1024 /*align*/ + 512 /*barriers*/;
+    const int fixed = SB * (half + prm.oh_groups * GROUP_BYTES) + 1024 /*align*/ + 512 /*barriers*/;
     int stagesR = (SMEM_BUDGET - fixed) / prm.r_bytes;
     if (stagesR > MAX_STAGES) stagesR = MAX_STAGES;
     if (stagesR < 2) return fail("dense_tc: not enough shared memory for 2 stages");
@@ -710,7 +689,7 @@ int tm_dense_onehot_sandwich_f32(const float* X, int64_t n, int64_t p, const flo
         slots += K[c];
     }
     if (slots > TC_ONEHOT_MAX_SLOTS)
-        return fail("tm_dense_onehot_sandwich_f32: more than 384 category columns in total");
+        return fail("tm_dense_onehot_sandwich_f32: more than 320 category columns in total");
     if (rows) {
         Scratch dm(sizeof(float) * (size_t)n, st);
         if (dm.err != cudaSuccess) return fail_cuda(dm.err, "scratch");

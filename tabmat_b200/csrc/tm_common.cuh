@@ -115,7 +115,7 @@ int symmetrize_from_upper(F* out, int64_t m, cudaStream_t st);
 // ---- tcgen05 dense kernel (dense_tc.cu) -----------------------------------------------
 // Categorical blocks with few levels that ride along the fp32 weighted SYRK as one-hot MMAs:
 // out[(off_c + codes_c[k] - drop_first_c) * p + b] += d[k] * X[k, b]   (off_c = sum of K before c)
-constexpr int TC_ONEHOT_MAX_SLOTS = 384;
+constexpr int TC_ONEHOT_MAX_SLOTS = 320;  // TMEM: 128 (SYRK) + 320 + 64 (operand ring) = 512
 struct TcOneHot {
     int ncat;
     const int32_t* codes[8];
