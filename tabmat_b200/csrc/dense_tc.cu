@@ -256,7 +256,10 @@ __device__ __forceinline__ void tl_stamp(const Params& prm, int it, int e) {
 }
 
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+// min-blocks 2 only caps the registers (<= 102/thread) so that the L2-atomic-bound scatter
+// kernels of a SplitMatrix sandwich can share the SM with this kernel's one resident CTA
+template <int MIN_BLOCKS>
+__global__ void __launch_bounds__(NUM_THREADS, MIN_BLOCKS)
 k_dense_syrk_tc(const __grid_constant__ CUtensorMap tmap, const Params prm) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* base = reinterpret_cast<uint8_t*>(
@@ -592,7 +595,7 @@ float* g_tc_dbg = nullptr;
 int g_tc_variant = 0;
 
 int dense_sandwich_tc_f32(const float* X, int64_t n, int64_t p, int c_order, const float* d,
-                          float* out, cudaStream_t st, const TcOneHot* oh) {
+                          float* out, cudaStream_t st, const TcOneHot* oh, bool share_sm) {
     using namespace tc;
     (void)c_order;
     PFN_encodeTiled enc = get_encode();
@@ -653,13 +656,18 @@ int dense_sandwich_tc_f32(const float* X, int64_t n, int64_t p, int c_order, con
 
     static bool attr_set = false;
     if (!attr_set) {
-        TM_CUDA(cudaFuncSetAttribute(k_dense_syrk_tc, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     227 * 1024));
+        TM_CUDA(cudaFuncSetAttribute(k_dense_syrk_tc<1>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        TM_CUDA(cudaFuncSetAttribute(k_dense_syrk_tc<2>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
     TM_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)(p * p), st));
     long long grid = prm.num_row_tiles < sm_count() ? prm.num_row_tiles : sm_count();
-    k_dense_syrk_tc<<<(unsigned)grid, NUM_THREADS, smem, st>>>(tmap, prm);
+    if (share_sm)
+        k_dense_syrk_tc<2><<<(unsigned)grid, NUM_THREADS, smem, st>>>(tmap, prm);
+    else
+        k_dense_syrk_tc<1><<<(unsigned)grid, NUM_THREADS, smem, st>>>(tmap, prm);
     TM_LAUNCHED();
     return symmetrize_from_upper<float>(out, p, st);
 }

@@ -162,7 +162,7 @@ int split_blocks(const tm_block_desc* blk, int nb, int64_t n, const F* d, const 
             oh.out = tmp.as<float>();
             int rc = dense_sandwich_tc_f32(static_cast<const float*>(D.data), n, D.ncols, 1, dd,
                                            reinterpret_cast<float*>(ws + self_off[dense_idx]), st,
-                                           oh.ncat ? &oh : nullptr);
+                                           oh.ncat ? &oh : nullptr, /*share_sm=*/side_used);
             if (rc) return rc;
             dense_self_done = true;
             int64_t o = 0;

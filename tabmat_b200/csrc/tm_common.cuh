@@ -124,7 +124,8 @@ struct TcOneHot {
     float* out;  // [sum K][p], overwritten
 };
 int dense_sandwich_tc_f32(const float* X, int64_t n, int64_t p, int c_order, const float* d,
-                          float* out, cudaStream_t st, const TcOneHot* oh = nullptr);
+                          float* out, cudaStream_t st, const TcOneHot* oh = nullptr,
+                          bool share_sm = false);
 bool dense_tc_eligible(int64_t n, int64_t p, int c_order, const void* X);
 extern int g_dense_f32_mode;
 
