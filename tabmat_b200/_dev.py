@@ -91,9 +91,20 @@ def idx32(x: Any) -> Optional[torch.Tensor]:
     return to_dev(a.astype(np.int32, copy=False).reshape(-1))
 
 
+_EMPTY_ANCHOR: dict = {}
+
+
 def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    """Device address for the C-ABI.  ``None`` -> NULL, which the entry points read as "all
+    rows / cols"; an EMPTY tensor (whose data_ptr is 0 too) gets the address of a one-element
+    anchor instead, so that an empty restriction stays an empty restriction."""
     if t is None:
         return None
+    if t.numel() == 0:
+        key = (t.device.index, t.dtype)
+        if key not in _EMPTY_ANCHOR:
+            _EMPTY_ANCHOR[key] = torch.zeros(4, dtype=t.dtype, device=t.device)
+        return _EMPTY_ANCHOR[key].data_ptr()
     return t.data_ptr()
 
 

@@ -417,6 +417,12 @@ class SplitMatrix(MatrixBase):
         check_matvec_dimensions(self, v, transpose=False)
         check_matvec_out_shape(self, out)
         v_t, host = _vec_in(v)
+        if v_t.dim() > 1 and any(isinstance(m, CategoricalMatrix) for m in self.matrices):
+            # the reference calls every block's matvec, and the categorical one is 1-d only
+            # (categorical_matrix.py:478-481)
+            raise NotImplementedError(
+                """CategoricalMatrix.matvec is only implemented for 1d arrays."""
+            )
         _, subset_cols, n_cols = self._split_col_subsets(cols)
         out_dtype = np.result_type(self.dtype, _dev.np_dtype(v_t.dtype)
                                    if v_t.dtype in (torch.float32, torch.float64) else np.float64)

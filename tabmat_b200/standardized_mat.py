@@ -19,6 +19,7 @@ from .matrix_base import MatrixBase, _vec_in
 from .sparse_matrix import SparseMatrix
 from .util import (
     check_matvec_dimensions,
+    check_matvec_out_shape,
     check_sandwich_compatible,
     check_transpose_matvec_out_shape,
 )
@@ -78,6 +79,7 @@ class StandardizedMatrix:
         if not _dev.is_dev(other_mat):
             other_mat = np.asarray(other_mat)
         check_matvec_dimensions(self, other_mat, transpose=False)
+        check_matvec_out_shape(self, out)
         v_t, host = _vec_in(other_mat)
         if v_t.dtype not in (torch.float32, torch.float64):
             v_t = v_t.to(torch.float64)
