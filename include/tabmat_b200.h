@@ -289,6 +289,12 @@ typedef struct tm_block_desc {
     const int32_t* csr_row;
     int64_t nnz;
     const int64_t* col_index;
+    /* categorical, optional (NULL = absent): rows with a valid category ordered by category
+     * (stable) and the K+1 segment offsets into that list; enables the sorted-gather kernel
+     * for the categorical x dense block */
+    const int32_t* cat_perm;
+    const int32_t* cat_segptr;
+    int64_t cat_nvalid;
 } tm_block_desc;
 
 /* Elements (of the block dtype) of the flat workspace that holds every self block and every

@@ -214,6 +214,24 @@ class CategoricalMatrix(MatrixBase):
             orig.mask = idx == len(self.categories) - 1
         return orig
 
+    def _sorted_perm(self):
+        """(perm, segptr, n_valid): the rows with a valid column ordered by column (stable) and
+        the shape[1]+1 segment offsets — built once and cached, the analogue of the reference's
+        cached CSR (sparse_matrix.py:133-143); feeds the sorted-gather categorical x dense
+        kernel."""
+        cached = self.__dict__.get("_perm_cache")
+        if cached is None:
+            col = self._codes.to(torch.int64) - int(self.drop_first)
+            order = torch.argsort(col, stable=True)
+            n_neg = int((col < 0).sum().item())
+            perm = order[n_neg:].to(torch.int32).contiguous()
+            counts = torch.bincount(col[col >= 0], minlength=self.shape[1])
+            segptr = torch.zeros(self.shape[1] + 1, dtype=torch.int64, device=col.device)
+            segptr[1:] = torch.cumsum(counts, 0)
+            cached = (perm, segptr.to(torch.int32).contiguous(), int(perm.numel()))
+            self.__dict__["_perm_cache"] = cached
+        return cached
+
     @property
     def _tdtype(self) -> torch.dtype:
         return _dev.torch_dtype(self.dtype)
@@ -393,6 +411,7 @@ class CategoricalMatrix(MatrixBase):
             sub = self._codes[_torch_index(row, self._codes.device)]
             new = CategoricalMatrix.__new__(CategoricalMatrix)
             new.__dict__.update(self.__dict__)
+            new.__dict__.pop("_perm_cache", None)
             new._codes = sub.contiguous()
             new.shape = (int(sub.numel()), self.shape[1])
             return new

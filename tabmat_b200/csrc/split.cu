@@ -118,40 +118,30 @@ int split_blocks(const tm_block_desc* blk, int nb, int64_t n, const F* d, const 
         fuse = D.c_order && D.ncols % W == 0 && D.ncols <= 64 * W &&
                (reinterpret_cast<uintptr_t>(D.data) & 15) == 0;
     }
-    // categorical blocks with few levels ride along the fp32 tensor-core SYRK as one-hot MMAs
+    // HBM / tensor bound work (the tcgen05 pass and the sorted-gather passes) goes to a side
+    // stream so that it overlaps with the L2-atomic-bound scatter passes on the caller's stream
     std::vector<char> on_tensor(nb, 0);
     bool dense_self_done = false;
     bool side_used = false;
     if (fuse && sizeof(F) == 4) {
         const tm_block_desc& D = blk[dense_idx];
-        static const bool onehot_off = getenv("TABMAT_B200_ONEHOT") && atoi(getenv("TABMAT_B200_ONEHOT")) == 0;
-        if (!onehot_off && g_dense_f32_mode != 1 && D.ncols <= 128 && n_rows_or_all(rows, n_rows, n) > 0 &&
-            dense_tc_eligible(n, D.ncols, 1, D.data)) {
-            TcOneHot oh;
-            oh.ncat = 0;
-            int64_t slots = 0;
-            int which[8];
-            for (int i = 0; i < nb && oh.ncat < 8; ++i) {
-                if (blk[i].kind != KIND_CAT || blk[i].ncols <= 0 || blk[i].ncols > 256) continue;
-                if (slots + blk[i].ncols > TC_ONEHOT_MAX_SLOTS) continue;
-                which[oh.ncat] = i;
-                oh.codes[oh.ncat] = static_cast<const int32_t*>(blk[i].data);
-                oh.K[oh.ncat] = (int)blk[i].ncols;
-                oh.drop_first[oh.ncat] = blk[i].drop_first;
-                slots += blk[i].ncols;
-                ++oh.ncat;
-            }
-            // The tensor-core pass is HBM / tensor bound while the scatter passes below are bound
-            // by the L2 atomic units: run it on a side stream so that the two overlap.
+        static const bool onehot_off =
+            getenv("TABMAT_B200_ONEHOT") && atoi(getenv("TABMAT_B200_ONEHOT")) == 0;
+        static const bool gather_off =
+            getenv("TABMAT_B200_GATHER") && atoi(getenv("TABMAT_B200_GATHER")) == 0;
+        const bool tc_ok = g_dense_f32_mode != 1 && n_rows_or_all(rows, n_rows, n) > 0 &&
+                           dense_tc_eligible(n, D.ncols, 1, D.data);
+        bool any_gather = false;
+        for (int i = 0; i < nb; ++i)
+            any_gather |= !gather_off && blk[i].kind == KIND_CAT && blk[i].cat_perm != nullptr;
+        if (tc_ok || any_gather) {
             cudaStream_t st = side_stream() ? side_stream() : as_stream(stream);
             side_used = st != as_stream(stream);
             if (side_used) {
                 TM_CUDA(cudaEventRecord(side_event(0), as_stream(stream)));
                 TM_CUDA(cudaStreamWaitEvent(st, side_event(0), 0));
             }
-            Scratch tmp(sizeof(float) * (size_t)(slots > 0 ? slots : 1) * (size_t)D.ncols, st);
             Scratch dm(rows ? sizeof(float) * (size_t)n : 0, st);
-            if (tmp.err != cudaSuccess) return fail_cuda(tmp.err, "scratch");
             if (dm.err != cudaSuccess) return fail_cuda(dm.err, "scratch");
             const float* dd = reinterpret_cast<const float*>(d);
             if (rows) {
@@ -159,20 +149,49 @@ int split_blocks(const tm_block_desc* blk, int nb, int64_t n, const F* d, const 
                 if (rc) return rc;
                 dd = dm.as<float>();
             }
-            oh.out = tmp.as<float>();
-            int rc = dense_sandwich_tc_f32(static_cast<const float*>(D.data), n, D.ncols, 1, dd,
-                                           reinterpret_cast<float*>(ws + self_off[dense_idx]), st,
-                                           oh.ncat ? &oh : nullptr, /*share_sm=*/side_used);
-            if (rc) return rc;
-            dense_self_done = true;
-            int64_t o = 0;
-            for (int c = 0; c < oh.ncat; ++c) {
-                int i = which[c];
+            if (tc_ok) {
+                TcOneHot oh;
+                oh.ncat = 0;
+                int64_t slots = 0;
+                int which[8];
+                for (int i = 0; i < nb && oh.ncat < 8 && D.ncols <= 128 && !onehot_off; ++i) {
+                    if (blk[i].kind != KIND_CAT || blk[i].ncols <= 0 || blk[i].ncols > 256) continue;
+                    if (slots + blk[i].ncols > TC_ONEHOT_MAX_SLOTS) continue;
+                    which[oh.ncat] = i;
+                    oh.codes[oh.ncat] = static_cast<const int32_t*>(blk[i].data);
+                    oh.K[oh.ncat] = (int)blk[i].ncols;
+                    oh.drop_first[oh.ncat] = blk[i].drop_first;
+                    slots += blk[i].ncols;
+                    ++oh.ncat;
+                }
+                Scratch tmp(sizeof(float) * (size_t)(slots > 0 ? slots : 1) * (size_t)D.ncols, st);
+                if (tmp.err != cudaSuccess) return fail_cuda(tmp.err, "scratch");
+                oh.out = tmp.as<float>();
+                int rc = dense_sandwich_tc_f32(static_cast<const float*>(D.data), n, D.ncols, 1, dd,
+                                               reinterpret_cast<float*>(ws + self_off[dense_idx]),
+                                               st, oh.ncat ? &oh : nullptr, /*share_sm=*/side_used);
+                if (rc) return rc;
+                dense_self_done = true;
+                int64_t o = 0;
+                for (int c = 0; c < oh.ncat; ++c) {
+                    int i = which[c];
+                    int a = i < dense_idx ? i : dense_idx, b = i < dense_idx ? dense_idx : i;
+                    TM_CUDA(cudaMemcpyAsync(ws + cross_off[a][b], tmp.as<float>() + o * D.ncols,
+                                            sizeof(float) * (size_t)(blk[i].ncols * D.ncols),
+                                            cudaMemcpyDeviceToDevice, st));
+                    o += blk[i].ncols;
+                    on_tensor[i] = 1;
+                }
+            }
+            // categorical blocks with a sorted row permutation: HBM-bound gather
+            for (int i = 0; i < nb && !gather_off; ++i) {
+                if (blk[i].kind != KIND_CAT || on_tensor[i] || !blk[i].cat_perm) continue;
                 int a = i < dense_idx ? i : dense_idx, b = i < dense_idx ? dense_idx : i;
-                TM_CUDA(cudaMemcpyAsync(ws + cross_off[a][b], tmp.as<float>() + o * D.ncols,
-                                        sizeof(float) * (size_t)(blk[i].ncols * D.ncols),
-                                        cudaMemcpyDeviceToDevice, st));
-                o += blk[i].ncols;
+                int rc = cat_dense_gather_f32(static_cast<const float*>(D.data), D.ncols, dd,
+                                              blk[i].cat_perm, blk[i].cat_segptr, blk[i].ncols,
+                                              blk[i].cat_nvalid,
+                                              reinterpret_cast<float*>(ws + cross_off[a][b]), st);
+                if (rc) return rc;
                 on_tensor[i] = 1;
             }
         }

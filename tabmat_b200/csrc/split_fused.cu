@@ -127,6 +127,122 @@ k_dense_cross_fused(const F* __restrict__ X, int64_t n, int P, const F* __restri
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// categorical x dense by SORTED GATHER: `perm` lists the rows with a valid category ordered by
+// category (built once per matrix, like the reference's cached CSR), `segptr[c]..segptr[c+1]`
+// is category c's slice of it.  A warp walks a chunk of consecutive perm entries, gathers the
+// 512-byte dense rows, accumulates d[k] * X[k, :] in registers and flushes once per category
+// run - HBM-bound gather traffic instead of one L2 RED per row, so it can overlap with the
+// RED-bound passes on another stream.
+// ---------------------------------------------------------------------------------------
+template <int NV>
+__global__ void __launch_bounds__(256)
+k_cat_dense_gather(const float* __restrict__ X, int P, const float* __restrict__ d,
+                   const int32_t* __restrict__ perm, const int32_t* __restrict__ segptr, int K,
+                   int64_t n_valid, int chunk, float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int chunks4 = P / 4;
+    const int64_t n_chunks = (n_valid + chunk - 1) / chunk;
+    for (int64_t ci = warp; ci < n_chunks; ci += nwarps) {
+        const int64_t t0 = ci * chunk;
+        const int64_t t1 = t0 + chunk < n_valid ? t0 + chunk : n_valid;
+        // category of entry t0: largest c with segptr[c] <= t0
+        int lo = 0, hi = K;
+        while (hi - lo > 1) {
+            int mid = (lo + hi) >> 1;
+            if ((int64_t)segptr[mid] <= t0) lo = mid; else hi = mid;
+        }
+        int c = lo;
+        int64_t bound = segptr[c + 1];
+        float4 acc[NV];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+        bool dirty = false;
+        for (int64_t tb = t0; tb < t1; tb += 32) {
+            const int cnt = (int)(t1 - tb < 32 ? t1 - tb : 32);
+            int k_l = 0;
+            float d_l = 0.f;
+            if (lane < cnt) {
+                k_l = perm[tb + lane];
+                d_l = d[k_l];
+            }
+            for (int q0 = 0; q0 < cnt; q0 += 4) {
+                float4 x[4][NV];
+                float dk[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int qq = q0 + u < cnt ? q0 + u : cnt - 1;
+                    const int k = __shfl_sync(0xffffffffu, k_l, qq);
+                    dk[u] = q0 + u < cnt ? __shfl_sync(0xffffffffu, d_l, qq) : 0.f;
+                    const float4* xr = reinterpret_cast<const float4*>(X + (int64_t)k * P);
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) {
+                        const int ch = lane + 32 * v;
+                        x[u][v] = ch < chunks4 ? __ldg(xr + ch) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int64_t t = tb + q0 + u;
+                    if (t >= t1) break;
+                    if (t >= bound) {  // category run ended: flush and advance (warp-uniform)
+                        if (dirty) {
+#pragma unroll
+                            for (int v = 0; v < NV; ++v) {
+                                const int ch = lane + 32 * v;
+                                if (ch < chunks4) red_add_vec(out + (int64_t)c * P + ch * 4, acc[v]);
+                                acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            }
+                            dirty = false;
+                        }
+                        while (t >= bound) {
+                            ++c;
+                            bound = segptr[c + 1];
+                        }
+                    }
+                    if (dk[u] != 0.f) {
+#pragma unroll
+                        for (int v = 0; v < NV; ++v) {
+                            acc[v].x = fmaf(dk[u], x[u][v].x, acc[v].x);
+                            acc[v].y = fmaf(dk[u], x[u][v].y, acc[v].y);
+                            acc[v].z = fmaf(dk[u], x[u][v].z, acc[v].z);
+                            acc[v].w = fmaf(dk[u], x[u][v].w, acc[v].w);
+                        }
+                        dirty = true;
+                    }
+                }
+            }
+        }
+        if (dirty) {
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                const int ch = lane + 32 * v;
+                if (ch < chunks4) red_add_vec(out + (int64_t)c * P + ch * 4, acc[v]);
+            }
+        }
+    }
+}
+
+// out (K x p) = sum over the sorted rows; overwrites out.  f32, row-major X, p % 4 == 0, p <= 256.
+int cat_dense_gather_f32(const float* X, int64_t p, const float* d, const int32_t* perm,
+                         const int32_t* segptr, int64_t K, int64_t n_valid, float* out,
+                         cudaStream_t st) {
+    if (K <= 0 || p <= 0) return 0;
+    TM_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)(K * p), st));
+    if (n_valid <= 0) return 0;
+    const int chunk = 256;
+    int64_t n_chunks = (n_valid + chunk - 1) / chunk;
+    int g = grid_for(n_chunks * 32, 256, sm_count() * 6);
+    if (p <= 128)
+        k_cat_dense_gather<1><<<g, 256, 0, st>>>(X, (int)p, d, perm, segptr, (int)K, n_valid, chunk, out);
+    else
+        k_cat_dense_gather<2><<<g, 256, 0, st>>>(X, (int)p, d, perm, segptr, (int)K, n_valid, chunk, out);
+    TM_LAUNCHED();
+    return 0;
+}
+
 // out[r, :] = sum over replicas of tab[(rep*K + r), :]
 template <typename F>
 __global__ void k_sum_replicas(const F* __restrict__ tab, int K, int copies, int64_t P,

@@ -123,6 +123,9 @@ struct TcOneHot {
     int drop_first[8];
     float* out;  // [sum K][p], overwritten
 };
+int cat_dense_gather_f32(const float* X, int64_t p, const float* d, const int32_t* perm,
+                         const int32_t* segptr, int64_t K, int64_t n_valid, float* out,
+                         cudaStream_t st);
 int dense_sandwich_tc_f32(const float* X, int64_t n, int64_t p, int c_order, const float* d,
                           float* out, cudaStream_t st, const TcOneHot* oh = nullptr,
                           bool share_sm = false);

@@ -94,15 +94,21 @@ class RowShardedMatrix:
         self.reduce_dtype = reduce_dtype
 
     # -- collectives ---------------------------------------------------------------------
-    def _allreduce(self, t: torch.Tensor) -> torch.Tensor:
+    def _allreduce(self, t: torch.Tensor, dst: Optional[int] = None) -> torch.Tensor:
+        """Sum over ranks, in place: replicated (allreduce) or only on rank ``dst`` (reduce)."""
         if self.world_size > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+            if dst is None:
+                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+            else:
+                dist.reduce(t, dst=dst, op=dist.ReduceOp.SUM, group=self.group)
         return t
 
     # -- hot path ------------------------------------------------------------------------
-    def sandwich(self, d_local, rows=None, cols=None) -> torch.Tensor:
-        """Replicated (X[rows, cols].T * d[rows]) @ X[rows, cols]; ``d_local`` is this rank's
-        slice of d, ``rows`` a sorted GLOBAL restriction (or None)."""
+    def sandwich(self, d_local, rows=None, cols=None, dst: Optional[int] = None):
+        """(X[rows, cols].T * d[rows]) @ X[rows, cols]; ``d_local`` is this rank's slice of d,
+        ``rows`` a sorted GLOBAL restriction (or None).  ``dst=None``: the result is replicated
+        on every rank (allreduce); ``dst=r``: it is reduced to rank ``r`` only, the other ranks
+        get ``None`` (MPI-style; saves the redundant copies when one process consumes it)."""
         local_rows = shard_rows(rows, self.lo, self.hi)
         if cols is None and hasattr(self.local, "_sandwich_blocks_dev"):
             # SplitMatrix: allreduce the flat block workspace (every structurally distinct
@@ -111,11 +117,16 @@ class RowShardedMatrix:
 
             ws = self.local._sandwich_blocks_dev(d_local, _dev.idx32(local_rows))
             if ws is not None:
-                self._allreduce(ws)
+                self._allreduce(ws, dst)
+                if dst is not None and self.rank != dst:
+                    return None
                 return self.local._assemble_dev(ws)
         part = self.local.sandwich(d_local, local_rows, cols)
         if self.world_size == 1:
             return part
+        if dst is not None:
+            self._allreduce(part, dst)
+            return part if self.rank == dst else None
         p = part.shape[0]
         if self.pack:
             v = pack_lower(part, self.reduce_dtype)

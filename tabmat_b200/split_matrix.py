@@ -9,6 +9,7 @@ at construction (split_matrix.py:85-141)."""
 
 from __future__ import annotations
 
+import os
 import warnings
 from collections.abc import Sequence
 from typing import Optional, Union
@@ -277,6 +278,15 @@ class SplitMatrix(MatrixBase):
             elif isinstance(mat, CategoricalMatrix):
                 ok = _dev.torch_dtype(mat.dtype) == tdtype
                 dsc.kind, dsc.data, dsc.drop_first = 2, mat._codes.data_ptr(), int(mat.drop_first)
+                # many levels: too wide for the one-hot tensor path.  Opt-in sorted-gather kernel
+                # (TABMAT_B200_GATHER=1): measured slower than the RED scatter pass on B200
+                # (5.5 ms vs 3.4 ms per block at n = 4e7), kept for machines / shapes where the
+                # L2 atomic units are the scarcer resource.
+                if (os.environ.get("TABMAT_B200_GATHER") == "1" and mat.shape[1] > 256
+                        and tdtype == torch.float32 and mat.shape[0] < 2**31):
+                    perm, segptr, n_valid = mat._sorted_perm()
+                    dsc.cat_perm, dsc.cat_segptr = perm.data_ptr(), segptr.data_ptr()
+                    dsc.cat_nvalid = n_valid
             else:
                 ok = False
         if ok:

@@ -66,6 +66,10 @@ def _worker(rank, world, port, n, p, q):
             res[f"sand_rc{pack}"] = S.sandwich(dl, rows, cols).numpy()
             res[f"tmv{pack}"] = S.transpose_matvec(vl, rows, cols).numpy()
             res[f"mv{pack}"] = S.matvec(torch.from_numpy(np.arange(p, dtype=np.float64))).numpy()
+            only0 = S.sandwich(dl, dst=0)
+            assert (only0 is None) == (rank != 0)
+            if rank == 0:
+                np.testing.assert_allclose(only0.numpy(), res[f"sand{pack}"], rtol=1e-10, atol=1e-10)
         full = _HostShard(X)
         dt, vt = torch.from_numpy(d), torch.from_numpy(v)
         for pack in (True, False):

@@ -112,3 +112,48 @@ def test_fused_dense_cross(dt, p, with_rows):
         ref = orc.cat_dense_sandwich(c, K, d, X, rows, None, df)
         cases.assert_close(o.cpu().numpy(), ref, dt, f"fused cat K={K}")
     cases.assert_close(out_s.cpu().numpy(), orc.csr_dense_sandwich(A, X, d, rows), dt, "fused sparse")
+
+
+@pytest.mark.parametrize("with_rows", [False, True])
+@pytest.mark.parametrize("p_dense", [128, 64, 200])
+@pytest.mark.parametrize("gather", ["0", "1"])
+def test_split_native_path_all_kernel_families(with_rows, p_dense, gather, monkeypatch):
+    """SplitMatrix.sandwich through tm_split_sandwich_* with every kernel family engaged: the
+    tcgen05 SYRK + one-hot MMAs (few levels), the sorted-gather kernel (many levels), the RED
+    scatter pass (sparse x dense), and the index-only blocks — against the oracle, block by
+    block, on a matrix with missing codes and drop_first."""
+    import scipy.sparse as sps
+
+    import tabmat_b200 as tm
+    from oracle import c_oracle as orc
+
+    monkeypatch.setenv("TABMAT_B200_GATHER", gather)  # read when the native plan is built
+    rng = np.random.default_rng(11 + p_dense)
+    n = 30_011
+    X = rng.standard_normal((n, p_dense)).astype(np.float32)
+    A = sps.random(n, 70, density=0.03, random_state=rng, format="csc").astype(np.float32)
+    specs = [(7, False, False), (300, True, True), (40, False, True), (1200, False, False)]
+    cats, codes = [], []
+    for K, df, missing in specs:
+        c = rng.integers(0, K, size=n).astype(np.int32)
+        if missing:
+            c[rng.random(n) < 0.1] = -1
+        codes.append(c)
+        cats.append(tm.CategoricalMatrix(c, categories=np.arange(K), drop_first=df,
+                                         dtype=np.float32, cat_missing_method="zero"))
+    S = tm.SplitMatrix([tm.DenseMatrix(X), tm.SparseMatrix(A)] + cats)
+    d = rng.standard_normal(n).astype(np.float32)
+    rows = np.sort(rng.choice(n, size=n // 3, replace=False)).astype(np.int32) if with_rows else None
+    got = S.sandwich(d, rows)
+    full = np.hstack([X.astype(np.float64), A.toarray().astype(np.float64)] + [
+        np.eye(K + 1)[c + 1][:, 1 + int(df):] for (K, df, _), c in zip(specs, codes)])
+    sel = full if rows is None else full[rows]
+    dd = d.astype(np.float64) if rows is None else d[rows].astype(np.float64)
+    ref = sel.T @ (dd[:, None] * sel)
+    cases.assert_close(got, ref, np.float32, "split native sandwich")
+    # block-level check of the two dense cross kernels against the oracle
+    o_dense = p_dense
+    o_cat3 = p_dense + 70 + 7 + 299 + 40
+    blk = got[o_cat3:o_cat3 + 1200, :o_dense]
+    cases.assert_close(blk, orc.cat_dense_sandwich(codes[3], 1200, d, X, rows), np.float32,
+                       "gather block vs oracle")
