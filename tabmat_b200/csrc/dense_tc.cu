@@ -44,7 +44,7 @@ constexpr int NUM_SCALE_WARPS = 8;
 constexpr int NUM_SCALE_THREADS = NUM_SCALE_WARPS * 32;
 constexpr int NUM_THREADS = 64 + NUM_SCALE_THREADS;  // producer warp + mma warp + scale warps
 constexpr int MAX_STAGES = 16;
-constexpr int SB = 2;                      // depth of the operand (A'/B'/one-hot) ring
+constexpr int MAX_SB = 4;                  // max depth of the operand (S / one-hot / T) ring
 constexpr int SMEM_BUDGET = 220 * 1024;
 
 struct Params {
@@ -56,6 +56,7 @@ struct Params {
     int mtiles;       // ceil(P/128): 128-wide output tile rows (1 or 2)
     long long num_row_tiles;
     int stagesR;      // depth of the TMA ring (raw X tiles)
+    int sb;           // depth of the operand ring (2..MAX_SB): S + one-hot in smem, T in TMEM
     int r_bytes;      // bytes of one raw stage: X tile | d (128 B) | one-hot codes (8 x 128 B)
     int aux_off;      // offset of d inside a stage (BK * P * 4 rounded up to 128)
     int tmem_cols;
@@ -266,6 +267,7 @@ k_dense_syrk_tc(const __grid_constant__ CUtensorMap tmap, const Params prm) {
         (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
 
     const int SR = prm.stagesR;
+    const int SB = prm.sb;
     const int P = prm.P;
     const uint32_t half_bytes = (uint32_t)prm.mtiles * TILE_BYTES;   // S of one slot
     const uint32_t oh_bytes = (uint32_t)prm.oh_groups * GROUP_BYTES;
@@ -277,9 +279,9 @@ k_dense_syrk_tc(const __grid_constant__ CUtensorMap tmap, const Params prm) {
     uint64_t* bars = reinterpret_cast<uint64_t*>(Rring + (size_t)SR * prm.r_bytes);
     uint64_t* full = bars;                          // [MAX_STAGES] TMA -> scale warps
     uint64_t* emptyR = bars + MAX_STAGES;           // [MAX_STAGES] scale warps -> producer
-    uint64_t* scaled = bars + 2 * MAX_STAGES;       // [SB] scale warps -> MMA
-    uint64_t* emptyB = bars + 2 * MAX_STAGES + SB;  // [SB] MMA -> scale warps
-    uint64_t* done = bars + 2 * MAX_STAGES + 2 * SB;
+    uint64_t* scaled = bars + 2 * MAX_STAGES;           // [SB] scale warps -> MMA
+    uint64_t* emptyB = bars + 2 * MAX_STAGES + MAX_SB;  // [SB] MMA -> scale warps
+    uint64_t* done = bars + 2 * MAX_STAGES + 2 * MAX_SB;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
@@ -373,9 +375,13 @@ k_dense_syrk_tc(const __grid_constant__ CUtensorMap tmap, const Params prm) {
     } else if (warp == 1) {
         // ===== MMA issuer =====
         const uint32_t idesc = make_idesc(128, 128);
-        for (int it = 0; it < my_count; ++it) {
-            const int b = it & (SB - 1);
-            const uint32_t phb = (uint32_t)((it / SB) & 1);
+        int b = 0;
+        uint32_t phb = 0;
+        for (int it = 0; it < my_count; ++it, ++b) {
+            if (b == SB) {
+                b = 0;
+                phb ^= 1;
+            }
             mbar_wait(&scaled[b], phb);
             tcgen05_fence_after();
             if (elect_one()) {
@@ -422,22 +428,25 @@ k_dense_syrk_tc(const __grid_constant__ CUtensorMap tmap, const Params prm) {
         const bool oh_thread = oh_c < prm.oh_ncat;
         const int my_off = oh_thread ? prm.oh_off[oh_c] : 0;
         const int my_K = oh_thread ? prm.oh_K[oh_c] : 0;
-        uint32_t prev0 = 0xffffffffu, prev1 = 0xffffffffu;  // one set in operand slot 0 / 1
+        uint32_t prev0 = 0xffffffffu, prev1 = 0xffffffffu, prev2 = 0xffffffffu,
+                 prev3 = 0xffffffffu;  // the one this thread set in operand slot 0..3
         // X column of this thread: TMEM lane quarter q = warp & 3 (a warp can only touch its own
         // quarter); the two warps of a quarter split the 8 row chunks (P <= 128) or the two
         // 128-column tiles (P > 128)
         const int q = warp & 3;
         const int h = w >> 2;
         const int my_col = (prm.mtiles == 2 ? h * 128 : 0) + q * 32 + lane;
-        int s = 0;
-        uint32_t ph = 0;
-        for (int it = 0; it < my_count; ++it, ++s) {
+        int s = 0, b = 0;
+        uint32_t ph = 0, phb = 0;
+        for (int it = 0; it < my_count; ++it, ++s, ++b) {
             if (s == SR) {
                 s = 0;
                 ph ^= 1;
             }
-            const int b = it & (SB - 1);
-            const uint32_t phb = (uint32_t)((it / SB) & 1);
+            if (b == SB) {
+                b = 0;
+                phb ^= 1;
+            }
             // one lane polls, the warp follows through __syncwarp
             if (lane == 0) mbar_wait(&emptyB[b], phb ^ 1);  // MMAs of iteration it-SB left slot b
             __syncwarp();
@@ -450,7 +459,7 @@ k_dense_syrk_tc(const __grid_constant__ CUtensorMap tmap, const Params prm) {
             const float* dsm = reinterpret_cast<const float*>(stage + prm.aux_off);
             if (prm.oh_groups) {
                 uint8_t* O = Sp + half_bytes;
-                const uint32_t pa = b ? prev1 : prev0;
+                const uint32_t pa = b == 0 ? prev0 : (b == 1 ? prev1 : (b == 2 ? prev2 : prev3));
                 if (pa != 0xffffffffu) *reinterpret_cast<float*>(O + pa) = 0.f;
                 uint32_t na = 0xffffffffu;
                 if (oh_thread) {
@@ -463,7 +472,10 @@ k_dense_syrk_tc(const __grid_constant__ CUtensorMap tmap, const Params prm) {
                         *reinterpret_cast<float*>(O + na) = 1.0f;
                     }
                 }
-                if (b) prev1 = na; else prev0 = na;
+                if (b == 0) prev0 = na;
+                else if (b == 1) prev1 = na;
+                else if (b == 2) prev2 = na;
+                else prev3 = na;
             }
             const float* R = reinterpret_cast<const float*>(Rring + (size_t)s * prm.r_bytes);
             {
@@ -642,12 +654,18 @@ int dense_sandwich_tc_f32(const float* X, int64_t n, int64_t p, int c_order, con
         prm.oh_out = oh->out;
         TM_CUDA(cudaMemsetAsync(oh->out, 0, sizeof(float) * (size_t)slots * (size_t)p, st));
     }
-    int cols_needed = ntiles * 128 + prm.oh_groups * 32 + SB * prm.mtiles * 32;
-    prm.tmem_cols = cols_needed <= 128 ? 128 : (cols_needed <= 256 ? 256 : 512);
     const int half = prm.mtiles * TILE_BYTES;
     prm.aux_off = (int)((BK * p * 4 + 127) / 128 * 128);
     prm.r_bytes = prm.aux_off + 128 + 8 * 128;
-    const int fixed = SB * (half + prm.oh_groups * GROUP_BYTES) + 1024 /*align*/ + 512 /*barriers*/;
+    // operand-ring depth: as deep as TMEM (512 columns) and shared memory (>= 3 raw stages) allow
+    int sb = MAX_SB;
+    while (sb > 2 && (ntiles * 128 + prm.oh_groups * 32 + sb * prm.mtiles * 32 > 512 ||
+                      (SMEM_BUDGET - sb * (half + prm.oh_groups * GROUP_BYTES) - 1536) / prm.r_bytes < 3))
+        --sb;
+    prm.sb = sb;
+    int cols_needed = ntiles * 128 + prm.oh_groups * 32 + sb * prm.mtiles * 32;
+    prm.tmem_cols = cols_needed <= 128 ? 128 : (cols_needed <= 256 ? 256 : 512);
+    const int fixed = sb * (half + prm.oh_groups * GROUP_BYTES) + 1024 /*align*/ + 512 /*barriers*/;
     int stagesR = (SMEM_BUDGET - fixed) / prm.r_bytes;
     if (stagesR > MAX_STAGES) stagesR = MAX_STAGES;
     if (stagesR < 2) return fail("dense_tc: not enough shared memory for 2 stages");

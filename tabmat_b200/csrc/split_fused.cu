@@ -75,51 +75,68 @@ k_dense_cross_fused(const F* __restrict__ X, int64_t n, int P, const F* __restri
     const F* csr_data = static_cast<const F*>(prm.csr_data);
     F* out_sparse = static_cast<F*>(prm.out_sparse);
 
-    for (int64_t t = warp; t < n_rows; t += nwarps) {
-        const int64_t k = row_at(rows, t);
-        const F dk = d[k];
-        if (dk == F(0)) continue;  // every term of row k is proportional to d[k]
-        VT y[NV];
-        const VT* xr = reinterpret_cast<const VT*>(X + k * (int64_t)P);
+    constexpr int U = 2;  // rows in flight per warp: all loads of U rows are issued before the REDs
+    for (int64_t t = warp; t < n_rows; t += (int64_t)U * nwarps) {
+        int64_t k[U];
+        F dk[U];
+        VT y[U][NV];
+        int code[U];
+        int e0[U], e1[U];
 #pragma unroll
-        for (int v = 0; v < NV; ++v) {
-            int c = lane + 32 * v;
-            y[v] = (c < chunks) ? V::scale(__ldg(xr + c), dk) : V::zero();
-        }
-        // lane i fetches the code of categorical block i; broadcast by shuffle
-        int my_code = -1;
-        if (lane < prm.n_cat) my_code = prm.codes[lane][k] - prm.drop_first[lane];
-#pragma unroll 1
-        for (int i = 0; i < prm.n_cat; ++i) {
-            int c = __shfl_sync(0xffffffffu, my_code, i);
-            if (c < 0) continue;
-            int rep = (int)(warp % prm.copies[i]);
-            F* orow = static_cast<F*>(prm.tab[i]) + ((int64_t)rep * prm.K[i] + c) * P;
+        for (int u = 0; u < U; ++u) {
+            const int64_t tu = t + (int64_t)u * nwarps;
+            const bool ok = tu < n_rows;
+            k[u] = ok ? row_at(rows, tu) : 0;
+            dk[u] = ok ? d[k[u]] : F(0);
+            const VT* xr = reinterpret_cast<const VT*>(X + k[u] * (int64_t)P);
 #pragma unroll
             for (int v = 0; v < NV; ++v) {
-                int ch = lane + 32 * v;
-                if (ch < chunks) red_add_vec(orow + ch * W, y[v]);
+                const int c = lane + 32 * v;
+                y[u][v] = (ok && c < chunks) ? __ldg(xr + c) : V::zero();
+            }
+            // lane i fetches the code of categorical block i; broadcast by shuffle later
+            code[u] = -1;
+            if (ok && lane < prm.n_cat) code[u] = prm.codes[lane][k[u]] - prm.drop_first[lane];
+            e0[u] = e1[u] = 0;
+            if (ok && out_sparse) {
+                e0[u] = prm.csr_indptr[k[u]];
+                e1[u] = prm.csr_indptr[k[u] + 1];
             }
         }
-        if (out_sparse) {
-            const int e0 = prm.csr_indptr[k], e1 = prm.csr_indptr[k + 1];
-            for (int eb = e0; eb < e1; eb += 32) {
-                int e = eb + lane;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (dk[u] == F(0)) continue;  // every term of row k is proportional to d[k]
+#pragma unroll
+            for (int v = 0; v < NV; ++v) y[u][v] = V::scale(y[u][v], dk[u]);
+#pragma unroll 1
+            for (int i = 0; i < prm.n_cat; ++i) {
+                const int c = __shfl_sync(0xffffffffu, code[u], i);
+                if (c < 0) continue;
+                const int rep = (int)((warp + u) % prm.copies[i]);
+                F* orow = static_cast<F*>(prm.tab[i]) + ((int64_t)rep * prm.K[i] + c) * P;
+#pragma unroll
+                for (int v = 0; v < NV; ++v) {
+                    const int ch = lane + 32 * v;
+                    if (ch < chunks) red_add_vec(orow + ch * W, y[u][v]);
+                }
+            }
+            for (int eb = e0[u]; eb < e1[u]; eb += 32) {
+                const int e = eb + lane;
                 int j = 0;
                 F a = F(0);
-                if (e < e1) {
+                if (e < e1[u]) {
                     j = prm.csr_indices[e];
                     a = csr_data[e];
                 }
-                int cnt = min(32, e1 - eb);
+                const int cnt = min(32, e1[u] - eb);
                 for (int q = 0; q < cnt; ++q) {
-                    int jj = __shfl_sync(0xffffffffu, j, q);
-                    F aa = __shfl_sync(0xffffffffu, a, q);
+                    const int jj = __shfl_sync(0xffffffffu, j, q);
+                    const F aa = __shfl_sync(0xffffffffu, a, q);
                     F* orow = out_sparse + (int64_t)jj * P;
 #pragma unroll
                     for (int v = 0; v < NV; ++v) {
-                        int ch = lane + 32 * v;
-                        if (ch < chunks) red_add_vec(orow + ch * W, V::scale(y[v], aa));
+                        const int ch = lane + 32 * v;
+                        if (ch < chunks) red_add_vec(orow + ch * W, V::scale(y[u][v], aa));
                     }
                 }
             }
