@@ -22,6 +22,7 @@ oracle/ref_split.py) on a bounded row sample of the same workload on the host co
 from __future__ import annotations
 
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -43,6 +44,11 @@ SPARSE_DENSITY = 1e-3
 CAT_LEVELS = (10, 50, 200, 1000, 2000)
 P_TOTAL = P_DENSE + SPARSE_BLOCKS * SPARSE_COLS + sum(CAT_LEVELS)
 METRIC = "SplitMatrix sandwich GFLOP/s"
+PASS_KERNEL = {
+    "tensor": "k_dense_syrk_tc (tcgen05 SYRK + one-hot MMAs: dense self, dense x few-level cats)",
+    "scatter": "k_dense_cross_fused (dense x many-level cats + dense x sparse, vector RED)",
+    "index": "index pass (k_sparse_sandwich, k_cat_sparse, k_cat_cat, k_cat_hist)",
+}
 WORKLOAD = ("SplitMatrix 128 dense + 3x1000 CSC @1e-3 + cat{10,50,200,1000,2000}, p=6388, "
             "f32, n=%d total rows")
 
@@ -415,8 +421,13 @@ def main():
         step()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     tm.reset_launch_count()
+    tm._lib.lib.tm_split_profile_enable(1)   # CUDA events around the three passes of every step
     total_ms = timed_loop(step, args.steps)
     launches = tm.launch_count()
+    pass_ms = (ctypes.c_float * 3)()
+    tm._lib.lib.tm_split_profile_read(pass_ms)
+    tm._lib.lib.tm_split_profile_enable(0)
+    pass_ms = {"tensor": float(pass_ms[0]), "scatter": float(pass_ms[1]), "index": float(pass_ms[2])}
     clocks = sampler.stop() if sampler else None
 
     # end to end through the public API: d from pinned host memory, result to pinned host
@@ -444,17 +455,41 @@ def main():
         dist.all_reduce(fl)
     flops, nnz = float(fl[0].item()), float(fl[1].item())
 
-    bd = block_breakdown(Xs, d) if (rank == 0) else None
+    bd = block_breakdown(Xs, d) if (rank == 0 and args.breakdown) else None
     if world > 1:
         dist.barrier()
 
     if rank == 0:
         ms_step = total_ms / args.steps
         e2e_step_ms = e2e_ms / args.steps
-        top = max((k for k in bd if not k.startswith("native.")), key=bd.get)
-        top_bytes = block_bytes(top, n_local, nnz_local)
-        achieved = top_bytes / (bd[top] * 1e-3) / 1e9
+        # dominant kernel = the longest of the three passes of tm_split_sandwich_blocks, timed
+        # with CUDA events on its own stream inside the timed region (the tensor-core pass runs
+        # concurrently on a side stream)
+        n_oh = sum(1 for K in CAT_LEVELS if K <= 256)
+        ps = SPARSE_BLOCKS * SPARSE_COLS
+        pass_bytes = {
+            # X + d + the few-level categoricals' codes in; dense self + their cross blocks out
+            "tensor": n_local * (P_DENSE * 4 + 4 + 4 * n_oh)
+            + 4 * (P_DENSE * P_DENSE + sum(K for K in CAT_LEVELS if K <= 256) * P_DENSE),
+            # X + d + many-level codes + CSR (data, indices, indptr) in; their cross blocks out
+            "scatter": n_local * (P_DENSE * 4 + 4 + 4 * (len(CAT_LEVELS) - n_oh)) + nnz_local * 8
+            + 4 * (n_local + 1) + 4 * (ps + sum(K for K in CAT_LEVELS if K > 256)) * P_DENSE,
+            # CSR + row ids + every code vector + d in; sparse self, cat x sparse, cat x cat out
+            "index": nnz_local * 12 + 4 * (n_local + 1) + n_local * (4 * len(CAT_LEVELS) + 4)
+            + 4 * (ps * ps + sum(CAT_LEVELS) * ps + sum(CAT_LEVELS)
+                   + sum(a * b for i, a in enumerate(CAT_LEVELS) for b in CAT_LEVELS[i + 1:])),
+        }
+        top = max(pass_ms, key=pass_ms.get)
+        top_bytes = pass_bytes[top]
+        achieved = top_bytes / (pass_ms[top] * 1e-3) / 1e9
+        # L2 RED payload of the scatter pass: one 512-byte row per many-level categorical and
+        # per sparse non-zero; the measured L2 atomic peak is 6.0 TB/s (tools/micro/red_bench.cu)
+        red_bytes = (n_local * (len(CAT_LEVELS) - n_oh) + nnz_local) * P_DENSE * 4
         whole_bytes = split_bytes(n_local, nnz_local)
+        try:
+            traffic = json.loads((ROOT / "profiles" / "traffic.json").read_text()).get(top)
+        except Exception:
+            traffic = None
         line = {
             "metric": METRIC, "value": flops / (ms_step * 1e-3) / 1e9, "unit": "GFLOP/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
@@ -474,12 +509,22 @@ def main():
                             + (" on rank 0 (reduce to rank 0)" if world > 1 else "")},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": hbm_peak,
-                         "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
-                         "peak_source": peak_src, "launch_ms": bd[top],
-                         "algorithmic_bytes": top_bytes},
-            "breakdown_ms": bd,
+            "roofline": {"bound": "hbm", "kernel": PASS_KERNEL[top], "achieved": achieved,
+                         "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                         "traffic": traffic, "peak_source": peak_src, "launch_ms": pass_ms[top],
+                         "algorithmic_bytes": top_bytes,
+                         "l2_red": {"payload_bytes": red_bytes,
+                                    "achieved_TBs": red_bytes / (pass_ms["scatter"] * 1e-3) / 1e12
+                                    if pass_ms["scatter"] > 0 else None,
+                                    "measured_peak_TBs": 6.0,
+                                    "note": "the scatter pass is bound by the L2 atomic units, "
+                                            "not by HBM"}},
+            "passes_ms": pass_ms,
+            "passes_hbm_frac": {k: (pass_bytes[k] / (v * 1e-3) / 1e9 / hbm_peak if v > 0 else None)
+                                for k, v in pass_ms.items()},
         }
+        if bd is not None:
+            line["breakdown_ms"] = bd
         if world == 1 and not args.no_cpu_baseline:
             try:
                 r = cpu_reference_run(args.cpu_rows, 3, 1)
@@ -488,7 +533,7 @@ def main():
             except Exception as e:  # pragma: no cover
                 line["cpu_baseline"] = {"value": None, "unit": "GFLOP/s", "cores": 0,
                                         "kind": "port", "sample": f"failed: {e!r}"}
-        if args.breakdown:
+        if args.breakdown and bd is not None:
             for k, v in sorted(bd.items(), key=lambda kv: -kv[1]):
                 print(f"  {k:24s} {v:9.3f} ms", file=sys.stderr)
         print(json.dumps(line), flush=True)

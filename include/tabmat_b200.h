@@ -297,6 +297,15 @@ typedef struct tm_block_desc {
     int64_t cat_nvalid;
 } tm_block_desc;
 
+/* Pass-level device timing of tm_split_sandwich_blocks_* (measurement aid): when enabled, CUDA
+ * events bracket the three passes on the stream each one runs on; `ms[3]` = {tensor-core pass
+ * (dense self + few-level categoricals, side stream), scatter pass (dense x many-level
+ * categoricals and dense x sparse, caller's stream), index pass (all blocks without the dense
+ * operand)}, averaged over the (at most 64 last) calls since tm_split_profile_enable(1); -1 for
+ * a pass that did not run. */
+void tm_split_profile_enable(int on);
+int tm_split_profile_read(float* ms);
+
 /* Elements (of the block dtype) of the flat workspace that holds every self block and every
  * cross block: for i: self_i (dense/sparse ncols_i^2, categorical ncols_i = the diagonal), then
  * for j > i: cross_ij (ncols_i * ncols_j). */

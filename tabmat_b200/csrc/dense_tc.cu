@@ -57,6 +57,7 @@ struct Params {
     long long num_row_tiles;
     int stagesR;      // depth of the TMA ring (raw X tiles)
     int sb;           // depth of the operand ring (2..MAX_SB): S + one-hot in smem, T in TMEM
+    int dual_acc;     // mtiles == 1 without one-hot blocks: two SYRK accumulators (even/odd k steps)
     int r_bytes;      // bytes of one raw stage: X tile | d (128 B) | one-hot codes (8 x 128 B)
     int aux_off;      // offset of d inside a stage (BK * P * 4 rounded up to 128)
     int tmem_cols;
@@ -117,6 +118,14 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tmap, 
         "l"((uint64_t)tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_1d(uint32_t dst_sa, const CUtensorMap* tmap, uint64_t* bar,
+                                            int c0) {
+    asm volatile(
+        "cp.async.bulk.tensor.1d.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3}], [%2];" ::"r"(dst_sa),
+        "l"((uint64_t)tmap), "r"(smem_u32(bar)), "r"(c0)
+        : "memory");
+}
 __device__ __forceinline__ void tcgen05_fence_before() {
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 }
@@ -158,6 +167,36 @@ __device__ __forceinline__ void tmem_st_x4(uint32_t taddr, uint32_t v0, uint32_t
     asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr),
                  "r"(v0), "r"(v1), "r"(v2), "r"(v3)
                  : "memory");
+}
+// explicit shared-space accesses on 32-bit shared addresses (pointers carved out of the dynamic
+// shared buffer otherwise degrade to generic LD.E / ST.E)
+__device__ __forceinline__ float lds_f32(uint32_t a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ int lds_s32(uint32_t a) {
+    int v;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ float4 lds_f32x4(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_u32x4(uint32_t a, uint4 v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z),
+                 "r"(v.w)
+                 : "memory");
+}
+__device__ __forceinline__ void sts_f32(uint32_t a, float v) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory");
+}
+__device__ __forceinline__ void sts_s32(uint32_t a, int v) {
+    asm volatile("st.shared.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
 }
 // one elected lane of a converged warp (the compiler then emits the tcgen05 instructions
 // straight-line instead of a per-active-lane serialisation loop)
@@ -221,32 +260,42 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
 // the MMAs), the d-scaled values to this lane's TMEM lane of the T operand (M side).  All 16
 // loads are issued before the math.  Lanes with c >= P write nothing to S (those rows stay
 // zero) and zeros to T (tcgen05.st is warp-collective).
-__device__ __forceinline__ void scale_col4(const float* __restrict__ R, int P,
-                                           const float* __restrict__ dsm, uint8_t* Sp,
+__device__ __forceinline__ void scale_col4(uint32_t R, int P, uint32_t dsm, uint32_t Sp,
                                            uint32_t t_addr, int c, int kb, int ks) {
+    // R, dsm, Sp: 32-bit shared addresses of the raw stage, its d vector and the S tile
     float x[4][4];
     const bool ok = c < P;
-    const float* r0 = R + c;
+    const uint32_t r0 = R + (uint32_t)c * 4u;
+    const uint32_t pitch = (uint32_t)P * 4u;
 #pragma unroll
     for (int u = 0; u < 4; ++u)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) x[u][i] = ok ? r0[(size_t)(4 * (kb + u * ks) + i) * P] : 0.f;
+        for (int i = 0; i < 4; ++i)
+            x[u][i] = ok ? lds_f32(r0 + (uint32_t)(4 * (kb + u * ks) + i) * pitch) : 0.f;
     const uint32_t tile_off = (uint32_t)(c >> 7) * TILE_BYTES;
     const uint32_t row = (uint32_t)c & 127u;
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
         const int k4 = kb + u * ks;
-        const float4 dv = *reinterpret_cast<const float4*>(dsm + 4 * k4);
+        const float4 dv = lds_f32x4(dsm + 16u * (uint32_t)k4);
         uint4 a;
         a.x = to_tf32(x[u][0]);
         a.y = to_tf32(x[u][1]);
         a.z = to_tf32(x[u][2]);
         a.w = to_tf32(x[u][3]);
-        if (ok) *reinterpret_cast<uint4*>(Sp + tile_off + kmajor_chunk_off(row, (uint32_t)k4)) = a;
+        if (ok) sts_u32x4(Sp + tile_off + kmajor_chunk_off(row, (uint32_t)k4), a);
         tmem_st_x4(t_addr + (uint32_t)(4 * k4), to_tf32(dv.x * x[u][0]), to_tf32(dv.y * x[u][1]),
                    to_tf32(dv.z * x[u][2]), to_tf32(dv.w * x[u][3]));
     }
 }
+
+// tensor maps of one launch: the X tile, the weight vector d and the one-hot code vectors
+// (1-d maps, 32 elements per stage; out-of-range rows read as zero)
+struct TmapSet {
+    CUtensorMap x;
+    CUtensorMap d;
+    CUtensorMap codes[8];
+};
 
 // bring-up timeline: cycle stamps of CTA 0's first TL_ITERS iterations (prm.dbg only)
 constexpr int TL_ITERS = 1024;
@@ -261,7 +310,7 @@ __device__ __forceinline__ void tl_stamp(const Params& prm, int it, int e) {
 // kernels of a SplitMatrix sandwich can share the SM with this kernel's one resident CTA
 template <int MIN_BLOCKS>
 __global__ void __launch_bounds__(NUM_THREADS, MIN_BLOCKS)
-k_dense_syrk_tc(const __grid_constant__ CUtensorMap tmap, const Params prm) {
+k_dense_syrk_tc(const __grid_constant__ TmapSet tmaps, const Params prm) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* base = reinterpret_cast<uint8_t*>(
         (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -298,7 +347,7 @@ k_dense_syrk_tc(const __grid_constant__ CUtensorMap tmap, const Params prm) {
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < SR; ++s) {
-            mbar_init(&full[s], 2);  // TMA expect_tx arrive + the producer warp's d/codes stores
+            mbar_init(&full[s], 1);
             mbar_init(&emptyR[s], NUM_SCALE_WARPS);
         }
         for (int b = 0; b < SB; ++b) {
@@ -307,7 +356,8 @@ k_dense_syrk_tc(const __grid_constant__ CUtensorMap tmap, const Params prm) {
         }
         mbar_init(done, 1);
         fence_barrier_init();
-        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmap) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmaps.x) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmaps.d) : "memory");
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
@@ -320,7 +370,7 @@ k_dense_syrk_tc(const __grid_constant__ CUtensorMap tmap, const Params prm) {
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const int syrk_tiles = prm.mtiles * (prm.mtiles + 1) / 2;
+    const int syrk_tiles = prm.dual_acc ? 2 : prm.mtiles * (prm.mtiles + 1) / 2;
     const uint32_t oh_col0 = (uint32_t)syrk_tiles * 128;  // first TMEM column of the one-hot block
     const uint32_t t_col0 = oh_col0 + (uint32_t)prm.oh_groups * 32;  // T operand ring (SB x mtiles x 32)
 
@@ -330,51 +380,46 @@ k_dense_syrk_tc(const __grid_constant__ CUtensorMap tmap, const Params prm) {
         my_count = (int)((prm.num_row_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
 
     if (warp == 0) {
-        // ===== producer warp: TMA for the X tile; d and the one-hot codes of the stage's 32
-        // rows go through registers into the stage's aux area (prefetched one stage ahead, so
-        // the scale warps never have a global load in flight when they fence) =====
-        float dreg = 0.f;
-        int creg[8];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) creg[c] = -1;
-        auto prefetch = [&](int it) {
-            const long long k = ((long long)blockIdx.x + (long long)it * gridDim.x) * BK + lane;
-            const bool ok = k < prm.n;
-            dreg = ok ? prm.d[k] : 0.f;
-#pragma unroll
-            for (int c = 0; c < 8; ++c)
-                if (c < prm.oh_ncat) creg[c] = ok ? prm.oh_codes[c][k] - prm.oh_df[c] : -1;
-        };
-        if (my_count > 0) prefetch(0);
-        int s = 0;
-        uint32_t ph = 0;
-        for (int it = 0; it < my_count; ++it, ++s) {
-            if (s == SR) {
-                s = 0;
-                ph ^= 1;
-            }
-            if (lane == 0) mbar_wait(&emptyR[s], ph ^ 1);
-            __syncwarp();
-            uint8_t* stage = Rring + (size_t)s * prm.r_bytes;
-            if (lane == 0) {
+        // ===== TMA producer (one lane): per stage one box of X plus 128 bytes of d and of each
+        // one-hot code vector, all landing in the stage and completing the same mbarrier - no
+        // thread of this CTA ever has a plain global load in flight =====
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            const uint32_t tx = (uint32_t)(BK * P * 4) + 128u * (1u + (uint32_t)prm.oh_ncat);
+            for (int it = 0; it < my_count; ++it, ++s) {
+                if (s == SR) {
+                    s = 0;
+                    ph ^= 1;
+                }
+                mbar_wait(&emptyR[s], ph ^ 1);
                 tl_stamp(prm, it, 0);
                 const long long k0 = ((long long)blockIdx.x + (long long)it * gridDim.x) * BK;
-                mbar_expect_tx(&full[s], (uint32_t)(BK * P * 4));
-                tma_load_2d(stage, &tmap, &full[s], 0, (int)k0);
+                uint8_t* stage = Rring + (size_t)s * prm.r_bytes;
+                const uint32_t aux = smem_u32(stage) + (uint32_t)prm.aux_off;
+                mbar_expect_tx(&full[s], tx);
+                tma_load_2d(stage, &tmaps.x, &full[s], 0, (int)k0);
+                tma_load_1d(aux, &tmaps.d, &full[s], (int)k0);
+                for (int c = 0; c < prm.oh_ncat; ++c)
+                    tma_load_1d(aux + 128u * (uint32_t)(c + 1), &tmaps.codes[c], &full[s], (int)k0);
             }
-            float* dsm = reinterpret_cast<float*>(stage + prm.aux_off);
-            int* csm = reinterpret_cast<int*>(stage + prm.aux_off + 128);
-            dsm[lane] = dreg;
-#pragma unroll
-            for (int c = 0; c < 8; ++c)
-                if (c < prm.oh_ncat) csm[c * 32 + lane] = creg[c];
-            if (it + 1 < my_count) prefetch(it + 1);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&full[s]);
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
+        // One thread issues; the per-MMA instruction count matters (a single thread's issue rate
+        // is what paces small MMAs), so the descriptors are precomputed and only advanced by
+        // constants.  With one 128-column tile the S tile and the one-hot rows are contiguous in
+        // shared memory and their accumulators contiguous in TMEM, so each 8-row K step is ONE
+        // MMA chain of N <= 256 pieces over [S ; one-hot]:  D[:, 0:128] is the SYRK tile and
+        // D[:, 128:] the one-hot block.  Without one-hot blocks the K steps alternate between two
+        // accumulator tiles (summed in the epilogue) to halve the dependent-accumulate stalls.
         const uint32_t idesc = make_idesc(128, 128);
+        const uint64_t desc0 = make_desc(smem_u32(Oper));      // slot 0, k step 0
+        const uint32_t slot16 = slot_bytes >> 4;               // descriptor units (16 B)
+        const int n_total = 128 + prm.oh_groups * 32;          // mtiles == 1: columns of [S ; O]
+        const int n1 = n_total > 256 ? 256 : n_total;
+        const int n2 = n_total - n1;
+        const uint32_t idesc1 = make_idesc(128, n1), idesc2 = make_idesc(128, n2 > 0 ? n2 : 16);
         int b = 0;
         uint32_t phb = 0;
         for (int it = 0; it < my_count; ++it, ++b) {
@@ -386,29 +431,34 @@ k_dense_syrk_tc(const __grid_constant__ CUtensorMap tmap, const Params prm) {
             tcgen05_fence_after();
             if (elect_one()) {
                 tl_stamp(prm, it, 4);
-                const uint32_t Sa = smem_u32(Oper + (size_t)b * slot_bytes);
-                const uint32_t Oa = Sa + half_bytes;
+                const uint64_t dS = desc0 + (uint64_t)((uint32_t)b * slot16);
                 const uint32_t Ta = tmem_base + t_col0 + (uint32_t)(b * prm.mtiles) * 32;
+                if (prm.mtiles == 1) {
 #pragma unroll
-                for (int ks = 0; ks < BK / 8; ++ks) {
-                    const uint32_t acc = (it > 0 || ks > 0) ? 1u : 0u;
-                    int tile = 0;
-                    for (int mt = 0; mt < prm.mtiles; ++mt) {
-                        const uint32_t ta = Ta + (uint32_t)mt * 32 + ks * 8;
-                        for (int nt = 0; nt <= mt; ++nt, ++tile) {
-                            const uint64_t db = make_desc(Sa + (uint32_t)nt * TILE_BYTES + ks * 32);
-                            tcgen05_mma_tf32_ts(tmem_base + (uint32_t)tile * 128, ta, db, idesc, acc);
+                    for (int ks = 0; ks < BK / 8; ++ks) {
+                        const uint32_t acc = (it > 0 || ks > 0) ? 1u : 0u;
+                        const uint64_t db = dS + (uint64_t)(ks * 2);   // +32 B per k step
+                        if (prm.dual_acc) {
+                            // even k steps -> tile 0, odd -> tile 1 (first use of each overwrites)
+                            const uint32_t acc2 = (it > 0 || ks > 1) ? 1u : 0u;
+                            tcgen05_mma_tf32_ts(tmem_base + (uint32_t)(ks & 1) * 128, Ta + ks * 8,
+                                                db, idesc, acc2);
+                        } else {
+                            tcgen05_mma_tf32_ts(tmem_base, Ta + ks * 8, db, idesc1, acc);
+                            if (n2 > 0)
+                                tcgen05_mma_tf32_ts(tmem_base + 256, Ta + ks * 8,
+                                                    db + (uint64_t)(256 * 128 / 16), idesc2, acc);
                         }
                     }
-                    // one-hot blocks: D'[dense col, slot] += (d*X)[:, col]^T * OneHot[:, slot]
-                    if (prm.oh_groups) {
-                        const uint32_t ta = Ta + ks * 8;
-                        for (int g0 = 0; g0 < prm.oh_groups; g0 += 8) {
-                            const int ng = prm.oh_groups - g0 < 8 ? prm.oh_groups - g0 : 8;
-                            const uint64_t db = make_desc(Oa + (uint32_t)g0 * GROUP_BYTES + ks * 32);
-                            tcgen05_mma_tf32_ts(tmem_base + oh_col0 + (uint32_t)g0 * 32, ta, db,
-                                                make_idesc(128, ng * 32), acc);
-                        }
+                } else {
+#pragma unroll
+                    for (int ks = 0; ks < BK / 8; ++ks) {
+                        const uint32_t acc = (it > 0 || ks > 0) ? 1u : 0u;
+                        const uint64_t d0 = dS + (uint64_t)(ks * 2);
+                        const uint64_t d1 = d0 + (uint64_t)(TILE_BYTES / 16);
+                        tcgen05_mma_tf32_ts(tmem_base, Ta + ks * 8, d0, idesc, acc);             // (0,0)
+                        tcgen05_mma_tf32_ts(tmem_base + 128, Ta + 32 + ks * 8, d0, idesc, acc);  // (1,0)
+                        tcgen05_mma_tf32_ts(tmem_base + 256, Ta + 32 + ks * 8, d1, idesc, acc);  // (1,1)
                     }
                 }
                 tcgen05_commit(&emptyB[b]);
@@ -428,6 +478,7 @@ k_dense_syrk_tc(const __grid_constant__ CUtensorMap tmap, const Params prm) {
         const bool oh_thread = oh_c < prm.oh_ncat;
         const int my_off = oh_thread ? prm.oh_off[oh_c] : 0;
         const int my_K = oh_thread ? prm.oh_K[oh_c] : 0;
+        const int my_df = oh_thread ? prm.oh_df[oh_c] : 0;
         uint32_t prev0 = 0xffffffffu, prev1 = 0xffffffffu, prev2 = 0xffffffffu,
                  prev3 = 0xffffffffu;  // the one this thread set in operand slot 0..3
         // X column of this thread: TMEM lane quarter q = warp & 3 (a warp can only touch its own
@@ -436,6 +487,7 @@ k_dense_syrk_tc(const __grid_constant__ CUtensorMap tmap, const Params prm) {
         const int q = warp & 3;
         const int h = w >> 2;
         const int my_col = (prm.mtiles == 2 ? h * 128 : 0) + q * 32 + lane;
+        const uint32_t oper_sa = smem_u32(Oper), rring_sa = smem_u32(Rring);
         int s = 0, b = 0;
         uint32_t ph = 0, phb = 0;
         for (int it = 0; it < my_count; ++it, ++s, ++b) {
@@ -451,25 +503,24 @@ k_dense_syrk_tc(const __grid_constant__ CUtensorMap tmap, const Params prm) {
             if (lane == 0) mbar_wait(&emptyB[b], phb ^ 1);  // MMAs of iteration it-SB left slot b
             __syncwarp();
             if (t == 0) tl_stamp(prm, it, 1);
-            uint8_t* Sp = Oper + (size_t)b * slot_bytes;
+            const uint32_t Sp = oper_sa + (uint32_t)b * slot_bytes;
             if (lane == 0) mbar_wait(&full[s], ph);
             __syncwarp();
             if (t == 0) tl_stamp(prm, it, 2);
-            const uint8_t* stage = Rring + (size_t)s * prm.r_bytes;
-            const float* dsm = reinterpret_cast<const float*>(stage + prm.aux_off);
+            const uint32_t stage = rring_sa + (uint32_t)s * (uint32_t)prm.r_bytes;
+            const uint32_t dsm = stage + (uint32_t)prm.aux_off;
             if (prm.oh_groups) {
-                uint8_t* O = Sp + half_bytes;
+                const uint32_t O = Sp + half_bytes;
                 const uint32_t pa = b == 0 ? prev0 : (b == 1 ? prev1 : (b == 2 ? prev2 : prev3));
-                if (pa != 0xffffffffu) *reinterpret_cast<float*>(O + pa) = 0.f;
+                if (pa != 0xffffffffu) sts_f32(O + pa, 0.f);
                 uint32_t na = 0xffffffffu;
                 if (oh_thread) {
-                    const int code =
-                        reinterpret_cast<const int*>(stage + prm.aux_off + 128)[oh_c * 32 + oh_r];
-                    if (code >= 0 && code < my_K && dsm[oh_r] != 0.f) {
+                    const int code = lds_s32(dsm + 128u + (uint32_t)(oh_c * 32 + oh_r) * 4u) - my_df;
+                    if (code >= 0 && code < my_K && lds_f32(dsm + (uint32_t)oh_r * 4u) != 0.f) {
                         const uint32_t slot = (uint32_t)(my_off + code);
                         na = kmajor_chunk_off(slot, (uint32_t)oh_r >> 2) +
                              (((uint32_t)oh_r & 3u) << 2);
-                        *reinterpret_cast<float*>(O + na) = 1.0f;
+                        sts_f32(O + na, 1.0f);
                     }
                 }
                 if (b == 0) prev0 = na;
@@ -477,7 +528,7 @@ k_dense_syrk_tc(const __grid_constant__ CUtensorMap tmap, const Params prm) {
                 else if (b == 2) prev2 = na;
                 else prev3 = na;
             }
-            const float* R = reinterpret_cast<const float*>(Rring + (size_t)s * prm.r_bytes);
+            const uint32_t R = stage;
             {
                 const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + t_col0 +
                                         (uint32_t)(b * prm.mtiles + (my_col >> 7)) * 32;
@@ -488,8 +539,10 @@ k_dense_syrk_tc(const __grid_constant__ CUtensorMap tmap, const Params prm) {
                     scale_col4(R, P, dsm, Sp, t_addr, my_col, 4, 1);
                 }
             }
+            if (t == 0) tl_stamp(prm, it, 6);
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             tcgen05_fence_before();
+            if (t == 0) tl_stamp(prm, it, 7);
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) {
@@ -509,11 +562,14 @@ k_dense_syrk_tc(const __grid_constant__ CUtensorMap tmap, const Params prm) {
                 for (int nt = 0; nt <= mt; ++nt, ++tile) {
                     const int C = mt * 128 + q * 32 + lane;  // output column (= X column of A)
 #pragma unroll 1
-                    for (int cc = 0; cc < 2; ++cc) {
-                        const int n0 = chalf * 64 + cc * 32;
+                    for (int cc = 0; cc < (prm.dual_acc ? 4 : 2); ++cc) {
+                        // dual_acc: the second accumulator tile (TMEM columns 128..255) holds the
+                        // odd k steps of the same output tile
+                        const int dup = cc >> 1;
+                        const int n0 = chalf * 64 + (cc & 1) * 32;
                         uint32_t v[32];
-                        uint32_t taddr =
-                            tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(tile * 128 + n0);
+                        uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) +
+                                         (uint32_t)((tile + dup) * 128 + n0);
                         TM_TMEM_LD_32x32B_X32(taddr, v);
                         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                         if (prm.dbg && blockIdx.x == 0) {
@@ -613,16 +669,45 @@ int dense_sandwich_tc_f32(const float* X, int64_t n, int64_t p, int c_order, con
     PFN_encodeTiled enc = get_encode();
     if (!enc) return fail("cuTensorMapEncodeTiled not available");
 
-    CUtensorMap tmap;
-    cuuint64_t gdim[2] = {(cuuint64_t)p, (cuuint64_t)n};
-    cuuint64_t gstride[1] = {(cuuint64_t)p * sizeof(float)};
-    cuuint32_t box[2] = {(cuuint32_t)p, (cuuint32_t)BK};  // one box = the whole row tile
-    cuuint32_t estr[2] = {1, 1};
-    CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(X), gdim,
-                      gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (cr != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed");
+    TmapSet tmaps;
+    memset(&tmaps, 0, sizeof(tmaps));
+    {
+        cuuint64_t gdim[2] = {(cuuint64_t)p, (cuuint64_t)n};
+        cuuint64_t gstride[1] = {(cuuint64_t)p * sizeof(float)};
+        cuuint32_t box[2] = {(cuuint32_t)p, (cuuint32_t)BK};  // one box = the whole row tile
+        cuuint32_t estr[2] = {1, 1};
+        CUresult cr = enc(&tmaps.x, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(X), gdim,
+                          gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed (X)");
+    }
+    auto encode_1d = [&](CUtensorMap* m, const void* ptr, CUtensorMapDataType dt) -> bool {
+        cuuint64_t gdim[1] = {(cuuint64_t)n};
+        cuuint64_t gstride[1] = {0};  // unused for rank 1
+        cuuint32_t box[1] = {(cuuint32_t)BK};
+        cuuint32_t estr[1] = {1};
+        return enc(m, dt, 1, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    };
+    // TMA needs 16-byte aligned global addresses: a misaligned d is staged through scratch
+    Scratch d_al(((reinterpret_cast<uintptr_t>(d) & 15) != 0) ? sizeof(float) * (size_t)n : 0, st);
+    if (d_al.err != cudaSuccess) return fail_cuda(d_al.err, "scratch");
+    if ((reinterpret_cast<uintptr_t>(d) & 15) != 0) {
+        TM_CUDA(cudaMemcpyAsync(d_al.p, d, sizeof(float) * (size_t)n, cudaMemcpyDeviceToDevice, st));
+        d = d_al.as<float>();
+    }
+    if (!encode_1d(&tmaps.d, d, CU_TENSOR_MAP_DATA_TYPE_FLOAT32))
+        return fail("cuTensorMapEncodeTiled failed (d)");
+    if (oh) {
+        for (int c = 0; c < oh->ncat && c < 8; ++c) {
+            if ((reinterpret_cast<uintptr_t>(oh->codes[c]) & 15) != 0)
+                return fail("dense_tc: categorical code vectors must be 16-byte aligned");
+            if (!encode_1d(&tmaps.codes[c], oh->codes[c], CU_TENSOR_MAP_DATA_TYPE_INT32))
+                return fail("cuTensorMapEncodeTiled failed (codes)");
+        }
+    }
 
     Params prm;
     memset(&prm, 0, sizeof(prm));
@@ -636,6 +721,8 @@ int dense_sandwich_tc_f32(const float* X, int64_t n, int64_t p, int c_order, con
     prm.dbg = g_tc_dbg;
     prm.variant = g_tc_variant;
     int ntiles = prm.mtiles * (prm.mtiles + 1) / 2;
+    prm.dual_acc = (prm.mtiles == 1 && !(oh && oh->ncat > 0)) ? 1 : 0;
+    if (prm.dual_acc) ntiles = 2;
     if (oh && oh->ncat > 0) {
         if (prm.mtiles != 1) return fail("dense_tc: one-hot blocks need p <= 128");
         if (oh->ncat > 8) return fail("dense_tc: at most 8 one-hot blocks");
@@ -683,9 +770,9 @@ int dense_sandwich_tc_f32(const float* X, int64_t n, int64_t p, int c_order, con
     TM_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)(p * p), st));
     long long grid = prm.num_row_tiles < sm_count() ? prm.num_row_tiles : sm_count();
     if (share_sm)
-        k_dense_syrk_tc<2><<<(unsigned)grid, NUM_THREADS, smem, st>>>(tmap, prm);
+        k_dense_syrk_tc<2><<<(unsigned)grid, NUM_THREADS, smem, st>>>(tmaps, prm);
     else
-        k_dense_syrk_tc<1><<<(unsigned)grid, NUM_THREADS, smem, st>>>(tmap, prm);
+        k_dense_syrk_tc<1><<<(unsigned)grid, NUM_THREADS, smem, st>>>(tmaps, prm);
     TM_LAUNCHED();
     return symmetrize_from_upper<float>(out, p, st);
 }

@@ -81,6 +81,22 @@ static cudaEvent_t side_event(int i) {
     return ev[i];
 }
 
+// ---- optional pass-level timing (tm_split_profile_*): CUDA events on the stream each pass
+// is launched on; bench.py reads them after synchronising ---------------------------------
+enum { PASS_TENSOR = 0, PASS_SCATTER = 1, PASS_INDEX = 2, PASS_COUNT = 3 };
+constexpr int PROF_RING = 64;  // calls kept since tm_split_profile_enable(1)
+static bool g_profile = false;
+static int g_prof_calls = 0;
+static cudaEvent_t g_pass_ev[PROF_RING][PASS_COUNT][2];
+static bool g_pass_used[PROF_RING][PASS_COUNT];
+static void pass_mark(int pass, int which, cudaStream_t st) {
+    if (!g_profile) return;
+    const int slot = g_prof_calls % PROF_RING;
+    if (!g_pass_ev[slot][pass][which]) cudaEventCreate(&g_pass_ev[slot][pass][which]);
+    cudaEventRecord(g_pass_ev[slot][pass][which], st);
+    if (which == 1) g_pass_used[slot][pass] = true;
+}
+
 static inline int64_t n_rows_or_all(const int32_t* rows, int64_t n_rows, int64_t n) {
     return rows ? n_rows : n;
 }
@@ -141,6 +157,7 @@ int split_blocks(const tm_block_desc* blk, int nb, int64_t n, const F* d, const 
                 TM_CUDA(cudaEventRecord(side_event(0), as_stream(stream)));
                 TM_CUDA(cudaStreamWaitEvent(st, side_event(0), 0));
             }
+            pass_mark(PASS_TENSOR, 0, st);
             Scratch dm(rows ? sizeof(float) * (size_t)n : 0, st);
             if (dm.err != cudaSuccess) return fail_cuda(dm.err, "scratch");
             const float* dd = reinterpret_cast<const float*>(d);
@@ -194,6 +211,7 @@ int split_blocks(const tm_block_desc* blk, int nb, int64_t n, const F* d, const 
                 if (rc) return rc;
                 on_tensor[i] = 1;
             }
+            pass_mark(PASS_TENSOR, 1, st);
         }
     }
     if (fuse) {
@@ -233,12 +251,15 @@ int split_blocks(const tm_block_desc* blk, int nb, int64_t n, const F* d, const 
                                     as_stream(stream)));
         }
         if (c > 0 || out_s) {
+            pass_mark(PASS_SCATTER, 0, as_stream(stream));
             int rc = dense_cross_sandwich(tag, static_cast<const F*>(D.data), n, D.ncols, d, rows,
                                           n_rows, c, codes, K, df, outs, sdata, sind, sptr, ps,
                                           out_s, stream);
             if (rc) return rc;
+            pass_mark(PASS_SCATTER, 1, as_stream(stream));
         }
     }
+    pass_mark(PASS_INDEX, 0, as_stream(stream));
 
     for (int i = 0; i < nb; ++i) {
         const tm_block_desc& bi = blk[i];
@@ -293,6 +314,8 @@ int split_blocks(const tm_block_desc* blk, int nb, int64_t n, const F* d, const 
             if (rc) return rc;
         }
     }
+    pass_mark(PASS_INDEX, 1, as_stream(stream));
+    if (g_profile) ++g_prof_calls;
     if (side_used) {  // join the side stream
         TM_CUDA(cudaEventRecord(side_event(1), side_stream()));
         TM_CUDA(cudaStreamWaitEvent(as_stream(stream), side_event(1), 0));
@@ -331,6 +354,30 @@ int split_assemble(const tm_block_desc* blk, int nb, const F* ws, double* out, i
 }  // namespace tmb
 
 extern "C" {
+
+void tm_split_profile_enable(int on) {
+    tmb::g_profile = on != 0;
+    tmb::g_prof_calls = 0;
+    for (int c = 0; c < tmb::PROF_RING; ++c)
+        for (int p = 0; p < tmb::PASS_COUNT; ++p) tmb::g_pass_used[c][p] = false;
+}
+int tm_split_profile_read(float* ms) {
+    const int calls = tmb::g_prof_calls < tmb::PROF_RING ? tmb::g_prof_calls : tmb::PROF_RING;
+    for (int p = 0; p < tmb::PASS_COUNT; ++p) {
+        double sum = 0;
+        int cnt = 0;
+        for (int c = 0; c < calls; ++c) {
+            if (!tmb::g_pass_used[c][p]) continue;
+            float t = 0.f;
+            if (cudaEventSynchronize(tmb::g_pass_ev[c][p][1]) != cudaSuccess) return 1;
+            cudaEventElapsedTime(&t, tmb::g_pass_ev[c][p][0], tmb::g_pass_ev[c][p][1]);
+            sum += t;
+            ++cnt;
+        }
+        ms[p] = cnt ? (float)(sum / cnt) : -1.f;
+    }
+    return 0;
+}
 
 int64_t tm_split_workspace_elems(const tm_block_desc* blocks, int n_blocks) {
     int64_t off = 0;

@@ -59,7 +59,17 @@ struct Vec<double> {
     static __device__ __forceinline__ T scale(T a, double s) { return make_double2(a.x * s, a.y * s); }
 };
 
+__device__ __forceinline__ const void* shfl_ptr(const void* p, int src) {
+    unsigned long long v = reinterpret_cast<unsigned long long>(p);
+    unsigned lo = __shfl_sync(0xffffffffu, (unsigned)v, src);
+    unsigned hi = __shfl_sync(0xffffffffu, (unsigned)(v >> 32), src);
+    return reinterpret_cast<const void*>(((unsigned long long)hi << 32) | lo);
+}
+
 // One warp per row; lane l owns the column chunks l, l+32, ... (W columns each); NV chunks/lane.
+// Destination rows are computed lane-parallel (lane i: categorical block i / the i-th non-zero
+// of the row) and broadcast with shuffles, so the per-destination cost is two shuffles, one
+// 64-bit add and the vector RED.
 template <typename F, int NV>
 __global__ void __launch_bounds__(256)
 k_dense_cross_fused(const F* __restrict__ X, int64_t n, int P, const F* __restrict__ d,
@@ -74,33 +84,48 @@ k_dense_cross_fused(const F* __restrict__ X, int64_t n, int P, const F* __restri
     const int chunks = P / W;  // P % W == 0 (checked by the host)
     const F* csr_data = static_cast<const F*>(prm.csr_data);
     F* out_sparse = static_cast<F*>(prm.out_sparse);
+    const int n_cat = prm.n_cat;
+
+    // lane i < n_cat serves categorical block i: its code vector, drop_first and the base of
+    // the table replica this warp adds into
+    const int32_t* my_codes = nullptr;
+    int my_df = 0;
+    F* my_tab = nullptr;
+    if (lane < n_cat) {
+        my_codes = prm.codes[lane];
+        my_df = prm.drop_first[lane];
+        my_tab = static_cast<F*>(prm.tab[lane]) +
+                 (int64_t)(warp % prm.copies[lane]) * prm.K[lane] * (int64_t)P;
+    }
+    const int64_t lane_off = (int64_t)lane * W;
 
     constexpr int U = 2;  // rows in flight per warp: all loads of U rows are issued before the REDs
     for (int64_t t = warp; t < n_rows; t += (int64_t)U * nwarps) {
-        int64_t k[U];
         F dk[U];
         VT y[U][NV];
-        int code[U];
+        const F* cat_dst[U];   // lane i: destination row of categorical block i (or nullptr)
         int e0[U], e1[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int64_t tu = t + (int64_t)u * nwarps;
             const bool ok = tu < n_rows;
-            k[u] = ok ? row_at(rows, tu) : 0;
-            dk[u] = ok ? d[k[u]] : F(0);
-            const VT* xr = reinterpret_cast<const VT*>(X + k[u] * (int64_t)P);
+            const int64_t k = ok ? row_at(rows, tu) : 0;
+            dk[u] = ok ? d[k] : F(0);
+            const VT* xr = reinterpret_cast<const VT*>(X + k * (int64_t)P);
 #pragma unroll
             for (int v = 0; v < NV; ++v) {
                 const int c = lane + 32 * v;
                 y[u][v] = (ok && c < chunks) ? __ldg(xr + c) : V::zero();
             }
-            // lane i fetches the code of categorical block i; broadcast by shuffle later
-            code[u] = -1;
-            if (ok && lane < prm.n_cat) code[u] = prm.codes[lane][k[u]] - prm.drop_first[lane];
+            cat_dst[u] = nullptr;
+            if (ok && lane < n_cat) {
+                const int c = my_codes[k] - my_df;
+                if (c >= 0) cat_dst[u] = my_tab + (int64_t)c * P;
+            }
             e0[u] = e1[u] = 0;
             if (ok && out_sparse) {
-                e0[u] = prm.csr_indptr[k[u]];
-                e1[u] = prm.csr_indptr[k[u] + 1];
+                e0[u] = prm.csr_indptr[k];
+                e1[u] = prm.csr_indptr[k + 1];
             }
         }
 #pragma unroll
@@ -108,35 +133,32 @@ k_dense_cross_fused(const F* __restrict__ X, int64_t n, int P, const F* __restri
             if (dk[u] == F(0)) continue;  // every term of row k is proportional to d[k]
 #pragma unroll
             for (int v = 0; v < NV; ++v) y[u][v] = V::scale(y[u][v], dk[u]);
-#pragma unroll 1
-            for (int i = 0; i < prm.n_cat; ++i) {
-                const int c = __shfl_sync(0xffffffffu, code[u], i);
-                if (c < 0) continue;
-                const int rep = (int)((warp + u) % prm.copies[i]);
-                F* orow = static_cast<F*>(prm.tab[i]) + ((int64_t)rep * prm.K[i] + c) * P;
+            for (int i = 0; i < n_cat; ++i) {
+                F* dst = const_cast<F*>(static_cast<const F*>(shfl_ptr(cat_dst[u], i)));
+                if (!dst) continue;
 #pragma unroll
                 for (int v = 0; v < NV; ++v) {
                     const int ch = lane + 32 * v;
-                    if (ch < chunks) red_add_vec(orow + ch * W, y[u][v]);
+                    if (ch < chunks) red_add_vec(dst + lane_off + (int64_t)v * 32 * W, y[u][v]);
                 }
             }
             for (int eb = e0[u]; eb < e1[u]; eb += 32) {
                 const int e = eb + lane;
-                int j = 0;
+                const F* sp_dst = nullptr;
                 F a = F(0);
                 if (e < e1[u]) {
-                    j = prm.csr_indices[e];
+                    sp_dst = out_sparse + (int64_t)prm.csr_indices[e] * P;
                     a = csr_data[e];
                 }
                 const int cnt = min(32, e1[u] - eb);
                 for (int q = 0; q < cnt; ++q) {
-                    const int jj = __shfl_sync(0xffffffffu, j, q);
+                    F* dst = const_cast<F*>(static_cast<const F*>(shfl_ptr(sp_dst, q)));
                     const F aa = __shfl_sync(0xffffffffu, a, q);
-                    F* orow = out_sparse + (int64_t)jj * P;
 #pragma unroll
                     for (int v = 0; v < NV; ++v) {
                         const int ch = lane + 32 * v;
-                        if (ch < chunks) red_add_vec(orow + ch * W, V::scale(y[u][v], aa));
+                        if (ch < chunks)
+                            red_add_vec(dst + lane_off + (int64_t)v * 32 * W, V::scale(y[u][v], aa));
                     }
                 }
             }
