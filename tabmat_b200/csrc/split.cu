@@ -214,50 +214,61 @@ int split_blocks(const tm_block_desc* blk, int nb, int64_t n, const F* d, const 
             pass_mark(PASS_TENSOR, 1, st);
         }
     }
+    auto scatter_pass = [&]() -> int {
     if (fuse) {
-        const tm_block_desc& D = blk[dense_idx];
-        const int32_t* codes[8];
-        int64_t K[8];
-        int32_t df[8];
-        F* outs[8];
-        int c = 0;
-        for (int i = 0; i < nb; ++i) {
-            if (blk[i].kind != KIND_CAT || on_tensor[i]) continue;
-            codes[c] = static_cast<const int32_t*>(blk[i].data);
-            K[c] = blk[i].ncols;
-            df[c] = blk[i].drop_first;
-            int a = i < dense_idx ? i : dense_idx, b = i < dense_idx ? dense_idx : i;
-            outs[c] = ws + cross_off[a][b];
-            ++c;
+            const tm_block_desc& D = blk[dense_idx];
+            const int32_t* codes[8];
+            int64_t K[8];
+            int32_t df[8];
+            F* outs[8];
+            int c = 0;
+            for (int i = 0; i < nb; ++i) {
+                if (blk[i].kind != KIND_CAT || on_tensor[i]) continue;
+                codes[c] = static_cast<const int32_t*>(blk[i].data);
+                K[c] = blk[i].ncols;
+                df[c] = blk[i].drop_first;
+                int a = i < dense_idx ? i : dense_idx, b = i < dense_idx ? dense_idx : i;
+                outs[c] = ws + cross_off[a][b];
+                ++c;
+            }
+            const F* sdata = nullptr;
+            const int32_t *sind = nullptr, *sptr = nullptr;
+            int64_t ps = 0;
+            F* out_s = nullptr;
+            if (sparse_idx >= 0 && blk[sparse_idx].nnz > 0) {
+                const tm_block_desc& S = blk[sparse_idx];
+                sdata = static_cast<const F*>(S.data);
+                sind = S.csr_indices;
+                sptr = S.csr_indptr;
+                ps = S.ncols;
+                int a = sparse_idx < dense_idx ? sparse_idx : dense_idx;
+                int b = sparse_idx < dense_idx ? dense_idx : sparse_idx;
+                out_s = ws + cross_off[a][b];
+            } else if (sparse_idx >= 0) {
+                int a = sparse_idx < dense_idx ? sparse_idx : dense_idx;
+                int b = sparse_idx < dense_idx ? dense_idx : sparse_idx;
+                TM_CUDA(cudaMemsetAsync(ws + cross_off[a][b], 0,
+                                        sizeof(F) * (size_t)(blk[a].ncols * blk[b].ncols),
+                                        as_stream(stream)));
+            }
+            if (c > 0 || out_s) {
+                pass_mark(PASS_SCATTER, 0, as_stream(stream));
+                int rc = dense_cross_sandwich(tag, static_cast<const F*>(D.data), n, D.ncols, d, rows,
+                                              n_rows, c, codes, K, df, outs, sdata, sind, sptr, ps,
+                                              out_s, stream);
+                if (rc) return rc;
+                pass_mark(PASS_SCATTER, 1, as_stream(stream));
+            }
         }
-        const F* sdata = nullptr;
-        const int32_t *sind = nullptr, *sptr = nullptr;
-        int64_t ps = 0;
-        F* out_s = nullptr;
-        if (sparse_idx >= 0 && blk[sparse_idx].nnz > 0) {
-            const tm_block_desc& S = blk[sparse_idx];
-            sdata = static_cast<const F*>(S.data);
-            sind = S.csr_indices;
-            sptr = S.csr_indptr;
-            ps = S.ncols;
-            int a = sparse_idx < dense_idx ? sparse_idx : dense_idx;
-            int b = sparse_idx < dense_idx ? dense_idx : sparse_idx;
-            out_s = ws + cross_off[a][b];
-        } else if (sparse_idx >= 0) {
-            int a = sparse_idx < dense_idx ? sparse_idx : dense_idx;
-            int b = sparse_idx < dense_idx ? dense_idx : sparse_idx;
-            TM_CUDA(cudaMemsetAsync(ws + cross_off[a][b], 0,
-                                    sizeof(F) * (size_t)(blk[a].ncols * blk[b].ncols),
-                                    as_stream(stream)));
-        }
-        if (c > 0 || out_s) {
-            pass_mark(PASS_SCATTER, 0, as_stream(stream));
-            int rc = dense_cross_sandwich(tag, static_cast<const F*>(D.data), n, D.ncols, d, rows,
-                                          n_rows, c, codes, K, df, outs, sdata, sind, sptr, ps,
-                                          out_s, stream);
-            if (rc) return rc;
-            pass_mark(PASS_SCATTER, 1, as_stream(stream));
-        }
+        return 0;
+    };
+    // order of the two passes on the caller's stream (the index pass first lets the lighter
+    // kernels share the SMs with the tensor pass; TABMAT_B200_SCATTER_FIRST=1 restores the other)
+    static const bool scatter_first =
+        getenv("TABMAT_B200_SCATTER_FIRST") && atoi(getenv("TABMAT_B200_SCATTER_FIRST")) == 1;
+    if (scatter_first) {
+        int rc = scatter_pass();
+        if (rc) return rc;
     }
     pass_mark(PASS_INDEX, 0, as_stream(stream));
 
@@ -315,6 +326,10 @@ int split_blocks(const tm_block_desc* blk, int nb, int64_t n, const F* d, const 
         }
     }
     pass_mark(PASS_INDEX, 1, as_stream(stream));
+    if (!scatter_first) {
+        int rc = scatter_pass();
+        if (rc) return rc;
+    }
     if (g_profile) ++g_prof_calls;
     if (side_used) {  // join the side stream
         TM_CUDA(cudaEventRecord(side_event(1), side_stream()));
