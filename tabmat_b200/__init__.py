@@ -10,6 +10,7 @@ There is no CPU fallback.
 
 from ._lib import TabmatB200Error, launch_count, reset_launch_count  # noqa: F401
 from .categorical_matrix import CategoricalMatrix
+from .constructor import from_csc, from_df, from_pandas
 from .dense_matrix import DenseMatrix
 from .matrix_base import MatrixBase
 from .sparse_matrix import SparseMatrix
@@ -27,4 +28,7 @@ __all__ = [
     "CategoricalMatrix",
     "as_tabmat",
     "hstack",
+    "from_csc",
+    "from_df",
+    "from_pandas",
 ]

@@ -236,6 +236,22 @@ def run_numpy(kind: str, args: dict):
     raise KeyError(kind)
 
 
+def constructor_frame(seed=5, n=60):
+    """The data frame both sides ingest (golden generator and tests/test_gpu_constructor.py)."""
+    import pandas as pd
+
+    rng = np.random.default_rng(seed)
+    return pd.DataFrame({
+        "dense_a": rng.standard_normal(n),
+        "sparse_a": np.where(rng.random(n) < 0.05, rng.standard_normal(n), 0.0),
+        "cat_big": pd.Categorical(rng.choice(list("abcdefg"), size=n)),
+        "flag": rng.random(n) < 0.5,
+        "cat_small": pd.Categorical(rng.choice(["u", "v"], size=n)),
+        "dense_b": rng.integers(0, 5, size=n),
+        "sparse_b": np.where(rng.random(n) < 0.08, 1.0, 0.0),
+    })
+
+
 def tolerance(dtype) -> float:
     """north_star: 1e-5 relative fp64 / 1e-3 fp32, normwise (max|delta| / max|ref|)."""
     return 1e-3 if np.dtype(dtype) == np.float32 else 1e-5

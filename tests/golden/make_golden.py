@@ -143,6 +143,31 @@ def class_level(seed=77, n=83):
     return out
 
 
+def constructor_level():
+    out = {}
+    df = cases.constructor_frame()
+    for pos in ("expand", "end"):
+        for df_first in (False, True):
+            X = tm.from_pandas(df, cat_position=pos, drop_first=df_first)
+            key = f"{pos}-df{int(df_first)}/"
+            out[key + "toarray"] = X.toarray()
+            out[key + "kinds"] = np.array([type(m).__name__ for m in X.matrices])
+            out[key + "index_concat"] = np.concatenate(X.indices)
+            out[key + "index_sizes"] = np.array([len(i) for i in X.indices])
+            d = np.linspace(0.5, 1.5, X.shape[0])
+            out[key + "sandwich"] = X.sandwich(d)
+    rng = np.random.default_rng(8)
+    A = sps.random(50, 12, density=0.2, random_state=rng, format="csc")
+    A[:, 3] = rng.standard_normal((50, 1))
+    A = sps.csc_matrix(A)
+    C = tm.from_csc(A, threshold=0.3)
+    out["csc/A_data"], out["csc/A_indices"], out["csc/A_indptr"] = A.data, A.indices, A.indptr
+    out["csc/toarray"] = C.toarray()
+    out["csc/index_concat"] = np.concatenate(C.indices)
+    out["csc/index_sizes"] = np.array([len(i) for i in C.indices])
+    return out
+
+
 def main():
     here = Path(__file__).resolve().parent
     boundary = {}
@@ -156,7 +181,9 @@ def main():
     np.savez_compressed(here / "boundary.npz", **boundary)
     cls = class_level()
     np.savez_compressed(here / "classes.npz", **cls)
-    print(f"wrote {count} boundary cases and {len(cls)} class-level arrays")
+    ctor = constructor_level()
+    np.savez_compressed(here / "constructors.npz", **ctor)
+    print(f"wrote {count} boundary cases, {len(cls)} class-level and {len(ctor)} constructor arrays")
 
 
 if __name__ == "__main__":

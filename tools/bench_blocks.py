@@ -20,7 +20,7 @@ PEAKS = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASU
 HBM = float(PEAKS.get("hbm_gbs", 6650.0))
 BF16 = float(PEAKS.get("bf16_tflops", 1590.0))
 reps = int(sys.argv[sys.argv.index("--reps") + 1]) if "--reps" in sys.argv else 10
-which = [a for a in sys.argv[1:] if a in ("c2", "c3", "c4", "c2f64")] or ["c2", "c3", "c4"]
+which = [a for a in sys.argv[1:] if a in ("c2", "c3", "c4", "c2f64", "c5mv")] or ["c2", "c3", "c4"]
 flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")
 
 
@@ -120,3 +120,17 @@ if "c4" in which:
     w = torch.randn(n, device="cuda", dtype=torch.float64, generator=g)
     ms, mn = timeit(lambda: A.transpose_matvec(w))
     emit("C4 sparse transpose_matvec f64", ms, mn, nnz * 12 + 4 * (p + 1) + n * 8 + p * 8, 2.0 * nnz)
+
+if "c5mv" in which:
+    sys.path.insert(0, str(ROOT))
+    import bench as B
+
+    n = 40_000_000
+    Xs, d, flops, nnz = B.device_split_matrix(n, seed=1000, device=torch.device("cuda", 0))
+    p = Xs.shape[1]
+    v = torch.randn(p, device="cuda", dtype=torch.float32, generator=g)
+    nbytes = n * (B.P_DENSE * 4 + len(B.CAT_LEVELS) * 4 + 4) + nnz * 8 + 4 * (n + 1)
+    ms, mn = timeit(lambda: Xs.matvec(v))
+    emit("C5 split matvec f32 n=4e7 p=6388", ms, mn, nbytes, 2.0 * (n * B.P_DENSE + nnz) + n * 5)
+    ms, mn = timeit(lambda: Xs.transpose_matvec(d))
+    emit("C5 split transpose_matvec f32 n=4e7", ms, mn, nbytes, 2.0 * (n * B.P_DENSE + nnz) + n * 5)
