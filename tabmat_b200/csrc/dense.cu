@@ -3,6 +3,8 @@
 // The fp32 unrestricted-column sandwich is served by the tcgen05 kernel in dense_tc.cu.
 //
 // Reference semantics: dense.pyx:19-122, dense_helpers-tmpl.cpp:161-417.
+#include <cstdlib>
+
 #include "tm_common.cuh"
 
 namespace tmb {
@@ -132,6 +134,152 @@ int dense_sandwich_generic(const F* X, int64_t n, int64_t p, int c_order, const 
                                                                   out, rps);
     TM_LAUNCHED();
     return symmetrize_from_lower<F>(out, m, st);
+}
+
+// ---------------------------------------------------------------------------------------
+// fp64 weighted SYRK on the FP64 tensor path: mma.sync m8n8k4 f64 (DMMA; tcgen05 has no fp64
+// kind).  128x128 output tiles (lower-triangular tile pairs), 8 warps as 4 (M) x 2 (N), warp
+// tile 32 x 64 = 4 x 8 m8n8 fragments, split-K over row chunks, d folded while staging the
+// B tile, fragments above the diagonal of a diagonal tile skipped.  Same restrictions
+// (rows / cols index lists, C or F order) as the generic kernel.
+// ---------------------------------------------------------------------------------------
+constexpr int DM_T = 128;   // output tile edge
+constexpr int DM_BK = 16;   // rows per shared-memory stage
+constexpr int DM_LD = 132;  // padded leading dimension (conflict-free fragment loads)
+
+__device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+template <bool C_ORDER>
+__global__ void __launch_bounds__(256)
+k_dense_sandwich_dmma(const double* __restrict__ X, int64_t n, int64_t p,
+                      const double* __restrict__ d, const int32_t* __restrict__ rows,
+                      int64_t n_rows, const int32_t* __restrict__ cols, int64_t m,
+                      double* __restrict__ out, int64_t rows_per_split) {
+    __shared__ double As[DM_BK][DM_LD];
+    __shared__ double Bs[DM_BK][DM_LD];
+
+    int idx = blockIdx.x;
+    int ti = (int)((sqrtf(8.0f * idx + 1.0f) - 1.0f) * 0.5f);
+    while ((ti + 1) * (ti + 2) / 2 <= idx) ++ti;
+    while (ti * (ti + 1) / 2 > idx) --ti;
+    const int tj = idx - ti * (ti + 1) / 2;
+    const bool diag_tile = ti == tj;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp >> 1, wn = warp & 1;  // warp tile: rows wm*32.., cols wn*64..
+    const int64_t a0 = (int64_t)ti * DM_T, b0 = (int64_t)tj * DM_T;
+    int64_t t_begin = (int64_t)blockIdx.y * rows_per_split;
+    int64_t t_end = t_begin + rows_per_split;
+    if (t_end > n_rows) t_end = n_rows;
+
+    double acc[4][8][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    // fragments of this warp that lie entirely above the diagonal of a diagonal tile are skipped
+    unsigned keep = 0;  // bit (i*8+j)
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int rmax = wm * 32 + i * 8 + 7, cmin = wn * 64 + j * 8;
+            if (!diag_tile || rmax >= cmin) keep |= 1u << (i * 8 + j);
+        }
+
+    for (int64_t t0 = t_begin; t0 < t_end; t0 += DM_BK) {
+#pragma unroll
+        for (int l = 0; l < (DM_BK * DM_T) / 256; ++l) {
+            const int e = tid + l * 256;
+            int kk, cc;
+            if (C_ORDER) {
+                kk = e >> 7;
+                cc = e & 127;
+            } else {
+                kk = e & (DM_BK - 1);
+                cc = e >> 4;
+            }
+            const int64_t t = t0 + kk;
+            double av = 0.0, bv = 0.0;
+            if (t < t_end) {
+                const int64_t k = row_at(rows, t);
+                const double dk = d[k];
+                const int64_t ca = a0 + cc, cb = b0 + cc;
+                if (ca < m) {
+                    const int64_t j = cols ? (int64_t)cols[ca] : ca;
+                    av = C_ORDER ? X[k * p + j] : X[j * n + k];
+                }
+                if (diag_tile) {
+                    bv = av * dk;
+                } else if (cb < m) {
+                    const int64_t j = cols ? (int64_t)cols[cb] : cb;
+                    bv = (C_ORDER ? X[k * p + j] : X[j * n + k]) * dk;
+                }
+            }
+            As[kk][cc] = av;
+            Bs[kk][cc] = bv;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int ks = 0; ks < DM_BK / 4; ++ks) {
+            const int kr = ks * 4 + (lane & 3);
+            double a[4], b[8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = As[kr][wm * 32 + i * 8 + (lane >> 2)];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) b[j] = Bs[kr][wn * 64 + j * 8 + (lane >> 2)];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (keep & (1u << (i * 8 + j))) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+        __syncthreads();
+    }
+
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int64_t a = a0 + wm * 32 + i * 8 + (lane >> 2);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (!(keep & (1u << (i * 8 + j)))) continue;
+            const int64_t b = b0 + wn * 64 + j * 8 + (lane & 3) * 2;
+            if (a < m) {
+                if (b < m && b <= a) red_add(&out[a * m + b], acc[i][j][0]);
+                if (b + 1 < m && b + 1 <= a) red_add(&out[a * m + b + 1], acc[i][j][1]);
+            }
+        }
+    }
+}
+
+int dense_sandwich_dmma(const double* X, int64_t n, int64_t p, int c_order, const double* d,
+                        const int32_t* rows, int64_t n_rows, const int32_t* cols, int64_t m,
+                        double* out, cudaStream_t st) {
+    TM_CUDA(cudaMemsetAsync(out, 0, sizeof(double) * (size_t)(m * m), st));
+    if (n_rows <= 0 || m <= 0) return 0;
+    int64_t T = (m + DM_T - 1) / DM_T;
+    int64_t npairs = T * (T + 1) / 2;
+    int64_t want = (int64_t)sm_count() * 2;
+    int64_t ksplit = (want + npairs - 1) / npairs;
+    int64_t max_split = (n_rows + DM_BK * 8 - 1) / (DM_BK * 8);
+    if (ksplit > max_split) ksplit = max_split;
+    if (ksplit < 1) ksplit = 1;
+    if (ksplit > 65535) ksplit = 65535;
+    int64_t rps = (n_rows + ksplit - 1) / ksplit;
+    rps = (rps + DM_BK - 1) / DM_BK * DM_BK;
+    ksplit = (n_rows + rps - 1) / rps;
+    dim3 grid((unsigned)npairs, (unsigned)ksplit);
+    if (c_order)
+        k_dense_sandwich_dmma<true><<<grid, 256, 0, st>>>(X, n, p, d, rows, n_rows, cols, m, out, rps);
+    else
+        k_dense_sandwich_dmma<false><<<grid, 256, 0, st>>>(X, n, p, d, rows, n_rows, cols, m, out, rps);
+    TM_LAUNCHED();
+    return symmetrize_from_lower<double>(out, m, st);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -341,8 +489,14 @@ int tm_dense_sandwich_f64(const double* X, int64_t n, int64_t p, int c_order, co
     if (!rows) n_rows = n;
     if (!cols) n_cols = p;
     if (n_cols <= 0) return 0;
-    return tmb::dense_sandwich_generic<double>(X, n, p, c_order, d, rows, n_rows, cols, n_cols, out,
-                                              tmb::as_stream(stream));
+    // fp64: DMMA tensor path (TABMAT_B200_F64_GENERIC=1 selects the CUDA-core kernel)
+    static const bool f64_generic =
+        getenv("TABMAT_B200_F64_GENERIC") && atoi(getenv("TABMAT_B200_F64_GENERIC")) == 1;
+    if (f64_generic)
+        return tmb::dense_sandwich_generic<double>(X, n, p, c_order, d, rows, n_rows, cols, n_cols,
+                                                  out, tmb::as_stream(stream));
+    return tmb::dense_sandwich_dmma(X, n, p, c_order, d, rows, n_rows, cols, n_cols, out,
+                                    tmb::as_stream(stream));
 }
 
 #define TM_DENSE_VEC_API(SUF, F)                                                                 \
