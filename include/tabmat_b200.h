@@ -297,6 +297,9 @@ typedef struct tm_block_desc {
     int64_t cat_nvalid;
 } tm_block_desc;
 
+/* sizeof(tm_block_desc) as compiled into the library (bindings check their struct mirror). */
+int64_t tm_sizeof_block_desc(void);
+
 /* Pass-level device timing of tm_split_sandwich_blocks_* (measurement aid): when enabled, CUDA
  * events bracket the three passes on the stream each one runs on; `ms[3]` = {tensor-core pass
  * (dense self + few-level categoricals, side stream), scatter pass (dense x many-level

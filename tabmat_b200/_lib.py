@@ -73,7 +73,7 @@ _SIGS = {
 #: every symbol include/tabmat_b200.h declares (checked by tests/test_capi_symbols.py)
 EXPORTED = ["tm_version", "tm_last_error", "tm_launch_count", "tm_reset_launch_count",
             "tm_has_tcgen05", "tm_set_dense_f32_mode", "tm_split_workspace_elems",
-            "tm_dense_onehot_sandwich_f32", "tm_split_profile_enable", "tm_split_profile_read"]
+            "tm_dense_onehot_sandwich_f32", "tm_split_profile_enable", "tm_split_profile_read", "tm_sizeof_block_desc"]
 for _name, _args in _SIGS.items():
     for _suf in ("f32", "f64"):
         _fn = getattr(lib, f"{_name}_{_suf}")
@@ -95,6 +95,9 @@ class BlockDesc(C.Structure):
 
 lib.tm_dense_onehot_sandwich_f32.argtypes = [P, I, I, P, P, I, N, P, P, P, P, P, P]
 lib.tm_dense_onehot_sandwich_f32.restype = c_int
+lib.tm_sizeof_block_desc.restype = c_i64
+if lib.tm_sizeof_block_desc() != C.sizeof(BlockDesc):  # pragma: no cover
+    raise ImportError("tm_block_desc layout mismatch between libtabmat_b200.so and _lib.BlockDesc")
 lib.tm_split_profile_enable.argtypes = [c_int]
 lib.tm_split_profile_enable.restype = None
 lib.tm_split_profile_read.argtypes = [C.c_void_p]

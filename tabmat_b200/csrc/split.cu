@@ -370,6 +370,8 @@ int split_assemble(const tm_block_desc* blk, int nb, const F* ws, double* out, i
 
 extern "C" {
 
+int64_t tm_sizeof_block_desc(void) { return (int64_t)sizeof(tm_block_desc); }
+
 void tm_split_profile_enable(int on) {
     tmb::g_profile = on != 0;
     tmb::g_prof_calls = 0;

@@ -32,6 +32,17 @@ def test_version_and_error_string():
     assert isinstance(_lib.lib.tm_last_error(), bytes)
 
 
+def test_block_descriptor_layout_matches_the_library():
+    from tabmat_b200 import _lib
+
+    assert _lib.lib.tm_sizeof_block_desc() == ctypes.sizeof(_lib.BlockDesc) == 96
+    descs = (_lib.BlockDesc * 2)()
+    descs[0].kind, descs[0].ncols = 0, 5          # dense 5 columns
+    descs[1].kind, descs[1].ncols = 2, 3          # categorical 3 columns
+    # self blocks 25 + 3 (diagonal), cross block 15
+    assert _lib.lib.tm_split_workspace_elems(descs, 2) == 43
+
+
 def test_product_path_does_not_touch_the_oracle():
     """Nothing under tabmat_b200/ may import or reference oracle/ (test infrastructure)."""
     pat = re.compile(r"(import|from)\s+oracle|c_oracle|ref_loader|libtabmat_oracle|oracle/_ref")
