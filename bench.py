@@ -44,9 +44,10 @@ SPARSE_DENSITY = 1e-3
 CAT_LEVELS = (10, 50, 200, 1000, 2000)
 P_TOTAL = P_DENSE + SPARSE_BLOCKS * SPARSE_COLS + sum(CAT_LEVELS)
 METRIC = "SplitMatrix sandwich GFLOP/s"
+ROW_ORDER_DEFAULT = "original"
 PASS_KERNEL = {
     "tensor": "k_dense_syrk_tc (tcgen05 SYRK + one-hot MMAs: dense self, dense x few-level cats)",
-    "scatter": "k_dense_cross_fused (dense x many-level cats + dense x sparse, vector RED)",
+    "scatter": "k_dense_cross_fused / k_dense_cross_runs (dense x many-level cats + dense x sparse, vector RED)",
     "index": "index pass (k_sparse_sandwich, k_cat_sparse, k_cat_cat, k_cat_hist)",
 }
 WORKLOAD = ("SplitMatrix 128 dense + 3x1000 CSC @1e-3 + cat{10,50,200,1000,2000}, p=6388, "
@@ -64,6 +65,12 @@ def parse_args():
                     help="rows of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--breakdown", action="store_true", help="print per-block times to stderr")
+    ap.add_argument("--row-order", default=os.environ.get("TABMAT_B200_BENCH_ROW_ORDER", ROW_ORDER_DEFAULT),
+                    choices=["original", "sorted"],
+                    help="'sorted': the resident matrix is stored with its rows sorted by the "
+                         "many-level categorical codes (tabmat_b200.RowSortedMatrix, built once "
+                         "like the reference's cached CSR); d arrives in the caller's order and "
+                         "is permuted inside the timed region")
     return ap.parse_args()
 
 
@@ -394,6 +401,11 @@ def main():
     lo, hi = shard_bounds(args.n, world, rank)
     n_local = hi - lo
     Xs, d, flops_local, nnz_local = device_split_matrix(n_local, seed=1000 + rank, device=device)
+    if args.row_order == "sorted":
+        Xo = Xs
+        Xs = tm.RowSortedMatrix.from_split(Xo)
+        del Xo
+        torch.cuda.empty_cache()
     S = RowShardedMatrix(Xs, args.n, pack=True, reduce_dtype=torch.float32)
     p = Xs.shape[1]
     assert p == P_TOTAL
@@ -455,7 +467,12 @@ def main():
         dist.all_reduce(fl)
     flops, nnz = float(fl[0].item()), float(fl[1].item())
 
-    bd = block_breakdown(Xs, d) if (rank == 0 and args.breakdown) else None
+    bd = None
+    if rank == 0 and args.breakdown:
+        if args.row_order == "sorted":
+            bd = block_breakdown(Xs.mat, Xs._gather(d))
+        else:
+            bd = block_breakdown(Xs, d)
     if world > 1:
         dist.barrier()
 
@@ -484,7 +501,10 @@ def main():
         achieved = top_bytes / (pass_ms[top] * 1e-3) / 1e9
         # L2 RED payload of the scatter pass: one 512-byte row per many-level categorical and
         # per sparse non-zero; the measured L2 atomic peak is 6.0 TB/s (tools/micro/red_bench.cu)
-        red_bytes = (n_local * (len(CAT_LEVELS) - n_oh) + nnz_local) * P_DENSE * 4
+        # (row-sorted storage: the many-level categorical runs collapse to one RED per run, so
+        # only the sparse non-zeros are left)
+        n_red_cat = 0 if args.row_order == "sorted" else len(CAT_LEVELS) - n_oh
+        red_bytes = (n_local * n_red_cat + nnz_local) * P_DENSE * 4
         whole_bytes = split_bytes(n_local, nnz_local)
         try:
             traffic = json.loads((ROOT / "profiles" / "traffic.json").read_text()).get(top)
@@ -498,6 +518,9 @@ def main():
             "config": {"workload": WORKLOAD % args.n, "rows_per_gpu": n_local, "p": p,
                        "nnz_sparse_total": nnz, "l2": "inputs (>20 GB per step) exceed the 126 MB L2",
                        "parallelism": f"row-shard x{world} + NCCL allreduce of the flat block workspace (f32, 90 MB)",
+                       "row_order": (args.row_order if args.row_order == "original" else
+                                     "sorted by (cat2000, cat1000) at construction; d permuted "
+                                     "inside the timed region"),
                        "algorithmic_flop_per_step": flops,
                        "whole_step_hbm_gbs": whole_bytes / (ms_step * 1e-3) / 1e9,
                        "whole_step_hbm_frac": whole_bytes / (ms_step * 1e-3) / 1e9 / hbm_peak},

@@ -48,6 +48,9 @@ int tm_has_tcgen05(void);
 /* Select the dense f32 sandwich implementation: 0 = auto (tcgen05 when eligible),
  * 1 = force the CUDA-core kernel, 2 = force tcgen05 (error when not eligible). */
 void tm_set_dense_f32_mode(int mode);
+/* Fused dense-operand cross pass of tm_split_sandwich_blocks_*: 0 = run-aggregating kernel only
+ * for blocks flagged TM row-sorted (tm_block_desc.flags bit 0), 1 = always, 2 = never. */
+void tm_set_cross_runs_mode(int mode);
 
 /* ---- dense block (reference: ext/dense.pyx) --------------------------------------- */
 /* dense_sandwich, dense.pyx:19-44 -> _dense{C,F}_sandwich, dense_helpers-tmpl.cpp:266-308.
@@ -281,7 +284,8 @@ typedef struct tm_block_desc {
     int32_t kind;       /* 0 dense, 1 sparse (CSR + row ids), 2 categorical */
     int32_t c_order;    /* dense: 1 row-major, 0 column-major */
     int32_t drop_first; /* categorical */
-    int32_t reserved;
+    int32_t flags;      /* bit 0 (categorical): the rows are stored sorted so that equal codes
+                         * form long runs -> the run-aggregating cross kernel is used */
     int64_t ncols;      /* block width (categorical: #categories - drop_first) */
     const void* data;   /* dense: X (n x ncols); sparse: CSR data; categorical: int32 codes */
     const int32_t* csr_indices;
@@ -332,6 +336,21 @@ int tm_split_sandwich_assemble_f32(const tm_block_desc* blocks, int n_blocks,
 int tm_split_sandwich_assemble_f64(const tm_block_desc* blocks, int n_blocks,
                                    const double* workspace, double* out, int64_t ld,
                                    tm_stream_t stream);
+
+/* ---- row-order permutation (no reference counterpart: the reference keeps the caller's row
+ * order; tabmat_b200.RowSortedMatrix stores the rows sorted by the many-level categorical codes
+ * and maps the length-n vectors of sandwich / transpose_matvec / matvec through `perm`,
+ * stored row i = original row perm[i]) ------------------------------------------------- */
+/* dst[i] (+)= src[perm[i]], i < n. */
+int tm_permute_gather_f32(const float* src, const int32_t* perm, int64_t n, float* dst,
+                          int accumulate, tm_stream_t stream);
+int tm_permute_gather_f64(const double* src, const int32_t* perm, int64_t n, double* dst,
+                          int accumulate, tm_stream_t stream);
+/* dst[perm[i]] (+)= src[i], i < n (perm must be a permutation: no duplicate targets). */
+int tm_permute_scatter_f32(const float* src, const int32_t* perm, int64_t n, float* dst,
+                           int accumulate, tm_stream_t stream);
+int tm_permute_scatter_f64(const double* src, const int32_t* perm, int64_t n, double* dst,
+                           int accumulate, tm_stream_t stream);
 
 /* ---- SplitMatrix assembly (reference: split_matrix.py:336-354, the numpy scatter) ---- */
 /* out[ri[a]*ld + ci[b]] = blk[a*nb + b]  (and, when mirror != 0, out[ci[b]*ld + ri[a]] too).

@@ -13,6 +13,7 @@ from .categorical_matrix import CategoricalMatrix
 from .constructor import from_csc, from_df, from_pandas
 from .dense_matrix import DenseMatrix
 from .matrix_base import MatrixBase
+from .row_order import RowSortedMatrix
 from .sparse_matrix import SparseMatrix
 from .split_matrix import SplitMatrix, as_tabmat, hstack
 from .standardized_mat import StandardizedMatrix
@@ -25,6 +26,7 @@ __all__ = [
     "StandardizedMatrix",
     "SparseMatrix",
     "SplitMatrix",
+    "RowSortedMatrix",
     "CategoricalMatrix",
     "as_tabmat",
     "hstack",

@@ -68,11 +68,14 @@ _SIGS = {
     "tm_split_sandwich_assemble": [P, N, P, P, I, P],
     "tm_scatter_block": [P, I, I, P, P, P, I, N, P],
     "tm_scatter_diag": [P, I, P, P, I, P],
+    "tm_permute_gather": [P, P, I, P, N, P],
+    "tm_permute_scatter": [P, P, I, P, N, P],
 }
 
 #: every symbol include/tabmat_b200.h declares (checked by tests/test_capi_symbols.py)
 EXPORTED = ["tm_version", "tm_last_error", "tm_launch_count", "tm_reset_launch_count",
-            "tm_has_tcgen05", "tm_set_dense_f32_mode", "tm_split_workspace_elems",
+            "tm_has_tcgen05", "tm_set_dense_f32_mode", "tm_set_cross_runs_mode",
+            "tm_split_workspace_elems",
             "tm_dense_onehot_sandwich_f32", "tm_split_profile_enable", "tm_split_profile_read", "tm_sizeof_block_desc"]
 for _name, _args in _SIGS.items():
     for _suf in ("f32", "f64"):
@@ -87,7 +90,7 @@ class BlockDesc(C.Structure):
     """ctypes mirror of ``tm_block_desc`` (include/tabmat_b200.h)."""
 
     _fields_ = [("kind", C.c_int32), ("c_order", C.c_int32), ("drop_first", C.c_int32),
-                ("reserved", C.c_int32), ("ncols", C.c_int64), ("data", C.c_void_p),
+                ("flags", C.c_int32), ("ncols", C.c_int64), ("data", C.c_void_p),
                 ("csr_indices", C.c_void_p), ("csr_indptr", C.c_void_p), ("csr_row", C.c_void_p),
                 ("nnz", C.c_int64), ("col_index", C.c_void_p), ("cat_perm", C.c_void_p),
                 ("cat_segptr", C.c_void_p), ("cat_nvalid", C.c_int64)]
@@ -111,6 +114,12 @@ lib.tm_reset_launch_count.restype = None
 lib.tm_has_tcgen05.restype = c_int
 lib.tm_set_dense_f32_mode.argtypes = [c_int]
 lib.tm_set_dense_f32_mode.restype = None
+lib.tm_set_cross_runs_mode.argtypes = [c_int]
+lib.tm_set_cross_runs_mode.restype = None
+# TABMAT_B200_CROSS_RUNS: 0 auto (run-aggregating cross kernel for row-sorted matrices) |
+# 1 always | 2 never
+if os.environ.get("TABMAT_B200_CROSS_RUNS"):
+    lib.tm_set_cross_runs_mode(int(os.environ["TABMAT_B200_CROSS_RUNS"]))
 # TABMAT_B200_DENSE_F32_MODE: 0 auto (tcgen05 when eligible) | 1 CUDA-core only | 2 force tcgen05
 if os.environ.get("TABMAT_B200_DENSE_F32_MODE"):
     lib.tm_set_dense_f32_mode(int(os.environ["TABMAT_B200_DENSE_F32_MODE"]))

@@ -401,20 +401,31 @@ class CategoricalMatrix(MatrixBase):
         self.dtype = np.dtype(dtype)
         return self
 
+    def _take_rows_dev(self, index) -> "CategoricalMatrix":
+        """X[index, :] (torch index: slice, bool / int64 CUDA tensor); stays categorical."""
+        sub = self._codes[index]
+        new = CategoricalMatrix.__new__(CategoricalMatrix)
+        new.__dict__.update(self.__dict__)
+        new.__dict__.pop("_perm_cache", None)
+        new.__dict__.pop("_run_sorted", None)
+        new._codes = sub.contiguous()
+        new.shape = (int(sub.numel()), self.shape[1])
+        return new
+
     def __getitem__(self, item):
+        if _dev.is_dev(item):
+            return self._take_rows_dev(item if item.dtype == torch.bool else item.to(torch.int64))
+        if isinstance(item, tuple) and len(item) == 2 and _dev.is_dev(item[0]) \
+                and isinstance(item[1], slice) and item[1] == slice(None, None, None):
+            return self._take_rows_dev(item[0] if item[0].dtype == torch.bool
+                                       else item[0].to(torch.int64))
         row, col = _check_indexer(item)
         if _is_indexer_full_length(self.shape[1], col):
             if isinstance(row, np.ndarray):
                 row = row.ravel()
             from .dense_matrix import _torch_index
 
-            sub = self._codes[_torch_index(row, self._codes.device)]
-            new = CategoricalMatrix.__new__(CategoricalMatrix)
-            new.__dict__.update(self.__dict__)
-            new.__dict__.pop("_perm_cache", None)
-            new._codes = sub.contiguous()
-            new.shape = (int(sub.numel()), self.shape[1])
-            return new
+            return self._take_rows_dev(_torch_index(row, self._codes.device))
         # column subset -> SparseMatrix, like the reference (issue #101 there)
         return self.to_sparse_matrix()[row, col]
 

@@ -4,6 +4,8 @@
 //
 // Reference semantics: categorical.pyx:23-218, split.pyx:32-111,
 // cat_split_helpers-tmpl.cpp:4-151, categorical_matrix.py:825-838 (cat x sparse).
+#include <cstdlib>
+
 #include "tm_common.cuh"
 
 namespace tmb {
@@ -47,10 +49,189 @@ k_cat_hist(const int32_t* __restrict__ codes, const F* __restrict__ w,
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Second-generation histogram kernels.  Differences to k_cat_hist / k_cat_cat above:
+//  * a warp takes UNR groups of 32 CONSECUTIVE rows per visit and issues all their loads before
+//    the first atomic (UNR x 32 x (4 + sizeof F) bytes in flight per warp);
+//  * equal keys in consecutive lanes are summed in registers first (segmented suffix sum over
+//    the maximal runs) and only the first lane of a run touches the table: on row-sorted
+//    matrices (tabmat_b200/row_order.py) a whole warp collapses to one or two atomics, on
+//    random codes the test costs one shuffle + one ballot;
+//  * the shared-memory table is replicated as often as 48 KB allow (thread t adds into replica
+//    t mod copies; a 10-level table ends up private to every thread): shared float atomics are
+//    compare-and-swap loops on sm_100 (ATOMS.CAST.SPIN), so fewer lanes per address means
+//    fewer retries.
+// ---------------------------------------------------------------------------------------
+template <typename F, typename KeyT>
+__device__ __forceinline__ bool warp_run_reduce(KeyT key, F& val, int lane) {
+    const unsigned FULL = 0xffffffffu;
+    const KeyT prev = __shfl_up_sync(FULL, key, 1);
+    const bool head = lane == 0 || prev != key;
+    const unsigned heads = __ballot_sync(FULL, head);
+    if (heads != FULL) {  // some run is longer than one lane
+        const unsigned above = heads & ~((2u << lane) - 1u);  // run heads in lanes > lane
+        const int end = above ? __ffs(above) - 2 : 31;        // last lane of this lane's run
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const F o = __shfl_down_sync(FULL, val, off);
+            if (lane + off <= end) val += o;
+        }
+    }
+    return head;
+}
+
+constexpr int CAT2_THREADS = 1024;
+
+template <typename F, bool USE_SMEM, int UNR>
+__global__ void __launch_bounds__(CAT2_THREADS, 1)
+k_cat_hist2(const int32_t* __restrict__ codes, const F* __restrict__ w,
+            const int32_t* __restrict__ rows, int64_t n_rows, int K, int drop_first,
+            const uint8_t* __restrict__ col_mask, F* __restrict__ out, int copies) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    F* table = reinterpret_cast<F*>(smem_raw);
+    if (USE_SMEM) {
+        for (int i = threadIdx.x; i < K * copies; i += blockDim.x) table[i] = F(0);
+        __syncthreads();
+    }
+    const int lane = threadIdx.x & 31;
+    F* tab = USE_SMEM ? table + (threadIdx.x % copies) * K : out;
+    const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t base = gw * (32 * UNR); base < n_rows; base += nw * (32 * UNR)) {
+        int c[UNR];
+        F v[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const int64_t t = base + u * 32 + lane;
+            c[u] = -1;
+            v[u] = F(0);
+            if (t < n_rows) {
+                const int64_t k = row_at(rows, t);
+                c[u] = codes[k] - drop_first;
+                v[u] = w[k];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            int key = c[u];
+            if (key >= 0 && col_mask && !col_mask[key]) key = -1;
+            if (key < 0) {
+                key = -1;
+                v[u] = F(0);
+            }
+            const bool head = warp_run_reduce<F, int>(key, v[u], lane);
+            if (head && key >= 0) {
+                if (USE_SMEM)
+                    atomicAdd(&tab[key], v[u]);
+                else
+                    red_add(&tab[key], v[u]);
+            }
+        }
+    }
+    if (USE_SMEM) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < K; i += blockDim.x) {
+            F s = F(0);
+            for (int r = 0; r < copies; ++r) s += table[r * K + i];
+            if (s != F(0)) red_add(&out[i], s);
+        }
+    }
+}
+
+template <typename F, bool USE_SMEM, int UNR>
+__global__ void __launch_bounds__(CAT2_THREADS, 1)
+k_cat_cat2(const int32_t* __restrict__ ic, const int32_t* __restrict__ jc,
+           const F* __restrict__ d, const int32_t* __restrict__ rows, int64_t n_rows, int Ki,
+           int Kj, int dfi, int dfj, F* __restrict__ out, int copies) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    F* table = reinterpret_cast<F*>(smem_raw);
+    const int tsz = Ki * Kj;
+    if (USE_SMEM) {
+        for (int i = threadIdx.x; i < tsz * copies; i += blockDim.x) table[i] = F(0);
+        __syncthreads();
+    }
+    const int lane = threadIdx.x & 31;
+    F* tab = USE_SMEM ? table + (threadIdx.x % copies) * tsz : out;
+    const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t base = gw * (32 * UNR); base < n_rows; base += nw * (32 * UNR)) {
+        long long key[UNR];  // Ki * Kj may exceed 2^31 on the global-memory path
+        F v[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const int64_t t = base + u * 32 + lane;
+            key[u] = -1;
+            v[u] = F(0);
+            if (t < n_rows) {
+                const int64_t k = row_at(rows, t);
+                const int i = ic[k] - dfi;
+                const int j = jc[k] - dfj;
+                if (i >= 0 && j >= 0) {
+                    key[u] = (long long)i * Kj + j;
+                    v[u] = d[k];
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const bool head = warp_run_reduce<F, long long>(key[u], v[u], lane);
+            if (head && key[u] >= 0) {
+                if (USE_SMEM)
+                    atomicAdd(&tab[key[u]], v[u]);
+                else
+                    red_add(&tab[key[u]], v[u]);
+            }
+        }
+    }
+    if (USE_SMEM) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < tsz; i += blockDim.x) {
+            F s = F(0);
+            for (int r = 0; r < copies; ++r) s += table[r * tsz + i];
+            if (s != F(0)) red_add(&out[i], s);
+        }
+    }
+}
+
+// TABMAT_B200_CAT_V1=1 selects the first-generation kernels (k_cat_hist / k_cat_cat)
+static bool cat_v1() {
+    static const bool v1 = getenv("TABMAT_B200_CAT_V1") && atoi(getenv("TABMAT_B200_CAT_V1")) == 1;
+    return v1;
+}
+constexpr int64_t CAT2_SMEM_BYTES = 48 * 1024;  // static limit: no opt-in attribute needed
+
+static inline int cat2_copies(int64_t table_bytes) {
+    int64_t c = CAT2_SMEM_BYTES / table_bytes;
+    return (int)(c < 1 ? 1 : (c > CAT2_THREADS ? CAT2_THREADS : c));
+}
+// one fat CTA per SM; fewer when the input is small
+static inline int cat2_grid(int64_t n_rows, int unr) {
+    return grid_for(n_rows, CAT2_THREADS * unr, sm_count());
+}
+
+template <typename F>
+int cat_hist2(const int32_t* codes, const F* w, const int32_t* rows, int64_t n_rows, int64_t K,
+              int drop_first, const uint8_t* col_mask, F* out, cudaStream_t st) {
+    constexpr int UNR = 8;
+    const int64_t tb = (int64_t)sizeof(F) * K;
+    const int g = cat2_grid(n_rows, UNR);
+    if (tb <= CAT_SMEM_TABLE_BYTES) {
+        const int copies = cat2_copies(tb);
+        k_cat_hist2<F, true, UNR><<<g, CAT2_THREADS, (size_t)(tb * copies), st>>>(
+            codes, w, rows, n_rows, (int)K, drop_first, col_mask, out, copies);
+    } else {
+        k_cat_hist2<F, false, UNR><<<g, CAT2_THREADS, 0, st>>>(codes, w, rows, n_rows, (int)K,
+                                                               drop_first, col_mask, out, 1);
+    }
+    TM_LAUNCHED();
+    return 0;
+}
+
 template <typename F>
 int cat_hist(const int32_t* codes, const F* w, const int32_t* rows, int64_t n_rows, int64_t K,
              int drop_first, const uint8_t* col_mask, F* out, cudaStream_t st) {
     if (n_rows <= 0 || K <= 0) return 0;
+    if (!cat_v1()) return cat_hist2<F>(codes, w, rows, n_rows, K, drop_first, col_mask, out, st);
     bool smem = (int64_t)sizeof(F) * K <= CAT_SMEM_TABLE_BYTES;
     // few, fat CTAs when privatised (each flushes K bins); more CTAs otherwise
     int g = grid_for(n_rows, CAT_THREADS * 8, sm_count() * (smem ? 2 : 4));
@@ -257,6 +438,21 @@ int cat_cat_sandwich(const int32_t* ic, const int32_t* jc, int64_t n, int64_t Ki
     if (!rows) n_rows = n;
     if (n_rows <= 0) return 0;
     bool smem = (int64_t)sizeof(F) * Ki * Kj <= CAT_SMEM_TABLE_BYTES;
+    if (!cat_v1()) {
+        constexpr int UNR = 4;
+        const int64_t tb = (int64_t)sizeof(F) * Ki * Kj;
+        const int g2 = cat2_grid(n_rows, UNR);
+        if (smem) {
+            const int copies = cat2_copies(tb);
+            k_cat_cat2<F, true, UNR><<<g2, CAT2_THREADS, (size_t)(tb * copies), st>>>(
+                ic, jc, d, rows, n_rows, (int)Ki, (int)Kj, dfi, dfj, out, copies);
+        } else {
+            k_cat_cat2<F, false, UNR><<<g2, CAT2_THREADS, 0, st>>>(
+                ic, jc, d, rows, n_rows, (int)Ki, (int)Kj, dfi, dfj, out, 1);
+        }
+        TM_LAUNCHED();
+        return 0;
+    }
     int g = grid_for(n_rows, CAT_THREADS * 8, sm_count() * (smem ? 2 : 4));
     if (smem)
         k_cat_cat<F, true><<<g, CAT_THREADS, sizeof(F) * (size_t)(Ki * Kj), st>>>(

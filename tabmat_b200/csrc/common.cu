@@ -180,9 +180,55 @@ int scatter_diag(const F* diag, int64_t na, const int64_t* ri, double* out, int6
     return 0;
 }
 
+// ---- row-order permutation of length-n vectors (tabmat_b200/row_order.py) ---------------
+// GATHER: dst[i] = src[perm[i]]   SCATTER: dst[perm[i]] = src[i] (or += when accumulate)
+template <typename F, bool GATHER>
+__global__ void k_permute(const F* __restrict__ src, const int32_t* __restrict__ perm, int64_t n,
+                          F* __restrict__ dst, int accumulate) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        const int64_t j = perm[i];
+        if (GATHER)
+            dst[i] = accumulate ? dst[i] + src[j] : src[j];
+        else
+            dst[j] = accumulate ? dst[j] + src[i] : src[i];
+    }
+}
+
+template <typename F>
+int permute(const F* src, const int32_t* perm, int64_t n, F* dst, int gather, int accumulate,
+            cudaStream_t st) {
+    if (n <= 0) return 0;
+    int g = grid_for(n, 256 * 4, sm_count() * 16);
+    if (gather)
+        k_permute<F, true><<<g, 256, 0, st>>>(src, perm, n, dst, accumulate);
+    else
+        k_permute<F, false><<<g, 256, 0, st>>>(src, perm, n, dst, accumulate);
+    TM_LAUNCHED();
+    return 0;
+}
+
 }  // namespace tmb
 
 extern "C" {
+
+int tm_permute_gather_f32(const float* src, const int32_t* perm, int64_t n, float* dst,
+                          int accumulate, tm_stream_t stream) {
+    return tmb::permute<float>(src, perm, n, dst, 1, accumulate, tmb::as_stream(stream));
+}
+int tm_permute_gather_f64(const double* src, const int32_t* perm, int64_t n, double* dst,
+                          int accumulate, tm_stream_t stream) {
+    return tmb::permute<double>(src, perm, n, dst, 1, accumulate, tmb::as_stream(stream));
+}
+int tm_permute_scatter_f32(const float* src, const int32_t* perm, int64_t n, float* dst,
+                           int accumulate, tm_stream_t stream) {
+    return tmb::permute<float>(src, perm, n, dst, 0, accumulate, tmb::as_stream(stream));
+}
+int tm_permute_scatter_f64(const double* src, const int32_t* perm, int64_t n, double* dst,
+                           int accumulate, tm_stream_t stream) {
+    return tmb::permute<double>(src, perm, n, dst, 0, accumulate, tmb::as_stream(stream));
+}
 
 int tm_version(void) { return 100; }
 const char* tm_last_error(void) { return tmb::g_err; }

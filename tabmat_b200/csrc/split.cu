@@ -56,8 +56,6 @@ TM_SHIM(cat_cat_sandwich, float, f32)
 TM_SHIM(cat_cat_sandwich, double, f64)
 TM_SHIM(cat_sparse_sandwich, float, f32)
 TM_SHIM(cat_sparse_sandwich, double, f64)
-TM_SHIM(dense_cross_sandwich, float, f32)
-TM_SHIM(dense_cross_sandwich, double, f64)
 TM_SHIM(scatter_block, float, f32)
 TM_SHIM(scatter_block, double, f64)
 TM_SHIM(scatter_diag, float, f32)
@@ -222,8 +220,10 @@ int split_blocks(const tm_block_desc* blk, int nb, int64_t n, const F* d, const 
             int32_t df[8];
             F* outs[8];
             int c = 0;
+            bool runs_hint = false;
             for (int i = 0; i < nb; ++i) {
                 if (blk[i].kind != KIND_CAT || on_tensor[i]) continue;
+                runs_hint |= (blk[i].flags & TM_BLOCK_FLAG_RUNS) != 0;
                 codes[c] = static_cast<const int32_t*>(blk[i].data);
                 K[c] = blk[i].ncols;
                 df[c] = blk[i].drop_first;
@@ -253,9 +253,9 @@ int split_blocks(const tm_block_desc* blk, int nb, int64_t n, const F* d, const 
             }
             if (c > 0 || out_s) {
                 pass_mark(PASS_SCATTER, 0, as_stream(stream));
-                int rc = dense_cross_sandwich(tag, static_cast<const F*>(D.data), n, D.ncols, d, rows,
+                int rc = dense_cross_fused<F>(static_cast<const F*>(D.data), n, D.ncols, d, rows,
                                               n_rows, c, codes, K, df, outs, sdata, sind, sptr, ps,
-                                              out_s, stream);
+                                              out_s, runs_hint ? 1 : 0, as_stream(stream));
                 if (rc) return rc;
                 pass_mark(PASS_SCATTER, 1, as_stream(stream));
             }

@@ -50,6 +50,9 @@ struct Vec<float> {
     static __device__ __forceinline__ T scale(T a, float s) {
         return make_float4(a.x * s, a.y * s, a.z * s, a.w * s);
     }
+    static __device__ __forceinline__ T add(T a, T b) {
+        return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+    }
 };
 template <>
 struct Vec<double> {
@@ -57,6 +60,7 @@ struct Vec<double> {
     static constexpr int W = 2;
     static __device__ __forceinline__ T zero() { return make_double2(0.0, 0.0); }
     static __device__ __forceinline__ T scale(T a, double s) { return make_double2(a.x * s, a.y * s); }
+    static __device__ __forceinline__ T add(T a, T b) { return make_double2(a.x + b.x, a.y + b.y); }
 };
 
 __device__ __forceinline__ const void* shfl_ptr(const void* p, int src) {
@@ -163,6 +167,180 @@ k_dense_cross_fused(const F* __restrict__ X, int64_t n, int P, const F* __restri
                 }
             }
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Run-aggregating variant for row-sorted SplitMatrices (tabmat_b200/row_order.py): a warp walks
+// `chunk` CONSECUTIVE rows; for each categorical block it keeps d[k] * X[k, :] summed in
+// registers for as long as the code does not change and issues ONE vector RED per run (and one
+// at the end of the chunk).  When the rows are stored sorted by (code_a, code_b) the runs of
+// block a span whole chunks and those of block b ~n / (K_a K_b) rows, so the categorical part
+// of the L2-atomic payload (one 512-byte RED per row and block in k_dense_cross_fused) all but
+// disappears; on unsorted rows every run has length 1 and the RED count is unchanged.  The
+// sparse part is the same per-non-zero vector RED as above.
+// Per 32-row group the row ids, weights, codes and CSR row bounds are loaded lane-parallel
+// (coalesced) and broadcast with shuffles.
+// ---------------------------------------------------------------------------------------
+template <typename F, int NV, int NC>
+__global__ void __launch_bounds__(256)
+k_dense_cross_runs(const F* __restrict__ X, int64_t n, int P, const F* __restrict__ d,
+                   const int32_t* __restrict__ rows, int64_t n_rows, int chunk,
+                   const FusedCrossParams prm) {
+    using V = Vec<F>;
+    using VT = typename V::T;
+    constexpr int W = V::W;
+    constexpr int NCA = NC > 0 ? NC : 1;
+    constexpr int U = 2;  // rows whose X loads are in flight together
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int chunks = P / W;
+    const F* csr_data = static_cast<const F*>(prm.csr_data);
+    F* out_sparse = static_cast<F*>(prm.out_sparse);
+    const int64_t lane_off = (int64_t)lane * W;
+
+    F* tab[NCA];
+    const int32_t* codes[NCA];
+    int df[NCA];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        codes[c] = prm.codes[c];
+        df[c] = prm.drop_first[c];
+        tab[c] = static_cast<F*>(prm.tab[c]) +
+                 (int64_t)(warp % prm.copies[c]) * prm.K[c] * (int64_t)P;
+    }
+
+    const int64_t n_chunks = (n_rows + chunk - 1) / chunk;
+    for (int64_t ci = warp; ci < n_chunks; ci += nwarps) {
+        const int64_t t0 = ci * chunk;
+        const int64_t t1 = t0 + chunk < n_rows ? t0 + chunk : n_rows;
+        VT acc[NCA][NV];
+        int cur[NCA];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            cur[c] = -1;
+#pragma unroll
+            for (int v = 0; v < NV; ++v) acc[c][v] = V::zero();
+        }
+        for (int64_t tb = t0; tb < t1; tb += 32) {
+            const int cnt = (int)(t1 - tb < 32 ? t1 - tb : 32);
+            // lane-parallel metadata of the 32-row group
+            int64_t k_l = 0;
+            F d_l = F(0);
+            int code_l[NCA];
+            int e0_l = 0, e1_l = 0;
+#pragma unroll
+            for (int c = 0; c < NC; ++c) code_l[c] = -1;
+            if (lane < cnt) {
+                k_l = row_at(rows, tb + lane);
+                d_l = d[k_l];
+#pragma unroll
+                for (int c = 0; c < NC; ++c) {
+                    const int cc = codes[c][k_l] - df[c];
+                    code_l[c] = cc < 0 ? -1 : cc;
+                }
+                if (out_sparse) {
+                    e0_l = prm.csr_indptr[k_l];
+                    e1_l = prm.csr_indptr[k_l + 1];
+                }
+            }
+            const unsigned klo_l = (unsigned)(unsigned long long)k_l;
+            const unsigned khi_l = (unsigned)((unsigned long long)k_l >> 32);
+            for (int q0 = 0; q0 < cnt; q0 += U) {
+                VT x[U][NV];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int qq = q0 + u < cnt ? q0 + u : cnt - 1;
+                    const unsigned lo = __shfl_sync(FULL, klo_l, qq);
+                    const unsigned hi = __shfl_sync(FULL, khi_l, qq);
+                    const int64_t k = (int64_t)(((unsigned long long)hi << 32) | lo);
+                    const VT* xr = reinterpret_cast<const VT*>(X + k * (int64_t)P);
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) {
+                        const int ch = lane + 32 * v;
+                        x[u][v] = ch < chunks ? __ldg(xr + ch) : V::zero();
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int q = q0 + u;
+                    if (q >= cnt) break;
+                    const F dk = __shfl_sync(FULL, d_l, q);
+                    int code_q[NCA];
+#pragma unroll
+                    for (int c = 0; c < NC; ++c) code_q[c] = __shfl_sync(FULL, code_l[c], q);
+                    const int e0 = __shfl_sync(FULL, e0_l, q);
+                    const int e1 = __shfl_sync(FULL, e1_l, q);
+                    if (dk == F(0)) continue;  // every term of row k is proportional to d[k]
+                    VT y[NV];
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) y[v] = V::scale(x[u][v], dk);
+#pragma unroll
+                    for (int c = 0; c < NC; ++c) {
+                        if (code_q[c] != cur[c]) {  // warp-uniform: a run of block c ends here
+                            if (cur[c] >= 0) {
+                                F* dst = tab[c] + (int64_t)cur[c] * P + lane_off;
+#pragma unroll
+                                for (int v = 0; v < NV; ++v) {
+                                    if (lane + 32 * v < chunks)
+                                        red_add_vec(dst + (int64_t)v * 32 * W, acc[c][v]);
+                                    acc[c][v] = V::zero();
+                                }
+                            }
+                            cur[c] = code_q[c];
+                        }
+                        if (code_q[c] >= 0) {
+#pragma unroll
+                            for (int v = 0; v < NV; ++v) acc[c][v] = V::add(acc[c][v], y[v]);
+                        }
+                    }
+                    for (int eb = e0; eb < e1; eb += 32) {
+                        const int e = eb + lane;
+                        const F* sp_dst = nullptr;
+                        F a = F(0);
+                        if (e < e1) {
+                            sp_dst = out_sparse + (int64_t)prm.csr_indices[e] * P;
+                            a = csr_data[e];
+                        }
+                        const int m = min(32, e1 - eb);
+                        for (int z = 0; z < m; ++z) {
+                            F* dst = const_cast<F*>(static_cast<const F*>(shfl_ptr(sp_dst, z)));
+                            const F aa = __shfl_sync(FULL, a, z);
+#pragma unroll
+                            for (int v = 0; v < NV; ++v) {
+                                if (lane + 32 * v < chunks)
+                                    red_add_vec(dst + lane_off + (int64_t)v * 32 * W,
+                                                V::scale(y[v], aa));
+                            }
+                        }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            if (cur[c] >= 0) {
+                F* dst = tab[c] + (int64_t)cur[c] * P + lane_off;
+#pragma unroll
+                for (int v = 0; v < NV; ++v)
+                    if (lane + 32 * v < chunks) red_add_vec(dst + (int64_t)v * 32 * W, acc[c][v]);
+            }
+        }
+    }
+}
+
+template <typename F, int NV>
+static void launch_cross_runs(int nc, int g, cudaStream_t st, const F* X, int64_t n, int P,
+                              const F* d, const int32_t* rows, int64_t n_rows, int chunk,
+                              const FusedCrossParams& prm) {
+    switch (nc) {
+        case 0: k_dense_cross_runs<F, NV, 0><<<g, 256, 0, st>>>(X, n, P, d, rows, n_rows, chunk, prm); break;
+        case 1: k_dense_cross_runs<F, NV, 1><<<g, 256, 0, st>>>(X, n, P, d, rows, n_rows, chunk, prm); break;
+        case 2: k_dense_cross_runs<F, NV, 2><<<g, 256, 0, st>>>(X, n, P, d, rows, n_rows, chunk, prm); break;
+        case 3: k_dense_cross_runs<F, NV, 3><<<g, 256, 0, st>>>(X, n, P, d, rows, n_rows, chunk, prm); break;
+        default: k_dense_cross_runs<F, NV, 4><<<g, 256, 0, st>>>(X, n, P, d, rows, n_rows, chunk, prm); break;
     }
 }
 
@@ -300,8 +478,10 @@ int dense_cross_fused(const F* X, int64_t n, int64_t p, const F* d, const int32_
                       int64_t n_rows, int n_cat, const int32_t* const* codes, const int64_t* K,
                       const int32_t* drop_first, F* const* out_cat, const F* csr_data,
                       const int32_t* csr_indices, const int32_t* csr_indptr, int64_t p_sparse,
-                      F* out_sparse, cudaStream_t st) {
+                      F* out_sparse, int runs, cudaStream_t st) {
     constexpr int W = Vec<F>::W;
+    if (g_cross_runs_mode == 1) runs = 1;
+    if (g_cross_runs_mode == 2 || n_cat > 4) runs = 0;
     if (n_cat > FC_MAX_CATS) return fail("tm_dense_cross_sandwich: more than 8 categorical blocks");
     if (p <= 0 || p % W != 0 || p > 64 * W)
         return fail("tm_dense_cross_sandwich: unsupported dense width");
@@ -346,7 +526,21 @@ int dense_cross_fused(const F* X, int64_t n, int64_t p, const F* d, const int32_
         prm.out_sparse = out_sparse;
         TM_CUDA(cudaMemsetAsync(out_sparse, 0, sizeof(F) * (size_t)(p_sparse * p), st));
     }
-    if (n_rows > 0) {
+    if (n_rows > 0 && runs) {
+        // consecutive rows per warp and visit: long enough for the run aggregation to pay,
+        // short enough that every warp of the grid gets several chunks
+        const int64_t warps_total = (int64_t)sm_count() * 8 * 8;
+        int64_t chunk = n_rows / (warps_total * 4);
+        chunk = chunk < 32 ? 32 : (chunk > 128 ? 128 : chunk / 32 * 32);
+        const int64_t n_chunks = (n_rows + chunk - 1) / chunk;
+        int g = grid_for(n_chunks * 32, 256, sm_count() * 8);
+        int nv = (int)((p / W + 31) / 32);
+        if (nv == 1)
+            launch_cross_runs<F, 1>(n_cat, g, st, X, n, (int)p, d, rows, n_rows, (int)chunk, prm);
+        else
+            launch_cross_runs<F, 2>(n_cat, g, st, X, n, (int)p, d, rows, n_rows, (int)chunk, prm);
+        TM_LAUNCHED();
+    } else if (n_rows > 0) {
         int g = grid_for(n_rows * 32, 256, sm_count() * 8);
         int nv = (int)((p / W + 31) / 32);
         if (nv == 1)
@@ -366,9 +560,23 @@ int dense_cross_fused(const F* X, int64_t n, int64_t p, const F* d, const int32_
     return 0;
 }
 
+int g_cross_runs_mode = 0;
+
+template int dense_cross_fused<float>(const float*, int64_t, int64_t, const float*, const int32_t*,
+                                      int64_t, int, const int32_t* const*, const int64_t*,
+                                      const int32_t*, float* const*, const float*, const int32_t*,
+                                      const int32_t*, int64_t, float*, int, cudaStream_t);
+template int dense_cross_fused<double>(const double*, int64_t, int64_t, const double*,
+                                       const int32_t*, int64_t, int, const int32_t* const*,
+                                       const int64_t*, const int32_t*, double* const*,
+                                       const double*, const int32_t*, const int32_t*, int64_t,
+                                       double*, int, cudaStream_t);
+
 }  // namespace tmb
 
 extern "C" {
+
+void tm_set_cross_runs_mode(int mode) { tmb::g_cross_runs_mode = mode; }
 
 int tm_dense_cross_sandwich_f32(const float* X, int64_t n, int64_t p, const float* d,
                                 const int32_t* rows, int64_t n_rows, int n_cat,
@@ -379,7 +587,7 @@ int tm_dense_cross_sandwich_f32(const float* X, int64_t n, int64_t p, const floa
                                 tm_stream_t stream) {
     return tmb::dense_cross_fused<float>(X, n, p, d, rows, n_rows, n_cat, codes, K, drop_first,
                                          out_cat, csr_data, csr_indices, csr_indptr, p_sparse,
-                                         out_sparse, tmb::as_stream(stream));
+                                         out_sparse, 0, tmb::as_stream(stream));
 }
 int tm_dense_cross_sandwich_f64(const double* X, int64_t n, int64_t p, const double* d,
                                 const int32_t* rows, int64_t n_rows, int n_cat,
@@ -390,7 +598,7 @@ int tm_dense_cross_sandwich_f64(const double* X, int64_t n, int64_t p, const dou
                                 tm_stream_t stream) {
     return tmb::dense_cross_fused<double>(X, n, p, d, rows, n_rows, n_cat, codes, K, drop_first,
                                           out_cat, csr_data, csr_indices, csr_indptr, p_sparse,
-                                          out_sparse, tmb::as_stream(stream));
+                                          out_sparse, 0, tmb::as_stream(stream));
 }
 
 }  // extern "C"

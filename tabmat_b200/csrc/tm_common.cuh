@@ -130,6 +130,18 @@ int dense_sandwich_tc_f32(const float* X, int64_t n, int64_t p, int c_order, con
                           float* out, cudaStream_t st, const TcOneHot* oh = nullptr,
                           bool share_sm = false);
 bool dense_tc_eligible(int64_t n, int64_t p, int c_order, const void* X);
+
+// ---- fused dense-operand cross blocks (split_fused.cu) ---------------------------------
+// `runs` != 0 selects the run-aggregating kernel (consecutive rows per warp, one RED per run of
+// equal codes) for row-sorted matrices.  g_cross_runs_mode: 0 = as asked, 1 = always, 2 = never.
+template <typename F>
+int dense_cross_fused(const F* X, int64_t n, int64_t p, const F* d, const int32_t* rows,
+                      int64_t n_rows, int n_cat, const int32_t* const* codes, const int64_t* K,
+                      const int32_t* drop_first, F* const* out_cat, const F* csr_data,
+                      const int32_t* csr_indices, const int32_t* csr_indptr, int64_t p_sparse,
+                      F* out_sparse, int runs, cudaStream_t st);
+extern int g_cross_runs_mode;
+constexpr int TM_BLOCK_FLAG_RUNS = 1;  // tm_block_desc.flags bit 0
 extern int g_dense_f32_mode;
 
 }  // namespace tmb

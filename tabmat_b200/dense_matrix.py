@@ -83,7 +83,19 @@ class DenseMatrix(MatrixBase):
             self._terms = self._colnames
 
     # ---- array-like surface ----------------------------------------------------------
+    def _take_rows_dev(self, rows_t: torch.Tensor) -> "DenseMatrix":
+        """X[rows_t, :] for an int64 CUDA index tensor; keeps the C / F storage order."""
+        A = self._array
+        if A.dim() == 2 and not A.is_contiguous() and A.t().is_contiguous():
+            sub = A.t().index_select(1, rows_t).t()
+        else:
+            sub = A.index_select(0, rows_t)
+        return type(self)(sub, column_names=self.column_names, term_names=self.term_names)
+
     def __getitem__(self, key):
+        if isinstance(key, tuple) and len(key) == 2 and _dev.is_dev(key[0]) \
+                and isinstance(key[1], slice) and key[1] == slice(None, None, None):
+            return self._take_rows_dev(key[0].to(torch.int64))
         row, col = _check_indexer(key)
         colnames = np.array(self.column_names, dtype=object)[col].ravel().tolist()
         terms = np.array(self.term_names, dtype=object)[col].ravel().tolist()

@@ -138,11 +138,45 @@ class SparseMatrix(MatrixBase):
         return self._host_csc
 
     def __getitem__(self, key):
+        if isinstance(key, tuple) and len(key) == 2 and _dev.is_dev(key[0]) \
+                and isinstance(key[1], slice) and key[1] == slice(None, None, None):
+            return self._take_rows_dev(key[0])
         row, col = _check_indexer(key)
+        if isinstance(col, slice) and col == slice(None, None, None):
+            # row subset (CV folds, row re-ordering): stays in HBM, no host round trip
+            return self._take_rows_dev(row)
         colnames = np.array(self.column_names, dtype=object)[col].ravel().tolist()
         terms = np.array(self.term_names, dtype=object)[col].ravel().tolist()
         return type(self)(self._array.__getitem__((row, col)), column_names=colnames,
                           term_names=terms)
+
+    def _take_rows_dev(self, row) -> "SparseMatrix":
+        """X[row, :] built on the device from the CSR arrays (``row``: slice, int / bool array
+        or CUDA index tensor; duplicates and any order allowed, like scipy's fancy indexing)."""
+        c = self._csr
+        n = self._shape[0]
+        dev = c.data.device
+        if isinstance(row, slice):
+            rows_t = torch.arange(n, device=dev)[row]
+        elif _dev.is_dev(row):
+            rows_t = row.nonzero().reshape(-1) if row.dtype == torch.bool else row.to(torch.int64)
+        else:
+            a = np.asarray(row).reshape(-1)
+            a = np.flatnonzero(a) if a.dtype == bool else a.astype(np.int64)
+            rows_t = torch.from_numpy(a).to(dev)
+        rows_t = torch.where(rows_t < 0, rows_t + n, rows_t)
+        m = int(rows_t.numel())
+        indptr = c.indptr.to(torch.int64)
+        counts = (indptr[1:] - indptr[:-1])[rows_t]
+        new_indptr = torch.zeros(m + 1, dtype=torch.int64, device=dev)
+        new_indptr[1:] = torch.cumsum(counts, 0)
+        nnz = int(new_indptr[-1].item()) if m else 0
+        new_row = torch.repeat_interleave(torch.arange(m, device=dev), counts, output_size=nnz)
+        src = indptr[rows_t][new_row] + (torch.arange(nnz, device=dev) - new_indptr[:-1][new_row])
+        del new_row, counts
+        return SparseMatrix.from_device_csr(
+            c.data[src], c.indices[src], new_indptr.to(torch.int32), (m, self._shape[1]),
+            column_names=self.column_names, term_names=self.term_names)
 
     @property
     def shape(self):  # type: ignore

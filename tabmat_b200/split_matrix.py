@@ -278,6 +278,8 @@ class SplitMatrix(MatrixBase):
             elif isinstance(mat, CategoricalMatrix):
                 ok = _dev.torch_dtype(mat.dtype) == tdtype
                 dsc.kind, dsc.data, dsc.drop_first = 2, mat._codes.data_ptr(), int(mat.drop_first)
+                # rows stored sorted by this block's codes (row_order.py): run-aggregating kernels
+                dsc.flags = 1 if getattr(mat, "_run_sorted", False) else 0
                 # many levels: too wide for the one-hot tensor path.  Opt-in sorted-gather kernel
                 # (TABMAT_B200_GATHER=1): measured slower than the RED scatter pass on B200
                 # (5.5 ms vs 3.4 ms per block at n = 4e7), kept for machines / shapes where the
@@ -505,6 +507,12 @@ class SplitMatrix(MatrixBase):
         if col == slice(None, None, None):
             if isinstance(row, int):
                 row = [row]
+            if not _dev.is_dev(row) and not isinstance(row, slice):
+                # one host -> device copy of the index for all blocks
+                a = np.asarray(row).reshape(-1)
+                a = np.flatnonzero(a) if a.dtype == bool else a.astype(np.int64)
+                row = torch.from_numpy(a).to(_dev.require_cuda())
+                row = torch.where(row < 0, row + self.shape[0], row)
             return SplitMatrix([mat[row, :] for mat in self.matrices], self.indices)
         raise NotImplementedError(f"Only row indexing is supported. Index passed was {key}.")
 
