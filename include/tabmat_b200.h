@@ -48,8 +48,8 @@ int tm_has_tcgen05(void);
 /* Select the dense f32 sandwich implementation: 0 = auto (tcgen05 when eligible),
  * 1 = force the CUDA-core kernel, 2 = force tcgen05 (error when not eligible). */
 void tm_set_dense_f32_mode(int mode);
-/* Fused dense-operand cross pass of tm_split_sandwich_blocks_*: 0 = run-aggregating kernel only
- * for blocks flagged TM row-sorted (tm_block_desc.flags bit 0), 1 = always, 2 = never. */
+/* Fused dense-operand cross pass (tm_dense_cross_sandwich_*, tm_split_sandwich_blocks_*):
+ * 0 / 1 = run-aggregating kernel (default), 2 = the one-row-per-visit kernel. */
 void tm_set_cross_runs_mode(int mode);
 
 /* ---- dense block (reference: ext/dense.pyx) --------------------------------------- */
@@ -299,6 +299,12 @@ typedef struct tm_block_desc {
     const int32_t* cat_perm;
     const int32_t* cat_segptr;
     int64_t cat_nvalid;
+    /* sparse, optional (NULL = absent): the CSC copy of the block (values, row ids sorted inside
+     * a column, ncols+1 offsets; sparse_matrix.py:133-143 keeps both forms too); enables the
+     * atomics-free categorical x sparse kernel */
+    const void* csc_data;
+    const int32_t* csc_indices;
+    const int32_t* csc_indptr;
 } tm_block_desc;
 
 /* sizeof(tm_block_desc) as compiled into the library (bindings check their struct mirror). */

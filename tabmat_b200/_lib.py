@@ -93,7 +93,8 @@ class BlockDesc(C.Structure):
                 ("flags", C.c_int32), ("ncols", C.c_int64), ("data", C.c_void_p),
                 ("csr_indices", C.c_void_p), ("csr_indptr", C.c_void_p), ("csr_row", C.c_void_p),
                 ("nnz", C.c_int64), ("col_index", C.c_void_p), ("cat_perm", C.c_void_p),
-                ("cat_segptr", C.c_void_p), ("cat_nvalid", C.c_int64)]
+                ("cat_segptr", C.c_void_p), ("cat_nvalid", C.c_int64), ("csc_data", C.c_void_p),
+                ("csc_indices", C.c_void_p), ("csc_indptr", C.c_void_p)]
 
 
 lib.tm_dense_onehot_sandwich_f32.argtypes = [P, I, I, P, P, I, N, P, P, P, P, P, P]

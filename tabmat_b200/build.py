@@ -16,7 +16,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libtabmat_b200.so"
 OBJ = PKG / "_build"
-SOURCES = ["common.cu", "dense.cu", "dense_tc.cu", "sparse.cu", "categorical.cu", "split_fused.cu", "split.cu"]
+SOURCES = ["common.cu", "dense.cu", "dense_tc.cu", "sparse.cu", "categorical.cu", "split_fused.cu", "split_index.cu", "split.cu"]
 HEADERS = [CSRC / "tm_common.cuh", PKG.parent / "include" / "tabmat_b200.h"]
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

@@ -220,10 +220,8 @@ int split_blocks(const tm_block_desc* blk, int nb, int64_t n, const F* d, const 
             int32_t df[8];
             F* outs[8];
             int c = 0;
-            bool runs_hint = false;
             for (int i = 0; i < nb; ++i) {
                 if (blk[i].kind != KIND_CAT || on_tensor[i]) continue;
-                runs_hint |= (blk[i].flags & TM_BLOCK_FLAG_RUNS) != 0;
                 codes[c] = static_cast<const int32_t*>(blk[i].data);
                 K[c] = blk[i].ncols;
                 df[c] = blk[i].drop_first;
@@ -255,7 +253,7 @@ int split_blocks(const tm_block_desc* blk, int nb, int64_t n, const F* d, const 
                 pass_mark(PASS_SCATTER, 0, as_stream(stream));
                 int rc = dense_cross_fused<F>(static_cast<const F*>(D.data), n, D.ncols, d, rows,
                                               n_rows, c, codes, K, df, outs, sdata, sind, sptr, ps,
-                                              out_s, runs_hint ? 1 : 0, as_stream(stream));
+                                              out_s, /*runs=*/1, as_stream(stream));
                 if (rc) return rc;
                 pass_mark(PASS_SCATTER, 1, as_stream(stream));
             }
@@ -272,11 +270,82 @@ int split_blocks(const tm_block_desc* blk, int nb, int64_t n, const F* d, const 
     }
     pass_mark(PASS_INDEX, 0, as_stream(stream));
 
+    // ---- fused index blocks (split_index.cu): all categorical self / pair blocks in one pass
+    // over 32-byte row records, categorical x sparse for all categorical blocks from the CSC
+    // copy without global atomics ----------------------------------------------------------
+    bool cats_fused = false, cat_sparse_fused = false;
+    {
+        int cats[8];
+        int nc = 0;
+        for (int i = 0; i < nb; ++i)
+            if (blk[i].kind == KIND_CAT) {
+                if (nc < 8) cats[nc] = i;
+                ++nc;
+            }
+        int64_t Kc[8];
+        const int32_t* cc[8];
+        int32_t dfc[8], runc[8];
+        bool ok = nc >= 1 && nc <= 7 && n_rows_or_all(rows, n_rows, n) > 0 && n > 0;
+        if (ok) {
+            for (int a = 0; a < nc; ++a) {
+                const tm_block_desc& b = blk[cats[a]];
+                Kc[a] = b.ncols;
+                cc[a] = static_cast<const int32_t*>(b.data);
+                dfc[a] = b.drop_first;
+                runc[a] = (b.flags & TM_BLOCK_FLAG_RUNS) ? 1 : 0;
+            }
+            ok = index_fused_eligible<F>(nc, Kc);
+        }
+        Scratch rec(ok ? index_record_bytes<F>(n) : 0, as_stream(stream));
+        Scratch dmi(ok && rows ? sizeof(F) * (size_t)n : 0, as_stream(stream));
+        if (rec.err != cudaSuccess) return fail_cuda(rec.err, "scratch");
+        if (dmi.err != cudaSuccess) return fail_cuda(dmi.err, "scratch");
+        if (ok) {
+            const F* dd = d;
+            if (rows) {
+                int rc = masked_weights<F>(d, n, rows, n_rows, dmi.as<F>(), as_stream(stream));
+                if (rc) return rc;
+                dd = dmi.as<F>();
+            }
+            int rc = index_pack_records<F>(dd, n, nc, cc, dfc, rec.p, as_stream(stream));
+            if (rc) return rc;
+            F* outs_self[8];
+            F* outs_pair[64];
+            for (int a = 0; a < nc; ++a) {
+                outs_self[a] = ws + self_off[cats[a]];
+                for (int b = a + 1; b < nc; ++b)
+                    outs_pair[a * nc + b] = ws + cross_off[cats[a]][cats[b]];
+            }
+            rc = index_cat_pairs<F>(rec.p, n, nc, Kc, runc, outs_self, outs_pair,
+                                    as_stream(stream));
+            if (rc) return rc;
+            cats_fused = true;
+            if (sparse_idx >= 0 && blk[sparse_idx].csc_indptr && blk[sparse_idx].csc_indices &&
+                blk[sparse_idx].csc_data &&
+                index_cat_sparse_fits<F>(nc, Kc, blk[sparse_idx].ncols)) {
+                const tm_block_desc& S = blk[sparse_idx];
+                F* outs[8];
+                for (int a = 0; a < nc; ++a) {
+                    const int lo = cats[a] < sparse_idx ? cats[a] : sparse_idx;
+                    const int hi = cats[a] < sparse_idx ? sparse_idx : cats[a];
+                    outs[a] = ws + cross_off[lo][hi];
+                }
+                rc = index_cat_sparse<F>(rec.p, nc, Kc, runc, static_cast<const F*>(S.csc_data),
+                                         S.csc_indices, S.csc_indptr, S.ncols, outs,
+                                         as_stream(stream));
+                if (rc) return rc;
+                cat_sparse_fused = true;
+            }
+        }
+    }
+
     for (int i = 0; i < nb; ++i) {
         const tm_block_desc& bi = blk[i];
         F* so = ws + self_off[i];
         int rc = 0;
         if (bi.kind == KIND_DENSE && dense_self_done)
+            rc = 0;
+        else if (bi.kind == KIND_CAT && cats_fused)
             rc = 0;
         else if (bi.kind == KIND_DENSE)
             rc = dense_sandwich(tag, static_cast<const F*>(bi.data), n, bi.ncols, bi.c_order, d,
@@ -294,6 +363,10 @@ int split_blocks(const tm_block_desc* blk, int nb, int64_t n, const F* d, const 
             F* co = ws + cross_off[i][j];
             const bool has_dense = bi.kind == KIND_DENSE || bj.kind == KIND_DENSE;
             if (fuse && has_dense) continue;
+            if (cats_fused && bi.kind == KIND_CAT && bj.kind == KIND_CAT) continue;
+            if (cat_sparse_fused && ((bi.kind == KIND_CAT && bj.kind == KIND_SPARSE) ||
+                                     (bi.kind == KIND_SPARSE && bj.kind == KIND_CAT)))
+                continue;
             // normalise to (a, b) = the kernel's native (rows, cols) orientation
             const tm_block_desc& a = cross_rows_are_j(bi, bj) ? bj : bi;
             const tm_block_desc& b = cross_rows_are_j(bi, bj) ? bi : bj;

@@ -480,6 +480,8 @@ int dense_cross_fused(const F* X, int64_t n, int64_t p, const F* d, const int32_
                       const int32_t* csr_indices, const int32_t* csr_indptr, int64_t p_sparse,
                       F* out_sparse, int runs, cudaStream_t st) {
     constexpr int W = Vec<F>::W;
+    // the run-aggregating kernel is also the faster one on unsorted rows (B200, n = 4e7:
+    // 18.1 ms vs 19.7 ms), so it is the default; mode 2 selects the one-row-per-visit kernel
     if (g_cross_runs_mode == 1) runs = 1;
     if (g_cross_runs_mode == 2 || n_cat > 4) runs = 0;
     if (n_cat > FC_MAX_CATS) return fail("tm_dense_cross_sandwich: more than 8 categorical blocks");
@@ -587,7 +589,7 @@ int tm_dense_cross_sandwich_f32(const float* X, int64_t n, int64_t p, const floa
                                 tm_stream_t stream) {
     return tmb::dense_cross_fused<float>(X, n, p, d, rows, n_rows, n_cat, codes, K, drop_first,
                                          out_cat, csr_data, csr_indices, csr_indptr, p_sparse,
-                                         out_sparse, 0, tmb::as_stream(stream));
+                                         out_sparse, 1, tmb::as_stream(stream));
 }
 int tm_dense_cross_sandwich_f64(const double* X, int64_t n, int64_t p, const double* d,
                                 const int32_t* rows, int64_t n_rows, int n_cat,
@@ -598,7 +600,7 @@ int tm_dense_cross_sandwich_f64(const double* X, int64_t n, int64_t p, const dou
                                 tm_stream_t stream) {
     return tmb::dense_cross_fused<double>(X, n, p, d, rows, n_rows, n_cat, codes, K, drop_first,
                                           out_cat, csr_data, csr_indices, csr_indptr, p_sparse,
-                                          out_sparse, 0, tmb::as_stream(stream));
+                                          out_sparse, 1, tmb::as_stream(stream));
 }
 
 }  // extern "C"

@@ -133,7 +133,8 @@ bool dense_tc_eligible(int64_t n, int64_t p, int c_order, const void* X);
 
 // ---- fused dense-operand cross blocks (split_fused.cu) ---------------------------------
 // `runs` != 0 selects the run-aggregating kernel (consecutive rows per warp, one RED per run of
-// equal codes) for row-sorted matrices.  g_cross_runs_mode: 0 = as asked, 1 = always, 2 = never.
+// equal codes; needs <= 4 categorical blocks).  g_cross_runs_mode: 0 = as asked, 1 = always,
+// 2 = never.
 template <typename F>
 int dense_cross_fused(const F* X, int64_t n, int64_t p, const F* d, const int32_t* rows,
                       int64_t n_rows, int n_cat, const int32_t* const* codes, const int64_t* K,
@@ -143,5 +144,24 @@ int dense_cross_fused(const F* X, int64_t n, int64_t p, const F* d, const int32_
 extern int g_cross_runs_mode;
 constexpr int TM_BLOCK_FLAG_RUNS = 1;  // tm_block_desc.flags bit 0
 extern int g_dense_f32_mode;
+
+// ---- fused index blocks (split_index.cu): categorical self / pair blocks and categorical x
+// sparse from 32-byte row records {d, codes}; see the header comment there ------------------
+template <typename F>
+bool index_fused_eligible(int n_cat, const int64_t* K);
+template <typename F>
+size_t index_record_bytes(int64_t n);
+template <typename F>
+int index_pack_records(const F* d, int64_t n, int n_cat, const int32_t* const* codes,
+                       const int32_t* drop_first, void* rec, cudaStream_t st);
+template <typename F>
+int index_cat_pairs(const void* rec, int64_t n, int n_cat, const int64_t* K, const int32_t* runs,
+                    F* const* outs_self, F* const* outs_pair, cudaStream_t st);
+template <typename F>
+bool index_cat_sparse_fits(int n_cat, const int64_t* K, int64_t p_s);
+template <typename F>
+int index_cat_sparse(const void* rec, int n_cat, const int64_t* K, const int32_t* runs,
+                     const F* csc_data, const int32_t* csc_row, const int32_t* csc_indptr,
+                     int64_t p_s, F* const* outs, cudaStream_t st);
 
 }  // namespace tmb

@@ -275,6 +275,9 @@ class SplitMatrix(MatrixBase):
                 dsc.kind, dsc.data, dsc.nnz = 1, c.data.data_ptr(), c.nnz
                 dsc.csr_indices, dsc.csr_indptr = c.indices.data_ptr(), c.indptr.data_ptr()
                 dsc.csr_row = c.row.data_ptr()
+                cc = mat._csc
+                dsc.csc_data, dsc.csc_indices = cc.data.data_ptr(), cc.indices.data_ptr()
+                dsc.csc_indptr = cc.indptr.data_ptr()
             elif isinstance(mat, CategoricalMatrix):
                 ok = _dev.torch_dtype(mat.dtype) == tdtype
                 dsc.kind, dsc.data, dsc.drop_first = 2, mat._codes.data_ptr(), int(mat.drop_first)
