@@ -343,6 +343,27 @@ int tm_split_sandwich_assemble_f64(const tm_block_desc* blocks, int n_blocks,
                                    const double* workspace, double* out, int64_t ld,
                                    tm_stream_t stream);
 
+/* Two-phase form of the two calls above, for callers that want the result in HOST memory:
+ * `part` 1 = the blocks without a dense operand (categorical / sparse self and cross blocks),
+ * 2 = the blocks with one, 0 = all.  After blocks_part(1) + assemble_part(1) the finished
+ * region of the p x p result can be copied to the host (tm_memcpy2d_to_host on another stream)
+ * while blocks_part(2) still runs; the region is 96 % of the matrix at the benchmark shape. */
+int tm_split_sandwich_blocks_part_f32(const tm_block_desc* blocks, int n_blocks, int64_t n,
+                                      const float* d, const int32_t* rows, int64_t n_rows,
+                                      float* workspace, int part, tm_stream_t stream);
+int tm_split_sandwich_blocks_part_f64(const tm_block_desc* blocks, int n_blocks, int64_t n,
+                                      const double* d, const int32_t* rows, int64_t n_rows,
+                                      double* workspace, int part, tm_stream_t stream);
+int tm_split_sandwich_assemble_part_f32(const tm_block_desc* blocks, int n_blocks,
+                                        const float* workspace, double* out, int64_t ld, int part,
+                                        tm_stream_t stream);
+int tm_split_sandwich_assemble_part_f64(const tm_block_desc* blocks, int n_blocks,
+                                        const double* workspace, double* out, int64_t ld, int part,
+                                        tm_stream_t stream);
+/* cudaMemcpy2DAsync device -> (pinned) host: `height` rows of `width_bytes`, pitches in bytes. */
+int tm_memcpy2d_to_host(void* dst_host, int64_t dst_pitch, const void* src_dev, int64_t src_pitch,
+                        int64_t width_bytes, int64_t height, tm_stream_t stream);
+
 /* ---- row-order permutation (no reference counterpart: the reference keeps the caller's row
  * order; tabmat_b200.RowSortedMatrix stores the rows sorted by the many-level categorical codes
  * and maps the length-n vectors of sandwich / transpose_matvec / matvec through `perm`,

@@ -66,6 +66,8 @@ _SIGS = {
     "tm_dense_cross_sandwich": [P, I, I, P, P, I, N, P, P, P, P, P, P, P, I, P, P],
     "tm_split_sandwich_blocks": [P, N, I, P, P, I, P, P],
     "tm_split_sandwich_assemble": [P, N, P, P, I, P],
+    "tm_split_sandwich_blocks_part": [P, N, I, P, P, I, P, N, P],
+    "tm_split_sandwich_assemble_part": [P, N, P, P, I, N, P],
     "tm_scatter_block": [P, I, I, P, P, P, I, N, P],
     "tm_scatter_diag": [P, I, P, P, I, P],
     "tm_permute_gather": [P, P, I, P, N, P],
@@ -75,7 +77,7 @@ _SIGS = {
 #: every symbol include/tabmat_b200.h declares (checked by tests/test_capi_symbols.py)
 EXPORTED = ["tm_version", "tm_last_error", "tm_launch_count", "tm_reset_launch_count",
             "tm_has_tcgen05", "tm_set_dense_f32_mode", "tm_set_cross_runs_mode",
-            "tm_split_workspace_elems",
+            "tm_split_workspace_elems", "tm_memcpy2d_to_host",
             "tm_dense_onehot_sandwich_f32", "tm_split_profile_enable", "tm_split_profile_read", "tm_sizeof_block_desc"]
 for _name, _args in _SIGS.items():
     for _suf in ("f32", "f64"):
@@ -115,6 +117,8 @@ lib.tm_reset_launch_count.restype = None
 lib.tm_has_tcgen05.restype = c_int
 lib.tm_set_dense_f32_mode.argtypes = [c_int]
 lib.tm_set_dense_f32_mode.restype = None
+lib.tm_memcpy2d_to_host.argtypes = [P, I, P, I, I, I, P]
+lib.tm_memcpy2d_to_host.restype = c_int
 lib.tm_set_cross_runs_mode.argtypes = [c_int]
 lib.tm_set_cross_runs_mode.restype = None
 # TABMAT_B200_CROSS_RUNS: 0 auto (run-aggregating cross kernel for row-sorted matrices) |

@@ -82,6 +82,50 @@ __device__ __forceinline__ bool warp_run_reduce(KeyT key, F& val, int lane) {
 
 constexpr int CAT2_THREADS = 1024;
 
+// N independent shared-memory float adds issued as a batch: all loads, then all compare-and-swaps,
+// then the (rare) retries.  atomicAdd(float*) on shared memory is a compare-and-swap loop on
+// sm_100, and N of them in a row serialise N round trips of ~300 cycles; batched they overlap.
+template <typename F>
+struct CasBits;
+template <>
+struct CasBits<float> {
+    using U = unsigned int;
+    static __device__ __forceinline__ U add(U bits, float v) {
+        return __float_as_uint(__uint_as_float(bits) + v);
+    }
+};
+template <>
+struct CasBits<double> {
+    using U = unsigned long long;
+    static __device__ __forceinline__ U add(U bits, double v) {
+        return (U)__double_as_longlong(__longlong_as_double((long long)bits) + v);
+    }
+};
+template <typename F, int N>
+__device__ __forceinline__ void smem_add_batch(F* tab, const int (&idx)[N], const F (&val)[N]) {
+    using CB = CasBits<F>;
+    using U = typename CB::U;
+    U* t = reinterpret_cast<U*>(tab);
+    U seen[N], want[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+        if (idx[i] >= 0) seen[i] = *reinterpret_cast<volatile U*>(t + idx[i]);
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+        if (idx[i] >= 0) {
+            want[i] = seen[i];
+            seen[i] = atomicCAS(t + idx[i], want[i], CB::add(want[i], val[i]));
+        }
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+        if (idx[i] >= 0) {
+            while (seen[i] != want[i]) {
+                want[i] = seen[i];
+                seen[i] = atomicCAS(t + idx[i], want[i], CB::add(want[i], val[i]));
+            }
+        }
+}
+
 template <typename F, bool USE_SMEM, int UNR>
 __global__ void __launch_bounds__(CAT2_THREADS, 1)
 k_cat_hist2(const int32_t* __restrict__ codes, const F* __restrict__ w,
@@ -97,35 +141,50 @@ k_cat_hist2(const int32_t* __restrict__ codes, const F* __restrict__ w,
     F* tab = USE_SMEM ? table + (threadIdx.x % copies) * K : out;
     const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t base = gw * (32 * UNR); base < n_rows; base += nw * (32 * UNR)) {
-        int c[UNR];
-        F v[UNR];
+    const int64_t step = nw * (32 * UNR);
+    int c[UNR], cn[UNR];
+    F v[UNR], vn[UNR];
+    auto load = [&](int64_t base, int (&cc)[UNR], F (&vv)[UNR]) {
 #pragma unroll
         for (int u = 0; u < UNR; ++u) {
             const int64_t t = base + u * 32 + lane;
-            c[u] = -1;
-            v[u] = F(0);
+            cc[u] = -1;
+            vv[u] = F(0);
             if (t < n_rows) {
                 const int64_t k = row_at(rows, t);
-                c[u] = codes[k] - drop_first;
-                v[u] = w[k];
+                cc[u] = codes[k] - drop_first;
+                vv[u] = w[k];
             }
+        }
+    };
+    int64_t base = gw * (32 * UNR);
+    if (base < n_rows) load(base, c, v);
+    for (; base < n_rows; base += step) {
+        // the next visit's loads are in flight while this visit's atomics run
+        if (base + step < n_rows) load(base + step, cn, vn);
+        int key[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            key[u] = c[u];
+            if (key[u] >= 0 && col_mask && !col_mask[key[u]]) key[u] = -1;
+            if (key[u] < 0) {
+                key[u] = -1;
+                v[u] = F(0);
+            }
+            const bool head = warp_run_reduce<F, int>(key[u], v[u], lane);
+            if (!head) key[u] = -1;
+        }
+        if (USE_SMEM) {
+            smem_add_batch<F, UNR>(tab, key, v);
+        } else {
+#pragma unroll
+            for (int u = 0; u < UNR; ++u)
+                if (key[u] >= 0) red_add(&tab[key[u]], v[u]);
         }
 #pragma unroll
         for (int u = 0; u < UNR; ++u) {
-            int key = c[u];
-            if (key >= 0 && col_mask && !col_mask[key]) key = -1;
-            if (key < 0) {
-                key = -1;
-                v[u] = F(0);
-            }
-            const bool head = warp_run_reduce<F, int>(key, v[u], lane);
-            if (head && key >= 0) {
-                if (USE_SMEM)
-                    atomicAdd(&tab[key], v[u]);
-                else
-                    red_add(&tab[key], v[u]);
-            }
+            c[u] = cn[u];
+            v[u] = vn[u];
         }
     }
     if (USE_SMEM) {
@@ -211,27 +270,37 @@ static inline int cat2_grid(int64_t n_rows, int unr) {
 
 template <typename F>
 int cat_hist2(const int32_t* codes, const F* w, const int32_t* rows, int64_t n_rows, int64_t K,
-              int drop_first, const uint8_t* col_mask, F* out, cudaStream_t st) {
-    constexpr int UNR = 8;
+              int drop_first, const uint8_t* col_mask, F* out, bool overwrite, cudaStream_t st) {
+    constexpr int UNR = sizeof(F) == 4 ? 6 : 3;  // x2 with the prefetched visit; 64 registers
     const int64_t tb = (int64_t)sizeof(F) * K;
     const int g = cat2_grid(n_rows, UNR);
     if (tb <= CAT_SMEM_TABLE_BYTES) {
         const int copies = cat2_copies(tb);
+        if (overwrite) TM_CUDA(cudaMemsetAsync(out, 0, sizeof(F) * (size_t)K, st));
         k_cat_hist2<F, true, UNR><<<g, CAT2_THREADS, (size_t)(tb * copies), st>>>(
             codes, w, rows, n_rows, (int)K, drop_first, col_mask, out, copies);
     } else {
-        k_cat_hist2<F, false, UNR><<<g, CAT2_THREADS, 0, st>>>(codes, w, rows, n_rows, (int)K,
-                                                               drop_first, col_mask, out, 1);
+        if (overwrite) TM_CUDA(cudaMemsetAsync(out, 0, sizeof(F) * (size_t)K, st));
+        k_cat_hist2<F, false, UNR><<<g, CAT2_THREADS, 0, st>>>(
+            codes, w, rows, n_rows, (int)K, drop_first, col_mask, out, 1);
     }
     TM_LAUNCHED();
     return 0;
 }
 
+// `overwrite`: out = histogram (cat sandwich) instead of out += histogram (transpose_matvec)
 template <typename F>
 int cat_hist(const int32_t* codes, const F* w, const int32_t* rows, int64_t n_rows, int64_t K,
-             int drop_first, const uint8_t* col_mask, F* out, cudaStream_t st) {
-    if (n_rows <= 0 || K <= 0) return 0;
-    if (!cat_v1()) return cat_hist2<F>(codes, w, rows, n_rows, K, drop_first, col_mask, out, st);
+             int drop_first, const uint8_t* col_mask, F* out, cudaStream_t st,
+             bool overwrite = false) {
+    if (K <= 0) return 0;
+    if (n_rows <= 0) {
+        if (overwrite) TM_CUDA(cudaMemsetAsync(out, 0, sizeof(F) * (size_t)K, st));
+        return 0;
+    }
+    if (!cat_v1())
+        return cat_hist2<F>(codes, w, rows, n_rows, K, drop_first, col_mask, out, overwrite, st);
+    if (overwrite) TM_CUDA(cudaMemsetAsync(out, 0, sizeof(F) * (size_t)K, st));
     bool smem = (int64_t)sizeof(F) * K <= CAT_SMEM_TABLE_BYTES;
     // few, fat CTAs when privatised (each flushes K bins); more CTAs otherwise
     int g = grid_for(n_rows, CAT_THREADS * 8, sm_count() * (smem ? 2 : 4));
@@ -389,9 +458,8 @@ template <typename F>
 int cat_sandwich(const int32_t* codes, int64_t n, const F* d, const int32_t* rows, int64_t n_rows,
                  int64_t K, int drop_first, F* out, cudaStream_t st) {
     if (K <= 0) return 0;
-    TM_CUDA(cudaMemsetAsync(out, 0, sizeof(F) * (size_t)K, st));
     if (!rows) n_rows = n;
-    return cat_hist<F>(codes, d, rows, n_rows, K, drop_first, nullptr, out, st);
+    return cat_hist<F>(codes, d, rows, n_rows, K, drop_first, nullptr, out, st, /*overwrite=*/true);
 }
 
 template <typename F>

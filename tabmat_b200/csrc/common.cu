@@ -6,6 +6,18 @@ namespace tmb {
 thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
 
+void keep_pool_memory() {
+    static thread_local int done_dev = -1;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev == done_dev) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    done_dev = dev;
+}
+
 int sm_count() {
     static int cached = 0;
     if (cached) return cached;

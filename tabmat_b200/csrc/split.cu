@@ -61,23 +61,37 @@ TM_SHIM(scatter_block, double, f64)
 TM_SHIM(scatter_diag, float, f32)
 TM_SHIM(scatter_diag, double, f64)
 
-// one non-blocking side stream + two events per thread (created lazily, never destroyed);
+// two non-blocking side streams + four events per thread (created lazily, never destroyed);
 // TABMAT_B200_SIDE_STREAM=0 keeps everything on the caller's stream
-static cudaStream_t side_stream() {
-    static thread_local cudaStream_t st = nullptr;
+static cudaStream_t side_stream(int which) {
+    static thread_local cudaStream_t st[2] = {nullptr, nullptr};
     static thread_local bool tried = false;
     if (!tried) {
         tried = true;
         const char* e = getenv("TABMAT_B200_SIDE_STREAM");
-        if (!(e && atoi(e) == 0)) cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+        if (!(e && atoi(e) == 0)) {
+            cudaStreamCreateWithFlags(&st[0], cudaStreamNonBlocking);
+            cudaStreamCreateWithFlags(&st[1], cudaStreamNonBlocking);
+        }
     }
-    return st;
+    return st[which];
 }
 static cudaEvent_t side_event(int i) {
-    static thread_local cudaEvent_t ev[2] = {nullptr, nullptr};
+    static thread_local cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     if (!ev[i]) cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming);
     return ev[i];
 }
+// pass schedule of tm_split_sandwich_blocks_* (see the switch at the end of split_blocks)
+static int initial_sched() {
+    const char* e = getenv("TABMAT_B200_SCHED");
+    if (e) return atoi(e);
+    const char* sf = getenv("TABMAT_B200_SCATTER_FIRST");
+    // default: serial.  Measured on B200 (n = 4e7): every schedule lands within 1 ms of the
+    // sum of the three passes timed alone (28.0-29.9 ms) — they all queue on the same L2
+    // slices — so the overlap buys nothing and the serial order keeps the pass timings clean.
+    return (sf && atoi(sf) == 1) ? 1 : 3;
+}
+static int g_split_sched = initial_sched();
 
 // ---- optional pass-level timing (tm_split_profile_*): CUDA events on the stream each pass
 // is launched on; bench.py reads them after synchronising ---------------------------------
@@ -101,7 +115,7 @@ static inline int64_t n_rows_or_all(const int32_t* rows, int64_t n_rows, int64_t
 
 template <typename F>
 int split_blocks(const tm_block_desc* blk, int nb, int64_t n, const F* d, const int32_t* rows,
-                 int64_t n_rows, F* ws, tm_stream_t stream) {
+                 int64_t n_rows, F* ws, tm_stream_t stream, int part = 0) {
     F* tag = nullptr;
     if (nb <= 0) return 0;
     if (nb > 64) return fail("tm_split_sandwich: more than 64 blocks");
@@ -132,294 +146,373 @@ int split_blocks(const tm_block_desc* blk, int nb, int64_t n, const F* d, const 
         fuse = D.c_order && D.ncols % W == 0 && D.ncols <= 64 * W &&
                (reinterpret_cast<uintptr_t>(D.data) & 15) == 0;
     }
-    // HBM / tensor bound work (the tcgen05 pass and the sorted-gather passes) goes to a side
-    // stream so that it overlaps with the L2-atomic-bound scatter passes on the caller's stream
+    // ---- plan of the tensor pass (host-side decisions only; launched by tensor_pass below) ----
+    // tcgen05 weighted SYRK of the dense block + one-hot MMAs for the few-level categoricals,
+    // and the opt-in sorted-gather kernel for categorical blocks that carry a row permutation.
     std::vector<char> on_tensor(nb, 0);
     bool dense_self_done = false;
-    bool side_used = false;
+    bool tc_ok = false, any_gather = false;
+    TcOneHot oh;
+    oh.ncat = 0;
+    int64_t oh_slots = 0;
+    int oh_which[8];
+    const int64_t nr_all = n_rows_or_all(rows, n_rows, n);
     if (fuse && sizeof(F) == 4) {
         const tm_block_desc& D = blk[dense_idx];
         static const bool onehot_off =
             getenv("TABMAT_B200_ONEHOT") && atoi(getenv("TABMAT_B200_ONEHOT")) == 0;
         static const bool gather_off =
             getenv("TABMAT_B200_GATHER") && atoi(getenv("TABMAT_B200_GATHER")) == 0;
-        const bool tc_ok = g_dense_f32_mode != 1 && n_rows_or_all(rows, n_rows, n) > 0 &&
-                           dense_tc_eligible(n, D.ncols, 1, D.data);
-        bool any_gather = false;
-        for (int i = 0; i < nb; ++i)
-            any_gather |= !gather_off && blk[i].kind == KIND_CAT && blk[i].cat_perm != nullptr;
-        if (tc_ok || any_gather) {
-            cudaStream_t st = side_stream() ? side_stream() : as_stream(stream);
-            side_used = st != as_stream(stream);
-            if (side_used) {
-                TM_CUDA(cudaEventRecord(side_event(0), as_stream(stream)));
-                TM_CUDA(cudaStreamWaitEvent(st, side_event(0), 0));
-            }
-            pass_mark(PASS_TENSOR, 0, st);
-            Scratch dm(rows ? sizeof(float) * (size_t)n : 0, st);
-            if (dm.err != cudaSuccess) return fail_cuda(dm.err, "scratch");
-            const float* dd = reinterpret_cast<const float*>(d);
-            if (rows) {
-                int rc = masked_weights<float>(dd, n, rows, n_rows, dm.as<float>(), st);
-                if (rc) return rc;
-                dd = dm.as<float>();
-            }
-            if (tc_ok) {
-                TcOneHot oh;
-                oh.ncat = 0;
-                int64_t slots = 0;
-                int which[8];
-                for (int i = 0; i < nb && oh.ncat < 8 && D.ncols <= 128 && !onehot_off; ++i) {
-                    if (blk[i].kind != KIND_CAT || blk[i].ncols <= 0 || blk[i].ncols > 256) continue;
-                    if (slots + blk[i].ncols > TC_ONEHOT_MAX_SLOTS) continue;
-                    which[oh.ncat] = i;
-                    oh.codes[oh.ncat] = static_cast<const int32_t*>(blk[i].data);
-                    oh.K[oh.ncat] = (int)blk[i].ncols;
-                    oh.drop_first[oh.ncat] = blk[i].drop_first;
-                    slots += blk[i].ncols;
-                    ++oh.ncat;
-                }
-                Scratch tmp(sizeof(float) * (size_t)(slots > 0 ? slots : 1) * (size_t)D.ncols, st);
-                if (tmp.err != cudaSuccess) return fail_cuda(tmp.err, "scratch");
-                oh.out = tmp.as<float>();
-                int rc = dense_sandwich_tc_f32(static_cast<const float*>(D.data), n, D.ncols, 1, dd,
-                                               reinterpret_cast<float*>(ws + self_off[dense_idx]),
-                                               st, oh.ncat ? &oh : nullptr, /*share_sm=*/side_used);
-                if (rc) return rc;
-                dense_self_done = true;
-                int64_t o = 0;
-                for (int c = 0; c < oh.ncat; ++c) {
-                    int i = which[c];
-                    int a = i < dense_idx ? i : dense_idx, b = i < dense_idx ? dense_idx : i;
-                    TM_CUDA(cudaMemcpyAsync(ws + cross_off[a][b], tmp.as<float>() + o * D.ncols,
-                                            sizeof(float) * (size_t)(blk[i].ncols * D.ncols),
-                                            cudaMemcpyDeviceToDevice, st));
-                    o += blk[i].ncols;
-                    on_tensor[i] = 1;
-                }
-            }
-            // categorical blocks with a sorted row permutation: HBM-bound gather
-            for (int i = 0; i < nb && !gather_off; ++i) {
-                if (blk[i].kind != KIND_CAT || on_tensor[i] || !blk[i].cat_perm) continue;
-                int a = i < dense_idx ? i : dense_idx, b = i < dense_idx ? dense_idx : i;
-                int rc = cat_dense_gather_f32(static_cast<const float*>(D.data), D.ncols, dd,
-                                              blk[i].cat_perm, blk[i].cat_segptr, blk[i].ncols,
-                                              blk[i].cat_nvalid,
-                                              reinterpret_cast<float*>(ws + cross_off[a][b]), st);
-                if (rc) return rc;
+        tc_ok = g_dense_f32_mode != 1 && nr_all > 0 && dense_tc_eligible(n, D.ncols, 1, D.data);
+        if (tc_ok) {
+            for (int i = 0; i < nb && oh.ncat < 8 && D.ncols <= 128 && !onehot_off; ++i) {
+                if (blk[i].kind != KIND_CAT || blk[i].ncols <= 0 || blk[i].ncols > 256) continue;
+                if (oh_slots + blk[i].ncols > TC_ONEHOT_MAX_SLOTS) continue;
+                oh_which[oh.ncat] = i;
+                oh.codes[oh.ncat] = static_cast<const int32_t*>(blk[i].data);
+                oh.K[oh.ncat] = (int)blk[i].ncols;
+                oh.drop_first[oh.ncat] = blk[i].drop_first;
+                oh_slots += blk[i].ncols;
                 on_tensor[i] = 1;
+                ++oh.ncat;
             }
-            pass_mark(PASS_TENSOR, 1, st);
+            dense_self_done = true;
         }
+        for (int i = 0; i < nb && !gather_off; ++i)
+            if (blk[i].kind == KIND_CAT && !on_tensor[i] && blk[i].cat_perm) {
+                on_tensor[i] = 2;
+                any_gather = true;
+            }
     }
-    auto scatter_pass = [&]() -> int {
-    if (fuse) {
-            const tm_block_desc& D = blk[dense_idx];
-            const int32_t* codes[8];
-            int64_t K[8];
-            int32_t df[8];
-            F* outs[8];
-            int c = 0;
-            for (int i = 0; i < nb; ++i) {
-                if (blk[i].kind != KIND_CAT || on_tensor[i]) continue;
-                codes[c] = static_cast<const int32_t*>(blk[i].data);
-                K[c] = blk[i].ncols;
-                df[c] = blk[i].drop_first;
+    const bool have_tensor = tc_ok || any_gather;
+
+    auto tensor_pass = [&](cudaStream_t st, bool share_sm) -> int {
+        if (!have_tensor) return 0;
+        const tm_block_desc& D = blk[dense_idx];
+        pass_mark(PASS_TENSOR, 0, st);
+        Scratch dm(rows ? sizeof(float) * (size_t)n : 0, st);
+        if (dm.err != cudaSuccess) return fail_cuda(dm.err, "scratch");
+        const float* dd = reinterpret_cast<const float*>(d);
+        if (rows) {
+            int rc = masked_weights<float>(dd, n, rows, n_rows, dm.as<float>(), st);
+            if (rc) return rc;
+            dd = dm.as<float>();
+        }
+        if (tc_ok) {
+            Scratch tmp(sizeof(float) * (size_t)(oh_slots > 0 ? oh_slots : 1) * (size_t)D.ncols, st);
+            if (tmp.err != cudaSuccess) return fail_cuda(tmp.err, "scratch");
+            oh.out = tmp.as<float>();
+            int rc = dense_sandwich_tc_f32(static_cast<const float*>(D.data), n, D.ncols, 1, dd,
+                                           reinterpret_cast<float*>(ws + self_off[dense_idx]), st,
+                                           oh.ncat ? &oh : nullptr, share_sm);
+            if (rc) return rc;
+            int64_t o = 0;
+            for (int c = 0; c < oh.ncat; ++c) {
+                int i = oh_which[c];
                 int a = i < dense_idx ? i : dense_idx, b = i < dense_idx ? dense_idx : i;
-                outs[c] = ws + cross_off[a][b];
-                ++c;
+                TM_CUDA(cudaMemcpyAsync(ws + cross_off[a][b], tmp.as<float>() + o * D.ncols,
+                                        sizeof(float) * (size_t)(blk[i].ncols * D.ncols),
+                                        cudaMemcpyDeviceToDevice, st));
+                o += blk[i].ncols;
             }
-            const F* sdata = nullptr;
-            const int32_t *sind = nullptr, *sptr = nullptr;
-            int64_t ps = 0;
-            F* out_s = nullptr;
-            if (sparse_idx >= 0 && blk[sparse_idx].nnz > 0) {
-                const tm_block_desc& S = blk[sparse_idx];
-                sdata = static_cast<const F*>(S.data);
-                sind = S.csr_indices;
-                sptr = S.csr_indptr;
-                ps = S.ncols;
-                int a = sparse_idx < dense_idx ? sparse_idx : dense_idx;
-                int b = sparse_idx < dense_idx ? dense_idx : sparse_idx;
-                out_s = ws + cross_off[a][b];
-            } else if (sparse_idx >= 0) {
-                int a = sparse_idx < dense_idx ? sparse_idx : dense_idx;
-                int b = sparse_idx < dense_idx ? dense_idx : sparse_idx;
-                TM_CUDA(cudaMemsetAsync(ws + cross_off[a][b], 0,
-                                        sizeof(F) * (size_t)(blk[a].ncols * blk[b].ncols),
-                                        as_stream(stream)));
-            }
-            if (c > 0 || out_s) {
-                pass_mark(PASS_SCATTER, 0, as_stream(stream));
-                int rc = dense_cross_fused<F>(static_cast<const F*>(D.data), n, D.ncols, d, rows,
-                                              n_rows, c, codes, K, df, outs, sdata, sind, sptr, ps,
-                                              out_s, /*runs=*/1, as_stream(stream));
-                if (rc) return rc;
-                pass_mark(PASS_SCATTER, 1, as_stream(stream));
-            }
+        }
+        // categorical blocks with a sorted row permutation: HBM-bound gather
+        for (int i = 0; i < nb; ++i) {
+            if (on_tensor[i] != 2) continue;
+            int a = i < dense_idx ? i : dense_idx, b = i < dense_idx ? dense_idx : i;
+            int rc = cat_dense_gather_f32(static_cast<const float*>(D.data), D.ncols, dd,
+                                          blk[i].cat_perm, blk[i].cat_segptr, blk[i].ncols,
+                                          blk[i].cat_nvalid,
+                                          reinterpret_cast<float*>(ws + cross_off[a][b]), st);
+            if (rc) return rc;
+        }
+        pass_mark(PASS_TENSOR, 1, st);
+        return 0;
+    };
+
+    // ---- scatter pass: dense x many-level categoricals + dense x sparse (vector REDs) -------
+    auto scatter_pass = [&](cudaStream_t st) -> int {
+        if (!fuse) return 0;
+        const tm_block_desc& D = blk[dense_idx];
+        const int32_t* codes[8];
+        int64_t K[8];
+        int32_t df[8];
+        F* outs[8];
+        int c = 0;
+        for (int i = 0; i < nb; ++i) {
+            if (blk[i].kind != KIND_CAT || on_tensor[i]) continue;
+            codes[c] = static_cast<const int32_t*>(blk[i].data);
+            K[c] = blk[i].ncols;
+            df[c] = blk[i].drop_first;
+            int a = i < dense_idx ? i : dense_idx, b = i < dense_idx ? dense_idx : i;
+            outs[c] = ws + cross_off[a][b];
+            ++c;
+        }
+        const F* sdata = nullptr;
+        const int32_t *sind = nullptr, *sptr = nullptr;
+        int64_t ps = 0;
+        F* out_s = nullptr;
+        if (sparse_idx >= 0 && blk[sparse_idx].nnz > 0) {
+            const tm_block_desc& S = blk[sparse_idx];
+            sdata = static_cast<const F*>(S.data);
+            sind = S.csr_indices;
+            sptr = S.csr_indptr;
+            ps = S.ncols;
+            int a = sparse_idx < dense_idx ? sparse_idx : dense_idx;
+            int b = sparse_idx < dense_idx ? dense_idx : sparse_idx;
+            out_s = ws + cross_off[a][b];
+        } else if (sparse_idx >= 0) {
+            int a = sparse_idx < dense_idx ? sparse_idx : dense_idx;
+            int b = sparse_idx < dense_idx ? dense_idx : sparse_idx;
+            TM_CUDA(cudaMemsetAsync(ws + cross_off[a][b], 0,
+                                    sizeof(F) * (size_t)(blk[a].ncols * blk[b].ncols), st));
+        }
+        if (c > 0 || out_s) {
+            pass_mark(PASS_SCATTER, 0, st);
+            int rc = dense_cross_fused<F>(static_cast<const F*>(D.data), n, D.ncols, d, rows,
+                                          n_rows, c, codes, K, df, outs, sdata, sind, sptr, ps,
+                                          out_s, /*runs=*/1, st);
+            if (rc) return rc;
+            pass_mark(PASS_SCATTER, 1, st);
         }
         return 0;
     };
-    // order of the two passes on the caller's stream (the index pass first lets the lighter
-    // kernels share the SMs with the tensor pass; TABMAT_B200_SCATTER_FIRST=1 restores the other)
-    static const bool scatter_first =
-        getenv("TABMAT_B200_SCATTER_FIRST") && atoi(getenv("TABMAT_B200_SCATTER_FIRST")) == 1;
-    if (scatter_first) {
-        int rc = scatter_pass();
-        if (rc) return rc;
-    }
-    pass_mark(PASS_INDEX, 0, as_stream(stream));
 
-    // ---- fused index blocks (split_index.cu): all categorical self / pair blocks in one pass
-    // over 32-byte row records, categorical x sparse for all categorical blocks from the CSC
-    // copy without global atomics ----------------------------------------------------------
-    bool cats_fused = false, cat_sparse_fused = false;
-    {
-        int cats[8];
-        int nc = 0;
-        for (int i = 0; i < nb; ++i)
-            if (blk[i].kind == KIND_CAT) {
-                if (nc < 8) cats[nc] = i;
-                ++nc;
-            }
-        int64_t Kc[8];
-        const int32_t* cc[8];
-        int32_t dfc[8], runc[8];
-        bool ok = nc >= 1 && nc <= 7 && n_rows_or_all(rows, n_rows, n) > 0 && n > 0;
-        if (ok) {
-            for (int a = 0; a < nc; ++a) {
-                const tm_block_desc& b = blk[cats[a]];
-                Kc[a] = b.ncols;
-                cc[a] = static_cast<const int32_t*>(b.data);
-                dfc[a] = b.drop_first;
-                runc[a] = (b.flags & TM_BLOCK_FLAG_RUNS) ? 1 : 0;
-            }
-            ok = index_fused_eligible<F>(nc, Kc);
-        }
-        Scratch rec(ok ? index_record_bytes<F>(n) : 0, as_stream(stream));
-        Scratch dmi(ok && rows ? sizeof(F) * (size_t)n : 0, as_stream(stream));
-        if (rec.err != cudaSuccess) return fail_cuda(rec.err, "scratch");
-        if (dmi.err != cudaSuccess) return fail_cuda(dmi.err, "scratch");
-        if (ok) {
-            const F* dd = d;
-            if (rows) {
-                int rc = masked_weights<F>(d, n, rows, n_rows, dmi.as<F>(), as_stream(stream));
-                if (rc) return rc;
-                dd = dmi.as<F>();
-            }
-            int rc = index_pack_records<F>(dd, n, nc, cc, dfc, rec.p, as_stream(stream));
-            if (rc) return rc;
-            F* outs_self[8];
-            F* outs_pair[64];
-            for (int a = 0; a < nc; ++a) {
-                outs_self[a] = ws + self_off[cats[a]];
-                for (int b = a + 1; b < nc; ++b)
-                    outs_pair[a * nc + b] = ws + cross_off[cats[a]][cats[b]];
-            }
-            rc = index_cat_pairs<F>(rec.p, n, nc, Kc, runc, outs_self, outs_pair,
-                                    as_stream(stream));
-            if (rc) return rc;
-            cats_fused = true;
-            if (sparse_idx >= 0 && blk[sparse_idx].csc_indptr && blk[sparse_idx].csc_indices &&
-                blk[sparse_idx].csc_data &&
-                index_cat_sparse_fits<F>(nc, Kc, blk[sparse_idx].ncols)) {
-                const tm_block_desc& S = blk[sparse_idx];
-                F* outs[8];
-                for (int a = 0; a < nc; ++a) {
-                    const int lo = cats[a] < sparse_idx ? cats[a] : sparse_idx;
-                    const int hi = cats[a] < sparse_idx ? sparse_idx : cats[a];
-                    outs[a] = ws + cross_off[lo][hi];
+    // ---- index pass: every block without the dense operand -----------------------------------
+    auto index_pass = [&](cudaStream_t st) -> int {
+        tm_stream_t stream = reinterpret_cast<tm_stream_t>(st);
+        pass_mark(PASS_INDEX, 0, st);
+        // fused index blocks (split_index.cu): all categorical self / pair blocks in one pass
+        // over 32-byte row records, categorical x sparse for all categorical blocks from the
+        // CSC copy without global atomics
+        bool cats_fused = false, cat_sparse_fused = false;
+        {
+            int cats[8];
+            int nc = 0;
+            for (int i = 0; i < nb; ++i)
+                if (blk[i].kind == KIND_CAT) {
+                    if (nc < 8) cats[nc] = i;
+                    ++nc;
                 }
-                rc = index_cat_sparse<F>(rec.p, nc, Kc, runc, static_cast<const F*>(S.csc_data),
-                                         S.csc_indices, S.csc_indptr, S.ncols, outs,
-                                         as_stream(stream));
+            int64_t Kc[8];
+            const int32_t* cc[8];
+            int32_t dfc[8], runc[8];
+            bool ok = nc >= 1 && nc <= 7 && nr_all > 0 && n > 0;
+            if (ok) {
+                for (int a = 0; a < nc; ++a) {
+                    const tm_block_desc& b = blk[cats[a]];
+                    Kc[a] = b.ncols;
+                    cc[a] = static_cast<const int32_t*>(b.data);
+                    dfc[a] = b.drop_first;
+                    runc[a] = (b.flags & TM_BLOCK_FLAG_RUNS) ? 1 : 0;
+                }
+                ok = index_fused_eligible<F>(nc, Kc);
+            }
+            Scratch rec(ok ? index_record_bytes<F>(n) : 0, st);
+            Scratch dmi(ok && rows ? sizeof(F) * (size_t)n : 0, st);
+            if (rec.err != cudaSuccess) return fail_cuda(rec.err, "scratch");
+            if (dmi.err != cudaSuccess) return fail_cuda(dmi.err, "scratch");
+            if (ok) {
+                const F* dd = d;
+                if (rows) {
+                    int rc = masked_weights<F>(d, n, rows, n_rows, dmi.as<F>(), st);
+                    if (rc) return rc;
+                    dd = dmi.as<F>();
+                }
+                int rc = index_pack_records<F>(dd, n, nc, cc, dfc, rec.p, st);
                 if (rc) return rc;
-                cat_sparse_fused = true;
+                F* outs_self[8];
+                F* outs_pair[64];
+                for (int a = 0; a < nc; ++a) {
+                    outs_self[a] = ws + self_off[cats[a]];
+                    for (int b = a + 1; b < nc; ++b)
+                        outs_pair[a * nc + b] = ws + cross_off[cats[a]][cats[b]];
+                }
+                rc = index_cat_pairs<F>(rec.p, n, nc, Kc, runc, outs_self, outs_pair, st);
+                if (rc) return rc;
+                cats_fused = true;
+                if (sparse_idx >= 0 && blk[sparse_idx].csc_indptr &&
+                    blk[sparse_idx].csc_indices && blk[sparse_idx].csc_data &&
+                    index_cat_sparse_fits<F>(nc, Kc, blk[sparse_idx].ncols)) {
+                    const tm_block_desc& S = blk[sparse_idx];
+                    F* outs[8];
+                    for (int a = 0; a < nc; ++a) {
+                        const int lo = cats[a] < sparse_idx ? cats[a] : sparse_idx;
+                        const int hi = cats[a] < sparse_idx ? sparse_idx : cats[a];
+                        outs[a] = ws + cross_off[lo][hi];
+                    }
+                    rc = index_cat_sparse<F>(rec.p, nc, Kc, runc,
+                                             static_cast<const F*>(S.csc_data), S.csc_indices,
+                                             S.csc_indptr, S.ncols, outs, st);
+                    if (rc) return rc;
+                    cat_sparse_fused = true;
+                }
             }
         }
-    }
-
-    for (int i = 0; i < nb; ++i) {
-        const tm_block_desc& bi = blk[i];
-        F* so = ws + self_off[i];
-        int rc = 0;
-        if (bi.kind == KIND_DENSE && dense_self_done)
-            rc = 0;
-        else if (bi.kind == KIND_CAT && cats_fused)
-            rc = 0;
-        else if (bi.kind == KIND_DENSE)
-            rc = dense_sandwich(tag, static_cast<const F*>(bi.data), n, bi.ncols, bi.c_order, d,
-                                rows, n_rows, (const int32_t*)nullptr, (int64_t)0, so, stream);
-        else if (bi.kind == KIND_SPARSE)
-            rc = sparse_sandwich(tag, static_cast<const F*>(bi.data), bi.csr_indices, bi.csr_indptr,
-                                 bi.csr_row, n, bi.ncols, bi.nnz, d, rows, n_rows,
-                                 (const int32_t*)nullptr, (int64_t)0, so, stream);
-        else
-            rc = cat_sandwich(tag, static_cast<const int32_t*>(bi.data), n, d, rows, n_rows,
-                              bi.ncols, (int)bi.drop_first, so, stream);
-        if (rc) return rc;
-        for (int j = i + 1; j < nb; ++j) {
-            const tm_block_desc& bj = blk[j];
-            F* co = ws + cross_off[i][j];
-            const bool has_dense = bi.kind == KIND_DENSE || bj.kind == KIND_DENSE;
-            if (fuse && has_dense) continue;
-            if (cats_fused && bi.kind == KIND_CAT && bj.kind == KIND_CAT) continue;
-            if (cat_sparse_fused && ((bi.kind == KIND_CAT && bj.kind == KIND_SPARSE) ||
-                                     (bi.kind == KIND_SPARSE && bj.kind == KIND_CAT)))
-                continue;
-            // normalise to (a, b) = the kernel's native (rows, cols) orientation
-            const tm_block_desc& a = cross_rows_are_j(bi, bj) ? bj : bi;
-            const tm_block_desc& b = cross_rows_are_j(bi, bj) ? bi : bj;
-            if (a.kind == KIND_SPARSE && b.kind == KIND_DENSE)
-                rc = csr_dense_sandwich(tag, static_cast<const F*>(a.data), a.csr_indices,
-                                        a.csr_indptr, n, a.ncols, static_cast<const F*>(b.data),
-                                        b.ncols, (int)b.c_order, d, rows, n_rows,
-                                        (const int32_t*)nullptr, (int64_t)0,
-                                        (const int32_t*)nullptr, (int64_t)0, co, stream);
-            else if (a.kind == KIND_CAT && b.kind == KIND_DENSE)
-                rc = cat_dense_sandwich(tag, static_cast<const int32_t*>(a.data), n, a.ncols,
-                                        (int)a.drop_first, d, static_cast<const F*>(b.data),
-                                        b.ncols, (int)b.c_order, rows, n_rows,
-                                        (const int32_t*)nullptr, (int64_t)0, co, stream);
-            else if (a.kind == KIND_CAT && b.kind == KIND_SPARSE)
-                rc = cat_sparse_sandwich(tag, static_cast<const int32_t*>(a.data), n, a.ncols,
-                                         (int)a.drop_first, d, static_cast<const F*>(b.data),
-                                         b.csr_indices, b.csr_indptr, b.csr_row, b.ncols, b.nnz,
-                                         rows, n_rows, (const int32_t*)nullptr, (int64_t)0, co,
-                                         stream);
-            else if (a.kind == KIND_CAT && b.kind == KIND_CAT)
-                rc = cat_cat_sandwich(tag, static_cast<const int32_t*>(a.data),
-                                      static_cast<const int32_t*>(b.data), n, a.ncols, b.ncols,
-                                      (int)a.drop_first, (int)b.drop_first, d, rows, n_rows, co,
-                                      stream);
+        for (int i = 0; i < nb; ++i) {
+            const tm_block_desc& bi = blk[i];
+            F* so = ws + self_off[i];
+            int rc = 0;
+            if (bi.kind == KIND_DENSE && dense_self_done)
+                rc = 0;
+            else if (bi.kind == KIND_CAT && cats_fused)
+                rc = 0;
+            else if (bi.kind == KIND_DENSE)
+                rc = dense_sandwich(tag, static_cast<const F*>(bi.data), n, bi.ncols, bi.c_order, d,
+                                    rows, n_rows, (const int32_t*)nullptr, (int64_t)0, so, stream);
+            else if (bi.kind == KIND_SPARSE)
+                rc = sparse_sandwich(tag, static_cast<const F*>(bi.data), bi.csr_indices,
+                                     bi.csr_indptr, bi.csr_row, n, bi.ncols, bi.nnz, d, rows,
+                                     n_rows, (const int32_t*)nullptr, (int64_t)0, so, stream);
             else
-                return fail("tm_split_sandwich: unsupported block pair (two dense or two sparse "
-                            "blocks must be merged first, split_matrix.py:85-141)");
+                rc = cat_sandwich(tag, static_cast<const int32_t*>(bi.data), n, d, rows, n_rows,
+                                  bi.ncols, (int)bi.drop_first, so, stream);
             if (rc) return rc;
+            for (int j = i + 1; j < nb; ++j) {
+                const tm_block_desc& bj = blk[j];
+                F* co = ws + cross_off[i][j];
+                const bool has_dense = bi.kind == KIND_DENSE || bj.kind == KIND_DENSE;
+                if (fuse && has_dense) continue;
+                if (cats_fused && bi.kind == KIND_CAT && bj.kind == KIND_CAT) continue;
+                if (cat_sparse_fused && ((bi.kind == KIND_CAT && bj.kind == KIND_SPARSE) ||
+                                         (bi.kind == KIND_SPARSE && bj.kind == KIND_CAT)))
+                    continue;
+                // normalise to (a, b) = the kernel's native (rows, cols) orientation
+                const tm_block_desc& a = cross_rows_are_j(bi, bj) ? bj : bi;
+                const tm_block_desc& b = cross_rows_are_j(bi, bj) ? bi : bj;
+                if (a.kind == KIND_SPARSE && b.kind == KIND_DENSE)
+                    rc = csr_dense_sandwich(tag, static_cast<const F*>(a.data), a.csr_indices,
+                                            a.csr_indptr, n, a.ncols,
+                                            static_cast<const F*>(b.data), b.ncols,
+                                            (int)b.c_order, d, rows, n_rows,
+                                            (const int32_t*)nullptr, (int64_t)0,
+                                            (const int32_t*)nullptr, (int64_t)0, co, stream);
+                else if (a.kind == KIND_CAT && b.kind == KIND_DENSE)
+                    rc = cat_dense_sandwich(tag, static_cast<const int32_t*>(a.data), n, a.ncols,
+                                            (int)a.drop_first, d, static_cast<const F*>(b.data),
+                                            b.ncols, (int)b.c_order, rows, n_rows,
+                                            (const int32_t*)nullptr, (int64_t)0, co, stream);
+                else if (a.kind == KIND_CAT && b.kind == KIND_SPARSE)
+                    rc = cat_sparse_sandwich(tag, static_cast<const int32_t*>(a.data), n, a.ncols,
+                                             (int)a.drop_first, d, static_cast<const F*>(b.data),
+                                             b.csr_indices, b.csr_indptr, b.csr_row, b.ncols,
+                                             b.nnz, rows, n_rows, (const int32_t*)nullptr,
+                                             (int64_t)0, co, stream);
+                else if (a.kind == KIND_CAT && b.kind == KIND_CAT)
+                    rc = cat_cat_sandwich(tag, static_cast<const int32_t*>(a.data),
+                                          static_cast<const int32_t*>(b.data), n, a.ncols, b.ncols,
+                                          (int)a.drop_first, (int)b.drop_first, d, rows, n_rows,
+                                          co, stream);
+                else
+                    return fail("tm_split_sandwich: unsupported block pair (two dense or two "
+                                "sparse blocks must be merged first, split_matrix.py:85-141)");
+                if (rc) return rc;
+            }
         }
+        pass_mark(PASS_INDEX, 1, st);
+        return 0;
+    };
+
+    // ---- schedule ---------------------------------------------------------------------------
+    // T = tensor pass (HBM / tensor pipe), I = index pass (shared-memory atomics + gathers),
+    // S = scatter pass (L2 atomic units).  TABMAT_B200_SCHED:
+    //   0  side: T   | main: I, S        1  side: T | main: S, I
+    //   2  side1: T  | side2: I | main: S (everything concurrent)
+    //   3  main: T, I, S (serial)        4  main: T, then side: I | main: S
+    //   5  main: I, then side: T | main: S
+    // TABMAT_B200_SIDE_STREAM=0 forces 3.
+    cudaStream_t main_st = as_stream(stream);
+    cudaStream_t s1 = side_stream(0), s2 = side_stream(1);
+    int sched = g_split_sched;
+    if (!s1 || !s2) sched = 3;
+    if (part == 1) {  // only the blocks without the dense operand (tm_split_sandwich_blocks_part)
+        int rc1 = index_pass(main_st);
+        if (g_profile && rc1 == 0) ++g_prof_calls;
+        return rc1;
     }
-    pass_mark(PASS_INDEX, 1, as_stream(stream));
-    if (!scatter_first) {
-        int rc = scatter_pass();
-        if (rc) return rc;
+    if (part == 2) {  // the rest
+        int rc2 = tensor_pass(main_st, false);
+        if (rc2 == 0) rc2 = scatter_pass(main_st);
+        return rc2;
     }
+    if (!have_tensor && (sched == 0 || sched == 1)) sched = 3;
+    auto fork_to = [&](cudaStream_t st, int ev) -> int {
+        TM_CUDA(cudaEventRecord(side_event(ev), main_st));
+        TM_CUDA(cudaStreamWaitEvent(st, side_event(ev), 0));
+        return 0;
+    };
+    auto join_from = [&](cudaStream_t st, int ev) -> int {
+        TM_CUDA(cudaEventRecord(side_event(ev), st));
+        TM_CUDA(cudaStreamWaitEvent(main_st, side_event(ev), 0));
+        return 0;
+    };
+    int rc = 0;
+#define TM_RC(x)          \
+    do {                  \
+        rc = (x);         \
+        if (rc) return rc; \
+    } while (0)
+    switch (sched) {
+        case 0:
+        case 1:
+            TM_RC(fork_to(s1, 0));
+            TM_RC(tensor_pass(s1, true));
+            if (sched == 0) {
+                TM_RC(index_pass(main_st));
+                TM_RC(scatter_pass(main_st));
+            } else {
+                TM_RC(scatter_pass(main_st));
+                TM_RC(index_pass(main_st));
+            }
+            TM_RC(join_from(s1, 1));
+            break;
+        case 2:
+            TM_RC(fork_to(s1, 0));
+            TM_RC(fork_to(s2, 2));
+            TM_RC(tensor_pass(s1, true));
+            TM_RC(scatter_pass(main_st));
+            TM_RC(index_pass(s2));
+            TM_RC(join_from(s1, 1));
+            TM_RC(join_from(s2, 3));
+            break;
+        case 4:
+            TM_RC(tensor_pass(main_st, false));
+            TM_RC(fork_to(s2, 2));
+            TM_RC(scatter_pass(main_st));
+            TM_RC(index_pass(s2));
+            TM_RC(join_from(s2, 3));
+            break;
+        case 5:
+            TM_RC(index_pass(main_st));
+            TM_RC(fork_to(s1, 0));
+            TM_RC(tensor_pass(s1, true));
+            TM_RC(scatter_pass(main_st));
+            TM_RC(join_from(s1, 1));
+            break;
+        default:
+            TM_RC(tensor_pass(main_st, false));
+            TM_RC(index_pass(main_st));
+            TM_RC(scatter_pass(main_st));
+            break;
+    }
+#undef TM_RC
     if (g_profile) ++g_prof_calls;
-    if (side_used) {  // join the side stream
-        TM_CUDA(cudaEventRecord(side_event(1), side_stream()));
-        TM_CUDA(cudaStreamWaitEvent(as_stream(stream), side_event(1), 0));
-    }
     return 0;
 }
 
 template <typename F>
 int split_assemble(const tm_block_desc* blk, int nb, const F* ws, double* out, int64_t ld,
-                   tm_stream_t stream) {
+                   tm_stream_t stream, int part = 0) {
     F* tag = nullptr;
     int64_t off = 0;
+    // part 1: blocks without a dense operand; part 2: blocks with one; 0: all
+    auto wanted = [part](bool has_dense) { return part == 0 || (part == 2) == has_dense; };
     for (int i = 0; i < nb; ++i) {
         const tm_block_desc& bi = blk[i];
-        int rc;
-        if (bi.kind == KIND_CAT)
+        int rc = 0;
+        if (!wanted(bi.kind == KIND_DENSE))
+            rc = 0;
+        else if (bi.kind == KIND_CAT)
             rc = scatter_diag(tag, ws + off, bi.ncols, bi.col_index, out, ld, stream);
         else
             rc = scatter_block(tag, ws + off, bi.ncols, bi.ncols, bi.col_index, bi.col_index, out,
@@ -430,9 +523,11 @@ int split_assemble(const tm_block_desc* blk, int nb, const F* ws, double* out, i
             const tm_block_desc& bj = blk[j];
             const tm_block_desc& a = cross_rows_are_j(bi, bj) ? bj : bi;
             const tm_block_desc& b = cross_rows_are_j(bi, bj) ? bi : bj;
-            rc = scatter_block(tag, ws + off, a.ncols, b.ncols, a.col_index, b.col_index, out, ld,
-                               1, stream);
-            if (rc) return rc;
+            if (wanted(bi.kind == KIND_DENSE || bj.kind == KIND_DENSE)) {
+                rc = scatter_block(tag, ws + off, a.ncols, b.ncols, a.col_index, b.col_index, out,
+                                   ld, 1, stream);
+                if (rc) return rc;
+            }
             off += bi.ncols * bj.ncols;
         }
     }
@@ -487,6 +582,34 @@ int tm_split_sandwich_blocks_f64(const tm_block_desc* blocks, int n_blocks, int6
                                  const double* d, const int32_t* rows, int64_t n_rows,
                                  double* workspace, tm_stream_t stream) {
     return tmb::split_blocks<double>(blocks, n_blocks, n, d, rows, n_rows, workspace, stream);
+}
+int tm_split_sandwich_blocks_part_f32(const tm_block_desc* blocks, int n_blocks, int64_t n,
+                                      const float* d, const int32_t* rows, int64_t n_rows,
+                                      float* workspace, int part, tm_stream_t stream) {
+    return tmb::split_blocks<float>(blocks, n_blocks, n, d, rows, n_rows, workspace, stream, part);
+}
+int tm_split_sandwich_blocks_part_f64(const tm_block_desc* blocks, int n_blocks, int64_t n,
+                                      const double* d, const int32_t* rows, int64_t n_rows,
+                                      double* workspace, int part, tm_stream_t stream) {
+    return tmb::split_blocks<double>(blocks, n_blocks, n, d, rows, n_rows, workspace, stream, part);
+}
+int tm_split_sandwich_assemble_part_f32(const tm_block_desc* blocks, int n_blocks,
+                                        const float* workspace, double* out, int64_t ld, int part,
+                                        tm_stream_t stream) {
+    return tmb::split_assemble<float>(blocks, n_blocks, workspace, out, ld, stream, part);
+}
+int tm_split_sandwich_assemble_part_f64(const tm_block_desc* blocks, int n_blocks,
+                                        const double* workspace, double* out, int64_t ld, int part,
+                                        tm_stream_t stream) {
+    return tmb::split_assemble<double>(blocks, n_blocks, workspace, out, ld, stream, part);
+}
+int tm_memcpy2d_to_host(void* dst_host, int64_t dst_pitch, const void* src_dev, int64_t src_pitch,
+                        int64_t width_bytes, int64_t height, tm_stream_t stream) {
+    if (width_bytes <= 0 || height <= 0) return 0;
+    TM_CUDA(cudaMemcpy2DAsync(dst_host, (size_t)dst_pitch, src_dev, (size_t)src_pitch,
+                              (size_t)width_bytes, (size_t)height, cudaMemcpyDeviceToHost,
+                              tmb::as_stream(stream)));
+    return 0;
 }
 int tm_split_sandwich_assemble_f32(const tm_block_desc* blocks, int n_blocks,
                                    const float* workspace, double* out, int64_t ld,

@@ -18,10 +18,10 @@
 //                      (tiny ones replicated per lane), the rest are L2 REDs with runs of equal
 //                      keys pre-summed in registers (row-sorted storage, row_order.py);
 //   k_cat_sparse_csc   categorical x sparse for ALL categorical blocks, driven by the CSC copy
-//                      of the sparse block: a CTA owns G columns j, walks their non-zeros,
-//                      gathers the 32-byte record of each row and accumulates
-//                      d[k] * A[k, j] into shared-memory columns out_i[:, j]; the columns are
-//                      then stored once — no global atomics at all, HBM-bound
+//                      of the sparse block: a CTA owns a column j, walks its non-zeros, gathers
+//                      the 32-byte record of each row and adds d[k] * A[k, j] to out_i[c_i, j]:
+//                      per-thread private shared-memory tables for blocks with few levels,
+//                      shared-memory atomics for mid-sized ones, L2 REDs for the widest
 //                      (8 bytes per non-zero streamed + one sector per non-zero gathered).
 #include <cstdlib>
 
@@ -124,20 +124,27 @@ struct PairParams {
     int smem_elems;                  // total shared-memory elements
 };
 
+constexpr int PAIRS_THREADS = 1024;
+
 template <typename F>
 __device__ __forceinline__ void pair_add(const PairParams& prm, F* smem, int t, long long key,
                                          long long size, F val, bool runs, int lane) {
     bool head = true;
     if (runs) head = run_reduce<F, long long>(key, val, lane);
     if (!head || key < 0) return;
-    if (prm.smem_off[t] >= 0)
-        atomicAdd(smem + prm.smem_off[t] + (long long)(lane % prm.copies[t]) * size + key, val);
-    else
+    if (prm.smem_off[t] >= 0) {
+        if (prm.copies[t] == PAIRS_THREADS)  // one replica per thread, [key][thread]: plain RMW
+            smem[prm.smem_off[t] + key * PAIRS_THREADS + threadIdx.x] += val;
+        else
+            atomicAdd(smem + prm.smem_off[t] + (long long)(lane % prm.copies[t]) * size + key,
+                      val);
+    } else {
         red_add(static_cast<F*>(prm.out[t]) + key, val);
+    }
 }
 
 template <typename F, int NC, int U>
-__global__ void __launch_bounds__(1024, 1)
+__global__ void __launch_bounds__(PAIRS_THREADS, 1)
 k_cat_pairs(const RowRec<F>* __restrict__ rec, int64_t n, const PairParams prm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     F* smem = reinterpret_cast<F*>(smem_raw);
@@ -193,6 +200,16 @@ k_cat_pairs(const RowRec<F>* __restrict__ rec, int64_t n, const PairParams prm) 
             const int size = jj == i ? prm.K[i] : prm.K[i] * prm.K[jj];  // fits: it is in smem
             const F* tab = smem + prm.smem_off[tt];
             F* out = static_cast<F*>(prm.out[tt]);
+            if (prm.copies[tt] == PAIRS_THREADS) {  // per-thread replicas: a warp sums one entry
+                for (int e = threadIdx.x >> 5; e < size; e += PAIRS_THREADS / 32) {
+                    F sum = F(0);
+                    for (int q = lane; q < PAIRS_THREADS; q += 32) sum += tab[e * PAIRS_THREADS + q];
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+                    if (lane == 0 && sum != F(0)) red_add(out + e, sum);
+                }
+                continue;
+            }
             for (int e = threadIdx.x; e < size; e += blockDim.x) {
                 F s = F(0);
                 for (int c = 0; c < prm.copies[tt]; ++c) s += tab[(long long)c * size + e];
@@ -205,83 +222,108 @@ k_cat_pairs(const RowRec<F>* __restrict__ rec, int64_t n, const PairParams prm) 
 // ---------------------------------------------------------------------------------------
 // categorical x sparse for all categorical blocks, CSC-driven, shared-memory column tables
 // ---------------------------------------------------------------------------------------
+enum { CS_PRIV = 0, CS_ATOM = 1, CS_L2 = 2 };
+constexpr int CS_THREADS = 256;
+
 struct CatSparseParams {
     int K[IDX_MAX_CATS];
-    int rep[IDX_MAX_CATS];       // replicas of block c's column table (lane % rep)
-    int off[IDX_MAX_CATS + 1];   // element offset of block c's table inside one column slot
+    int mode[IDX_MAX_CATS];      // CS_PRIV: one replica per thread, [level][thread], plain RMW
+                                 // CS_ATOM: shared-memory atomics, `rep` replicas (lane % rep)
+                                 // CS_L2:   scalar REDs straight into out (zero-filled by the host)
+    int rep[IDX_MAX_CATS];
+    int off[IDX_MAX_CATS];       // element offset of block c's shared-memory table
     int runs[IDX_MAX_CATS];
-    void* out[IDX_MAX_CATS];     // K_c x p_s, row-major; every element is written
-    int G;                       // sparse columns per CTA visit
+    void* out[IDX_MAX_CATS];     // K_c x p_s, row-major
+    int smem_elems;
 };
 
+// One CTA per sparse column j (grid-stride).  Per non-zero (k, j, a): val = d[k] * a from the
+// row record, then per categorical block one update of out_c[code_c[k], j]:
+//   few levels   -> the thread's private column table in shared memory (no atomics),
+//   some levels  -> shared-memory atomics on a replicated column table,
+//   many levels  -> scalar L2 RED (the addresses of one column are p_s * 4 bytes apart, so they
+//                   never share a sector; runs of equal codes are pre-summed when the rows are
+//                   stored sorted by that block).
+// Shared-memory and L2 atomics run at about the same aggregate rate on B200, so splitting the
+// blocks between them roughly doubles the update rate.
 template <typename F, int NC, int U>
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(CS_THREADS)
 k_cat_sparse_csc(const F* __restrict__ data, const int32_t* __restrict__ row_idx,
                  const int32_t* __restrict__ indptr, int p_s,
                  const RowRec<F>* __restrict__ rec, const CatSparseParams prm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     F* smem = reinterpret_cast<F*>(smem_raw);
-    const int slot = prm.off[NC];  // elements per column slot
-    const int G = prm.G;
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
-    const int nwib = blockDim.x >> 5;
-    const int n_groups = (p_s + G - 1) / G;
-    for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
-        const int j0 = grp * G;
-        const int gc = min(G, p_s - j0);
-        for (int i = threadIdx.x; i < gc * slot; i += blockDim.x) smem[i] = F(0);
+    constexpr int NW = CS_THREADS / 32;
+    for (int j = blockIdx.x; j < p_s; j += gridDim.x) {
+        for (int i = threadIdx.x; i < prm.smem_elems; i += CS_THREADS) smem[i] = F(0);
         __syncthreads();
-        for (int g = 0; g < gc; ++g) {
-            F* tab = smem + g * slot;
-            const int e0 = indptr[j0 + g], e1 = indptr[j0 + g + 1];
-            for (int eb = e0 + wib * (32 * U); eb < e1; eb += nwib * (32 * U)) {
-                RowRec<F> r[U];
-                F a[U];
+        const int e0 = indptr[j], e1 = indptr[j + 1];
+        for (int eb = e0 + wib * (32 * U); eb < e1; eb += NW * (32 * U)) {
+            RowRec<F> r[U];
+            F a[U];
 #pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int e = eb + u * 32 + lane;
-                    a[u] = F(0);
-                    int k = -1;
-                    if (e < e1) {
-                        k = row_idx[e];
-                        a[u] = data[e];
-                    }
-                    if (k >= 0) {
-                        r[u] = load_rec<F>(rec, k);
-                    } else {
-                        r[u].d = F(0);
-#pragma unroll
-                        for (int c = 0; c < rec_max_cats<F>(); ++c) r[u].c[c] = -1;
-                    }
+            for (int u = 0; u < U; ++u) {
+                const int e = eb + u * 32 + lane;
+                a[u] = F(0);
+                int k = -1;
+                if (e < e1) {
+                    k = row_idx[e];
+                    a[u] = data[e];
                 }
+                if (k >= 0) {
+                    r[u] = load_rec<F>(rec, k);
+                } else {
+                    r[u].d = F(0);
 #pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const F val0 = r[u].d * a[u];
+                    for (int c = 0; c < rec_max_cats<F>(); ++c) r[u].c[c] = -1;
+                }
+            }
 #pragma unroll
-                    for (int c = 0; c < NC; ++c) {
-                        int key = r[u].c[c];
-                        F val = val0;
-                        bool head = true;
-                        if (prm.runs[c]) head = run_reduce<F, int>(key, val, lane);
-                        if (head && key >= 0)
-                            atomicAdd(tab + prm.off[c] + (lane % prm.rep[c]) * prm.K[c] + key, val);
+            for (int u = 0; u < U; ++u) {
+                const F val0 = r[u].d * a[u];
+#pragma unroll
+                for (int c = 0; c < NC; ++c) {
+                    int key = r[u].c[c];
+                    if (prm.mode[c] == CS_PRIV) {
+                        if (key >= 0) smem[prm.off[c] + key * CS_THREADS + threadIdx.x] += val0;
+                        continue;
                     }
+                    F val = val0;
+                    bool head = true;
+                    if (prm.runs[c]) head = run_reduce<F, int>(key, val, lane);
+                    if (!head || key < 0) continue;
+                    if (prm.mode[c] == CS_ATOM)
+                        atomicAdd(smem + prm.off[c] + (lane % prm.rep[c]) * prm.K[c] + key, val);
+                    else
+                        red_add(static_cast<F*>(prm.out[c]) + (int64_t)key * p_s + j, val);
                 }
             }
         }
         __syncthreads();
-        // store the gc columns: g fastest so that a thread group writes consecutive j
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
             F* out = static_cast<F*>(prm.out[c]);
-            const int Kc = prm.K[c], rep = prm.rep[c];
-            for (int i = threadIdx.x; i < Kc * gc; i += blockDim.x) {
-                const int lvl = i / gc, g = i - lvl * gc;
-                const F* tab = smem + g * slot + prm.off[c] + lvl;
-                F s = F(0);
-                for (int q = 0; q < rep; ++q) s += tab[q * Kc];
-                out[(int64_t)lvl * p_s + j0 + g] = s;
+            const int Kc = prm.K[c];
+            if (prm.mode[c] == CS_PRIV) {
+                for (int lvl = wib; lvl < Kc; lvl += NW) {
+                    const F* tab = smem + prm.off[c] + lvl * CS_THREADS;
+                    F sum = F(0);
+#pragma unroll
+                    for (int q = 0; q < NW; ++q) sum += tab[q * 32 + lane];
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+                    if (lane == 0) out[(int64_t)lvl * p_s + j] = sum;
+                }
+            } else if (prm.mode[c] == CS_ATOM) {
+                const int rep = prm.rep[c];
+                for (int lvl = threadIdx.x; lvl < Kc; lvl += CS_THREADS) {
+                    const F* tab = smem + prm.off[c] + lvl;
+                    F sum = F(0);
+                    for (int q = 0; q < rep; ++q) sum += tab[q * Kc];
+                    out[(int64_t)lvl * p_s + j] = sum;
+                }
             }
         }
         __syncthreads();
@@ -349,7 +391,7 @@ template int index_pack_records<float>(const float*, int64_t, int, const int32_t
 template int index_pack_records<double>(const double*, int64_t, int, const int32_t* const*,
                                         const int32_t*, void*, cudaStream_t);
 
-constexpr size_t IDX_SMEM_BUDGET = 160 * 1024;
+constexpr size_t IDX_SMEM_BUDGET = 200 * 1024;
 
 template <typename F, int NC>
 static int launch_pairs(const RowRec<F>* rec, int64_t n, const PairParams& prm, cudaStream_t st) {
@@ -362,8 +404,8 @@ static int launch_pairs(const RowRec<F>* rec, int64_t n, const PairParams& prm, 
                                      (int)IDX_SMEM_BUDGET));
         attr_set = true;
     }
-    const int g = grid_for(n, 1024 * U, sm_count());
-    k_cat_pairs<F, NC, U><<<g, 1024, smem, st>>>(rec, n, prm);
+    const int g = grid_for(n, PAIRS_THREADS * U, sm_count());
+    k_cat_pairs<F, NC, U><<<g, PAIRS_THREADS, smem, st>>>(rec, n, prm);
     TM_LAUNCHED();
     return 0;
 }
@@ -395,23 +437,46 @@ int index_cat_pairs(const void* rec_v, int64_t n, int n_cat, const int64_t* K, c
         TM_CUDA(cudaMemsetAsync(prm.out[t], 0, sizeof(F) * (size_t)size[t], st));
     }
     if (n <= 0) return 0;
-    // shared-memory placement: smallest tables first, tiny ones replicated (up to one per lane)
-    size_t budget = IDX_SMEM_BUDGET / sizeof(F);
+    // Placement (rates measured with tools/micro/atom_bench.cu on B200): shared-memory float
+    // atomics — compare-and-swap loops — sustain 2-3 lane-adds per clock and SM on tables of
+    // >= 500 entries (6-9e11 adds/s in aggregate; 0.2 on 10 entries, hence the replicas), scalar
+    // L2 REDs 1.9e11/s on tables of >= 200k entries and collapse below ~50k (5.6e10/s on 10k,
+    // 7e9/s on 500).  So: smallest tables first into shared memory until it is full, only the
+    // rest as L2 REDs; a self block with <= 16 levels gets one replica per thread and plain
+    // read-modify-write (6 lane-adds per clock and SM).
+    const size_t budget = IDX_SMEM_BUDGET / sizeof(F);
     size_t used = 0;
     bool placed[IDX_MAX_TARGETS] = {false};
+    // first pass: which tables fit at all (one replica each), smallest first
+    int order[IDX_MAX_TARGETS];
+    int n_fit = 0;
+    size_t need = 0;
     for (;;) {
         int best = -1;
         for (int t = 0; t < nt; ++t)
             if (!placed[t] && (best < 0 || size[t] < size[best])) best = t;
         if (best < 0) break;
         placed[best] = true;
-        if ((size_t)size[best] > budget - used) continue;  // larger ones will not fit either
+        if (need + (size_t)size[best] > budget) continue;
+        need += (size_t)size[best];
+        order[n_fit++] = best;
+    }
+    // second pass: what is left goes to replicas of the tiny tables
+    size_t spare = budget - need;
+    for (int q = 0; q < n_fit; ++q) {
+        const int t = order[q];
+        const size_t sz = (size_t)size[t];
         int copies = 1;
-        while (copies < 32 && (int64_t)size[best] * copies * 2 <= 1024) copies *= 2;
-        if ((size_t)size[best] * copies > budget - used) copies = 1;
-        prm.smem_off[best] = (int)used;
-        prm.copies[best] = copies;
-        used += (size_t)size[best] * copies;
+        if (t < n_cat && sz <= 16 && sz * (PAIRS_THREADS - 1) <= spare / 2) {
+            copies = PAIRS_THREADS;  // private per thread
+        } else {
+            while (copies < 32 && sz * copies * 4 <= 2048 && sz * (2 * copies - 1) <= spare)
+                copies *= 2;
+        }
+        spare -= sz * (copies - 1);
+        prm.smem_off[t] = (int)used;
+        prm.copies[t] = copies;
+        used += sz * copies;
     }
     prm.smem_elems = (int)used;
     switch (n_cat) {
@@ -429,80 +494,98 @@ template int index_cat_pairs<float>(const void*, int64_t, int, const int64_t*, c
 template int index_cat_pairs<double>(const void*, int64_t, int, const int64_t*, const int32_t*,
                                      double* const*, double* const*, cudaStream_t);
 
+constexpr size_t CS_SMEM_BUDGET = 72 * 1024;  // three CTAs of 256 threads per SM
+
 template <typename F, int NC>
 static int launch_cat_sparse(const F* data, const int32_t* row_idx, const int32_t* indptr,
                              int p_s, const RowRec<F>* rec, const CatSparseParams& prm,
-                             size_t smem, cudaStream_t st) {
+                             cudaStream_t st) {
     constexpr int U = 2;
     static bool attr_set = false;
     if (!attr_set) {
         TM_CUDA(cudaFuncSetAttribute(k_cat_sparse_csc<F, NC, U>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)IDX_SMEM_BUDGET));
+                                     (int)CS_SMEM_BUDGET));
         attr_set = true;
     }
-    const int n_groups = (p_s + prm.G - 1) / prm.G;
-    const int g = n_groups < sm_count() * 4 ? n_groups : sm_count() * 4;
-    k_cat_sparse_csc<F, NC, U><<<g, 512, smem, st>>>(data, row_idx, indptr, p_s, rec, prm);
+    const size_t smem = sizeof(F) * (size_t)(prm.smem_elems > 0 ? prm.smem_elems : 1);
+    const int g = p_s < sm_count() * 12 ? p_s : sm_count() * 12;
+    k_cat_sparse_csc<F, NC, U><<<g, CS_THREADS, smem, st>>>(data, row_idx, indptr, p_s, rec, prm);
     TM_LAUNCHED();
     return 0;
 }
 
-// can the column tables of all blocks (with their replicas) live in shared memory?
+// Per block: private per-thread tables for <= 64 levels while they fit, shared-memory atomics
+// up to 512 levels, L2 REDs beyond (and for whatever does not fit).
 template <typename F>
-static bool cat_sparse_layout(int n_cat, const int64_t* K, const int32_t* runs, int64_t p_s,
+static void cat_sparse_layout(int n_cat, const int64_t* K, const int32_t* runs,
                               CatSparseParams& prm) {
     memset(&prm, 0, sizeof(prm));
-    int64_t slot = 0;
+    const int64_t budget = (int64_t)(CS_SMEM_BUDGET / sizeof(F));
+    int64_t used = 0;
     for (int c = 0; c < n_cat; ++c) {
-        int rep = 1;
-        while (rep < 8 && K[c] * rep * 2 <= 2048) rep *= 2;
         prm.K[c] = (int)K[c];
-        prm.rep[c] = rep;
         prm.runs[c] = runs ? runs[c] : 0;
-        prm.off[c] = (int)slot;
-        slot += K[c] * rep;
+        prm.rep[c] = 1;
+        prm.mode[c] = CS_L2;
     }
-    prm.off[n_cat] = (int)slot;
-    const int64_t budget = (int64_t)(IDX_SMEM_BUDGET / sizeof(F));
-    if (slot > budget) return false;
-    int64_t G = budget / slot;
-    if (G > 8) G = 8;
-    // enough CTAs to fill the machine a few times over
-    while (G > 1 && (p_s + G - 1) / G < (int64_t)sm_count() * 4) --G;
-    prm.G = (int)G;
-    return true;
+    // smallest blocks first
+    bool done[IDX_MAX_CATS] = {false};
+    for (int it = 0; it < n_cat; ++it) {
+        int best = -1;
+        for (int c = 0; c < n_cat; ++c)
+            if (!done[c] && (best < 0 || K[c] < K[best])) best = c;
+        done[best] = true;
+        const int64_t Kb = K[best];
+        if (Kb <= 64 && used + Kb * CS_THREADS <= budget - 2048) {
+            prm.mode[best] = CS_PRIV;
+            prm.off[best] = (int)used;
+            used += Kb * CS_THREADS;
+        } else if (Kb <= 512) {
+            int rep = 1;
+            while (rep < 8 && Kb * rep * 2 <= 2048) rep *= 2;
+            if (used + Kb * rep > budget) rep = 1;
+            if (used + Kb * rep > budget) continue;  // stays CS_L2
+            prm.mode[best] = CS_ATOM;
+            prm.rep[best] = rep;
+            prm.off[best] = (int)used;
+            used += Kb * rep;
+        }
+    }
+    prm.smem_elems = (int)used;
 }
 
 template <typename F>
 bool index_cat_sparse_fits(int n_cat, const int64_t* K, int64_t p_s) {
-    CatSparseParams prm;
-    return p_s > 0 && p_s < (1ll << 31) && cat_sparse_layout<F>(n_cat, K, nullptr, p_s, prm);
+    (void)K;
+    return n_cat >= 1 && p_s > 0 && p_s < (1ll << 31);
 }
 template bool index_cat_sparse_fits<float>(int, const int64_t*, int64_t);
 template bool index_cat_sparse_fits<double>(int, const int64_t*, int64_t);
 
-// outs[c]: K_c x p_s row-major, fully overwritten.
+// outs[c]: K_c x p_s row-major, overwritten.
 template <typename F>
 int index_cat_sparse(const void* rec_v, int n_cat, const int64_t* K, const int32_t* runs,
                      const F* csc_data, const int32_t* csc_row, const int32_t* csc_indptr,
                      int64_t p_s, F* const* outs, cudaStream_t st) {
     const RowRec<F>* rec = static_cast<const RowRec<F>*>(rec_v);
     CatSparseParams prm;
-    if (!cat_sparse_layout<F>(n_cat, K, runs, p_s, prm))
-        return fail("index_cat_sparse: column tables exceed shared memory");
-    for (int c = 0; c < n_cat; ++c) prm.out[c] = outs[c];
-    const size_t smem = sizeof(F) * (size_t)prm.off[n_cat] * (size_t)prm.G;
+    cat_sparse_layout<F>(n_cat, K, runs, prm);
+    for (int c = 0; c < n_cat; ++c) {
+        prm.out[c] = outs[c];
+        if (prm.mode[c] == CS_L2)
+            TM_CUDA(cudaMemsetAsync(outs[c], 0, sizeof(F) * (size_t)(K[c] * p_s), st));
+    }
     switch (n_cat) {
-        case 1: return launch_cat_sparse<F, 1>(csc_data, csc_row, csc_indptr, (int)p_s, rec, prm, smem, st);
-        case 2: return launch_cat_sparse<F, 2>(csc_data, csc_row, csc_indptr, (int)p_s, rec, prm, smem, st);
-        case 3: return launch_cat_sparse<F, 3>(csc_data, csc_row, csc_indptr, (int)p_s, rec, prm, smem, st);
-        case 4: return launch_cat_sparse<F, 4>(csc_data, csc_row, csc_indptr, (int)p_s, rec, prm, smem, st);
-        case 5: return launch_cat_sparse<F, 5>(csc_data, csc_row, csc_indptr, (int)p_s, rec, prm, smem, st);
-        case 6: return launch_cat_sparse<F, 6>(csc_data, csc_row, csc_indptr, (int)p_s, rec, prm, smem, st);
+        case 1: return launch_cat_sparse<F, 1>(csc_data, csc_row, csc_indptr, (int)p_s, rec, prm, st);
+        case 2: return launch_cat_sparse<F, 2>(csc_data, csc_row, csc_indptr, (int)p_s, rec, prm, st);
+        case 3: return launch_cat_sparse<F, 3>(csc_data, csc_row, csc_indptr, (int)p_s, rec, prm, st);
+        case 4: return launch_cat_sparse<F, 4>(csc_data, csc_row, csc_indptr, (int)p_s, rec, prm, st);
+        case 5: return launch_cat_sparse<F, 5>(csc_data, csc_row, csc_indptr, (int)p_s, rec, prm, st);
+        case 6: return launch_cat_sparse<F, 6>(csc_data, csc_row, csc_indptr, (int)p_s, rec, prm, st);
         default:
-            return launch_cat_sparse<F, rec_max_cats<F>()>(csc_data, csc_row, csc_indptr, (int)p_s, rec,
-                                                           prm, smem, st);
+            return launch_cat_sparse<F, rec_max_cats<F>()>(csc_data, csc_row, csc_indptr, (int)p_s,
+                                                           rec, prm, st);
     }
 }
 template int index_cat_sparse<float>(const void*, int, const int64_t*, const int32_t*, const float*,

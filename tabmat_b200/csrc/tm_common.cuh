@@ -43,12 +43,17 @@ inline cudaStream_t as_stream(tm_stream_t s) { return reinterpret_cast<cudaStrea
 int sm_count();
 
 // ---- stream-ordered scratch (device workspace arena; replaces reference alloc.h) -------
+// The default memory pool gives unused memory back to the driver at every synchronisation
+// (release threshold 0), so a caller that synchronises between calls paid a fresh physical
+// allocation per scratch buffer (~0.1-0.2 ms each).  Keep it cached instead.
+void keep_pool_memory();
 struct Scratch {
     void* p = nullptr;
     cudaStream_t s = nullptr;
     cudaError_t err = cudaSuccess;
     Scratch(size_t bytes, cudaStream_t st) : s(st) {
         if (bytes == 0) bytes = 16;
+        keep_pool_memory();
         err = cudaMallocAsync(&p, bytes, st);
     }
     ~Scratch() {

@@ -136,6 +136,30 @@ class RowShardedMatrix:
             return self._allreduce(part.to(self.reduce_dtype)).to(part.dtype)
         return self._allreduce(part)
 
+    def sandwich_into(self, d_local, out, rows=None, dst: Optional[int] = 0):
+        """``sandwich`` with host buffers: ``d_local`` (this rank's slice, host or device) in,
+        the p x p float64 result into the host array ``out`` on rank ``dst`` (every rank when
+        ``dst`` is None).  One rank: the two-phase path of ``SplitMatrix.sandwich_into`` (host
+        copy overlapped with compute).  Asynchronous on the current stream."""
+        if self.world_size == 1 and hasattr(self.local, "sandwich_into"):
+            return self.local.sandwich_into(d_local, out, shard_rows(rows, self.lo, self.hi))
+        from . import _dev
+        from ._lib import check, lib
+
+        if not _dev.is_dev(d_local):
+            src = d_local if isinstance(d_local, torch.Tensor) else torch.from_numpy(d_local)
+            d_dev = torch.empty(src.shape, dtype=src.dtype, device=_dev.require_cuda())
+            d_dev.copy_(src, non_blocking=True)
+            d_local = d_dev
+        res = self.sandwich(d_local, rows, dst=dst)
+        if res is None:
+            return None
+        p = res.shape[0]
+        ptr = out.data_ptr() if isinstance(out, torch.Tensor) else out.ctypes.data
+        check(lib.tm_memcpy2d_to_host(ptr, p * 8, res.data_ptr(), p * 8, p * 8, p,
+                                      _dev.stream_ptr()))
+        return out
+
     def transpose_matvec(self, v_local, rows=None, cols=None) -> torch.Tensor:
         """Replicated X[rows, cols].T @ v[rows] (length-p allreduce)."""
         part = self.local.transpose_matvec(v_local, shard_rows(rows, self.lo, self.hi), cols)

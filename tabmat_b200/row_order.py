@@ -157,6 +157,18 @@ class RowSortedMatrix(MatrixBase):
         out = self.mat._sandwich_dev(self._gather(d_t), self._rows_in(rows), cols)
         return _dev.ret(out, host)
 
+    def sandwich_into(self, d, out, rows=None):
+        """Host-buffer form of :meth:`sandwich` (see ``SplitMatrix.sandwich_into``): ``d`` from
+        host or device memory in the caller's row order, the result into the host array ``out``."""
+        if _dev.is_dev(d):
+            d_t = d.contiguous()
+        else:
+            src = d if isinstance(d, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(d))
+            d_t = torch.empty(src.shape, dtype=src.dtype, device=_dev.require_cuda())
+            d_t.copy_(src, non_blocking=True)
+        check_sandwich_compatible(self, d_t)
+        return self.mat._sandwich_into_dev(self._gather(d_t), self._rows_in(rows), out)
+
     def _sandwich_blocks_dev(self, d_t: torch.Tensor, rows_t):
         """Flat block workspace (for the row-sharded allreduce, distributed.py)."""
         return self.mat._sandwich_blocks_dev(self._gather(d_t), self._rows_in(rows_t))

@@ -319,6 +319,102 @@ class SplitMatrix(MatrixBase):
             descs, len(self.matrices), _dev.ptr(ws), _dev.ptr(out), p, _dev.stream_ptr()))
         return out
 
+    # ---- result straight into host memory, copy overlapped with the dense-operand passes ----
+    def _column_runs(self):
+        """[(start, stop, is_dense)]: maximal runs of consecutive result columns that belong to
+        the dense block / to the other blocks."""
+        runs = self.__dict__.get("_col_runs")
+        if runs is None:
+            p = self.shape[1]
+            is_dense = np.zeros(p, dtype=bool)
+            for mat, idx in zip(self.matrices, self.indices):
+                if isinstance(mat, DenseMatrix):
+                    is_dense[idx] = True
+            cuts = np.flatnonzero(np.diff(is_dense.astype(np.int8))) + 1
+            edges = [0, *cuts.tolist(), p]
+            runs = [(a, b, bool(is_dense[a])) for a, b in zip(edges[:-1], edges[1:])]
+            self.__dict__["_col_runs"] = runs
+        return runs
+
+    def sandwich_into(self, d, out, rows=None):
+        """``out[:] = X[rows].T @ diag(d[rows]) @ X[rows]`` for a HOST float64 ``out`` (p x p,
+        C-contiguous numpy array or CPU tensor; pinned memory gives full PCIe speed).
+
+        The host-buffer form of :meth:`sandwich` (split_matrix.py:324-356 returns a fresh
+        ndarray): ``d`` may live on the host (pinned or not) or on the device.  The blocks
+        without a dense operand are computed, placed and copied to the host first, while the
+        tensor-core and scatter passes of the dense block still run (two-phase C-ABI calls
+        ``tm_split_sandwich_blocks_part`` / ``_assemble_part`` / ``tm_memcpy2d_to_host``).
+        Asynchronous on the current CUDA stream: ``out`` is complete after
+        ``torch.cuda.current_stream().synchronize()``.
+        """
+        if _dev.is_dev(d):
+            d_t = d.contiguous()
+        else:
+            src = d if isinstance(d, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(d))
+            d_t = torch.empty(src.shape, dtype=src.dtype, device=_dev.require_cuda())
+            d_t.copy_(src, non_blocking=True)
+        check_sandwich_compatible(self, d_t)
+        return self._sandwich_into_dev(d_t, _dev.idx32(rows), out)
+
+    def _sandwich_into_dev(self, d_t: torch.Tensor, rows_t, out):
+        p = self.shape[1]
+        if isinstance(out, torch.Tensor):
+            ok = (not out.is_cuda) and out.dtype == torch.float64 and out.is_contiguous()
+            out_ptr = out.data_ptr()
+        else:
+            ok = (isinstance(out, np.ndarray) and out.dtype == np.float64
+                  and out.flags["C_CONTIGUOUS"] and out.flags["WRITEABLE"])
+            out_ptr = out.ctypes.data if ok else 0
+        if not ok or tuple(out.shape) != (p, p):
+            raise ValueError(f"out must be a C-contiguous host float64 array of shape {(p, p)}")
+        st = _dev.stream_ptr()
+        row_bytes = p * 8
+        suf = _dev.suffix(d_t.dtype)
+
+        def copy2d(buf, r0, r1, c0, c1, stream):
+            o = (r0 * p + c0) * 8
+            check(lib.tm_memcpy2d_to_host(out_ptr + o, row_bytes, buf.data_ptr() + o, row_bytes,
+                                          (c1 - c0) * 8, r1 - r0, stream))
+
+        plan = self._native_plan(d_t.dtype)
+        runs = self._column_runs()
+        dense_runs = [r for r in runs if r[2]]
+        other_runs = [r for r in runs if not r[2]]
+        if plan is None or not dense_runs or not other_runs or len(runs) > 6:
+            res = self._sandwich_dev(d_t, rows_t, None)
+            copy2d(res, 0, p, 0, p, st)
+            return out
+        descs, elems = plan
+        nb = len(self.matrices)
+        ws = torch.empty(elems, dtype=d_t.dtype, device=d_t.device)
+        buf = torch.empty((p, p), dtype=torch.float64, device=d_t.device)
+        args = (descs, nb, self.shape[0], _dev.ptr(d_t), _dev.ptr(rows_t), _dev.length(rows_t),
+                _dev.ptr(ws))
+        # phase 1: everything without the dense operand, then its host copy on a second stream
+        check(fn("tm_split_sandwich_blocks_part", suf)(*args, 1, st))
+        check(fn("tm_split_sandwich_assemble_part", suf)(descs, nb, _dev.ptr(ws), _dev.ptr(buf), p,
+                                                        1, st))
+        cs = self.__dict__.get("_copy_stream")
+        if cs is None:
+            cs = self.__dict__["_copy_stream"] = torch.cuda.Stream()
+        cs.wait_stream(torch.cuda.current_stream())
+        for (r0, r1, _) in other_runs:
+            for (c0, c1, _) in other_runs:
+                copy2d(buf, r0, r1, c0, c1, cs.cuda_stream)
+        # phase 2: the dense block's own and cross blocks
+        check(fn("tm_split_sandwich_blocks_part", suf)(*args, 2, st))
+        check(fn("tm_split_sandwich_assemble_part", suf)(descs, nb, _dev.ptr(ws), _dev.ptr(buf), p,
+                                                        2, st))
+        for (r0, r1, _) in dense_runs:
+            copy2d(buf, r0, r1, 0, p, st)
+        for (r0, r1, _) in other_runs:
+            for (c0, c1, _) in dense_runs:
+                copy2d(buf, r0, r1, c0, c1, st)
+        torch.cuda.current_stream().wait_stream(cs)
+        buf.record_stream(cs)
+        return out
+
     def _sandwich_dev(self, d_t: torch.Tensor, rows_t, cols) -> torch.Tensor:
         if cols is None:
             ws = self._sandwich_blocks_dev(d_t, rows_t)

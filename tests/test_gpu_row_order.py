@@ -258,3 +258,49 @@ def test_row_sharded_wrapper_accepts_row_sorted_shards():
     got = R.sandwich(torch.from_numpy(d).cuda(), rows=rows)
     ref = (full[rows] * d.astype(np.float64)[rows, None]).T @ full[rows]
     cases.assert_close(got.cpu().numpy(), ref, dt, "row-sharded(row-sorted) sandwich rows")
+
+
+@pytest.mark.parametrize("suf", ["f32", "f64"])
+@pytest.mark.parametrize("layout", ["dense-first", "dense-middle", "no-dense", "dense-only"])
+def test_sandwich_into_host_buffer(suf, layout):
+    """Two-phase host-buffer path (blocks without the dense operand are copied to the host
+    while the dense passes run) == the plain sandwich, for every column layout."""
+    import torch
+
+    import tabmat_b200 as tm
+
+    dt = cases.DTYPES[suf]
+    n = 4099
+    mats, full, d, rng = _mats(dt, n, seed=31)
+    if layout == "no-dense":
+        mats = mats[1:]
+    elif layout == "dense-only":
+        mats = mats[:1]
+    p = sum(m.shape[1] for m in mats)
+    indices = None
+    if layout == "dense-middle":
+        # dense columns at result positions 40..47, everything else around them
+        order = list(range(8, 48)) + list(range(0, 8)) + list(range(48, p))
+        pos = np.empty(p, dtype=np.int64)
+        pos[order] = np.arange(p)
+        indices, o = [], 0
+        for m in mats:
+            indices.append(np.sort(pos[o:o + m.shape[1]]))
+            o += m.shape[1]
+    X = tm.SplitMatrix(mats, indices)
+    rows = np.sort(rng.choice(n, size=n // 2, replace=False)).astype(np.int32)
+    variants = [X] if layout in ("no-dense", "dense-only") else [X, tm.RowSortedMatrix.from_split(X)]
+    for M in variants:
+        for r in (None, rows):
+            ref = X.sandwich(d, r)
+            out_np = np.full((p, p), np.nan)
+            assert M.sandwich_into(d, out_np, r) is out_np
+            torch.cuda.synchronize()
+            cases.assert_close(out_np, ref, dt, f"sandwich_into numpy {layout}")
+            out_t = torch.full((p, p), float("nan"), dtype=torch.float64).pin_memory()
+            d_pinned = torch.from_numpy(d).pin_memory()
+            M.sandwich_into(d_pinned, out_t, r)
+            torch.cuda.synchronize()
+            cases.assert_close(out_t.numpy(), ref, dt, f"sandwich_into pinned {layout}")
+    with pytest.raises(ValueError):
+        X.sandwich_into(d, np.zeros((p, p), dtype=np.float32))
