@@ -284,8 +284,9 @@ typedef struct tm_block_desc {
     int32_t kind;       /* 0 dense, 1 sparse (CSR + row ids), 2 categorical */
     int32_t c_order;    /* dense: 1 row-major, 0 column-major */
     int32_t drop_first; /* categorical */
-    int32_t flags;      /* bit 0 (categorical): the rows are stored sorted so that equal codes
-                         * form long runs -> the run-aggregating cross kernel is used */
+    int32_t flags;      /* categorical: bit 0 = the rows are stored sorted by (among others) this
+                         * block's codes, so equal codes form runs that the kernels pre-sum;
+                         * bit 1 = this block is the primary sort key */
     int64_t ncols;      /* block width (categorical: #categories - drop_first) */
     const void* data;   /* dense: X (n x ncols); sparse: CSR data; categorical: int32 codes */
     const int32_t* csr_indices;
@@ -305,7 +306,15 @@ typedef struct tm_block_desc {
     const void* csc_data;
     const int32_t* csc_indices;
     const int32_t* csc_indptr;
+    /* 0 / 1: plain CSC (ncols + 1 offsets).  B > 1: the CSC arrays are ROW-BLOCKED: the rows are
+     * cut into B blocks of TM_CSC_ROW_BLOCK rows and the non-zeros are ordered by (row block,
+     * column, row); csc_indptr then has B * ncols + 1 offsets, entry b * ncols + j = start of
+     * column j inside row block b; csc_indices still holds global row ids.  Keeps the per-row
+     * gathers of the categorical x sparse kernel inside the L2. */
+    int64_t csc_row_blocks;
 } tm_block_desc;
+
+#define TM_CSC_ROW_BLOCK (1 << 20)
 
 /* sizeof(tm_block_desc) as compiled into the library (bindings check their struct mirror). */
 int64_t tm_sizeof_block_desc(void);
@@ -321,8 +330,12 @@ int tm_split_profile_read(float* ms);
 
 /* Elements (of the block dtype) of the flat workspace that holds every self block and every
  * cross block: for i: self_i (dense/sparse ncols_i^2, categorical ncols_i = the diagonal), then
- * for j > i: cross_ij (ncols_i * ncols_j). */
+ * for j > i: cross_ij (ncols_i * ncols_j); every block starts at a multiple of 4 elements. */
 int64_t tm_split_workspace_elems(const tm_block_desc* blocks, int n_blocks);
+/* Elements at the head of the workspace that belong to block 0 (its self block and its cross
+ * blocks with every other block): when block 0 is the dense block this is exactly the part
+ * tm_split_sandwich_blocks_part(…, 2) writes, the rest is what part 1 writes. */
+int64_t tm_split_workspace_head_elems(const tm_block_desc* blocks, int n_blocks);
 /* Every block of X[rows,:]^T diag(d[rows]) X[rows,:] into `workspace` (overwrites).  All blocks
  * share the dtype of the entry point; dense and sparse blocks must already be merged
  * (split_matrix.py:85-141).  Cross blocks that share the dense operand are computed in one

@@ -77,7 +77,7 @@ _SIGS = {
 #: every symbol include/tabmat_b200.h declares (checked by tests/test_capi_symbols.py)
 EXPORTED = ["tm_version", "tm_last_error", "tm_launch_count", "tm_reset_launch_count",
             "tm_has_tcgen05", "tm_set_dense_f32_mode", "tm_set_cross_runs_mode",
-            "tm_split_workspace_elems", "tm_memcpy2d_to_host",
+            "tm_split_workspace_elems", "tm_split_workspace_head_elems", "tm_memcpy2d_to_host",
             "tm_dense_onehot_sandwich_f32", "tm_split_profile_enable", "tm_split_profile_read", "tm_sizeof_block_desc"]
 for _name, _args in _SIGS.items():
     for _suf in ("f32", "f64"):
@@ -96,7 +96,10 @@ class BlockDesc(C.Structure):
                 ("csr_indices", C.c_void_p), ("csr_indptr", C.c_void_p), ("csr_row", C.c_void_p),
                 ("nnz", C.c_int64), ("col_index", C.c_void_p), ("cat_perm", C.c_void_p),
                 ("cat_segptr", C.c_void_p), ("cat_nvalid", C.c_int64), ("csc_data", C.c_void_p),
-                ("csc_indices", C.c_void_p), ("csc_indptr", C.c_void_p)]
+                ("csc_indices", C.c_void_p), ("csc_indptr", C.c_void_p), ("csc_row_blocks", C.c_int64)]
+
+#: rows per block of the row-blocked CSC copy (TM_CSC_ROW_BLOCK in include/tabmat_b200.h)
+CSC_ROW_BLOCK = 1 << 20
 
 
 lib.tm_dense_onehot_sandwich_f32.argtypes = [P, I, I, P, P, I, N, P, P, P, P, P, P]
@@ -110,6 +113,8 @@ lib.tm_split_profile_read.argtypes = [C.c_void_p]
 lib.tm_split_profile_read.restype = c_int
 lib.tm_split_workspace_elems.argtypes = [C.c_void_p, c_int]
 lib.tm_split_workspace_elems.restype = c_i64
+lib.tm_split_workspace_head_elems.argtypes = [C.c_void_p, c_int]
+lib.tm_split_workspace_head_elems.restype = c_i64
 lib.tm_version.restype = c_int
 lib.tm_last_error.restype = C.c_char_p
 lib.tm_launch_count.restype = c_i64

@@ -82,50 +82,6 @@ __device__ __forceinline__ bool warp_run_reduce(KeyT key, F& val, int lane) {
 
 constexpr int CAT2_THREADS = 1024;
 
-// N independent shared-memory float adds issued as a batch: all loads, then all compare-and-swaps,
-// then the (rare) retries.  atomicAdd(float*) on shared memory is a compare-and-swap loop on
-// sm_100, and N of them in a row serialise N round trips of ~300 cycles; batched they overlap.
-template <typename F>
-struct CasBits;
-template <>
-struct CasBits<float> {
-    using U = unsigned int;
-    static __device__ __forceinline__ U add(U bits, float v) {
-        return __float_as_uint(__uint_as_float(bits) + v);
-    }
-};
-template <>
-struct CasBits<double> {
-    using U = unsigned long long;
-    static __device__ __forceinline__ U add(U bits, double v) {
-        return (U)__double_as_longlong(__longlong_as_double((long long)bits) + v);
-    }
-};
-template <typename F, int N>
-__device__ __forceinline__ void smem_add_batch(F* tab, const int (&idx)[N], const F (&val)[N]) {
-    using CB = CasBits<F>;
-    using U = typename CB::U;
-    U* t = reinterpret_cast<U*>(tab);
-    U seen[N], want[N];
-#pragma unroll
-    for (int i = 0; i < N; ++i)
-        if (idx[i] >= 0) seen[i] = *reinterpret_cast<volatile U*>(t + idx[i]);
-#pragma unroll
-    for (int i = 0; i < N; ++i)
-        if (idx[i] >= 0) {
-            want[i] = seen[i];
-            seen[i] = atomicCAS(t + idx[i], want[i], CB::add(want[i], val[i]));
-        }
-#pragma unroll
-    for (int i = 0; i < N; ++i)
-        if (idx[i] >= 0) {
-            while (seen[i] != want[i]) {
-                want[i] = seen[i];
-                seen[i] = atomicCAS(t + idx[i], want[i], CB::add(want[i], val[i]));
-            }
-        }
-}
-
 template <typename F, bool USE_SMEM, int UNR>
 __global__ void __launch_bounds__(CAT2_THREADS, 1)
 k_cat_hist2(const int32_t* __restrict__ codes, const F* __restrict__ w,
@@ -141,50 +97,35 @@ k_cat_hist2(const int32_t* __restrict__ codes, const F* __restrict__ w,
     F* tab = USE_SMEM ? table + (threadIdx.x % copies) * K : out;
     const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    const int64_t step = nw * (32 * UNR);
-    int c[UNR], cn[UNR];
-    F v[UNR], vn[UNR];
-    auto load = [&](int64_t base, int (&cc)[UNR], F (&vv)[UNR]) {
+    for (int64_t base = gw * (32 * UNR); base < n_rows; base += nw * (32 * UNR)) {
+        int c[UNR];
+        F v[UNR];
 #pragma unroll
         for (int u = 0; u < UNR; ++u) {
             const int64_t t = base + u * 32 + lane;
-            cc[u] = -1;
-            vv[u] = F(0);
+            c[u] = -1;
+            v[u] = F(0);
             if (t < n_rows) {
                 const int64_t k = row_at(rows, t);
-                cc[u] = codes[k] - drop_first;
-                vv[u] = w[k];
+                c[u] = codes[k] - drop_first;
+                v[u] = w[k];
             }
         }
-    };
-    int64_t base = gw * (32 * UNR);
-    if (base < n_rows) load(base, c, v);
-    for (; base < n_rows; base += step) {
-        // the next visit's loads are in flight while this visit's atomics run
-        if (base + step < n_rows) load(base + step, cn, vn);
-        int key[UNR];
 #pragma unroll
         for (int u = 0; u < UNR; ++u) {
-            key[u] = c[u];
-            if (key[u] >= 0 && col_mask && !col_mask[key[u]]) key[u] = -1;
-            if (key[u] < 0) {
-                key[u] = -1;
+            int key = c[u];
+            if (key >= 0 && col_mask && !col_mask[key]) key = -1;
+            if (key < 0) {
+                key = -1;
                 v[u] = F(0);
             }
-            const bool head = warp_run_reduce<F, int>(key[u], v[u], lane);
-            if (!head) key[u] = -1;
-        }
-        if (USE_SMEM) {
-            smem_add_batch<F, UNR>(tab, key, v);
-        } else {
-#pragma unroll
-            for (int u = 0; u < UNR; ++u)
-                if (key[u] >= 0) red_add(&tab[key[u]], v[u]);
-        }
-#pragma unroll
-        for (int u = 0; u < UNR; ++u) {
-            c[u] = cn[u];
-            v[u] = vn[u];
+            const bool head = warp_run_reduce<F, int>(key, v[u], lane);
+            if (head && key >= 0) {
+                if (USE_SMEM)
+                    atomicAdd(&tab[key], v[u]);
+                else
+                    red_add(&tab[key], v[u]);
+            }
         }
     }
     if (USE_SMEM) {
@@ -271,7 +212,7 @@ static inline int cat2_grid(int64_t n_rows, int unr) {
 template <typename F>
 int cat_hist2(const int32_t* codes, const F* w, const int32_t* rows, int64_t n_rows, int64_t K,
               int drop_first, const uint8_t* col_mask, F* out, bool overwrite, cudaStream_t st) {
-    constexpr int UNR = sizeof(F) == 4 ? 6 : 3;  // x2 with the prefetched visit; 64 registers
+    constexpr int UNR = 8;
     const int64_t tb = (int64_t)sizeof(F) * K;
     const int g = cat2_grid(n_rows, UNR);
     if (tb <= CAT_SMEM_TABLE_BYTES) {

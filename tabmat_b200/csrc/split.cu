@@ -27,6 +27,10 @@ enum { KIND_DENSE = 0, KIND_SPARSE = 1, KIND_CAT = 2 };
 static inline int64_t self_elems(const tm_block_desc& b) {
     return b.kind == KIND_CAT ? b.ncols : b.ncols * b.ncols;
 }
+// every block of the workspace starts at a multiple of 4 elements: the scatter kernels write
+// 16-byte vector REDs (an odd-width categorical block in front of the dense block used to leave
+// the dense cross blocks misaligned)
+static inline int64_t ws_pad(int64_t elems) { return (elems + 3) & ~int64_t(3); }
 
 // orientation of the stored cross block of blocks (i, j), i < j: returns true when the stored
 // rows belong to block j (i.e. the kernel's native orientation is (j, i))
@@ -125,10 +129,10 @@ int split_blocks(const tm_block_desc* blk, int nb, int64_t n, const F* d, const 
     int64_t off = 0;
     for (int i = 0; i < nb; ++i) {
         self_off[i] = off;
-        off += self_elems(blk[i]);
+        off += ws_pad(self_elems(blk[i]));
         for (int j = i + 1; j < nb; ++j) {
             cross_off[i][j] = off;
-            off += blk[i].ncols * blk[j].ncols;
+            off += ws_pad(blk[i].ncols * blk[j].ncols);
         }
     }
     // can the dense-operand cross blocks be fused into one pass?
@@ -296,7 +300,7 @@ int split_blocks(const tm_block_desc* blk, int nb, int64_t n, const F* d, const 
                 }
             int64_t Kc[8];
             const int32_t* cc[8];
-            int32_t dfc[8], runc[8];
+            int32_t dfc[8], runc[8], runp[8];
             bool ok = nc >= 1 && nc <= 7 && nr_all > 0 && n > 0;
             if (ok) {
                 for (int a = 0; a < nc; ++a) {
@@ -305,6 +309,9 @@ int split_blocks(const tm_block_desc* blk, int nb, int64_t n, const F* d, const 
                     cc[a] = static_cast<const int32_t*>(b.data);
                     dfc[a] = b.drop_first;
                     runc[a] = (b.flags & TM_BLOCK_FLAG_RUNS) ? 1 : 0;
+                    // down a CSC column the rows are ~n/nnz_col apart: only the primary sort
+                    // key still forms runs there
+                    runp[a] = (b.flags & TM_BLOCK_FLAG_PRIMARY) ? 1 : 0;
                 }
                 ok = index_fused_eligible<F>(nc, Kc);
             }
@@ -341,9 +348,11 @@ int split_blocks(const tm_block_desc* blk, int nb, int64_t n, const F* d, const 
                         const int hi = cats[a] < sparse_idx ? sparse_idx : cats[a];
                         outs[a] = ws + cross_off[lo][hi];
                     }
-                    rc = index_cat_sparse<F>(rec.p, nc, Kc, runc,
+                    rc = index_cat_sparse<F>(rec.p, nc, Kc, runp,
                                              static_cast<const F*>(S.csc_data), S.csc_indices,
-                                             S.csc_indptr, S.ncols, outs, st);
+                                             S.csc_indptr, S.ncols,
+                                             (int)(S.csc_row_blocks > 1 ? S.csc_row_blocks : 1),
+                                             outs, st);
                     if (rc) return rc;
                     cat_sparse_fused = true;
                 }
@@ -518,7 +527,7 @@ int split_assemble(const tm_block_desc* blk, int nb, const F* ws, double* out, i
             rc = scatter_block(tag, ws + off, bi.ncols, bi.ncols, bi.col_index, bi.col_index, out,
                                ld, 0, stream);
         if (rc) return rc;
-        off += self_elems(bi);
+        off += ws_pad(self_elems(bi));
         for (int j = i + 1; j < nb; ++j) {
             const tm_block_desc& bj = blk[j];
             const tm_block_desc& a = cross_rows_are_j(bi, bj) ? bj : bi;
@@ -528,7 +537,7 @@ int split_assemble(const tm_block_desc* blk, int nb, const F* ws, double* out, i
                                    ld, 1, stream);
                 if (rc) return rc;
             }
-            off += bi.ncols * bj.ncols;
+            off += ws_pad(bi.ncols * bj.ncols);
         }
     }
     return 0;
@@ -567,9 +576,17 @@ int tm_split_profile_read(float* ms) {
 int64_t tm_split_workspace_elems(const tm_block_desc* blocks, int n_blocks) {
     int64_t off = 0;
     for (int i = 0; i < n_blocks; ++i) {
-        off += tmb::self_elems(blocks[i]);
-        for (int j = i + 1; j < n_blocks; ++j) off += blocks[i].ncols * blocks[j].ncols;
+        off += tmb::ws_pad(tmb::self_elems(blocks[i]));
+        for (int j = i + 1; j < n_blocks; ++j)
+            off += tmb::ws_pad(blocks[i].ncols * blocks[j].ncols);
     }
+    return off;
+}
+
+int64_t tm_split_workspace_head_elems(const tm_block_desc* blocks, int n_blocks) {
+    if (n_blocks <= 0) return 0;
+    int64_t off = tmb::ws_pad(tmb::self_elems(blocks[0]));
+    for (int j = 1; j < n_blocks; ++j) off += tmb::ws_pad(blocks[0].ncols * blocks[j].ncols);
     return off;
 }
 

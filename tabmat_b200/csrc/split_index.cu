@@ -222,30 +222,36 @@ k_cat_pairs(const RowRec<F>* __restrict__ rec, int64_t n, const PairParams prm) 
 // ---------------------------------------------------------------------------------------
 // categorical x sparse for all categorical blocks, CSC-driven, shared-memory column tables
 // ---------------------------------------------------------------------------------------
-enum { CS_PRIV = 0, CS_ATOM = 1, CS_L2 = 2 };
+enum { CS_PRIV = 0, CS_ATOM = 1, CS_L2 = 2, CS_REG = 3 };
 constexpr int CS_THREADS = 256;
+constexpr int CS_REG_MAX = 16;
 
 struct CatSparseParams {
     int K[IDX_MAX_CATS];
     int mode[IDX_MAX_CATS];      // CS_PRIV: one replica per thread, [level][thread], plain RMW
                                  // CS_ATOM: shared-memory atomics, `rep` replicas (lane % rep)
                                  // CS_L2:   scalar REDs straight into out (zero-filled by the host)
+                                 // CS_REG:  <= 16 levels summed in registers (one block at most)
     int rep[IDX_MAX_CATS];
     int off[IDX_MAX_CATS];       // element offset of block c's shared-memory table
     int runs[IDX_MAX_CATS];
     void* out[IDX_MAX_CATS];     // K_c x p_s, row-major
     int smem_elems;
+    int n_row_blocks;            // > 1: row-blocked CSC, `indptr` has n_row_blocks * p_s + 1 entries
+                                 // and every out is zero-filled and accumulated into
 };
 
-// One CTA per sparse column j (grid-stride).  Per non-zero (k, j, a): val = d[k] * a from the
-// row record, then per categorical block one update of out_c[code_c[k], j]:
-//   few levels   -> the thread's private column table in shared memory (no atomics),
+// One CTA per work item = (row block, sparse column j), row block slowest.  Per non-zero
+// (k, j, a): val = d[k] * a from the 32-byte row record, then per categorical block one update
+// of out_c[code_c[k], j]:
+//   <= 16 levels -> predicated adds into registers (one block), reduced per warp at the end,
+//   few levels   -> the thread's private column table in shared memory (plain CSC only),
 //   some levels  -> shared-memory atomics on a replicated column table,
-//   many levels  -> scalar L2 RED (the addresses of one column are p_s * 4 bytes apart, so they
-//                   never share a sector; runs of equal codes are pre-summed when the rows are
-//                   stored sorted by that block).
-// Shared-memory and L2 atomics run at about the same aggregate rate on B200, so splitting the
-// blocks between them roughly doubles the update rate.
+//   many levels  -> scalar L2 RED (the addresses of one column are p_s * 4 bytes apart; runs of
+//                   equal codes are pre-summed when the rows are stored sorted by that block).
+// Row blocks (2^20 rows = 32 MB of records) keep the record gathers inside L2: with the plain
+// CSC order every non-zero is a random 32-byte read over n * 32 bytes of records, which costs a
+// 64-byte DRAM access each (7.7 GB and 3.6 ms at the benchmark shape, the whole kernel time).
 template <typename F, int NC, int U>
 __global__ void __launch_bounds__(CS_THREADS)
 k_cat_sparse_csc(const F* __restrict__ data, const int32_t* __restrict__ row_idx,
@@ -256,10 +262,16 @@ k_cat_sparse_csc(const F* __restrict__ data, const int32_t* __restrict__ row_idx
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
     constexpr int NW = CS_THREADS / 32;
-    for (int j = blockIdx.x; j < p_s; j += gridDim.x) {
+    const bool accumulate = prm.n_row_blocks > 1;
+    const int64_t n_items = (int64_t)(accumulate ? prm.n_row_blocks : 1) * p_s;
+    for (int64_t w = blockIdx.x; w < n_items; w += gridDim.x) {
+        const int j = (int)(w % p_s);
         for (int i = threadIdx.x; i < prm.smem_elems; i += CS_THREADS) smem[i] = F(0);
+        F racc[CS_REG_MAX];
+#pragma unroll
+        for (int l = 0; l < CS_REG_MAX; ++l) racc[l] = F(0);
         __syncthreads();
-        const int e0 = indptr[j], e1 = indptr[j + 1];
+        const int e0 = indptr[w], e1 = indptr[w + 1];
         for (int eb = e0 + wib * (32 * U); eb < e1; eb += NW * (32 * U)) {
             RowRec<F> r[U];
             F a[U];
@@ -286,6 +298,11 @@ k_cat_sparse_csc(const F* __restrict__ data, const int32_t* __restrict__ row_idx
 #pragma unroll
                 for (int c = 0; c < NC; ++c) {
                     int key = r[u].c[c];
+                    if (prm.mode[c] == CS_REG) {
+#pragma unroll
+                        for (int l = 0; l < CS_REG_MAX; ++l) racc[l] += key == l ? val0 : F(0);
+                        continue;
+                    }
                     if (prm.mode[c] == CS_PRIV) {
                         if (key >= 0) smem[prm.off[c] + key * CS_THREADS + threadIdx.x] += val0;
                         continue;
@@ -301,6 +318,17 @@ k_cat_sparse_csc(const F* __restrict__ data, const int32_t* __restrict__ row_idx
                 }
             }
         }
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            if (prm.mode[c] != CS_REG) continue;
+#pragma unroll
+            for (int l = 0; l < CS_REG_MAX; ++l) {
+                F sum = racc[l];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+                if (lane == 0 && l < prm.K[c] && sum != F(0)) atomicAdd(smem + prm.off[c] + l, sum);
+            }
+        }
         __syncthreads();
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
@@ -314,15 +342,21 @@ k_cat_sparse_csc(const F* __restrict__ data, const int32_t* __restrict__ row_idx
                     for (int q = 0; q < NW; ++q) sum += tab[q * 32 + lane];
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-                    if (lane == 0) out[(int64_t)lvl * p_s + j] = sum;
+                    if (lane == 0) {
+                        F* dst = out + (int64_t)lvl * p_s + j;
+                        if (!accumulate) *dst = sum;
+                        else if (sum != F(0)) red_add(dst, sum);
+                    }
                 }
-            } else if (prm.mode[c] == CS_ATOM) {
+            } else if (prm.mode[c] == CS_ATOM || prm.mode[c] == CS_REG) {
                 const int rep = prm.rep[c];
                 for (int lvl = threadIdx.x; lvl < Kc; lvl += CS_THREADS) {
                     const F* tab = smem + prm.off[c] + lvl;
                     F sum = F(0);
                     for (int q = 0; q < rep; ++q) sum += tab[q * Kc];
-                    out[(int64_t)lvl * p_s + j] = sum;
+                    F* dst = out + (int64_t)lvl * p_s + j;
+                    if (!accumulate) *dst = sum;
+                    else if (sum != F(0)) red_add(dst, sum);
                 }
             }
         }
@@ -509,18 +543,24 @@ static int launch_cat_sparse(const F* data, const int32_t* row_idx, const int32_
         attr_set = true;
     }
     const size_t smem = sizeof(F) * (size_t)(prm.smem_elems > 0 ? prm.smem_elems : 1);
-    const int g = p_s < sm_count() * 12 ? p_s : sm_count() * 12;
+    const int64_t items = (int64_t)(prm.n_row_blocks > 1 ? prm.n_row_blocks : 1) * p_s;
+    const int g = (int)(items < (int64_t)sm_count() * 12 ? items : (int64_t)sm_count() * 12);
     k_cat_sparse_csc<F, NC, U><<<g, CS_THREADS, smem, st>>>(data, row_idx, indptr, p_s, rec, prm);
     TM_LAUNCHED();
     return 0;
 }
 
-// Per block: private per-thread tables for <= 64 levels while they fit, shared-memory atomics
-// up to 512 levels, L2 REDs beyond (and for whatever does not fit).
+// Plain CSC: private per-thread tables for <= 64 levels while they fit, shared-memory atomics
+// up to 512 levels, L2 REDs beyond (and for whatever does not fit).  Row-blocked CSC (work items
+// of ~1000 non-zeros): the smallest block with <= 16 levels in registers, small replicated
+// tables with shared-memory atomics (zeroing and flushing a private table would cost more than
+// the item itself), L2 REDs beyond.
 template <typename F>
-static void cat_sparse_layout(int n_cat, const int64_t* K, const int32_t* runs,
+static void cat_sparse_layout(int n_cat, const int64_t* K, const int32_t* runs, int n_row_blocks,
                               CatSparseParams& prm) {
     memset(&prm, 0, sizeof(prm));
+    prm.n_row_blocks = n_row_blocks;
+    const bool blocked = n_row_blocks > 1;
     const int64_t budget = (int64_t)(CS_SMEM_BUDGET / sizeof(F));
     int64_t used = 0;
     for (int c = 0; c < n_cat; ++c) {
@@ -531,19 +571,26 @@ static void cat_sparse_layout(int n_cat, const int64_t* K, const int32_t* runs,
     }
     // smallest blocks first
     bool done[IDX_MAX_CATS] = {false};
+    bool reg_used = false;
     for (int it = 0; it < n_cat; ++it) {
         int best = -1;
         for (int c = 0; c < n_cat; ++c)
             if (!done[c] && (best < 0 || K[c] < K[best])) best = c;
         done[best] = true;
         const int64_t Kb = K[best];
-        if (Kb <= 64 && used + Kb * CS_THREADS <= budget - 2048) {
+        if (blocked && !reg_used && Kb <= CS_REG_MAX) {
+            reg_used = true;
+            prm.mode[best] = CS_REG;
+            prm.off[best] = (int)used;
+            used += Kb;
+        } else if (!blocked && Kb <= 64 && used + Kb * CS_THREADS <= budget - 2048) {
             prm.mode[best] = CS_PRIV;
             prm.off[best] = (int)used;
             used += Kb * CS_THREADS;
         } else if (Kb <= 512) {
             int rep = 1;
-            while (rep < 8 && Kb * rep * 2 <= 2048) rep *= 2;
+            const int64_t cap = blocked ? 512 : 2048;  // table elements incl. replicas
+            while (rep < 8 && Kb * rep * 2 <= cap) rep *= 2;
             if (used + Kb * rep > budget) rep = 1;
             if (used + Kb * rep > budget) continue;  // stays CS_L2
             prm.mode[best] = CS_ATOM;
@@ -563,17 +610,18 @@ bool index_cat_sparse_fits(int n_cat, const int64_t* K, int64_t p_s) {
 template bool index_cat_sparse_fits<float>(int, const int64_t*, int64_t);
 template bool index_cat_sparse_fits<double>(int, const int64_t*, int64_t);
 
-// outs[c]: K_c x p_s row-major, overwritten.
+// outs[c]: K_c x p_s row-major, overwritten.  n_row_blocks > 1: the CSC arrays are row-blocked
+// (blocks of TM_CSC_ROW_BLOCK rows, block slowest, then column, then row).
 template <typename F>
 int index_cat_sparse(const void* rec_v, int n_cat, const int64_t* K, const int32_t* runs,
                      const F* csc_data, const int32_t* csc_row, const int32_t* csc_indptr,
-                     int64_t p_s, F* const* outs, cudaStream_t st) {
+                     int64_t p_s, int n_row_blocks, F* const* outs, cudaStream_t st) {
     const RowRec<F>* rec = static_cast<const RowRec<F>*>(rec_v);
     CatSparseParams prm;
-    cat_sparse_layout<F>(n_cat, K, runs, prm);
+    cat_sparse_layout<F>(n_cat, K, runs, n_row_blocks, prm);
     for (int c = 0; c < n_cat; ++c) {
         prm.out[c] = outs[c];
-        if (prm.mode[c] == CS_L2)
+        if (prm.mode[c] == CS_L2 || n_row_blocks > 1)
             TM_CUDA(cudaMemsetAsync(outs[c], 0, sizeof(F) * (size_t)(K[c] * p_s), st));
     }
     switch (n_cat) {
@@ -589,10 +637,10 @@ int index_cat_sparse(const void* rec_v, int n_cat, const int64_t* K, const int32
     }
 }
 template int index_cat_sparse<float>(const void*, int, const int64_t*, const int32_t*, const float*,
-                                     const int32_t*, const int32_t*, int64_t, float* const*,
+                                     const int32_t*, const int32_t*, int64_t, int, float* const*,
                                      cudaStream_t);
 template int index_cat_sparse<double>(const void*, int, const int64_t*, const int32_t*,
-                                      const double*, const int32_t*, const int32_t*, int64_t,
+                                      const double*, const int32_t*, const int32_t*, int64_t, int,
                                       double* const*, cudaStream_t);
 
 }  // namespace tmb

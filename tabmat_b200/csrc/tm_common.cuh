@@ -147,7 +147,8 @@ int dense_cross_fused(const F* X, int64_t n, int64_t p, const F* d, const int32_
                       const int32_t* csr_indices, const int32_t* csr_indptr, int64_t p_sparse,
                       F* out_sparse, int runs, cudaStream_t st);
 extern int g_cross_runs_mode;
-constexpr int TM_BLOCK_FLAG_RUNS = 1;  // tm_block_desc.flags bit 0
+constexpr int TM_BLOCK_FLAG_RUNS = 1;     // tm_block_desc.flags bit 0
+constexpr int TM_BLOCK_FLAG_PRIMARY = 2;  // bit 1: the primary sort key
 extern int g_dense_f32_mode;
 
 // ---- fused index blocks (split_index.cu): categorical self / pair blocks and categorical x
@@ -167,6 +168,6 @@ bool index_cat_sparse_fits(int n_cat, const int64_t* K, int64_t p_s);
 template <typename F>
 int index_cat_sparse(const void* rec, int n_cat, const int64_t* K, const int32_t* runs,
                      const F* csc_data, const int32_t* csc_row, const int32_t* csc_indptr,
-                     int64_t p_s, F* const* outs, cudaStream_t st);
+                     int64_t p_s, int n_row_blocks, F* const* outs, cudaStream_t st);
 
 }  // namespace tmb

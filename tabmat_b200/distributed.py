@@ -141,8 +141,17 @@ class RowShardedMatrix:
         the p x p float64 result into the host array ``out`` on rank ``dst`` (every rank when
         ``dst`` is None).  One rank: the two-phase path of ``SplitMatrix.sandwich_into`` (host
         copy overlapped with compute).  Asynchronous on the current stream."""
-        if self.world_size == 1 and hasattr(self.local, "sandwich_into"):
-            return self.local.sandwich_into(d_local, out, shard_rows(rows, self.lo, self.hi))
+        if hasattr(self.local, "sandwich_into"):
+            if self.world_size == 1:
+                return self.local.sandwich_into(d_local, out, shard_rows(rows, self.lo, self.hi))
+
+            def reduce(ws):  # sum a slice of the flat block workspace over the ranks
+                if ws.numel():
+                    self._allreduce(ws, dst)
+                return dst is None or self.rank == dst
+
+            return self.local.sandwich_into(d_local, out, shard_rows(rows, self.lo, self.hi),
+                                            reduce=reduce)
         from . import _dev
         from ._lib import check, lib
 

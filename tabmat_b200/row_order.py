@@ -105,9 +105,10 @@ class RowSortedMatrix(MatrixBase):
         else:
             sorted_mat = SplitMatrix([m[perm, :] if not isinstance(m, CategoricalMatrix)
                                       else m[perm] for m in X.matrices], X.indices)
-        for b in blocks:
-            # block order is preserved by the SplitMatrix constructor for already-combined input
-            sorted_mat.matrices[b]._run_sorted = True
+        for q, b in enumerate(blocks):
+            # block order is preserved by the SplitMatrix constructor for already-combined input;
+            # tm_block_desc.flags: bit 0 = sort key, bit 1 = primary sort key
+            sorted_mat.matrices[b]._run_sorted = 3 if q == 0 else 1
         return cls(sorted_mat, perm, blocks)
 
     @property
@@ -157,7 +158,7 @@ class RowSortedMatrix(MatrixBase):
         out = self.mat._sandwich_dev(self._gather(d_t), self._rows_in(rows), cols)
         return _dev.ret(out, host)
 
-    def sandwich_into(self, d, out, rows=None):
+    def sandwich_into(self, d, out, rows=None, reduce=None):
         """Host-buffer form of :meth:`sandwich` (see ``SplitMatrix.sandwich_into``): ``d`` from
         host or device memory in the caller's row order, the result into the host array ``out``."""
         if _dev.is_dev(d):
@@ -167,7 +168,7 @@ class RowSortedMatrix(MatrixBase):
             d_t = torch.empty(src.shape, dtype=src.dtype, device=_dev.require_cuda())
             d_t.copy_(src, non_blocking=True)
         check_sandwich_compatible(self, d_t)
-        return self.mat._sandwich_into_dev(self._gather(d_t), self._rows_in(rows), out)
+        return self.mat._sandwich_into_dev(self._gather(d_t), self._rows_in(rows), out, reduce)
 
     def _sandwich_blocks_dev(self, d_t: torch.Tensor, rows_t):
         """Flat block workspace (for the row-sharded allreduce, distributed.py)."""
@@ -223,8 +224,8 @@ class RowSortedMatrix(MatrixBase):
     def astype(self, dtype, order="K", casting="unsafe", copy=True):
         new = RowSortedMatrix(self.mat.astype(dtype, order, casting, copy), self._perm,
                               self.sort_blocks)
-        for b in self.sort_blocks:
-            new.mat.matrices[b]._run_sorted = True
+        for q, b in enumerate(self.sort_blocks):
+            new.mat.matrices[b]._run_sorted = 3 if q == 0 else 1
         return new
 
     def multiply(self, other):

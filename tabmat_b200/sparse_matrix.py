@@ -112,6 +112,27 @@ class SparseMatrix(MatrixBase):
         self._init_names(column_names, term_names)
         return self
 
+    def _row_blocked_csc(self, block_rows: int):
+        """(data, row ids, offsets, n_blocks): the non-zeros ordered by (row block, column, row)
+        with ``n_blocks * ncols + 1`` offsets — the row-blocked CSC copy that keeps the per-row
+        gathers of the categorical x sparse kernel inside the L2 (built once and cached, like
+        the reference's cached CSR, sparse_matrix.py:133-143)."""
+        cached = self.__dict__.get("_bcsc")
+        if cached is None or cached[4] != block_rows:
+            c = self._csr
+            n, p = self._shape
+            n_blocks = max(1, -(-n // block_rows))
+            key = (c.row.to(torch.int64) // block_rows) * p + c.indices.to(torch.int64)
+            order = torch.argsort(key, stable=True)  # CSR order is row-major: rows stay sorted
+            counts = torch.bincount(key, minlength=n_blocks * p)
+            del key
+            ptr = torch.zeros(n_blocks * p + 1, dtype=torch.int64, device=c.data.device)
+            ptr[1:] = torch.cumsum(counts, 0)
+            cached = (c.data[order].contiguous(), c.row[order].contiguous(),
+                      ptr.to(torch.int32).contiguous(), n_blocks, block_rows)
+            self.__dict__["_bcsc"] = cached
+        return cached[:4]
+
     def _init_names(self, column_names, term_names):
         if column_names is not None:
             if len(column_names) != self.shape[1]:

@@ -19,7 +19,7 @@ import torch
 from scipy import sparse as sps
 
 from . import _dev
-from ._lib import BlockDesc, check, fn, lib
+from ._lib import CSC_ROW_BLOCK, BlockDesc, check, fn, lib
 from .categorical_matrix import CategoricalMatrix
 from .dense_matrix import DenseMatrix, _accumulate_out
 from .ext.split import dense_cross_sandwich, is_sorted, split_col_subsets
@@ -275,14 +275,25 @@ class SplitMatrix(MatrixBase):
                 dsc.kind, dsc.data, dsc.nnz = 1, c.data.data_ptr(), c.nnz
                 dsc.csr_indices, dsc.csr_indptr = c.indices.data_ptr(), c.indptr.data_ptr()
                 dsc.csr_row = c.row.data_ptr()
-                cc = mat._csc
-                dsc.csc_data, dsc.csc_indices = cc.data.data_ptr(), cc.indices.data_ptr()
-                dsc.csc_indptr = cc.indptr.data_ptr()
+                if (os.environ.get("TABMAT_B200_CSC_ROW_BLOCKS") == "1" and c.nnz
+                        and mat.shape[0] > CSC_ROW_BLOCK + CSC_ROW_BLOCK // 2):
+                    # opt-in: row-blocked CSC (record gathers of one work item stay inside a
+                    # 32 MB window).  Measured slower than the plain CSC order on B200 (4.1 ms vs
+                    # 3.6 ms at n = 4e7): columns are walked top-down by all CTAs at the same
+                    # pace, so the plain order already keeps the gathers in a moving window,
+                    # and the per-item zero / flush of the column tables costs more.
+                    bd, br, bp, nblk = mat._row_blocked_csc(CSC_ROW_BLOCK)
+                    dsc.csc_data, dsc.csc_indices = bd.data_ptr(), br.data_ptr()
+                    dsc.csc_indptr, dsc.csc_row_blocks = bp.data_ptr(), nblk
+                else:
+                    cc = mat._csc
+                    dsc.csc_data, dsc.csc_indices = cc.data.data_ptr(), cc.indices.data_ptr()
+                    dsc.csc_indptr, dsc.csc_row_blocks = cc.indptr.data_ptr(), 0
             elif isinstance(mat, CategoricalMatrix):
                 ok = _dev.torch_dtype(mat.dtype) == tdtype
                 dsc.kind, dsc.data, dsc.drop_first = 2, mat._codes.data_ptr(), int(mat.drop_first)
                 # rows stored sorted by this block's codes (row_order.py): run-aggregating kernels
-                dsc.flags = 1 if getattr(mat, "_run_sorted", False) else 0
+                dsc.flags = int(getattr(mat, "_run_sorted", 0))  # 1 sort key, 3 primary key
                 # many levels: too wide for the one-hot tensor path.  Opt-in sorted-gather kernel
                 # (TABMAT_B200_GATHER=1): measured slower than the RED scatter pass on B200
                 # (5.5 ms vs 3.4 ms per block at n = 4e7), kept for machines / shapes where the
@@ -336,7 +347,7 @@ class SplitMatrix(MatrixBase):
             self.__dict__["_col_runs"] = runs
         return runs
 
-    def sandwich_into(self, d, out, rows=None):
+    def sandwich_into(self, d, out, rows=None, reduce=None):
         """``out[:] = X[rows].T @ diag(d[rows]) @ X[rows]`` for a HOST float64 ``out`` (p x p,
         C-contiguous numpy array or CPU tensor; pinned memory gives full PCIe speed).
 
@@ -355,9 +366,12 @@ class SplitMatrix(MatrixBase):
             d_t = torch.empty(src.shape, dtype=src.dtype, device=_dev.require_cuda())
             d_t.copy_(src, non_blocking=True)
         check_sandwich_compatible(self, d_t)
-        return self._sandwich_into_dev(d_t, _dev.idx32(rows), out)
+        return self._sandwich_into_dev(d_t, _dev.idx32(rows), out, reduce)
 
-    def _sandwich_into_dev(self, d_t: torch.Tensor, rows_t, out):
+    def _sandwich_into_dev(self, d_t: torch.Tensor, rows_t, out, reduce=None):
+        """``reduce(ws_slice) -> bool`` (row-sharded callers): sum the slice of the flat block
+        workspace over the ranks in place and tell whether this rank holds the result (and so
+        places and copies it)."""
         p = self.shape[1]
         if isinstance(out, torch.Tensor):
             ok = (not out.is_cuda) and out.dtype == torch.float64 and out.is_contiguous()
@@ -381,29 +395,54 @@ class SplitMatrix(MatrixBase):
         runs = self._column_runs()
         dense_runs = [r for r in runs if r[2]]
         other_runs = [r for r in runs if not r[2]]
-        if plan is None or not dense_runs or not other_runs or len(runs) > 6:
-            res = self._sandwich_dev(d_t, rows_t, None)
+        # with a collective in between, the two phases need the dense block's part of the
+        # workspace to be one contiguous piece: true when the dense block comes first
+        two_phase = (plan is not None and dense_runs and other_runs and len(runs) <= 6
+                     and (reduce is None or isinstance(self.matrices[0], DenseMatrix)))
+        if not two_phase:
+            if reduce is not None and plan is not None:
+                ws = self._sandwich_blocks_dev(d_t, rows_t)
+                if not reduce(ws):
+                    return None
+                res = self._assemble_dev(ws)
+            elif reduce is not None:
+                res = self._sandwich_dev(d_t, rows_t, None)
+                if not reduce(res):
+                    return None
+            else:
+                res = self._sandwich_dev(d_t, rows_t, None)
             copy2d(res, 0, p, 0, p, st)
             return out
         descs, elems = plan
         nb = len(self.matrices)
         ws = torch.empty(elems, dtype=d_t.dtype, device=d_t.device)
-        buf = torch.empty((p, p), dtype=torch.float64, device=d_t.device)
         args = (descs, nb, self.shape[0], _dev.ptr(d_t), _dev.ptr(rows_t), _dev.length(rows_t),
                 _dev.ptr(ws))
+        # elements of the dense block's self + cross blocks at the head of the workspace
+        head = (int(lib.tm_split_workspace_head_elems(descs, nb))
+                if isinstance(self.matrices[0], DenseMatrix) else 0)
         # phase 1: everything without the dense operand, then its host copy on a second stream
         check(fn("tm_split_sandwich_blocks_part", suf)(*args, 1, st))
-        check(fn("tm_split_sandwich_assemble_part", suf)(descs, nb, _dev.ptr(ws), _dev.ptr(buf), p,
-                                                        1, st))
-        cs = self.__dict__.get("_copy_stream")
-        if cs is None:
-            cs = self.__dict__["_copy_stream"] = torch.cuda.Stream()
-        cs.wait_stream(torch.cuda.current_stream())
-        for (r0, r1, _) in other_runs:
-            for (c0, c1, _) in other_runs:
-                copy2d(buf, r0, r1, c0, c1, cs.cuda_stream)
+        mine = True if reduce is None else reduce(ws[head:])
+        buf = None
+        cs = None
+        if mine:
+            buf = torch.empty((p, p), dtype=torch.float64, device=d_t.device)
+            check(fn("tm_split_sandwich_assemble_part", suf)(descs, nb, _dev.ptr(ws),
+                                                            _dev.ptr(buf), p, 1, st))
+            cs = self.__dict__.get("_copy_stream")
+            if cs is None:
+                cs = self.__dict__["_copy_stream"] = torch.cuda.Stream()
+            cs.wait_stream(torch.cuda.current_stream())
+            for (r0, r1, _) in other_runs:
+                for (c0, c1, _) in other_runs:
+                    copy2d(buf, r0, r1, c0, c1, cs.cuda_stream)
         # phase 2: the dense block's own and cross blocks
         check(fn("tm_split_sandwich_blocks_part", suf)(*args, 2, st))
+        if reduce is not None:
+            reduce(ws[:head])
+        if not mine:
+            return None
         check(fn("tm_split_sandwich_assemble_part", suf)(descs, nb, _dev.ptr(ws), _dev.ptr(buf), p,
                                                         2, st))
         for (r0, r1, _) in dense_runs:

@@ -35,12 +35,13 @@ def test_version_and_error_string():
 def test_block_descriptor_layout_matches_the_library():
     from tabmat_b200 import _lib
 
-    assert _lib.lib.tm_sizeof_block_desc() == ctypes.sizeof(_lib.BlockDesc) == 120
+    assert _lib.lib.tm_sizeof_block_desc() == ctypes.sizeof(_lib.BlockDesc) == 128
     descs = (_lib.BlockDesc * 2)()
     descs[0].kind, descs[0].ncols = 0, 5          # dense 5 columns
     descs[1].kind, descs[1].ncols = 2, 3          # categorical 3 columns
-    # self blocks 25 + 3 (diagonal), cross block 15
-    assert _lib.lib.tm_split_workspace_elems(descs, 2) == 43
+    # self blocks 25 + 3 (diagonal), cross block 15, each padded to a multiple of 4 elements
+    assert _lib.lib.tm_split_workspace_elems(descs, 2) == 28 + 16 + 4
+    assert _lib.lib.tm_split_workspace_head_elems(descs, 2) == 28 + 16
 
 
 def test_product_path_does_not_touch_the_oracle():

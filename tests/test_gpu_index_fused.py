@@ -97,3 +97,29 @@ def test_fused_index_counts_are_exact():
         Ac = A.tocoo()
         np.add.at(cs, (c1[Ac.row], Ac.col), 1.0)
         np.testing.assert_array_equal(got[o[1]:o[2], o[0]:o[1]], cs)
+
+
+@pytest.mark.parametrize("suf", ["f32", "f64"])
+@pytest.mark.parametrize("levels", [(5,), (10, 50, 200, 1000, 2000), (300, 40), (4, 9, 300, 7, 2, 40)],
+                         ids=lambda lv: "x".join(map(str, lv)))
+def test_row_blocked_csc_path(suf, levels, monkeypatch):
+    """Row-blocked CSC copy of the sparse block (many-row matrices): shrink the block so that a
+    6007-row matrix spans 7 row blocks and compare with the dense recomputation."""
+    import tabmat_b200 as tm
+    from tabmat_b200 import split_matrix
+
+    monkeypatch.setattr(split_matrix, "CSC_ROW_BLOCK", 1000)
+    monkeypatch.setenv("TABMAT_B200_CSC_ROW_BLOCKS", "1")  # opt-in layout
+    dt = cases.DTYPES[suf]
+    n = 6007
+    X, full, d, rng = _build(dt, n, levels, seed=99)
+    plan = X._native_plan(tm._dev.torch_dtype(dt))
+    assert plan is not None and plan[0][1].csc_row_blocks == 7
+    rows = np.sort(rng.choice(n, size=n // 3, replace=False)).astype(np.int32)
+    S = tm.RowSortedMatrix.from_split(X)
+    for r in (None, rows):
+        F = full if r is None else full[r]
+        dd = d.astype(np.float64) if r is None else d.astype(np.float64)[r]
+        ref = (F * dd[:, None]).T @ F
+        cases.assert_close(X.sandwich(d, r), ref, dt, f"row-blocked csc {levels}")
+        cases.assert_close(S.sandwich(d, r), ref, dt, f"row-blocked csc, sorted rows {levels}")

@@ -304,3 +304,41 @@ def test_sandwich_into_host_buffer(suf, layout):
             cases.assert_close(out_t.numpy(), ref, dt, f"sandwich_into pinned {layout}")
     with pytest.raises(ValueError):
         X.sandwich_into(d, np.zeros((p, p), dtype=np.float32))
+
+
+@pytest.mark.parametrize("dense_first", [True, False])
+def test_sandwich_into_with_a_collective_between_the_phases(dense_first):
+    """The row-sharded caller's hook: `reduce` sees the index part of the flat workspace first,
+    then the dense block's part (both contiguous when the dense block comes first), and decides
+    whether this rank holds the result."""
+    import torch
+
+    import tabmat_b200 as tm
+
+    dt = np.float32
+    n = 3001
+    mats, full, d, rng = _mats(dt, n, seed=41)
+    if not dense_first:
+        mats = mats[1:] + mats[:1]
+        full = np.hstack([full[:, 8:], full[:, :8]])
+    X = tm.SplitMatrix(mats)
+    p = X.shape[1]
+    ref = (full * d.astype(np.float64)[:, None]).T @ full
+    seen = []
+
+    def twice(ws):  # a two-rank sum where both ranks hold the same shard
+        seen.append(int(ws.numel()))
+        ws *= 2
+        return True
+
+    for M in (X, tm.RowSortedMatrix.from_split(X)):
+        seen.clear()
+        out = np.full((p, p), np.nan)
+        assert M.sandwich_into(d, out, reduce=twice) is out
+        torch.cuda.synchronize()
+        cases.assert_close(out, 2 * ref, dt, "sandwich_into with reduce hook")
+        if dense_first:
+            assert seen[1] == 8 * p and len(seen) == 2  # index part, then the dense block's part
+        else:
+            assert len(seen) == 1  # one collective over the whole workspace
+        assert M.sandwich_into(d, out, reduce=lambda ws: False) is None
