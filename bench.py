@@ -48,7 +48,7 @@ ROW_ORDER_DEFAULT = "sorted"
 PASS_KERNEL = {
     "tensor": "k_dense_syrk_tc (tcgen05 SYRK + one-hot MMAs: dense self, dense x few-level cats)",
     "scatter": "k_dense_cross_fused / k_dense_cross_runs (dense x many-level cats + dense x sparse, vector RED)",
-    "index": "index pass (k_sparse_sandwich, k_cat_sparse, k_cat_cat, k_cat_hist)",
+    "index": "index pass (k_pack_records, k_cat_pairs, k_cat_sparse_csc, k_sparse_sandwich)",
 }
 WORKLOAD = ("SplitMatrix 128 dense + 3x1000 CSC @1e-3 + cat{10,50,200,1000,2000}, p=6388, "
             "f32, n=%d total rows")
@@ -519,6 +519,8 @@ def main():
                        "row_order": (args.row_order if args.row_order == "original" else
                                      "sorted by (cat2000, cat1000) at construction; d permuted "
                                      "inside the timed region"),
+                       "pass_schedule": "serial (tensor, index, scatter): overlapping them on side "
+                                        "streams measured within 1 ms of the serial sum",
                        "algorithmic_flop_per_step": flops,
                        "whole_step_hbm_gbs": whole_bytes / (ms_step * 1e-3) / 1e9,
                        "whole_step_hbm_frac": whole_bytes / (ms_step * 1e-3) / 1e9 / hbm_peak},

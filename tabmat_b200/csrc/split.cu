@@ -509,6 +509,63 @@ int split_blocks(const tm_block_desc* blk, int nb, int64_t n, const F* d, const 
     return 0;
 }
 
+// ---- placement of all blocks in ONE launch -------------------------------------------------
+// A job = one stored block (na x nb at `src`, destination rows ri / columns ci; diag: the
+// vector of a categorical self block).  32 x 32 tiles of all jobs are numbered consecutively;
+// a CTA finds its job by a linear scan of the (at most 64) tile prefixes.  The per-block
+// launches this replaces cost ~5 us each (28 of them at the benchmark shape = half of the
+// placement time, and 4 % of a step at 8 GPUs).
+constexpr int ASM_MAX_JOBS = 64;
+struct AsmJobs {
+    const void* src[ASM_MAX_JOBS];
+    const int64_t* ri[ASM_MAX_JOBS];
+    const int64_t* ci[ASM_MAX_JOBS];
+    int na[ASM_MAX_JOBS];
+    int nb[ASM_MAX_JOBS];
+    int tile0[ASM_MAX_JOBS + 1];   // first tile of the job
+    unsigned char kind[ASM_MAX_JOBS];  // 0 block, 1 block + mirror, 2 diagonal
+    int n_jobs;
+};
+
+template <typename F>
+__global__ void __launch_bounds__(256)
+k_assemble_all(const AsmJobs jobs, double* __restrict__ out, int64_t ld) {
+    __shared__ F tile[32][33];
+    const int t = blockIdx.x;
+    int q = 0;
+    while (q + 1 < jobs.n_jobs && t >= jobs.tile0[q + 1]) ++q;
+    const int na = jobs.na[q], nb = jobs.nb[q];
+    const int tiles_x = (nb + 31) / 32;
+    const int local = t - jobs.tile0[q];
+    const int64_t a0 = (int64_t)(local / tiles_x) * 32, b0 = (int64_t)(local % tiles_x) * 32;
+    const int64_t* __restrict__ ri = jobs.ri[q];
+    const int64_t* __restrict__ ci = jobs.ci[q];
+    const F* __restrict__ src = static_cast<const F*>(jobs.src[q]);
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int kind = jobs.kind[q];
+    if (kind == 2) {  // diagonal block: na == nb, src = the diagonal
+        for (int i = ty; i < 32; i += 8) {
+            const int64_t a = a0 + i, b = b0 + tx;
+            if (a < na && b < nb) out[ri[a] * ld + ri[b]] = a == b ? (double)src[a] : 0.0;
+        }
+        return;
+    }
+    for (int i = ty; i < 32; i += 8) {
+        const int64_t a = a0 + i, b = b0 + tx;
+        if (a < na && b < nb) {
+            const F v = src[a * nb + b];
+            tile[i][tx] = v;
+            out[ri[a] * ld + ci[b]] = (double)v;
+        }
+    }
+    if (kind != 1) return;
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+        const int64_t b = b0 + i, a = a0 + tx;
+        if (a < na && b < nb) out[ci[b] * ld + ri[a]] = (double)tile[tx][i];
+    }
+}
+
 template <typename F>
 int split_assemble(const tm_block_desc* blk, int nb, const F* ws, double* out, int64_t ld,
                    tm_stream_t stream, int part = 0) {
@@ -516,6 +573,49 @@ int split_assemble(const tm_block_desc* blk, int nb, const F* ws, double* out, i
     int64_t off = 0;
     // part 1: blocks without a dense operand; part 2: blocks with one; 0: all
     auto wanted = [part](bool has_dense) { return part == 0 || (part == 2) == has_dense; };
+    static const bool one_launch =
+        !(getenv("TABMAT_B200_ASSEMBLE_FUSED") && atoi(getenv("TABMAT_B200_ASSEMBLE_FUSED")) == 0);
+    bool all_indexed = true;
+    for (int i = 0; i < nb; ++i) all_indexed &= blk[i].col_index != nullptr;
+    if (one_launch && all_indexed && nb * (nb + 1) / 2 <= ASM_MAX_JOBS) {
+        AsmJobs jobs;
+        memset(&jobs, 0, sizeof(jobs));
+        int nj = 0;
+        int64_t tiles = 0;
+        auto add = [&](const F* src, const tm_block_desc& a, const tm_block_desc& b, int kind) {
+            if (a.ncols <= 0 || b.ncols <= 0) return;
+            jobs.src[nj] = src;
+            jobs.ri[nj] = a.col_index;
+            jobs.ci[nj] = b.col_index;
+            jobs.na[nj] = (int)a.ncols;
+            jobs.nb[nj] = (int)b.ncols;
+            jobs.kind[nj] = (unsigned char)kind;
+            jobs.tile0[nj] = (int)tiles;
+            tiles += ((a.ncols + 31) / 32) * ((b.ncols + 31) / 32);
+            ++nj;
+        };
+        for (int i = 0; i < nb; ++i) {
+            const tm_block_desc& bi = blk[i];
+            if (wanted(bi.kind == KIND_DENSE)) add(ws + off, bi, bi, bi.kind == KIND_CAT ? 2 : 0);
+            off += ws_pad(self_elems(bi));
+            for (int j = i + 1; j < nb; ++j) {
+                const tm_block_desc& bj = blk[j];
+                const tm_block_desc& a = cross_rows_are_j(bi, bj) ? bj : bi;
+                const tm_block_desc& b = cross_rows_are_j(bi, bj) ? bi : bj;
+                if (wanted(bi.kind == KIND_DENSE || bj.kind == KIND_DENSE)) add(ws + off, a, b, 1);
+                off += ws_pad(bi.ncols * bj.ncols);
+            }
+        }
+        jobs.tile0[nj] = (int)tiles;
+        jobs.n_jobs = nj;
+        if (nj == 0 || tiles == 0) return 0;
+        if (tiles < (int64_t)kMaxGridX) {
+            k_assemble_all<F><<<(unsigned)tiles, 256, 0, as_stream(stream)>>>(jobs, out, ld);
+            TM_LAUNCHED();
+            return 0;
+        }
+        off = 0;  // absurdly large: fall through to the per-block launches
+    }
     for (int i = 0; i < nb; ++i) {
         const tm_block_desc& bi = blk[i];
         int rc = 0;

@@ -222,36 +222,31 @@ k_cat_pairs(const RowRec<F>* __restrict__ rec, int64_t n, const PairParams prm) 
 // ---------------------------------------------------------------------------------------
 // categorical x sparse for all categorical blocks, CSC-driven, shared-memory column tables
 // ---------------------------------------------------------------------------------------
-enum { CS_PRIV = 0, CS_ATOM = 1, CS_L2 = 2, CS_REG = 3 };
+enum { CS_PRIV = 0, CS_ATOM = 1, CS_L2 = 2 };
 constexpr int CS_THREADS = 256;
-constexpr int CS_REG_MAX = 16;
 
 struct CatSparseParams {
     int K[IDX_MAX_CATS];
     int mode[IDX_MAX_CATS];      // CS_PRIV: one replica per thread, [level][thread], plain RMW
                                  // CS_ATOM: shared-memory atomics, `rep` replicas (lane % rep)
                                  // CS_L2:   scalar REDs straight into out (zero-filled by the host)
-                                 // CS_REG:  <= 16 levels summed in registers (one block at most)
     int rep[IDX_MAX_CATS];
     int off[IDX_MAX_CATS];       // element offset of block c's shared-memory table
     int runs[IDX_MAX_CATS];
     void* out[IDX_MAX_CATS];     // K_c x p_s, row-major
     int smem_elems;
-    int n_row_blocks;            // > 1: row-blocked CSC, `indptr` has n_row_blocks * p_s + 1 entries
-                                 // and every out is zero-filled and accumulated into
 };
 
-// One CTA per work item = (row block, sparse column j), row block slowest.  Per non-zero
-// (k, j, a): val = d[k] * a from the 32-byte row record, then per categorical block one update
-// of out_c[code_c[k], j]:
-//   <= 16 levels -> predicated adds into registers (one block), reduced per warp at the end,
-//   few levels   -> the thread's private column table in shared memory (plain CSC only),
+// One CTA per sparse column j (grid-stride), plain CSC.  Per non-zero (k, j, a): val = d[k] * a
+// from the 32-byte row record, then per categorical block one update of out_c[code_c[k], j]:
+//   few levels   -> the thread's private column table in shared memory (no atomics),
 //   some levels  -> shared-memory atomics on a replicated column table,
-//   many levels  -> scalar L2 RED (the addresses of one column are p_s * 4 bytes apart; runs of
-//                   equal codes are pre-summed when the rows are stored sorted by that block).
-// Row blocks (2^20 rows = 32 MB of records) keep the record gathers inside L2: with the plain
-// CSC order every non-zero is a random 32-byte read over n * 32 bytes of records, which costs a
-// 64-byte DRAM access each (7.7 GB and 3.6 ms at the benchmark shape, the whole kernel time).
+//   many levels  -> scalar L2 RED (the addresses of one column are p_s * 4 bytes apart, so they
+//                   never share a sector; runs of equal codes are pre-summed when the rows are
+//                   stored sorted with that block as the primary key).
+// ncu (profiles/ncu_step_r1c_summary.csv): 3.6 ms at the benchmark shape, latency-bound on the
+// record gathers — 8.7 GB of DRAM reads, i.e. one 64-byte access per non-zero; the row-blocked
+// variant below keeps them in L2.
 template <typename F, int NC, int U>
 __global__ void __launch_bounds__(CS_THREADS)
 k_cat_sparse_csc(const F* __restrict__ data, const int32_t* __restrict__ row_idx,
@@ -262,16 +257,10 @@ k_cat_sparse_csc(const F* __restrict__ data, const int32_t* __restrict__ row_idx
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
     constexpr int NW = CS_THREADS / 32;
-    const bool accumulate = prm.n_row_blocks > 1;
-    const int64_t n_items = (int64_t)(accumulate ? prm.n_row_blocks : 1) * p_s;
-    for (int64_t w = blockIdx.x; w < n_items; w += gridDim.x) {
-        const int j = (int)(w % p_s);
+    for (int j = blockIdx.x; j < p_s; j += gridDim.x) {
         for (int i = threadIdx.x; i < prm.smem_elems; i += CS_THREADS) smem[i] = F(0);
-        F racc[CS_REG_MAX];
-#pragma unroll
-        for (int l = 0; l < CS_REG_MAX; ++l) racc[l] = F(0);
         __syncthreads();
-        const int e0 = indptr[w], e1 = indptr[w + 1];
+        const int e0 = indptr[j], e1 = indptr[j + 1];
         for (int eb = e0 + wib * (32 * U); eb < e1; eb += NW * (32 * U)) {
             RowRec<F> r[U];
             F a[U];
@@ -298,11 +287,6 @@ k_cat_sparse_csc(const F* __restrict__ data, const int32_t* __restrict__ row_idx
 #pragma unroll
                 for (int c = 0; c < NC; ++c) {
                     int key = r[u].c[c];
-                    if (prm.mode[c] == CS_REG) {
-#pragma unroll
-                        for (int l = 0; l < CS_REG_MAX; ++l) racc[l] += key == l ? val0 : F(0);
-                        continue;
-                    }
                     if (prm.mode[c] == CS_PRIV) {
                         if (key >= 0) smem[prm.off[c] + key * CS_THREADS + threadIdx.x] += val0;
                         continue;
@@ -318,17 +302,6 @@ k_cat_sparse_csc(const F* __restrict__ data, const int32_t* __restrict__ row_idx
                 }
             }
         }
-#pragma unroll
-        for (int c = 0; c < NC; ++c) {
-            if (prm.mode[c] != CS_REG) continue;
-#pragma unroll
-            for (int l = 0; l < CS_REG_MAX; ++l) {
-                F sum = racc[l];
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-                if (lane == 0 && l < prm.K[c] && sum != F(0)) atomicAdd(smem + prm.off[c] + l, sum);
-            }
-        }
         __syncthreads();
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
@@ -342,25 +315,106 @@ k_cat_sparse_csc(const F* __restrict__ data, const int32_t* __restrict__ row_idx
                     for (int q = 0; q < NW; ++q) sum += tab[q * 32 + lane];
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-                    if (lane == 0) {
-                        F* dst = out + (int64_t)lvl * p_s + j;
-                        if (!accumulate) *dst = sum;
-                        else if (sum != F(0)) red_add(dst, sum);
-                    }
+                    if (lane == 0) out[(int64_t)lvl * p_s + j] = sum;
                 }
-            } else if (prm.mode[c] == CS_ATOM || prm.mode[c] == CS_REG) {
+            } else if (prm.mode[c] == CS_ATOM) {
                 const int rep = prm.rep[c];
                 for (int lvl = threadIdx.x; lvl < Kc; lvl += CS_THREADS) {
                     const F* tab = smem + prm.off[c] + lvl;
                     F sum = F(0);
                     for (int q = 0; q < rep; ++q) sum += tab[q * Kc];
-                    F* dst = out + (int64_t)lvl * p_s + j;
-                    if (!accumulate) *dst = sum;
-                    else if (sum != F(0)) red_add(dst, sum);
+                    out[(int64_t)lvl * p_s + j] = sum;
                 }
             }
         }
         __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// categorical x sparse over the ROW-BLOCKED CSC copy, column-owner form.
+// A CTA owns a contiguous set of sparse columns for the whole kernel and keeps their column
+// tables (blocks with <= 512 levels, replicated) in shared memory; it walks the row blocks in
+// order and, inside a row block, the non-zeros of its columns.  The grid is one resident wave,
+// every CTA has the same expected work per row block, so all CTAs gather row records from the
+// same window of `block_rows * 32` bytes at any time — the gathers hit L2 instead of costing a
+// 64-byte DRAM access per non-zero (8.7 GB of DRAM reads per launch in k_cat_sparse_csc above).
+// No barriers in the main loop, no zero-fill or flush per work item; wide blocks take L2 REDs.
+// ---------------------------------------------------------------------------------------
+constexpr int CO_THREADS = 256;
+
+struct ColOwnerParams {
+    int K[IDX_MAX_CATS];
+    int in_smem[IDX_MAX_CATS];
+    int rep[IDX_MAX_CATS];
+    int off[IDX_MAX_CATS];       // offset of block c's table inside one column slot
+    int runs[IDX_MAX_CATS];
+    void* out[IDX_MAX_CATS];
+    int slot;                    // shared-memory elements per owned column
+    int cols_per_cta;
+    int n_row_blocks;
+};
+
+template <typename F, int NC>
+__global__ void __launch_bounds__(CO_THREADS)
+k_cat_sparse_cols(const F* __restrict__ data, const int32_t* __restrict__ row_idx,
+                  const int32_t* __restrict__ indptr, int p_s,
+                  const RowRec<F>* __restrict__ rec, const ColOwnerParams prm) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    F* smem = reinterpret_cast<F*>(smem_raw);
+    const int lane = threadIdx.x & 31;
+    const int c0 = blockIdx.x * prm.cols_per_cta;
+    const int c1 = min(p_s, c0 + prm.cols_per_cta);
+    if (c0 >= c1) return;
+    for (int i = threadIdx.x; i < (c1 - c0) * prm.slot; i += CO_THREADS) smem[i] = F(0);
+    __syncthreads();
+    for (int blk = 0; blk < prm.n_row_blocks; ++blk) {
+        const int64_t base = (int64_t)blk * p_s;
+        for (int j = c0; j < c1; ++j) {
+            F* tab = smem + (j - c0) * prm.slot;
+            const int e0 = indptr[base + j], e1 = indptr[base + j + 1];
+            // warp-uniform trip count (run_reduce needs whole warps)
+            for (int eb = e0 + (threadIdx.x & ~31); eb < e1; eb += CO_THREADS) {
+                const int e = eb + lane;
+                RowRec<F> r;
+                F a = F(0);
+                if (e < e1) {
+                    a = data[e];
+                    r = load_rec<F>(rec, row_idx[e]);
+                } else {
+                    r.d = F(0);
+#pragma unroll
+                    for (int c = 0; c < rec_max_cats<F>(); ++c) r.c[c] = -1;
+                }
+                const F val0 = r.d * a;
+#pragma unroll
+                for (int c = 0; c < NC; ++c) {
+                    int key = r.c[c];
+                    F val = val0;
+                    bool head = true;
+                    if (prm.runs[c]) head = run_reduce<F, int>(key, val, lane);
+                    if (!head || key < 0) continue;
+                    if (prm.in_smem[c])
+                        atomicAdd(tab + prm.off[c] + (lane % prm.rep[c]) * prm.K[c] + key, val);
+                    else
+                        red_add(static_cast<F*>(prm.out[c]) + (int64_t)key * p_s + j, val);
+                }
+            }
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        if (!prm.in_smem[c]) continue;
+        F* out = static_cast<F*>(prm.out[c]);
+        const int Kc = prm.K[c], rep = prm.rep[c], nco = c1 - c0;
+        for (int i = threadIdx.x; i < Kc * nco; i += CO_THREADS) {
+            const int lvl = i / nco, jj = i - lvl * nco;  // consecutive threads, consecutive j
+            const F* t = smem + jj * prm.slot + prm.off[c] + lvl;
+            F sum = F(0);
+            for (int q = 0; q < rep; ++q) sum += t[q * Kc];
+            out[(int64_t)lvl * p_s + c0 + jj] = sum;
+        }
     }
 }
 
@@ -543,24 +597,18 @@ static int launch_cat_sparse(const F* data, const int32_t* row_idx, const int32_
         attr_set = true;
     }
     const size_t smem = sizeof(F) * (size_t)(prm.smem_elems > 0 ? prm.smem_elems : 1);
-    const int64_t items = (int64_t)(prm.n_row_blocks > 1 ? prm.n_row_blocks : 1) * p_s;
-    const int g = (int)(items < (int64_t)sm_count() * 12 ? items : (int64_t)sm_count() * 12);
+    const int g = p_s < sm_count() * 12 ? p_s : sm_count() * 12;
     k_cat_sparse_csc<F, NC, U><<<g, CS_THREADS, smem, st>>>(data, row_idx, indptr, p_s, rec, prm);
     TM_LAUNCHED();
     return 0;
 }
 
-// Plain CSC: private per-thread tables for <= 64 levels while they fit, shared-memory atomics
-// up to 512 levels, L2 REDs beyond (and for whatever does not fit).  Row-blocked CSC (work items
-// of ~1000 non-zeros): the smallest block with <= 16 levels in registers, small replicated
-// tables with shared-memory atomics (zeroing and flushing a private table would cost more than
-// the item itself), L2 REDs beyond.
+// Private per-thread tables for <= 64 levels while they fit, shared-memory atomics up to 512
+// levels, L2 REDs beyond (and for whatever does not fit).
 template <typename F>
-static void cat_sparse_layout(int n_cat, const int64_t* K, const int32_t* runs, int n_row_blocks,
+static void cat_sparse_layout(int n_cat, const int64_t* K, const int32_t* runs,
                               CatSparseParams& prm) {
     memset(&prm, 0, sizeof(prm));
-    prm.n_row_blocks = n_row_blocks;
-    const bool blocked = n_row_blocks > 1;
     const int64_t budget = (int64_t)(CS_SMEM_BUDGET / sizeof(F));
     int64_t used = 0;
     for (int c = 0; c < n_cat; ++c) {
@@ -571,26 +619,19 @@ static void cat_sparse_layout(int n_cat, const int64_t* K, const int32_t* runs, 
     }
     // smallest blocks first
     bool done[IDX_MAX_CATS] = {false};
-    bool reg_used = false;
     for (int it = 0; it < n_cat; ++it) {
         int best = -1;
         for (int c = 0; c < n_cat; ++c)
             if (!done[c] && (best < 0 || K[c] < K[best])) best = c;
         done[best] = true;
         const int64_t Kb = K[best];
-        if (blocked && !reg_used && Kb <= CS_REG_MAX) {
-            reg_used = true;
-            prm.mode[best] = CS_REG;
-            prm.off[best] = (int)used;
-            used += Kb;
-        } else if (!blocked && Kb <= 64 && used + Kb * CS_THREADS <= budget - 2048) {
+        if (Kb <= 64 && used + Kb * CS_THREADS <= budget - 2048) {
             prm.mode[best] = CS_PRIV;
             prm.off[best] = (int)used;
             used += Kb * CS_THREADS;
         } else if (Kb <= 512) {
             int rep = 1;
-            const int64_t cap = blocked ? 512 : 2048;  // table elements incl. replicas
-            while (rep < 8 && Kb * rep * 2 <= cap) rep *= 2;
+            while (rep < 8 && Kb * rep * 2 <= 2048) rep *= 2;
             if (used + Kb * rep > budget) rep = 1;
             if (used + Kb * rep > budget) continue;  // stays CS_L2
             prm.mode[best] = CS_ATOM;
@@ -610,6 +651,68 @@ bool index_cat_sparse_fits(int n_cat, const int64_t* K, int64_t p_s) {
 template bool index_cat_sparse_fits<float>(int, const int64_t*, int64_t);
 template bool index_cat_sparse_fits<double>(int, const int64_t*, int64_t);
 
+template <typename F, int NC>
+static int launch_cat_sparse_cols(const F* data, const int32_t* row_idx, const int32_t* indptr,
+                                  int p_s, const RowRec<F>* rec, const ColOwnerParams& prm, int grid,
+                                  cudaStream_t st) {
+    const size_t smem = sizeof(F) * (size_t)prm.slot * (size_t)prm.cols_per_cta;
+    k_cat_sparse_cols<F, NC><<<grid, CO_THREADS, smem > 0 ? smem : 16, st>>>(data, row_idx, indptr,
+                                                                          p_s, rec, prm);
+    TM_LAUNCHED();
+    return 0;
+}
+
+template <typename F>
+static int cat_sparse_cols(const RowRec<F>* rec, int n_cat, const int64_t* K, const int32_t* runs,
+                           const F* csc_data, const int32_t* csc_row, const int32_t* csc_indptr,
+                           int64_t p_s, int n_row_blocks, F* const* outs, cudaStream_t st) {
+    ColOwnerParams prm;
+    memset(&prm, 0, sizeof(prm));
+    prm.n_row_blocks = n_row_blocks;
+    // one resident wave: 4 CTAs of 256 threads per SM
+    int grid = sm_count() * 4;
+    if (grid > p_s) grid = (int)p_s;
+    prm.cols_per_cta = (int)((p_s + grid - 1) / grid);
+    grid = (int)((p_s + prm.cols_per_cta - 1) / prm.cols_per_cta);
+    const int64_t budget = (int64_t)(40 * 1024 / sizeof(F)) / prm.cols_per_cta;  // per column
+    int64_t slot = 0;
+    bool done[IDX_MAX_CATS] = {false};
+    for (int it = 0; it < n_cat; ++it) {  // smallest blocks first
+        int best = -1;
+        for (int c = 0; c < n_cat; ++c)
+            if (!done[c] && (best < 0 || K[c] < K[best])) best = c;
+        done[best] = true;
+        prm.K[best] = (int)K[best];
+        prm.runs[best] = runs ? runs[best] : 0;
+        prm.rep[best] = 1;
+        if (K[best] <= 512 && slot + K[best] <= budget) {
+            int rep = 1;
+            while (rep < 8 && K[best] * rep * 2 <= 256 && slot + K[best] * rep * 2 <= budget) rep *= 2;
+            prm.in_smem[best] = 1;
+            prm.rep[best] = rep;
+            prm.off[best] = (int)slot;
+            slot += K[best] * rep;
+        }
+    }
+    prm.slot = (int)slot;
+    for (int c = 0; c < n_cat; ++c) {
+        prm.out[c] = outs[c];
+        if (!prm.in_smem[c])
+            TM_CUDA(cudaMemsetAsync(outs[c], 0, sizeof(F) * (size_t)(K[c] * p_s), st));
+    }
+    switch (n_cat) {
+        case 1: return launch_cat_sparse_cols<F, 1>(csc_data, csc_row, csc_indptr, (int)p_s, rec, prm, grid, st);
+        case 2: return launch_cat_sparse_cols<F, 2>(csc_data, csc_row, csc_indptr, (int)p_s, rec, prm, grid, st);
+        case 3: return launch_cat_sparse_cols<F, 3>(csc_data, csc_row, csc_indptr, (int)p_s, rec, prm, grid, st);
+        case 4: return launch_cat_sparse_cols<F, 4>(csc_data, csc_row, csc_indptr, (int)p_s, rec, prm, grid, st);
+        case 5: return launch_cat_sparse_cols<F, 5>(csc_data, csc_row, csc_indptr, (int)p_s, rec, prm, grid, st);
+        case 6: return launch_cat_sparse_cols<F, 6>(csc_data, csc_row, csc_indptr, (int)p_s, rec, prm, grid, st);
+        default:
+            return launch_cat_sparse_cols<F, rec_max_cats<F>()>(csc_data, csc_row, csc_indptr, (int)p_s,
+                                                                rec, prm, grid, st);
+    }
+}
+
 // outs[c]: K_c x p_s row-major, overwritten.  n_row_blocks > 1: the CSC arrays are row-blocked
 // (blocks of TM_CSC_ROW_BLOCK rows, block slowest, then column, then row).
 template <typename F>
@@ -617,11 +720,14 @@ int index_cat_sparse(const void* rec_v, int n_cat, const int64_t* K, const int32
                      const F* csc_data, const int32_t* csc_row, const int32_t* csc_indptr,
                      int64_t p_s, int n_row_blocks, F* const* outs, cudaStream_t st) {
     const RowRec<F>* rec = static_cast<const RowRec<F>*>(rec_v);
+    if (n_row_blocks > 1)
+        return cat_sparse_cols<F>(rec, n_cat, K, runs, csc_data, csc_row, csc_indptr, p_s,
+                                  n_row_blocks, outs, st);
     CatSparseParams prm;
-    cat_sparse_layout<F>(n_cat, K, runs, n_row_blocks, prm);
+    cat_sparse_layout<F>(n_cat, K, runs, prm);
     for (int c = 0; c < n_cat; ++c) {
         prm.out[c] = outs[c];
-        if (prm.mode[c] == CS_L2 || n_row_blocks > 1)
+        if (prm.mode[c] == CS_L2)
             TM_CUDA(cudaMemsetAsync(outs[c], 0, sizeof(F) * (size_t)(K[c] * p_s), st));
     }
     switch (n_cat) {

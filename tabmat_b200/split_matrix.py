@@ -275,14 +275,14 @@ class SplitMatrix(MatrixBase):
                 dsc.kind, dsc.data, dsc.nnz = 1, c.data.data_ptr(), c.nnz
                 dsc.csr_indices, dsc.csr_indptr = c.indices.data_ptr(), c.indptr.data_ptr()
                 dsc.csr_row = c.row.data_ptr()
+                block_rows = int(os.environ.get("TABMAT_B200_CSC_ROW_BLOCK", CSC_ROW_BLOCK))
                 if (os.environ.get("TABMAT_B200_CSC_ROW_BLOCKS") == "1" and c.nnz
-                        and mat.shape[0] > CSC_ROW_BLOCK + CSC_ROW_BLOCK // 2):
-                    # opt-in: row-blocked CSC (record gathers of one work item stay inside a
-                    # 32 MB window).  Measured slower than the plain CSC order on B200 (4.1 ms vs
-                    # 3.6 ms at n = 4e7): columns are walked top-down by all CTAs at the same
-                    # pace, so the plain order already keeps the gathers in a moving window,
-                    # and the per-item zero / flush of the column tables costs more.
-                    bd, br, bp, nblk = mat._row_blocked_csc(CSC_ROW_BLOCK)
+                        and mat.shape[0] > block_rows + block_rows // 2):
+                    # opt-in: row-blocked CSC + the column-owner kernel (k_cat_sparse_cols): the
+                    # record gathers stay inside a moving window of block_rows * 32 bytes.
+                    # Measured on B200 at n = 4e7: index pass 6.9 ms vs 7.6 ms with the plain
+                    # CSC order; costs one more copy of the non-zeros, so it stays opt-in.
+                    bd, br, bp, nblk = mat._row_blocked_csc(block_rows)
                     dsc.csc_data, dsc.csc_indices = bd.data_ptr(), br.data_ptr()
                     dsc.csc_indptr, dsc.csc_row_blocks = bp.data_ptr(), nblk
                 else:
