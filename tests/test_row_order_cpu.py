@@ -149,3 +149,43 @@ def test_sparse_row_take_matches_scipy(cpu_plumbing):
         csc = sps.csc_matrix((sub._csc.data.numpy(), sub._csc.indices.numpy(),
                               sub._csc.indptr.numpy()), shape=sub.shape)
         np.testing.assert_array_equal(csc.toarray(), ref.toarray())
+
+
+def test_choose_sort_blocks_prefers_wide_categoricals():
+    class Cat(tm.CategoricalMatrix):
+        def __init__(self, K):  # shape only
+            self.shape = (10, K)
+
+    class Other:
+        shape = (10, 5)
+
+    mats = [Other(), Cat(10), Cat(2000), Cat(300), Cat(1000)]
+    assert row_order.choose_sort_blocks(mats) == [2, 4]          # two widest blocks > 256 levels
+    assert row_order.choose_sort_blocks(mats, max_keys=1) == [2]
+    assert row_order.choose_sort_blocks([Other(), Cat(10), Cat(50)]) == [2]  # else the widest
+    assert row_order.choose_sort_blocks([Other()]) == []
+
+
+def test_column_runs_of_a_split_matrix():
+    """_column_runs: maximal runs of result columns owned by the dense block / by the others
+    (drives the two-phase host copy of sandwich_into)."""
+    from tabmat_b200.split_matrix import SplitMatrix
+
+    class D(tm.DenseMatrix):
+        def __init__(self):
+            pass
+
+    class C(tm.CategoricalMatrix):
+        def __init__(self):
+            pass
+
+    S = SplitMatrix.__new__(SplitMatrix)
+    S.matrices = [D(), C(), C()]
+    S.shape = (3, 10)
+    S.indices = [np.array([3, 4, 5]), np.array([0, 1, 2, 9]), np.array([6, 7, 8])]
+    assert S._column_runs() == [(0, 3, False), (3, 6, True), (6, 10, False)]
+    S2 = SplitMatrix.__new__(SplitMatrix)
+    S2.matrices = [D(), C()]
+    S2.shape = (3, 5)
+    S2.indices = [np.array([0, 1]), np.array([2, 3, 4])]
+    assert S2._column_runs() == [(0, 2, True), (2, 5, False)]
