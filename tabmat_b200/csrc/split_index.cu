@@ -22,7 +22,10 @@
 //                      the 32-byte record of each row and adds d[k] * A[k, j] to out_i[c_i, j]:
 //                      per-thread private shared-memory tables for blocks with few levels,
 //                      shared-memory atomics for mid-sized ones, L2 REDs for the widest
-//                      (8 bytes per non-zero streamed + one sector per non-zero gathered).
+//                      (8 bytes per non-zero streamed + one sector per non-zero gathered);
+//   k_cat_sparse_cols  the same over a ROW-BLOCKED CSC copy (opt-in): a CTA owns a few columns
+//                      for the whole kernel and all CTAs sweep the row blocks at the same pace,
+//                      so the record gathers stay inside L2.
 #include <cstdlib>
 
 #include "tm_common.cuh"
