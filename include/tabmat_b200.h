@@ -51,6 +51,11 @@ void tm_set_dense_f32_mode(int mode);
 /* Fused dense-operand cross pass (tm_dense_cross_sandwich_*, tm_split_sandwich_blocks_*):
  * 0 / 1 = run-aggregating kernel (default), 2 = the one-row-per-visit kernel. */
 void tm_set_cross_runs_mode(int mode);
+/* SplitMatrix sandwich, f32: number of scatter warps appended to the tcgen05 kernel, which then
+ * also issues the vector REDs of the dense x sparse and dense x many-level categorical blocks
+ * from the TMA-staged tile (the dense block is read once per sandwich).  0 = off (separate
+ * scatter pass over the dense block), 4 (default) or 8; other values are ignored. */
+void tm_set_tc_scatter_warps(int warps);
 
 /* ---- dense block (reference: ext/dense.pyx) --------------------------------------- */
 /* dense_sandwich, dense.pyx:19-44 -> _dense{C,F}_sandwich, dense_helpers-tmpl.cpp:266-308.

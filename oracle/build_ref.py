@@ -113,7 +113,40 @@ def build(force: bool = False, verbose: bool = True) -> bool:
     return is_built()
 
 
+PKG = OUT / "tabmat"
+
+
+def package_installed() -> bool:
+    return (PKG / "split_matrix.py").exists() and all(
+        (PKG / "ext" / so_name(m)).exists() for m in MODULES)
+
+
+def install_package(verbose: bool = True) -> bool:
+    """Install the reference's stock Python package into ``oracle/_ref/tabmat`` (git-ignored,
+    like ``pip install --target``; never committed): the unmodified ``src/tabmat/*.py`` and
+    ``benchmark/`` files plus the extension modules built above, so that
+    ``bench.py --impl reference`` runs the reference's own ``tabmat.SplitMatrix.sandwich``
+    (split_matrix.py:324-356) on the GPU box, where ``/root/reference`` does not exist."""
+    src = REF_ROOT / "src" / "tabmat"
+    if not src.exists() or not is_built():
+        return package_installed()
+    (PKG / "ext").mkdir(parents=True, exist_ok=True)
+    for f in src.iterdir():
+        if f.suffix == ".py":
+            shutil.copy(f, PKG / f.name)
+    if (src / "benchmark").exists():
+        shutil.copytree(src / "benchmark", PKG / "benchmark", dirs_exist_ok=True,
+                        ignore=shutil.ignore_patterns("__pycache__", "*.pyc"))
+    (PKG / "ext" / "__init__.py").write_text("")
+    for m in MODULES:
+        shutil.copy(OUT / so_name(m), PKG / "ext" / so_name(m))
+    if verbose:
+        print(f"[oracle] reference package installed into {PKG}")
+    return package_installed()
+
+
 if __name__ == "__main__":
     ok = build(force="--force" in sys.argv)
+    ok = ok and install_package()
     print("oracle/_ref built:", ok)
     sys.exit(0 if ok else 1)

@@ -100,6 +100,63 @@ class _StubModule(types.ModuleType):
         return type(name, (_Anything,), {})
 
 
+_STUBS = (
+    "formulaic",
+    "formulaic.errors",
+    "formulaic.materializers",
+    "formulaic.materializers.types",
+    "formulaic.materializers.base",
+    "formulaic.parser",
+    "formulaic.parser.types",
+    "formulaic.transforms",
+    "formulaic.utils",
+    "formulaic.utils.layered_mapping",
+    "formulaic.utils.null_handling",
+    "interface_meta",
+)
+
+
+def package_available() -> bool:
+    """Is the stock reference package installed under ``oracle/_ref/tabmat``
+    (``oracle/build_ref.py:install_package``)?  True on the GPU box too."""
+    suf = sysconfig.get_config_var("EXT_SUFFIX")
+    pkg = REF_DIR / "tabmat"
+    return (pkg / "split_matrix.py").exists() and all(
+        (pkg / "ext" / f"{m}{suf}").exists() for m in MODULES)
+
+
+def set_omp_threads(n: int) -> int:
+    """Make the OpenMP runtime the reference kernels link against use ``n`` threads, whatever
+    OMP_NUM_THREADS says (torch.distributed.run exports OMP_NUM_THREADS=1 to every rank when
+    nproc > 1).  Returns the thread count in force afterwards."""
+    import ctypes
+
+    os.environ["OMP_NUM_THREADS"] = str(n)
+    try:
+        gomp = ctypes.CDLL("libgomp.so.1")
+        gomp.omp_set_num_threads(int(n))
+        return int(gomp.omp_get_max_threads())
+    except OSError:
+        return n
+
+
+def import_installed_package():
+    """``import tabmat`` = the unmodified reference package from ``oracle/_ref/tabmat`` (works
+    wherever ``oracle/_ref`` travelled to; the absent formulaic / interface_meta dependencies
+    are stubbed, which only disables ``from_formula``)."""
+    if "tabmat" in sys.modules:
+        return sys.modules["tabmat"]
+    if not package_available():
+        raise ImportError("oracle/_ref/tabmat is not installed (python oracle/build_ref.py)")
+    for name in _STUBS:
+        if name not in sys.modules:
+            sys.modules[name] = _StubModule(name)
+    sys.path.insert(0, str(REF_DIR))
+    import tabmat  # noqa: E402
+
+    return tabmat
+
+
 def import_reference_package(reference_root: str = "/root/reference"):
     """Import the reference ``tabmat`` package against the oracle build (container only)."""
     if "tabmat" in sys.modules:

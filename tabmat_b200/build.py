@@ -36,13 +36,28 @@ def _stale(target: Path, deps) -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> Path:
+    """(Re)build the library when a source is newer than it.  Safe under one-process-per-GPU
+    launches: an exclusive file lock serialises the ranks (the first one builds, the others find
+    everything up to date), objects and the library are written to temporary names and moved
+    into place atomically, so no rank can ever load a half-written file."""
+    import fcntl
+
     OBJ.mkdir(exist_ok=True)
+    with open(OBJ / ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            return _build_locked(force, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(force: bool, verbose: bool) -> Path:
     jobs = []
     for src in SOURCES:
         s = CSRC / src
         o = OBJ / (src + ".o")
         if force or _stale(o, [s, *HEADERS]):
-            cmd = [NVCC, *FLAGS, "-c", str(s), "-o", str(o)]
+            cmd = [NVCC, *FLAGS, "-c", str(s), "-o", str(o) + ".tmp"]
             if verbose:
                 cmd.insert(1, "-Xptxas=-v")
             jobs.append(cmd)
@@ -53,13 +68,16 @@ def build(force: bool = False, verbose: bool = False) -> Path:
             raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
         if verbose:
             print(r.stdout + r.stderr)
+        out = cmd[-1]
+        if out.endswith(".tmp"):
+            os.replace(out, out[:-4])
 
     if jobs:
         with ThreadPoolExecutor(max_workers=len(jobs)) as ex:
             list(ex.map(run, jobs))
     objs = [str(OBJ / (s + ".o")) for s in SOURCES]
     if force or jobs or _stale(LIB, objs):
-        cmd = [NVCC, "-shared", "-o", str(LIB), *objs, "-lcudart"]
+        cmd = [NVCC, "-shared", *objs, "-lcudart", "-o", str(LIB) + ".tmp"]
         run(cmd)
     return LIB
 

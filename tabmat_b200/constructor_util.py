@@ -33,7 +33,7 @@ def _split_sparse_and_dense_parts(
     names = [None] * n_cols if column_names is None else list(column_names)
     terms = names if term_names is None else list(term_names)
     dense = DenseMatrix(
-        np.asfortranarray(arg1[:, dense_cols].toarray()),
+        arg1[:, dense_cols].toarray(),   # row-major: the layout the device kernels stream
         column_names=[names[i] for i in dense_cols],
         term_names=[terms[i] for i in dense_cols],
     )

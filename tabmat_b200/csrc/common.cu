@@ -19,13 +19,17 @@ void keep_pool_memory() {
 }
 
 int sm_count() {
-    static int cached = 0;
-    if (cached) return cached;
-    int dev = 0, n = 148;
-    if (cudaGetDevice(&dev) == cudaSuccess)
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    cached = n > 0 ? n : 148;
-    return cached;
+    // cached per device: a process may drive several GPUs
+    static std::atomic<int> cached[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+    int n = cached[dev].load(std::memory_order_relaxed);
+    if (n) return n;
+    n = 148;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+    cached[dev].store(n, std::memory_order_relaxed);
+    return n;
 }
 
 __global__ void k_build_pos_map(const int32_t* __restrict__ list, int64_t m,
@@ -65,7 +69,9 @@ __global__ void k_masked_weights(const F* __restrict__ d, const int32_t* __restr
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (; i < n_rows; i += stride) {
         int32_t k = rows[i];
-        dmask[k] = d[k];
+        // a row listed twice counts twice, like the index-list gather of the passes that walk
+        // `rows` directly (the reference's dense kernels treat `rows` as a multiset)
+        red_add(dmask + k, d[k]);
     }
 }
 

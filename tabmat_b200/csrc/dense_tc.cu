@@ -29,6 +29,8 @@
 // CUDA-core kernel in dense.cu.
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "tm_common.cuh"
 
 namespace tmb {
@@ -73,6 +75,19 @@ struct Params {
     float* oh_out;    // [oh_slots][P], accumulated with RED
     float* dbg;       // debug dump (tools/tc_debug.py); nullptr in production
     int variant;      // bring-up switches (0 in production)
+    // fused scatter work (SCW > 0 only; P <= 128): extra warps read the raw stage and issue the
+    // vector REDs of dense x sparse and dense x many-level categoricals (split_fused.cu does the
+    // same from a second pass over X)
+    int sc_ncat;                       // <= TC_SCATTER_MAX_CATS
+    const int32_t* sc_codes[TC_SCATTER_MAX_CATS];
+    float* sc_tab[TC_SCATTER_MAX_CATS];
+    int sc_K[TC_SCATTER_MAX_CATS];
+    int sc_copies[TC_SCATTER_MAX_CATS];
+    int sc_df[TC_SCATTER_MAX_CATS];
+    const float* csr_data;
+    const int32_t* csr_indices;
+    const int32_t* csr_indptr;
+    float* out_sparse;                 // [p_sparse][P] or nullptr
 };
 
 // ---- PTX wrappers ----------------------------------------------------------------------
@@ -217,6 +232,12 @@ __device__ __forceinline__ uint32_t to_tf32(float x) {
     return r;
 }
 
+__device__ __forceinline__ void red_add_v4(float* p, float4 v) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y),
+                 "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+
 // UMMA shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
 //   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 | [32,46) stride byte offset >> 4
 //   [46,48) version = 1 (Blackwell) | [61,64) layout type (2 = SWIZZLE_128B)
@@ -308,8 +329,9 @@ __device__ __forceinline__ void tl_stamp(const Params& prm, int it, int e) {
 // ---------------------------------------------------------------------------------------
 // min-blocks 2 only caps the registers (<= 102/thread) so that the L2-atomic-bound scatter
 // kernels of a SplitMatrix sandwich can share the SM with this kernel's one resident CTA
-template <int MIN_BLOCKS>
-__global__ void __launch_bounds__(NUM_THREADS, MIN_BLOCKS)
+// SCW = number of scatter warps appended after the scale warps (0: plain SYRK + one-hot kernel)
+template <int MIN_BLOCKS, int SCW>
+__global__ void __launch_bounds__(NUM_THREADS + 32 * SCW, MIN_BLOCKS)
 k_dense_syrk_tc(const __grid_constant__ TmapSet tmaps, const Params prm) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* base = reinterpret_cast<uint8_t*>(
@@ -340,7 +362,7 @@ k_dense_syrk_tc(const __grid_constant__ TmapSet tmaps, const Params prm) {
     // one-hot tiles are all-zero except for the ones set (and cleared again) per stage
     {
         uint4* z = reinterpret_cast<uint4*>(Oper);
-        for (uint32_t i = threadIdx.x; i < SB * slot_bytes / 16; i += NUM_THREADS)
+        for (uint32_t i = threadIdx.x; i < SB * slot_bytes / 16; i += NUM_THREADS + 32 * SCW)
             z[i] = make_uint4(0, 0, 0, 0);
         fence_proxy_async();
     }
@@ -348,7 +370,7 @@ k_dense_syrk_tc(const __grid_constant__ TmapSet tmaps, const Params prm) {
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < SR; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&emptyR[s], NUM_SCALE_WARPS);
+            mbar_init(&emptyR[s], NUM_SCALE_WARPS + SCW);
         }
         for (int b = 0; b < SB; ++b) {
             mbar_init(&scaled[b], NUM_SCALE_WARPS);  // one arrive per scale warp
@@ -468,6 +490,153 @@ k_dense_syrk_tc(const __grid_constant__ TmapSet tmaps, const Params prm) {
         }
         if (elect_one()) tcgen05_commit(done);
         __syncwarp();
+    } else if (SCW > 0 && warp >= 2 + NUM_SCALE_WARPS) {
+        // ===== scatter warps: vector REDs of the cross blocks that share the dense operand =====
+        // Warp ws owns rows [ws * RPW, (ws + 1) * RPW) of every row tile of this CTA.  It copies
+        // its rows from the raw stage into registers (one LDS.128 per row: lane l holds columns
+        // 4l..4l+3), releases the stage, and then issues
+        //   out_sparse[j, :]      += A[k, j] * d[k] * X[k, :]     per non-zero (k, j)
+        //   tab_c[code_c[k], :]   += d[k] * X[k, :]               summed in registers over runs of
+        //                                                          equal codes (row-sorted storage)
+        // The CSR slice and the codes of a tile are prefetched one tile ahead (indptr two tiles
+        // ahead) with plain loads into registers, lane-parallel, and broadcast with shuffles.
+        constexpr int RPW = SCW > 0 ? BK / SCW : 1;       // rows per warp and tile (8 or 4)
+        constexpr int NCM = TC_SCATTER_MAX_CATS;
+        const unsigned FULL = 0xffffffffu;
+        const int ws = warp - (2 + NUM_SCALE_WARPS);
+        const int r0 = ws * RPW;
+        const bool lane_ok = lane * 4 < P;
+        const int nc = prm.sc_ncat;
+        const bool has_sp = prm.out_sparse != nullptr;
+        const uint32_t rring_sa = smem_u32(Rring);
+        float* tab[NCM];
+        float4 acc[NCM];
+        int cur[NCM];
+#pragma unroll
+        for (int c = 0; c < NCM; ++c) {
+            cur[c] = -1;
+            acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+            tab[c] = nullptr;
+            if (c < nc)
+                tab[c] = prm.sc_tab[c] +
+                         (size_t)((blockIdx.x * SCW + ws) % prm.sc_copies[c]) * (size_t)prm.sc_K[c] * P +
+                         lane * 4;
+        }
+        float* const osp = prm.out_sparse + lane * 4;
+        auto tile_row0 = [&](int it) -> long long {
+            return ((long long)blockIdx.x + (long long)it * gridDim.x) * BK + r0;
+        };
+        // indptr of rows k .. k + RPW (lanes 0..RPW), clamped to n (rows past the end are empty)
+        auto load_ip = [&](int it) -> int {
+            if (!has_sp || it >= my_count || lane > RPW) return 0;
+            long long k = tile_row0(it) + lane;
+            if (k > prm.n) k = prm.n;
+            return __ldg(prm.csr_indptr + k);
+        };
+        int ip_cur = load_ip(0), ip_nxt = load_ip(1);
+        int idx_cur = 0, idx_nxt = 0;
+        float val_cur = 0.f, val_nxt = 0.f;
+        int code_cur[NCM], code_nxt[NCM];
+#pragma unroll
+        for (int c = 0; c < NCM; ++c) code_cur[c] = code_nxt[c] = -1;
+        auto load_entries = [&](int it, int ip, int& idx, float& val, int (&code)[NCM]) {
+            idx = 0;
+            val = 0.f;
+#pragma unroll
+            for (int c = 0; c < NCM; ++c) code[c] = -1;
+            if (it >= my_count) return;
+            if (has_sp) {
+                const int e0 = __shfl_sync(FULL, ip, 0), e1 = __shfl_sync(FULL, ip, RPW);
+                if (e0 + lane < e1) {
+                    idx = __ldg(prm.csr_indices + e0 + lane);
+                    val = __ldg(prm.csr_data + e0 + lane);
+                }
+            }
+            const long long k = tile_row0(it) + lane;
+            if (lane < RPW && k < prm.n) {
+#pragma unroll
+                for (int c = 0; c < NCM; ++c)
+                    if (c < nc) {
+                        const int v = __ldg(prm.sc_codes[c] + k) - prm.sc_df[c];
+                        code[c] = v < 0 ? -1 : v;
+                    }
+            }
+        };
+        load_entries(0, ip_cur, idx_cur, val_cur, code_cur);
+        int s = 0;
+        uint32_t ph = 0;
+        for (int it = 0; it < my_count; ++it, ++s) {
+            if (s == SR) {
+                s = 0;
+                ph ^= 1;
+            }
+            // prefetch: entries of tile it + 1 (its indptr was requested a tile ago), indptr of it + 2
+            load_entries(it + 1, ip_nxt, idx_nxt, val_nxt, code_nxt);
+            const int ip_nn = load_ip(it + 2);
+            if (lane == 0) mbar_wait(&full[s], ph);
+            __syncwarp();
+            const uint32_t stage = rring_sa + (uint32_t)s * (uint32_t)prm.r_bytes;
+            float4 y[RPW];
+            float dq[RPW];
+#pragma unroll
+            for (int q = 0; q < RPW; ++q) {
+                y[q] = lane_ok ? lds_f32x4(stage + (uint32_t)(r0 + q) * (uint32_t)P * 4u + (uint32_t)lane * 16u)
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
+                dq[q] = lds_f32(stage + (uint32_t)prm.aux_off + (uint32_t)(r0 + q) * 4u);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&emptyR[s]);  // the raw stage can be refilled
+            const int ebase = __shfl_sync(FULL, ip_cur, 0);
+#pragma unroll
+            for (int q = 0; q < RPW; ++q) {
+                const float dk = dq[q];
+                int e0 = __shfl_sync(FULL, ip_cur, q), e1 = __shfl_sync(FULL, ip_cur, q + 1);
+                int cq[NCM];
+#pragma unroll
+                for (int c = 0; c < NCM; ++c) cq[c] = __shfl_sync(FULL, code_cur[c], q);
+                if (dk == 0.f) continue;  // every term of row k is proportional to d[k]
+                const float4 yy = make_float4(y[q].x * dk, y[q].y * dk, y[q].z * dk, y[q].w * dk);
+#pragma unroll
+                for (int c = 0; c < NCM; ++c) {
+                    if (c >= nc) continue;
+                    if (cq[c] != cur[c]) {  // warp-uniform: a run of block c ends here
+                        if (cur[c] >= 0 && lane_ok) red_add_v4(tab[c] + (size_t)cur[c] * P, acc[c]);
+                        acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        cur[c] = cq[c];
+                    }
+                    if (cq[c] >= 0) {
+                        acc[c].x += yy.x;
+                        acc[c].y += yy.y;
+                        acc[c].z += yy.z;
+                        acc[c].w += yy.w;
+                    }
+                }
+                for (int e = e0; e < e1; ++e) {
+                    const int off = e - ebase;
+                    int j;
+                    float a;
+                    if (off < 32) {  // warp-uniform
+                        j = __shfl_sync(FULL, idx_cur, off);
+                        a = __shfl_sync(FULL, val_cur, off);
+                    } else {         // more than 32 non-zeros in RPW rows: straight from memory
+                        j = __ldg(prm.csr_indices + e);
+                        a = __ldg(prm.csr_data + e);
+                    }
+                    if (lane_ok)
+                        red_add_v4(osp + (size_t)j * P,
+                                   make_float4(yy.x * a, yy.y * a, yy.z * a, yy.w * a));
+                }
+            }
+            ip_cur = ip_nxt;
+            ip_nxt = ip_nn;
+            idx_cur = idx_nxt;
+            val_cur = val_nxt;
+#pragma unroll
+            for (int c = 0; c < NCM; ++c) code_cur[c] = code_nxt[c];
+        }
+#pragma unroll
+        for (int c = 0; c < NCM; ++c)
+            if (c < nc && cur[c] >= 0 && lane_ok) red_add_v4(tab[c] + (size_t)cur[c] * P, acc[c]);
     } else {
         // ===== scale warps, then epilogue =====
         const int w = warp - 2;                // 0..7
@@ -662,8 +831,32 @@ bool dense_tc_eligible(int64_t n, int64_t p, int c_order, const void* X) {
 float* g_tc_dbg = nullptr;
 int g_tc_variant = 0;
 
+// scatter warps of the fused form: TABMAT_B200_TC_SCW = 0 (off: separate scatter pass), 4
+// (default) or 8
+int g_tc_scatter_warps = [] {
+    const char* e = getenv("TABMAT_B200_TC_SCW");
+    int v = e ? atoi(e) : 4;
+    return (v == 0 || v == 4 || v == 8) ? v : 4;
+}();
+static int tc_scatter_warps() { return g_tc_scatter_warps; }
+bool dense_tc_scatter_eligible(int64_t p, int n_cat) {
+    return tc_scatter_warps() > 0 && p <= 128 && n_cat <= TC_SCATTER_MAX_CATS;
+}
+
+template <int MB, int SCW>
+static int launch_tc(const tc::TmapSet& tmaps, const tc::Params& prm, unsigned grid, size_t smem,
+                     cudaStream_t st) {
+    // per device and cheap: set on every launch rather than cached in a process-wide static
+    TM_CUDA(cudaFuncSetAttribute(tc::k_dense_syrk_tc<MB, SCW>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    tc::k_dense_syrk_tc<MB, SCW><<<grid, tc::NUM_THREADS + 32 * SCW, smem, st>>>(tmaps, prm);
+    TM_LAUNCHED();
+    return 0;
+}
+
 int dense_sandwich_tc_f32(const float* X, int64_t n, int64_t p, int c_order, const float* d,
-                          float* out, cudaStream_t st, const TcOneHot* oh, bool share_sm) {
+                          float* out, cudaStream_t st, const TcOneHot* oh, bool share_sm,
+                          const FusedCrossParams* scatter) {
     using namespace tc;
     (void)c_order;
     PFN_encodeTiled enc = get_encode();
@@ -744,8 +937,32 @@ int dense_sandwich_tc_f32(const float* X, int64_t n, int64_t p, int c_order, con
     const int half = prm.mtiles * TILE_BYTES;
     prm.aux_off = (int)((BK * p * 4 + 127) / 128 * 128);
     prm.r_bytes = prm.aux_off + 128 + 8 * 128;
+    int scw = 0;
+    if (scatter && (scatter->n_cat > 0 || scatter->out_sparse)) {
+        if (!dense_tc_scatter_eligible(p, scatter->n_cat))
+            return fail("dense_tc: scatter work not eligible for the fused form");
+        scw = tc_scatter_warps();
+        prm.sc_ncat = scatter->n_cat;
+        for (int c = 0; c < scatter->n_cat; ++c) {
+            prm.sc_codes[c] = scatter->codes[c];
+            prm.sc_tab[c] = static_cast<float*>(scatter->tab[c]);
+            prm.sc_K[c] = scatter->K[c];
+            prm.sc_copies[c] = scatter->copies[c] > 0 ? scatter->copies[c] : 1;
+            prm.sc_df[c] = scatter->drop_first[c];
+        }
+        prm.csr_data = static_cast<const float*>(scatter->csr_data);
+        prm.csr_indices = scatter->csr_indices;
+        prm.csr_indptr = scatter->csr_indptr;
+        prm.out_sparse = static_cast<float*>(scatter->out_sparse);
+    }
     // operand-ring depth: as deep as TMEM (512 columns) and shared memory (>= 3 raw stages) allow
-    int sb = MAX_SB;
+    // (TABMAT_B200_TC_SB caps it: a shallower operand ring leaves room for more raw stages)
+    static const int sb_cap = [] {
+        const char* e = getenv("TABMAT_B200_TC_SB");
+        int v = e ? atoi(e) : MAX_SB;
+        return v < 2 ? 2 : (v > MAX_SB ? MAX_SB : v);
+    }();
+    int sb = sb_cap;
     while (sb > 2 && (ntiles * 128 + prm.oh_groups * 32 + sb * prm.mtiles * 32 > 512 ||
                       (SMEM_BUDGET - sb * (half + prm.oh_groups * GROUP_BYTES) - 1536) / prm.r_bytes < 3))
         --sb;
@@ -759,21 +976,18 @@ int dense_sandwich_tc_f32(const float* X, int64_t n, int64_t p, int c_order, con
     prm.stagesR = stagesR;
     size_t smem = (size_t)stagesR * prm.r_bytes + fixed;
 
-    static bool attr_set = false;
-    if (!attr_set) {
-        TM_CUDA(cudaFuncSetAttribute(k_dense_syrk_tc<1>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        TM_CUDA(cudaFuncSetAttribute(k_dense_syrk_tc<2>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set = true;
-    }
     TM_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)(p * p), st));
     long long grid = prm.num_row_tiles < sm_count() ? prm.num_row_tiles : sm_count();
-    if (share_sm)
-        k_dense_syrk_tc<2><<<(unsigned)grid, NUM_THREADS, smem, st>>>(tmaps, prm);
+    int rc;
+    if (scw == 8)
+        rc = launch_tc<1, 8>(tmaps, prm, (unsigned)grid, smem, st);
+    else if (scw == 4)
+        rc = launch_tc<1, 4>(tmaps, prm, (unsigned)grid, smem, st);
+    else if (share_sm)
+        rc = launch_tc<2, 0>(tmaps, prm, (unsigned)grid, smem, st);
     else
-        k_dense_syrk_tc<1><<<(unsigned)grid, NUM_THREADS, smem, st>>>(tmaps, prm);
-    TM_LAUNCHED();
+        rc = launch_tc<1, 0>(tmaps, prm, (unsigned)grid, smem, st);
+    if (rc) return rc;
     return symmetrize_from_upper<float>(out, p, st);
 }
 
@@ -817,6 +1031,9 @@ int tm_has_tcgen05(void) {
     return tmb::tc::device_cc_major() == 10 && tmb::tc::get_encode() != nullptr ? 1 : 0;
 }
 void tm_set_dense_f32_mode(int mode) { tmb::g_dense_f32_mode = mode; }
+void tm_set_tc_scatter_warps(int warps) {
+    if (warps == 0 || warps == 4 || warps == 8) tmb::g_tc_scatter_warps = warps;
+}
 /* test hook (not part of the public header): device buffer of >= 65536 + 3*128*128 floats */
 void tm_debug_set_tc_buffer(float* buf) { tmb::g_tc_dbg = buf; }
 void tm_debug_set_tc_variant(int v) { tmb::g_tc_variant = v; }

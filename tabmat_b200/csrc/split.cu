@@ -189,6 +189,49 @@ int split_blocks(const tm_block_desc* blk, int nb, int64_t n, const F* d, const 
             }
     }
     const bool have_tensor = tc_ok || any_gather;
+    // fused form: the scatter work (dense x many-level categoricals, dense x sparse) rides along
+    // the tcgen05 kernel as extra warps reading the TMA-staged tile, so X is read once
+    int n_scatter_cats = 0;
+    for (int i = 0; i < nb; ++i)
+        if (blk[i].kind == KIND_CAT && !on_tensor[i]) ++n_scatter_cats;
+    const bool scatter_in_tc =
+        tc_ok && fuse && dense_tc_scatter_eligible(blk[dense_idx].ncols, n_scatter_cats) &&
+        (n_scatter_cats > 0 || (sparse_idx >= 0 && blk[sparse_idx].nnz > 0));
+
+    // destinations and sources of the scatter work (shared by the fused tensor pass and the
+    // stand-alone scatter pass)
+    struct ScatterPlan {
+        const int32_t* codes[8];
+        int64_t K[8];
+        int32_t df[8];
+        F* outs[8];
+        int c = 0;
+        const F* sdata = nullptr;
+        const int32_t *sind = nullptr, *sptr = nullptr;
+        int64_t ps = 0;
+        F* out_s = nullptr;
+    } sp;
+    if (fuse) {
+        for (int i = 0; i < nb; ++i) {
+            if (blk[i].kind != KIND_CAT || on_tensor[i]) continue;
+            sp.codes[sp.c] = static_cast<const int32_t*>(blk[i].data);
+            sp.K[sp.c] = blk[i].ncols;
+            sp.df[sp.c] = blk[i].drop_first;
+            int a = i < dense_idx ? i : dense_idx, b = i < dense_idx ? dense_idx : i;
+            sp.outs[sp.c] = ws + cross_off[a][b];
+            ++sp.c;
+        }
+        if (sparse_idx >= 0 && blk[sparse_idx].nnz > 0) {
+            const tm_block_desc& S = blk[sparse_idx];
+            sp.sdata = static_cast<const F*>(S.data);
+            sp.sind = S.csr_indices;
+            sp.sptr = S.csr_indptr;
+            sp.ps = S.ncols;
+            int a = sparse_idx < dense_idx ? sparse_idx : dense_idx;
+            int b = sparse_idx < dense_idx ? dense_idx : sparse_idx;
+            sp.out_s = ws + cross_off[a][b];
+        }
+    }
 
     auto tensor_pass = [&](cudaStream_t st, bool share_sm) -> int {
         if (!have_tensor) return 0;
@@ -206,10 +249,25 @@ int split_blocks(const tm_block_desc* blk, int nb, int64_t n, const F* d, const 
             Scratch tmp(sizeof(float) * (size_t)(oh_slots > 0 ? oh_slots : 1) * (size_t)D.ncols, st);
             if (tmp.err != cudaSuccess) return fail_cuda(tmp.err, "scratch");
             oh.out = tmp.as<float>();
+            FusedCrossParams fc;
+            CrossScratch fscr;
+            if (scatter_in_tc) {
+                int rc = cross_prepare<float>(
+                    D.ncols, sp.c, sp.codes, sp.K, sp.df, reinterpret_cast<float* const*>(sp.outs),
+                    reinterpret_cast<const float*>(sp.sdata), sp.sind, sp.sptr, sp.ps,
+                    reinterpret_cast<float*>(sp.out_s), fc, fscr, st);
+                if (rc) return rc;
+            }
             int rc = dense_sandwich_tc_f32(static_cast<const float*>(D.data), n, D.ncols, 1, dd,
                                            reinterpret_cast<float*>(ws + self_off[dense_idx]), st,
-                                           oh.ncat ? &oh : nullptr, share_sm);
+                                           oh.ncat ? &oh : nullptr, share_sm,
+                                           scatter_in_tc ? &fc : nullptr);
             if (rc) return rc;
+            if (scatter_in_tc) {
+                rc = cross_finish<float>(D.ncols, sp.c, sp.K,
+                                         reinterpret_cast<float* const*>(sp.outs), fc, st);
+                if (rc) return rc;
+            }
             int64_t o = 0;
             for (int c = 0; c < oh.ncat; ++c) {
                 int i = oh_which[c];
@@ -238,44 +296,18 @@ int split_blocks(const tm_block_desc* blk, int nb, int64_t n, const F* d, const 
     auto scatter_pass = [&](cudaStream_t st) -> int {
         if (!fuse) return 0;
         const tm_block_desc& D = blk[dense_idx];
-        const int32_t* codes[8];
-        int64_t K[8];
-        int32_t df[8];
-        F* outs[8];
-        int c = 0;
-        for (int i = 0; i < nb; ++i) {
-            if (blk[i].kind != KIND_CAT || on_tensor[i]) continue;
-            codes[c] = static_cast<const int32_t*>(blk[i].data);
-            K[c] = blk[i].ncols;
-            df[c] = blk[i].drop_first;
-            int a = i < dense_idx ? i : dense_idx, b = i < dense_idx ? dense_idx : i;
-            outs[c] = ws + cross_off[a][b];
-            ++c;
-        }
-        const F* sdata = nullptr;
-        const int32_t *sind = nullptr, *sptr = nullptr;
-        int64_t ps = 0;
-        F* out_s = nullptr;
-        if (sparse_idx >= 0 && blk[sparse_idx].nnz > 0) {
-            const tm_block_desc& S = blk[sparse_idx];
-            sdata = static_cast<const F*>(S.data);
-            sind = S.csr_indices;
-            sptr = S.csr_indptr;
-            ps = S.ncols;
-            int a = sparse_idx < dense_idx ? sparse_idx : dense_idx;
-            int b = sparse_idx < dense_idx ? dense_idx : sparse_idx;
-            out_s = ws + cross_off[a][b];
-        } else if (sparse_idx >= 0) {
+        if (sparse_idx >= 0 && !sp.out_s) {  // empty sparse block: its cross block is zero
             int a = sparse_idx < dense_idx ? sparse_idx : dense_idx;
             int b = sparse_idx < dense_idx ? dense_idx : sparse_idx;
             TM_CUDA(cudaMemsetAsync(ws + cross_off[a][b], 0,
                                     sizeof(F) * (size_t)(blk[a].ncols * blk[b].ncols), st));
         }
-        if (c > 0 || out_s) {
+        if (scatter_in_tc) return 0;  // done by the scatter warps of the tcgen05 kernel
+        if (sp.c > 0 || sp.out_s) {
             pass_mark(PASS_SCATTER, 0, st);
             int rc = dense_cross_fused<F>(static_cast<const F*>(D.data), n, D.ncols, d, rows,
-                                          n_rows, c, codes, K, df, outs, sdata, sind, sptr, ps,
-                                          out_s, /*runs=*/1, st);
+                                          n_rows, sp.c, sp.codes, sp.K, sp.df, sp.outs, sp.sdata,
+                                          sp.sind, sp.sptr, sp.ps, sp.out_s, /*runs=*/1, st);
             if (rc) return rc;
             pass_mark(PASS_SCATTER, 1, st);
         }

@@ -15,21 +15,6 @@
 
 namespace tmb {
 
-constexpr int FC_MAX_CATS = 8;
-
-struct FusedCrossParams {
-    const int32_t* codes[FC_MAX_CATS];
-    void* tab[FC_MAX_CATS];       // K_i * copies_i rows of P values (scratch when copies_i > 1)
-    int K[FC_MAX_CATS];
-    int copies[FC_MAX_CATS];
-    int drop_first[FC_MAX_CATS];
-    int n_cat;
-    const void* csr_data;
-    const int32_t* csr_indices;
-    const int32_t* csr_indptr;
-    void* out_sparse;             // p_sparse x P, or nullptr
-};
-
 __device__ __forceinline__ void red_add_vec(float* p, float4 v) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y),
                  "f"(v.z), "f"(v.w)
@@ -474,23 +459,11 @@ __global__ void k_sum_replicas(const F* __restrict__ tab, int K, int copies, int
 }
 
 template <typename F>
-int dense_cross_fused(const F* X, int64_t n, int64_t p, const F* d, const int32_t* rows,
-                      int64_t n_rows, int n_cat, const int32_t* const* codes, const int64_t* K,
-                      const int32_t* drop_first, F* const* out_cat, const F* csr_data,
-                      const int32_t* csr_indices, const int32_t* csr_indptr, int64_t p_sparse,
-                      F* out_sparse, int runs, cudaStream_t st) {
-    constexpr int W = Vec<F>::W;
-    // the run-aggregating kernel is also the faster one on unsorted rows (B200, n = 4e7:
-    // 18.1 ms vs 19.7 ms), so it is the default; mode 2 selects the one-row-per-visit kernel
-    if (g_cross_runs_mode == 1) runs = 1;
-    if (g_cross_runs_mode == 2 || n_cat > 4) runs = 0;
+int cross_prepare(int64_t p, int n_cat, const int32_t* const* codes, const int64_t* K,
+                  const int32_t* drop_first, F* const* out_cat, const F* csr_data,
+                  const int32_t* csr_indices, const int32_t* csr_indptr, int64_t p_sparse,
+                  F* out_sparse, FusedCrossParams& prm, CrossScratch& scr, cudaStream_t st) {
     if (n_cat > FC_MAX_CATS) return fail("tm_dense_cross_sandwich: more than 8 categorical blocks");
-    if (p <= 0 || p % W != 0 || p > 64 * W)
-        return fail("tm_dense_cross_sandwich: unsupported dense width");
-    if ((reinterpret_cast<uintptr_t>(X) & 15) != 0)
-        return fail("tm_dense_cross_sandwich: X must be 16-byte aligned");
-    if (!rows) n_rows = n;
-    FusedCrossParams prm;
     memset(&prm, 0, sizeof(prm));
     prm.n_cat = n_cat;
     size_t scratch_elems = 0;
@@ -509,13 +482,16 @@ int dense_cross_fused(const F* X, int64_t n, int64_t p, const F* d, const int32_
             scratch_elems += (size_t)copies * (size_t)K[i] * (size_t)p;
         }
     }
-    Scratch scr(scratch_elems * sizeof(F), st);
-    if (scr.err != cudaSuccess) return fail_cuda(scr.err, "scratch");
-    if (scratch_elems) TM_CUDA(cudaMemsetAsync(scr.p, 0, scratch_elems * sizeof(F), st));
+    if (scratch_elems) {
+        keep_pool_memory();
+        TM_CUDA(cudaMallocAsync(&scr.p, scratch_elems * sizeof(F), st));
+        scr.s = st;
+        TM_CUDA(cudaMemsetAsync(scr.p, 0, scratch_elems * sizeof(F), st));
+    }
     for (int i = 0; i < n_cat; ++i) {
         if (K[i] <= 0) continue;
         if (prm.copies[i] > 1) {
-            prm.tab[i] = scr.as<F>() + offs[i];
+            prm.tab[i] = static_cast<F*>(scr.p) + offs[i];
         } else {
             prm.tab[i] = out_cat[i];
             TM_CUDA(cudaMemsetAsync(out_cat[i], 0, sizeof(F) * (size_t)(K[i] * p), st));
@@ -528,6 +504,50 @@ int dense_cross_fused(const F* X, int64_t n, int64_t p, const F* d, const int32_
         prm.out_sparse = out_sparse;
         TM_CUDA(cudaMemsetAsync(out_sparse, 0, sizeof(F) * (size_t)(p_sparse * p), st));
     }
+    return 0;
+}
+
+template <typename F>
+int cross_finish(int64_t p, int n_cat, const int64_t* K, F* const* out_cat,
+                 const FusedCrossParams& prm, cudaStream_t st) {
+    for (int i = 0; i < n_cat; ++i) {
+        if (K[i] > 0 && prm.copies[i] > 1) {
+            int g = grid_for(K[i] * p, 256, sm_count() * 4);
+            k_sum_replicas<F><<<g, 256, 0, st>>>(static_cast<const F*>(prm.tab[i]), prm.K[i],
+                                                 prm.copies[i], p, out_cat[i]);
+            TM_LAUNCHED();
+        }
+    }
+    return 0;
+}
+template int cross_prepare<float>(int64_t, int, const int32_t* const*, const int64_t*,
+                                  const int32_t*, float* const*, const float*, const int32_t*,
+                                  const int32_t*, int64_t, float*, FusedCrossParams&,
+                                  CrossScratch&, cudaStream_t);
+template int cross_finish<float>(int64_t, int, const int64_t*, float* const*,
+                                 const FusedCrossParams&, cudaStream_t);
+
+template <typename F>
+int dense_cross_fused(const F* X, int64_t n, int64_t p, const F* d, const int32_t* rows,
+                      int64_t n_rows, int n_cat, const int32_t* const* codes, const int64_t* K,
+                      const int32_t* drop_first, F* const* out_cat, const F* csr_data,
+                      const int32_t* csr_indices, const int32_t* csr_indptr, int64_t p_sparse,
+                      F* out_sparse, int runs, cudaStream_t st) {
+    constexpr int W = Vec<F>::W;
+    // the run-aggregating kernel is also the faster one on unsorted rows (B200, n = 4e7:
+    // 18.1 ms vs 19.7 ms), so it is the default; mode 2 selects the one-row-per-visit kernel
+    if (g_cross_runs_mode == 1) runs = 1;
+    if (g_cross_runs_mode == 2 || n_cat > 4) runs = 0;
+    if (p <= 0 || p % W != 0 || p > 64 * W)
+        return fail("tm_dense_cross_sandwich: unsupported dense width");
+    if ((reinterpret_cast<uintptr_t>(X) & 15) != 0)
+        return fail("tm_dense_cross_sandwich: X must be 16-byte aligned");
+    if (!rows) n_rows = n;
+    FusedCrossParams prm;
+    CrossScratch scr;
+    int rc = cross_prepare<F>(p, n_cat, codes, K, drop_first, out_cat, csr_data, csr_indices,
+                              csr_indptr, p_sparse, out_sparse, prm, scr, st);
+    if (rc) return rc;
     if (n_rows > 0 && runs) {
         // consecutive rows per warp and visit: long enough for the run aggregation to pay,
         // short enough that every warp of the grid gets several chunks
@@ -551,15 +571,7 @@ int dense_cross_fused(const F* X, int64_t n, int64_t p, const F* d, const int32_
             k_dense_cross_fused<F, 2><<<g, 256, 0, st>>>(X, n, (int)p, d, rows, n_rows, prm);
         TM_LAUNCHED();
     }
-    for (int i = 0; i < n_cat; ++i) {
-        if (K[i] > 0 && prm.copies[i] > 1) {
-            int g = grid_for(K[i] * p, 256, sm_count() * 4);
-            k_sum_replicas<F><<<g, 256, 0, st>>>(static_cast<const F*>(prm.tab[i]), prm.K[i],
-                                                 prm.copies[i], p, out_cat[i]);
-            TM_LAUNCHED();
-        }
-    }
-    return 0;
+    return cross_finish<F>(p, n_cat, K, out_cat, prm, st);
 }
 
 int g_cross_runs_mode = 0;

@@ -488,13 +488,10 @@ template <typename F, int NC>
 static int launch_pairs(const RowRec<F>* rec, int64_t n, const PairParams& prm, cudaStream_t st) {
     constexpr int U = 2;
     const size_t smem = sizeof(F) * (size_t)prm.smem_elems;
-    static bool attr_set = false;
-    if (!attr_set) {
-        TM_CUDA(cudaFuncSetAttribute(k_cat_pairs<F, NC, U>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)IDX_SMEM_BUDGET));
-        attr_set = true;
-    }
+    // per device and cheap: set on every launch rather than cached in a process-wide static
+    TM_CUDA(cudaFuncSetAttribute(k_cat_pairs<F, NC, U>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)IDX_SMEM_BUDGET));
     const int g = grid_for(n, PAIRS_THREADS * U, sm_count());
     k_cat_pairs<F, NC, U><<<g, PAIRS_THREADS, smem, st>>>(rec, n, prm);
     TM_LAUNCHED();
@@ -592,13 +589,9 @@ static int launch_cat_sparse(const F* data, const int32_t* row_idx, const int32_
                              int p_s, const RowRec<F>* rec, const CatSparseParams& prm,
                              cudaStream_t st) {
     constexpr int U = 2;
-    static bool attr_set = false;
-    if (!attr_set) {
-        TM_CUDA(cudaFuncSetAttribute(k_cat_sparse_csc<F, NC, U>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)CS_SMEM_BUDGET));
-        attr_set = true;
-    }
+    TM_CUDA(cudaFuncSetAttribute(k_cat_sparse_csc<F, NC, U>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)CS_SMEM_BUDGET));
     const size_t smem = sizeof(F) * (size_t)(prm.smem_elems > 0 ? prm.smem_elems : 1);
     const int g = p_s < sm_count() * 12 ? p_s : sm_count() * 12;
     k_cat_sparse_csc<F, NC, U><<<g, CS_THREADS, smem, st>>>(data, row_idx, indptr, p_s, rec, prm);

@@ -128,12 +128,32 @@ struct TcOneHot {
     int drop_first[8];
     float* out;  // [sum K][p], overwritten
 };
+// Scatter work that can ride along the tcgen05 kernel (dense_tc.cu, "fused" form): the
+// dense x many-level categorical blocks (run-aggregated vector REDs) and dense x sparse (one
+// vector RED per non-zero) are issued by extra warps from the TMA-staged X tile, so the dense
+// block is read from HBM once per sandwich.  Filled by cross_prepare (split_fused.cu).
+constexpr int FC_MAX_CATS = 8;
+struct FusedCrossParams {
+    const int32_t* codes[FC_MAX_CATS];
+    void* tab[FC_MAX_CATS];       // K_i * copies_i rows of P values (scratch when copies_i > 1)
+    int K[FC_MAX_CATS];
+    int copies[FC_MAX_CATS];
+    int drop_first[FC_MAX_CATS];
+    int n_cat;
+    const void* csr_data;
+    const int32_t* csr_indices;
+    const int32_t* csr_indptr;
+    void* out_sparse;             // p_sparse x P, or nullptr
+};
+constexpr int TC_SCATTER_MAX_CATS = 4;
 int cat_dense_gather_f32(const float* X, int64_t p, const float* d, const int32_t* perm,
                          const int32_t* segptr, int64_t K, int64_t n_valid, float* out,
                          cudaStream_t st);
 int dense_sandwich_tc_f32(const float* X, int64_t n, int64_t p, int c_order, const float* d,
                           float* out, cudaStream_t st, const TcOneHot* oh = nullptr,
-                          bool share_sm = false);
+                          bool share_sm = false, const FusedCrossParams* scatter = nullptr);
+// does the tcgen05 kernel take the scatter work of `n_cat` many-level blocks along (p <= 128)?
+bool dense_tc_scatter_eligible(int64_t p, int n_cat);
 bool dense_tc_eligible(int64_t n, int64_t p, int c_order, const void* X);
 
 // ---- fused dense-operand cross blocks (split_fused.cu) ---------------------------------
@@ -147,6 +167,24 @@ int dense_cross_fused(const F* X, int64_t n, int64_t p, const F* d, const int32_
                       const int32_t* csr_indices, const int32_t* csr_indptr, int64_t p_sparse,
                       F* out_sparse, int runs, cudaStream_t st);
 extern int g_cross_runs_mode;
+// The two halves of dense_cross_fused around the kernel launch: zero-fill the destinations,
+// set up the replicated tables of few-level blocks (scratch handed back through `scr`, the
+// caller owns it until cross_finish has been enqueued), and sum the replicas afterwards.
+struct CrossScratch {
+    void* p = nullptr;
+    cudaStream_t s = nullptr;
+    ~CrossScratch() {
+        if (p) cudaFreeAsync(p, s);
+    }
+};
+template <typename F>
+int cross_prepare(int64_t p, int n_cat, const int32_t* const* codes, const int64_t* K,
+                  const int32_t* drop_first, F* const* out_cat, const F* csr_data,
+                  const int32_t* csr_indices, const int32_t* csr_indptr, int64_t p_sparse,
+                  F* out_sparse, FusedCrossParams& prm, CrossScratch& scr, cudaStream_t st);
+template <typename F>
+int cross_finish(int64_t p, int n_cat, const int64_t* K, F* const* out_cat,
+                 const FusedCrossParams& prm, cudaStream_t st);
 constexpr int TM_BLOCK_FLAG_RUNS = 1;     // tm_block_desc.flags bit 0
 constexpr int TM_BLOCK_FLAG_PRIMARY = 2;  // bit 1: the primary sort key
 extern int g_dense_f32_mode;

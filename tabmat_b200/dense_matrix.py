@@ -56,11 +56,15 @@ def _dense_to_dev(input_array) -> torch.Tensor:
         if not a.flags.writeable:
             a = a.copy()
         return torch.from_numpy(a).to(dev)
-    # F order: upload the transposed (C-contiguous) buffer and view it back
+    # F order on the host (what pandas' to_numpy and the reference's constructors produce,
+    # constructor_util.py:36): upload the transposed (C-contiguous) buffer and store the block
+    # ROW-MAJOR in HBM.  The storage order is this library's choice, like the cached CSR: the
+    # TMA / tcgen05 SYRK, the one-hot MMAs and the fused scatter warps all stream row tiles, and
+    # a host-built matrix would otherwise never reach them (one transposing copy at upload).
     at = a.T
     if not at.flags.writeable:
         at = at.copy()
-    return torch.from_numpy(at).to(dev).t()
+    return torch.from_numpy(at).to(dev).t().contiguous()
 
 
 class DenseMatrix(MatrixBase):

@@ -127,6 +127,8 @@ class RowShardedMatrix:
         if dst is not None:
             self._allreduce(part, dst)
             return part if self.rank == dst else None
+        if part.dim() == 1:  # a categorical block's sandwich is its diagonal
+            return self._allreduce(part)
         p = part.shape[0]
         if self.pack:
             v = pack_lower(part, self.reduce_dtype)
