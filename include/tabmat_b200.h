@@ -353,7 +353,10 @@ int tm_split_sandwich_blocks_f64(const tm_block_desc* blocks, int n_blocks, int6
                                  double* workspace, tm_stream_t stream);
 /* Place the workspace into the p x p float64 result (split_matrix.py:336-354); `ld` = p.
  * Separate from the block computation so that a row-sharded caller can allreduce the flat
- * workspace in between. */
+ * workspace in between.  A column whose entry in its block's `col_index` is negative is
+ * dropped: with col_index[j] = position of column j in a sorted `cols` selection (or -1) and
+ * ld = len(cols) this yields X[:, cols]^T D X[:, cols] (split.pyx:157-209 split_col_subsets +
+ * split_matrix.py:334-354) from the same fused block computation. */
 int tm_split_sandwich_assemble_f32(const tm_block_desc* blocks, int n_blocks,
                                    const float* workspace, double* out, int64_t ld,
                                    tm_stream_t stream);

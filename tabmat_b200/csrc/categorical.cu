@@ -209,9 +209,125 @@ static inline int cat2_grid(int64_t n_rows, int unr) {
     return grid_for(n_rows, CAT2_THREADS * unr, sm_count());
 }
 
+// ---------------------------------------------------------------------------------------
+// Third generation, the unrestricted case (all rows, no column mask, table in shared memory):
+// the shape tools/micro/hist_bench.cu found fastest for an 80 MB one-shot stream (25.5 us
+// against 25.6 us for a kernel that only reads the 80 MB): 16-byte loads (4 consecutive rows per
+// thread), V of them in flight per thread, two CTAs of 1024 threads per SM.  Equal codes in
+// consecutive rows are merged inside the thread first, and a warp whose 128 rows all carry the
+// same code (row-sorted storage) adds them with one shuffle tree and ONE atomic.
+// ---------------------------------------------------------------------------------------
+template <typename F>
+struct Ld4;
+template <>
+struct Ld4<float> {
+    static __device__ __forceinline__ void load(const float* w, int64_t t4, float (&v)[4]) {
+        const float4 x = __ldg(reinterpret_cast<const float4*>(w) + t4);
+        v[0] = x.x, v[1] = x.y, v[2] = x.z, v[3] = x.w;
+    }
+};
+template <>
+struct Ld4<double> {
+    static __device__ __forceinline__ void load(const double* w, int64_t t4, double (&v)[4]) {
+        const double2 a = __ldg(reinterpret_cast<const double2*>(w) + 2 * t4);
+        const double2 b = __ldg(reinterpret_cast<const double2*>(w) + 2 * t4 + 1);
+        v[0] = a.x, v[1] = a.y, v[2] = b.x, v[3] = b.y;
+    }
+};
+
+template <typename F, int V>
+__global__ void __launch_bounds__(CAT2_THREADS, 2)
+k_cat_hist_vec(const int32_t* __restrict__ codes, const F* __restrict__ w, int64_t n, int K,
+               int drop_first, F* __restrict__ out, int copies) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    F* table = reinterpret_cast<F*>(smem_raw);
+    for (int i = threadIdx.x; i < K * copies; i += CAT2_THREADS) table[i] = F(0);
+    __syncthreads();
+    F* tab = table + (threadIdx.x % copies) * K;
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int64_t n4 = n >> 2;
+    const int64_t stride = (int64_t)gridDim.x * CAT2_THREADS;
+    // all threads of a warp run the same number of iterations (t differs by < 32)
+    const int64_t t_warp0 = (int64_t)blockIdx.x * CAT2_THREADS + (threadIdx.x & ~31);
+    for (int64_t tw = t_warp0; tw < n4; tw += stride * V) {
+        int4 c[V];
+        F v[V][4];
+#pragma unroll
+        for (int u = 0; u < V; ++u) {
+            const int64_t tt = tw + lane + u * stride;
+            c[u] = make_int4(-1, -1, -1, -1);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v[u][i] = F(0);
+            if (tt < n4) {
+                c[u] = __ldg(reinterpret_cast<const int4*>(codes) + tt);
+                Ld4<F>::load(w, tt, v[u]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < V; ++u) {
+            int k0 = c[u].x - drop_first, k1 = c[u].y - drop_first, k2 = c[u].z - drop_first,
+                k3 = c[u].w - drop_first;
+            if (c[u].x < 0) k0 = -1;   // rows past the end
+            // merge equal neighbours: the sum travels to the last row of the run
+            if (k1 == k0) { v[u][1] += v[u][0]; k0 = -1; }
+            if (k2 == k1) { v[u][2] += v[u][1]; k1 = -1; }
+            if (k3 == k2) { v[u][3] += v[u][2]; k2 = -1; }
+            // the whole warp on one code (row-sorted storage): one atomic for 128 rows
+            const bool one = k0 < 0 && k1 < 0 && k2 < 0;
+            const int kf = __shfl_sync(FULL, k3, 0);
+            if (__all_sync(FULL, one && k3 == kf)) {
+                F sum = v[u][3];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(FULL, sum, o);
+                if (lane == 0 && kf >= 0) atomicAdd(&tab[kf], sum);
+                continue;
+            }
+            if (k0 >= 0) atomicAdd(&tab[k0], v[u][0]);
+            if (k1 >= 0) atomicAdd(&tab[k1], v[u][1]);
+            if (k2 >= 0) atomicAdd(&tab[k2], v[u][2]);
+            if (k3 >= 0) atomicAdd(&tab[k3], v[u][3]);
+        }
+    }
+    // the n % 4 last rows
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+        const int64_t k = (n4 << 2) + threadIdx.x;
+        const int key = codes[k] - drop_first;
+        if (key >= 0) atomicAdd(&tab[key], w[k]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < K; i += CAT2_THREADS) {
+        F s = F(0);
+        for (int r = 0; r < copies; ++r) s += table[r * K + i];
+        if (s != F(0)) red_add(&out[i], s);
+    }
+}
+
+static bool cat_vec_off() {
+    static const bool off = getenv("TABMAT_B200_CAT_VEC") && atoi(getenv("TABMAT_B200_CAT_VEC")) == 0;
+    return off;
+}
+
 template <typename F>
 int cat_hist2(const int32_t* codes, const F* w, const int32_t* rows, int64_t n_rows, int64_t K,
               int drop_first, const uint8_t* col_mask, F* out, bool overwrite, cudaStream_t st) {
+    constexpr int64_t VEC_TABLE_BYTES = 32 * 1024;   // x copies <= 96 KB per CTA, two CTAs per SM
+    const int64_t tbv = (int64_t)sizeof(F) * K;
+    if (!rows && !col_mask && !cat_vec_off() && tbv <= VEC_TABLE_BYTES && n_rows >= 4096 &&
+        ((reinterpret_cast<uintptr_t>(codes) | reinterpret_cast<uintptr_t>(w)) & 15) == 0) {
+        constexpr int V = sizeof(F) == 4 ? 2 : 1;   // 32 registers per thread at 2 x 1024 threads
+        int64_t cp = (96 * 1024) / tbv;
+        const int copies = (int)(cp < 1 ? 1 : (cp > 32 ? 32 : cp));
+        const size_t smem = (size_t)(tbv * copies);
+        TM_CUDA(cudaFuncSetAttribute(k_cat_hist_vec<F, V>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        if (overwrite) TM_CUDA(cudaMemsetAsync(out, 0, sizeof(F) * (size_t)K, st));
+        const int g = grid_for(n_rows >> 2, CAT2_THREADS * V, sm_count() * 2);
+        k_cat_hist_vec<F, V><<<g, CAT2_THREADS, smem, st>>>(codes, w, n_rows, (int)K, drop_first,
+                                                            out, copies);
+        TM_LAUNCHED();
+        return 0;
+    }
     constexpr int UNR = 8;
     const int64_t tb = (int64_t)sizeof(F) * K;
     const int g = cat2_grid(n_rows, UNR);
@@ -268,6 +384,48 @@ __global__ void k_cat_matvec(const int32_t* __restrict__ codes, int64_t n,
         if (c < 0) continue;
         if (col_mask && !col_mask[c]) continue;
         out[i] += v[c];
+    }
+}
+
+// unrestricted case with 16-byte accesses: 4 consecutive rows per thread, two loads in flight
+template <typename F>
+__global__ void __launch_bounds__(256)
+k_cat_matvec_vec(const int32_t* __restrict__ codes, int64_t n, const F* __restrict__ v,
+                 int drop_first, F* __restrict__ out) {
+    const int64_t n4 = n >> 2;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n4; t += 2 * stride) {
+        const int64_t t2 = t + stride;
+        const bool two = t2 < n4;
+        int4 c[2];
+        F o[2][4];
+        c[0] = __ldg(reinterpret_cast<const int4*>(codes) + t);
+        if (two) c[1] = __ldg(reinterpret_cast<const int4*>(codes) + t2);
+        Ld4<F>::load(out, t, o[0]);
+        if (two) Ld4<F>::load(out, t2, o[1]);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (u == 1 && !two) break;
+            const int k0 = c[u].x - drop_first, k1 = c[u].y - drop_first, k2 = c[u].z - drop_first,
+                      k3 = c[u].w - drop_first;
+            if (k0 >= 0) o[u][0] += __ldg(v + k0);
+            if (k1 >= 0) o[u][1] += __ldg(v + k1);
+            if (k2 >= 0) o[u][2] += __ldg(v + k2);
+            if (k3 >= 0) o[u][3] += __ldg(v + k3);
+            F* dst = out + 4 * (u == 0 ? t : t2);
+            if (sizeof(F) == 4) {
+                *reinterpret_cast<float4*>(dst) = make_float4((float)o[u][0], (float)o[u][1],
+                                                              (float)o[u][2], (float)o[u][3]);
+            } else {
+                reinterpret_cast<double2*>(dst)[0] = make_double2((double)o[u][0], (double)o[u][1]);
+                reinterpret_cast<double2*>(dst)[1] = make_double2((double)o[u][2], (double)o[u][3]);
+            }
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+        const int64_t i = (n4 << 2) + threadIdx.x;
+        const int c = codes[i] - drop_first;
+        if (c >= 0) out[i] += v[c];
     }
 }
 
@@ -430,6 +588,13 @@ int cat_matvec(const int32_t* codes, int64_t n, const F* v, const int32_t* cols,
         int rc = build_mask(cols, n_cols, K, mask.as<uint8_t>(), st);
         if (rc) return rc;
         k_cat_matvec<F><<<g, 256, 0, st>>>(codes, n, v, drop_first, mask.as<uint8_t>(), out);
+        TM_LAUNCHED();
+        return 0;
+    }
+    if (!cat_vec_off() && n >= 4096 &&
+        ((reinterpret_cast<uintptr_t>(codes) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) {
+        const int gv = grid_for(n >> 2, 256 * 2, sm_count() * 16);
+        k_cat_matvec_vec<F><<<gv, 256, 0, st>>>(codes, n, v, drop_first, out);
         TM_LAUNCHED();
         return 0;
     }

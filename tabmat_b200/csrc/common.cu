@@ -149,7 +149,7 @@ __global__ void k_scatter_block(const F* __restrict__ blk, int64_t na, int64_t n
             F v = blk[a * nb + b];
             tile[i][threadIdx.x] = v;
             int64_t r = ri ? ri[a] : a, c = ci ? ci[b] : b;
-            out[r * ld + c] = (double)v;
+            if (r >= 0 && c >= 0) out[r * ld + c] = (double)v;   // negative = column not selected
         }
     }
     if (!mirror) return;
@@ -158,7 +158,7 @@ __global__ void k_scatter_block(const F* __restrict__ blk, int64_t na, int64_t n
         int64_t b = b0 + i, a = a0 + threadIdx.x;
         if (a < na && b < nb) {
             int64_t r = ri ? ri[a] : a, c = ci ? ci[b] : b;
-            out[c * ld + r] = (double)tile[threadIdx.x][i];
+            if (r >= 0 && c >= 0) out[c * ld + r] = (double)tile[threadIdx.x][i];
         }
     }
 }
@@ -170,9 +170,10 @@ __global__ void k_scatter_diag(const F* __restrict__ diag, int64_t na,
     int64_t a = (int64_t)blockIdx.y * 8 + threadIdx.y;
     if (a >= na) return;
     int64_t r = ri ? ri[a] : a;
+    if (r < 0) return;
     for (int64_t b = (int64_t)blockIdx.x * 32 + threadIdx.x; b < na; b += (int64_t)gridDim.x * 32) {
         int64_t c = ri ? ri[b] : b;
-        out[r * ld + c] = (a == b) ? (double)diag[a] : 0.0;
+        if (c >= 0) out[r * ld + c] = (a == b) ? (double)diag[a] : 0.0;
     }
 }
 

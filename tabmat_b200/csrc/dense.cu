@@ -453,6 +453,18 @@ int dense_colreduce(const F* X, int64_t n, int64_t p, int c_order, const F* w, c
 }
 
 
+// out[a * m + b] = full[cols[a] * p + cols[b]]
+template <typename F>
+__global__ void k_select_square(const F* __restrict__ full, int64_t p,
+                                const int32_t* __restrict__ cols, int64_t m, F* __restrict__ out) {
+    const int64_t total = m * m;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int64_t a = i / m, b = i - a * m;
+        out[i] = full[(int64_t)cols[a] * p + cols[b]];
+    }
+}
+
 }  // namespace tmb
 
 extern "C" {
@@ -464,20 +476,32 @@ int tm_dense_sandwich_f32(const float* X, int64_t n, int64_t p, int c_order, con
     if (!rows) n_rows = n;
     if (!cols) n_cols = p;
     if (n_cols <= 0) return 0;
-    bool want_tc = tmb::g_dense_f32_mode != 1 && cols == nullptr && n_rows > 0 &&
+    // A column selection (dense.pyx:19-44 `cols`) stays on the tensor path while it keeps at
+    // least a fifth of the columns: the kernel is bound by streaming X, so the full p x p costs
+    // the same as any subset and a tiny kernel picks the selected rows / columns out of it.
+    // Narrower selections are cheaper on the CUDA-core kernel (cost ~ n m^2).
+    const bool cols_ok = cols == nullptr || n_cols * 5 >= p || tmb::g_dense_f32_mode == 2;
+    bool want_tc = tmb::g_dense_f32_mode != 1 && cols_ok && n_rows > 0 &&
                    tmb::dense_tc_eligible(n, p, c_order, X);
     if (tmb::g_dense_f32_mode == 2 && !want_tc)
         return tmb::fail("tm_dense_sandwich_f32: tcgen05 path forced but not eligible");
     if (want_tc) {
+        tmb::Scratch dm(rows ? sizeof(float) * (size_t)n : 0, st);
+        tmb::Scratch full(cols ? sizeof(float) * (size_t)(p * p) : 0, st);
+        if (dm.err != cudaSuccess) return tmb::fail_cuda(dm.err, "scratch");
+        if (full.err != cudaSuccess) return tmb::fail_cuda(full.err, "scratch");
         if (rows) {
-            // fold the row restriction into the weights (rows are unique)
-            tmb::Scratch dm(sizeof(float) * (size_t)n, st);
-            if (dm.err != cudaSuccess) return tmb::fail_cuda(dm.err, "scratch");
+            // fold the row restriction into the weights
             int rc = tmb::masked_weights<float>(d, n, rows, n_rows, dm.as<float>(), st);
             if (rc) return rc;
-            return tmb::dense_sandwich_tc_f32(X, n, p, c_order, dm.as<float>(), out, st);
+            d = dm.as<float>();
         }
-        return tmb::dense_sandwich_tc_f32(X, n, p, c_order, d, out, st);
+        int rc = tmb::dense_sandwich_tc_f32(X, n, p, c_order, d, cols ? full.as<float>() : out, st);
+        if (rc || !cols) return rc;
+        tmb::k_select_square<float><<<tmb::grid_for(n_cols * n_cols, 256, tmb::sm_count() * 8), 256,
+                                      0, st>>>(full.as<float>(), p, cols, n_cols, out);
+        TM_LAUNCHED();
+        return 0;
     }
     return tmb::dense_sandwich_generic<float>(X, n, p, c_order, d, rows, n_rows, cols, n_cols, out,
                                              st);

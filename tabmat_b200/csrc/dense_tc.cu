@@ -78,6 +78,7 @@ struct Params {
     // fused scatter work (SCW > 0 only; P <= 128): extra warps read the raw stage and issue the
     // vector REDs of dense x sparse and dense x many-level categoricals (split_fused.cu does the
     // same from a second pass over X)
+    int f_order;      // X is column-major: the TMA box lands K-major (SWIZZLE_128B) in the stage
     int sc_ncat;                       // <= TC_SCATTER_MAX_CATS
     const int32_t* sc_codes[TC_SCATTER_MAX_CATS];
     float* sc_tab[TC_SCATTER_MAX_CATS];
@@ -310,6 +311,36 @@ __device__ __forceinline__ void scale_col4(uint32_t R, int P, uint32_t dsm, uint
     }
 }
 
+// The same for a COLUMN-MAJOR X (dense_helpers-tmpl.cpp:266-308 has C and F variants too): the
+// TMA box [32 rows x P columns] of the (P x n) row-major array lands K-major in the stage - one
+// 128-byte row of 32 k-values per X column, 16-byte chunks XOR-swizzled by the TMA unit
+// (SWIZZLE_128B) so that the 32 lanes of a warp, one column each, read a chunk without bank
+// conflicts.  No transpose is needed: a lane reads its 4 consecutive k as one LDS.128.
+__device__ __forceinline__ void scale_col4_f(uint32_t R, int P, uint32_t dsm, uint32_t Sp,
+                                             uint32_t t_addr, int c, int kb, int ks) {
+    const bool ok = c < P;
+    const uint32_t tile_off = (uint32_t)(c >> 7) * TILE_BYTES;
+    const uint32_t row = (uint32_t)c & 127u;
+    float4 x[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+        x[u] = ok ? lds_f32x4(R + kmajor_chunk_off((uint32_t)c, (uint32_t)(kb + u * ks)))
+                  : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int k4 = kb + u * ks;
+        const float4 dv = lds_f32x4(dsm + 16u * (uint32_t)k4);
+        uint4 a;
+        a.x = to_tf32(x[u].x);
+        a.y = to_tf32(x[u].y);
+        a.z = to_tf32(x[u].z);
+        a.w = to_tf32(x[u].w);
+        if (ok) sts_u32x4(Sp + tile_off + kmajor_chunk_off(row, (uint32_t)k4), a);
+        tmem_st_x4(t_addr + (uint32_t)(4 * k4), to_tf32(dv.x * x[u].x), to_tf32(dv.y * x[u].y),
+                   to_tf32(dv.z * x[u].z), to_tf32(dv.w * x[u].w));
+    }
+}
+
 // tensor maps of one launch: the X tile, the weight vector d and the one-hot code vectors
 // (1-d maps, 32 elements per stage; out-of-range rows read as zero)
 struct TmapSet {
@@ -420,7 +451,10 @@ k_dense_syrk_tc(const __grid_constant__ TmapSet tmaps, const Params prm) {
                 uint8_t* stage = Rring + (size_t)s * prm.r_bytes;
                 const uint32_t aux = smem_u32(stage) + (uint32_t)prm.aux_off;
                 mbar_expect_tx(&full[s], tx);
-                tma_load_2d(stage, &tmaps.x, &full[s], 0, (int)k0);
+                if (prm.f_order)
+                    tma_load_2d(stage, &tmaps.x, &full[s], (int)k0, 0);   // (k, column) coordinates
+                else
+                    tma_load_2d(stage, &tmaps.x, &full[s], 0, (int)k0);
                 tma_load_1d(aux, &tmaps.d, &full[s], (int)k0);
                 for (int c = 0; c < prm.oh_ncat; ++c)
                     tma_load_1d(aux + 128u * (uint32_t)(c + 1), &tmaps.codes[c], &full[s], (int)k0);
@@ -701,7 +735,14 @@ k_dense_syrk_tc(const __grid_constant__ TmapSet tmaps, const Params prm) {
             {
                 const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + t_col0 +
                                         (uint32_t)(b * prm.mtiles + (my_col >> 7)) * 32;
-                if (prm.mtiles == 1) {
+                if (prm.f_order) {
+                    if (prm.mtiles == 1) {
+                        scale_col4_f(R, P, dsm, Sp, t_addr, my_col, h, 2);
+                    } else {
+                        scale_col4_f(R, P, dsm, Sp, t_addr, my_col, 0, 1);
+                        scale_col4_f(R, P, dsm, Sp, t_addr, my_col, 4, 1);
+                    }
+                } else if (prm.mtiles == 1) {
                     scale_col4(R, P, dsm, Sp, t_addr, my_col, h, 2);
                 } else {
                     scale_col4(R, P, dsm, Sp, t_addr, my_col, 0, 1);
@@ -820,8 +861,9 @@ static int device_cc_major() {
 }  // namespace tc
 
 bool dense_tc_eligible(int64_t n, int64_t p, int c_order, const void* X) {
-    if (!c_order) return false;
-    if (p < 8 || p > 256 || (p % 4) != 0) return false;     // TMA: row pitch multiple of 16 B
+    if (p < 8 || p > 256) return false;
+    // TMA: the pitch of the outer dimension must be a multiple of 16 bytes
+    if (c_order ? (p % 4) != 0 : (n % 4) != 0) return false;
     if ((reinterpret_cast<uintptr_t>(X) & 15) != 0) return false;
     if (n < 1 || n > 0x7fffffffLL) return false;
     if (tc::device_cc_major() != 10) return false;
@@ -858,13 +900,25 @@ int dense_sandwich_tc_f32(const float* X, int64_t n, int64_t p, int c_order, con
                           float* out, cudaStream_t st, const TcOneHot* oh, bool share_sm,
                           const FusedCrossParams* scatter) {
     using namespace tc;
-    (void)c_order;
     PFN_encodeTiled enc = get_encode();
     if (!enc) return fail("cuTensorMapEncodeTiled not available");
+    if (!c_order && (oh || scatter))
+        return fail("dense_tc: one-hot / scatter work needs a row-major dense block");
 
     TmapSet tmaps;
     memset(&tmaps, 0, sizeof(tmaps));
-    {
+    if (!c_order) {
+        // column-major X = (p x n) row-major: box of 32 consecutive rows (inner) x p columns
+        cuuint64_t gdim[2] = {(cuuint64_t)n, (cuuint64_t)p};
+        cuuint64_t gstride[1] = {(cuuint64_t)n * sizeof(float)};
+        cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)p};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult cr = enc(&tmaps.x, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(X), gdim,
+                          gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed (X, column-major)");
+    } else {
         cuuint64_t gdim[2] = {(cuuint64_t)p, (cuuint64_t)n};
         cuuint64_t gstride[1] = {(cuuint64_t)p * sizeof(float)};
         cuuint32_t box[2] = {(cuuint32_t)p, (cuuint32_t)BK};  // one box = the whole row tile
@@ -935,8 +989,10 @@ int dense_sandwich_tc_f32(const float* X, int64_t n, int64_t p, int c_order, con
         TM_CUDA(cudaMemsetAsync(oh->out, 0, sizeof(float) * (size_t)slots * (size_t)p, st));
     }
     const int half = prm.mtiles * TILE_BYTES;
+    prm.f_order = c_order ? 0 : 1;
     prm.aux_off = (int)((BK * p * 4 + 127) / 128 * 128);
     prm.r_bytes = prm.aux_off + 128 + 8 * 128;
+    if (prm.f_order) prm.r_bytes = (prm.r_bytes + 1023) / 1024 * 1024;  // swizzle atom = 8 x 128 B
     int scw = 0;
     if (scatter && (scatter->n_cat > 0 || scatter->out_sparse)) {
         if (!dense_tc_scatter_eligible(p, scatter->n_cat))

@@ -578,23 +578,26 @@ k_assemble_all(const AsmJobs jobs, double* __restrict__ out, int64_t ld) {
     if (kind == 2) {  // diagonal block: na == nb, src = the diagonal
         for (int i = ty; i < 32; i += 8) {
             const int64_t a = a0 + i, b = b0 + tx;
-            if (a < na && b < nb) out[ri[a] * ld + ri[b]] = a == b ? (double)src[a] : 0.0;
+            if (a < na && b < nb && ri[a] >= 0 && ri[b] >= 0)
+                out[ri[a] * ld + ri[b]] = a == b ? (double)src[a] : 0.0;
         }
         return;
     }
+    // a negative destination = the column is not in the caller's `cols` selection
     for (int i = ty; i < 32; i += 8) {
         const int64_t a = a0 + i, b = b0 + tx;
         if (a < na && b < nb) {
             const F v = src[a * nb + b];
             tile[i][tx] = v;
-            out[ri[a] * ld + ci[b]] = (double)v;
+            if (ri[a] >= 0 && ci[b] >= 0) out[ri[a] * ld + ci[b]] = (double)v;
         }
     }
     if (kind != 1) return;
     __syncthreads();
     for (int i = ty; i < 32; i += 8) {
         const int64_t b = b0 + i, a = a0 + tx;
-        if (a < na && b < nb) out[ci[b] * ld + ri[a]] = (double)tile[tx][i];
+        if (a < na && b < nb && ri[a] >= 0 && ci[b] >= 0)
+            out[ci[b] * ld + ri[a]] = (double)tile[tx][i];
     }
 }
 

@@ -110,7 +110,7 @@ class RowShardedMatrix:
         on every rank (allreduce); ``dst=r``: it is reduced to rank ``r`` only, the other ranks
         get ``None`` (MPI-style; saves the redundant copies when one process consumes it)."""
         local_rows = shard_rows(rows, self.lo, self.hi)
-        if cols is None and hasattr(self.local, "_sandwich_blocks_dev"):
+        if hasattr(self.local, "_sandwich_blocks_dev"):
             # SplitMatrix: allreduce the flat block workspace (every structurally distinct
             # entry once, block dtype) and assemble the p x p float64 after the collective
             from . import _dev
@@ -120,7 +120,8 @@ class RowShardedMatrix:
                 self._allreduce(ws, dst)
                 if dst is not None and self.rank != dst:
                     return None
-                return self.local._assemble_dev(ws)
+                # a `cols` selection is applied by the assembly (negative destinations dropped)
+                return self.local._assemble_dev(ws, cols)
         part = self.local.sandwich(d_local, local_rows, cols)
         if self.world_size == 1:
             return part

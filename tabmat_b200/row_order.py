@@ -174,8 +174,8 @@ class RowSortedMatrix(MatrixBase):
         """Flat block workspace (for the row-sharded allreduce, distributed.py)."""
         return self.mat._sandwich_blocks_dev(self._gather(d_t), self._rows_in(rows_t))
 
-    def _assemble_dev(self, ws: torch.Tensor) -> torch.Tensor:
-        return self.mat._assemble_dev(ws)
+    def _assemble_dev(self, ws: torch.Tensor, cols=None) -> torch.Tensor:
+        return self.mat._assemble_dev(ws, cols)
 
     def transpose_matvec(self, v, rows=None, cols=None, out=None):
         """X[rows, cols].T @ v[rows] (split_matrix.py:419-460)."""

@@ -9,6 +9,7 @@ at construction (split_matrix.py:85-141)."""
 
 from __future__ import annotations
 
+import ctypes as C
 import os
 import warnings
 from collections.abc import Sequence
@@ -322,12 +323,31 @@ class SplitMatrix(MatrixBase):
             _dev.length(rows_t), _dev.ptr(ws), _dev.stream_ptr()))
         return ws
 
-    def _assemble_dev(self, ws: torch.Tensor) -> torch.Tensor:
+    def _assemble_dev(self, ws: torch.Tensor, cols=None) -> torch.Tensor:
+        """Place the flat block workspace into the float64 result.  With ``cols`` (sorted,
+        unique column ids, split.pyx:157-209) only the selected rows / columns are placed: the
+        blocks are computed whole by the fused passes and the selection costs nothing extra."""
         descs, _ = self._native_plan(ws.dtype)
         p = self.shape[1]
+        keep = None
+        if cols is not None:
+            cols = np.asarray(_dev.to_host(cols) if _dev.is_dev(cols) else cols).astype(np.int64)
+            dest = np.full(p, -1, dtype=np.int64)
+            dest[cols] = np.arange(len(cols), dtype=np.int64)
+            p = len(cols)
+            sel = (BlockDesc * len(self.matrices))()
+            keep = []
+            for b, idx in enumerate(self.indices):
+                C.memmove(C.byref(sel[b]), C.byref(descs[b]), C.sizeof(BlockDesc))
+                t = _dev.to_dev(dest[idx])
+                keep.append(t)
+                sel[b].col_index = t.data_ptr()
+            descs = sel
         out = torch.empty((p, p), dtype=torch.float64, device=ws.device)
-        check(fn("tm_split_sandwich_assemble", _dev.suffix(ws.dtype))(
-            descs, len(self.matrices), _dev.ptr(ws), _dev.ptr(out), p, _dev.stream_ptr()))
+        if p:
+            check(fn("tm_split_sandwich_assemble", _dev.suffix(ws.dtype))(
+                descs, len(self.matrices), _dev.ptr(ws), _dev.ptr(out), p, _dev.stream_ptr()))
+        del keep
         return out
 
     # ---- result straight into host memory, copy overlapped with the dense-operand passes ----
@@ -455,10 +475,10 @@ class SplitMatrix(MatrixBase):
         return out
 
     def _sandwich_dev(self, d_t: torch.Tensor, rows_t, cols) -> torch.Tensor:
-        if cols is None:
+        if cols is None or self._cols_on_native_path(cols):
             ws = self._sandwich_blocks_dev(d_t, rows_t)
             if ws is not None:
-                return self._assemble_dev(ws)
+                return self._assemble_dev(ws, cols)
         subset_cols_indices, subset_cols, n_cols = self._split_col_subsets(cols)
         if cols is None:
             pos_t = self._dev_indices()
@@ -505,6 +525,15 @@ class SplitMatrix(MatrixBase):
                     _dev.ptr(res), mi, mj, _dev.ptr(pos_t[i]), _dev.ptr(pos_t[j]), _dev.ptr(out),
                     n_cols, 1, st))
         return out
+
+    def _cols_on_native_path(self, cols) -> bool:
+        """An active-set ``cols`` (glum's normal call) goes through the fused whole-matrix
+        passes + a selecting assembly when it keeps a fair share of the columns; a narrow
+        selection is cheaper block by block with the restricted per-pair kernels."""
+        if os.environ.get("TABMAT_B200_COLS_NATIVE") == "0":
+            return False
+        m = len(cols)
+        return m * 8 >= self.shape[1] or self.shape[0] >= 1_000_000
 
     def _fused_dense_cross(self, d_t: torch.Tensor, rows_t) -> dict:
         """{(a, b): block a rows x dense-block b cols} for every categorical / sparse block a,

@@ -121,3 +121,51 @@ def test_onehot_fused_dense_and_small_cats(n, p, with_rows):
         ref = orc.cat_dense_sandwich(c, K, d, X, rows, None, df)
         cases.assert_close(got[o:o + K], ref, np.float32, f"one-hot cat K={K}")
         o += K
+
+
+@pytest.mark.parametrize("n,p", [(4, 8), (32, 64), (36, 128), (1000, 132), (4100, 256),
+                                 (300_004, 256), (70_000, 96), (5000, 37), (260, 12)])
+def test_tcgen05_syrk_column_major(n, p, force_mode):
+    """F-ordered X (dense_helpers-tmpl.cpp:266-308 has a C and an F variant): the TMA box lands
+    K-major in shared memory, no transpose; needs n % 4 == 0 (TMA pitch), any 8 <= p <= 256."""
+    from tests.gpu_runner import run_cuda
+
+    rng = np.random.default_rng(n + p)
+    X = np.asfortranarray(rng.standard_normal((n, p)).astype(np.float32))
+    d = rng.standard_normal(n).astype(np.float32)
+    rows = np.sort(rng.choice(n, size=max(1, n // 2), replace=False)).astype(np.int32)
+    Xd = X.astype(np.float64)
+    for r in (None, rows):
+        force_mode(2)
+        got = run_cuda("dense_sandwich", dict(X=X, d=d, rows=r, cols=None))
+        Xr, dr = (Xd, d) if r is None else (Xd[r], d[r])
+        ref = Xr.T @ (dr.astype(np.float64)[:, None] * Xr)
+        cases.assert_close(got, ref, np.float32, f"tcgen05 F-order n={n} p={p} rows={r is not None}")
+        assert np.array_equal(got, got.T)
+
+
+@pytest.mark.parametrize("order", ["C", "F"])
+@pytest.mark.parametrize("frac", [0.9, 0.5, 0.25, 0.05])
+def test_tcgen05_syrk_column_selection(order, frac, force_mode):
+    """`cols` (dense.pyx:19-44): full SYRK on the tensor cores + selection while the selection
+    keeps >= 1/5 of the columns, the CUDA-core kernel below that; both against float64."""
+    from tests.gpu_runner import run_cuda
+
+    rng = np.random.default_rng(int(frac * 100))
+    n, p = 20_000, 128
+    X = rng.standard_normal((n, p)).astype(np.float32)
+    if order == "F":
+        X = np.asfortranarray(X)
+    d = rng.random(n).astype(np.float32)
+    cols = np.sort(rng.choice(p, size=max(1, int(p * frac)), replace=False)).astype(np.int32)
+    rows = np.sort(rng.choice(n, size=n // 3, replace=False)).astype(np.int32)
+    force_mode(0)
+    for r in (None, rows):
+        got = run_cuda("dense_sandwich", dict(X=X, d=d, rows=r, cols=cols))
+        Xs = X.astype(np.float64)[:, cols]
+        Xr, dr = (Xs, d) if r is None else (Xs[r], d[r])
+        cases.assert_close(got, Xr.T @ (dr.astype(np.float64)[:, None] * Xr), np.float32,
+                           f"cols {order} frac={frac}")
+    if frac >= 0.2:
+        force_mode(2)   # must be accepted: the selection is eligible for the tensor path
+        run_cuda("dense_sandwich", dict(X=X, d=d, rows=None, cols=cols))

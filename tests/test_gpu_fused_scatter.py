@@ -106,3 +106,31 @@ def test_fused_scatter_counts_are_exact():
     nnz_col = np.asarray((A != 0).sum(axis=0)).ravel().astype(np.float64)
     assert np.array_equal(out[16 + 90:, :16], np.repeat(counts[:, None], 16, axis=1))
     assert np.array_equal(out[16:16 + 90, :16], np.repeat(nnz_col[:, None], 16, axis=1))
+
+
+@pytest.mark.parametrize("frac", [0.5, 0.03])
+def test_cols_selection_on_the_native_path(frac, monkeypatch):
+    """``cols`` (glum's active set): the fused whole-matrix passes + a selecting assembly give
+    the same X[:, cols]^T D X[:, cols] as the restricted per-pair kernels and as float64
+    recomputation (reference: split.pyx:157-209 + split_matrix.py:334-354)."""
+    import tabmat_b200 as tm
+
+    n, pd, ps, dens, levels = CASES[0]
+    X, full, d, rng = _build(n, pd, ps, dens, levels, seed=77)
+    p = X.shape[1]
+    cols = np.sort(rng.choice(p, size=max(2, int(p * frac)), replace=False)).astype(np.int32)
+    rows = np.sort(rng.choice(n, size=n // 2, replace=False)).astype(np.int32)
+    S = tm.RowSortedMatrix.from_split(X)
+    assert X._cols_on_native_path(cols) == (frac >= 0.125)
+    for r in (None, rows):
+        F = (full if r is None else full[r])[:, cols]
+        dd = d.astype(np.float64) if r is None else d.astype(np.float64)[r]
+        ref = (F * dd[:, None]).T @ F
+        monkeypatch.setattr(type(X), "_cols_on_native_path", lambda self, c: True)
+        a = X.sandwich(d, r, cols)
+        b = S.sandwich(d, r, cols)
+        monkeypatch.setattr(type(X), "_cols_on_native_path", lambda self, c: False)
+        c = X.sandwich(d, r, cols)
+        for got, what in ((a, "native"), (b, "native, sorted rows"), (c, "per-pair")):
+            assert got.shape == ref.shape
+            cases.assert_close(got, ref, np.float32, f"cols {what}")
