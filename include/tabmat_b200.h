@@ -317,6 +317,13 @@ typedef struct tm_block_desc {
      * column j inside row block b; csc_indices still holds global row ids.  Keeps the per-row
      * gathers of the categorical x sparse kernel inside the L2. */
     int64_t csc_row_blocks;
+    /* sparse, optional: for every non-zero of the CSC arrays above (same order) the categorical
+     * codes of its row, bit-packed: the categorical blocks of the SplitMatrix in block order,
+     * block c in the next w_c = bit_length(ncols_c) bits from bit 0 upwards, value
+     * code - drop_first, all ones = no category (missing / dropped); at most 64 bits in total.
+     * Built once per matrix (like the reference's cached CSR, sparse_matrix.py:133-143): the
+     * categorical x sparse kernel then streams the codes and gathers only d[row]. */
+    const uint64_t* csc_cat_codes;
 } tm_block_desc;
 
 #define TM_CSC_ROW_BLOCK (1 << 20)

@@ -97,7 +97,8 @@ class BlockDesc(C.Structure):
                 ("csr_indices", C.c_void_p), ("csr_indptr", C.c_void_p), ("csr_row", C.c_void_p),
                 ("nnz", C.c_int64), ("col_index", C.c_void_p), ("cat_perm", C.c_void_p),
                 ("cat_segptr", C.c_void_p), ("cat_nvalid", C.c_int64), ("csc_data", C.c_void_p),
-                ("csc_indices", C.c_void_p), ("csc_indptr", C.c_void_p), ("csc_row_blocks", C.c_int64)]
+                ("csc_indices", C.c_void_p), ("csc_indptr", C.c_void_p), ("csc_row_blocks", C.c_int64),
+                ("csc_cat_codes", C.c_void_p)]
 
 #: rows per block of the row-blocked CSC copy (TM_CSC_ROW_BLOCK in include/tabmat_b200.h)
 CSC_ROW_BLOCK = 1 << 20

@@ -347,7 +347,18 @@ int split_blocks(const tm_block_desc* blk, int nb, int64_t n, const F* d, const 
                 }
                 ok = index_fused_eligible<F>(nc, Kc);
             }
-            Scratch rec(ok ? index_record_bytes<F>(n) : 0, st);
+            // categorical x sparse from the CSC copy: with the bit-packed codes of the
+            // non-zeros' rows (built once per matrix) nothing is packed per call; without them
+            // the 32-byte row records {d, codes} are built first and gathered per non-zero
+            const bool want_cs = ok && sparse_idx >= 0 && blk[sparse_idx].csc_indptr &&
+                                 blk[sparse_idx].csc_indices && blk[sparse_idx].csc_data &&
+                                 index_cat_sparse_fits<F>(nc, Kc, blk[sparse_idx].ncols);
+            static const bool packed_off =
+                getenv("TABMAT_B200_CSC_PACKED") && atoi(getenv("TABMAT_B200_CSC_PACKED")) == 0;
+            const bool use_packed = want_cs && !packed_off && blk[sparse_idx].csc_cat_codes &&
+                                    index_pack_fits(nc, Kc);
+            const bool need_rec = want_cs && !use_packed;
+            Scratch rec(need_rec ? index_record_bytes<F>(n) : 0, st);
             Scratch dmi(ok && rows ? sizeof(F) * (size_t)n : 0, st);
             if (rec.err != cudaSuccess) return fail_cuda(rec.err, "scratch");
             if (dmi.err != cudaSuccess) return fail_cuda(dmi.err, "scratch");
@@ -358,8 +369,11 @@ int split_blocks(const tm_block_desc* blk, int nb, int64_t n, const F* d, const 
                     if (rc) return rc;
                     dd = dmi.as<F>();
                 }
-                int rc = index_pack_records<F>(dd, n, nc, cc, dfc, rec.p, st);
-                if (rc) return rc;
+                int rc = 0;
+                if (need_rec) {
+                    rc = index_pack_records<F>(dd, n, nc, cc, dfc, rec.p, st);
+                    if (rc) return rc;
+                }
                 F* outs_self[8];
                 F* outs_pair[64];
                 for (int a = 0; a < nc; ++a) {
@@ -367,12 +381,11 @@ int split_blocks(const tm_block_desc* blk, int nb, int64_t n, const F* d, const 
                     for (int b = a + 1; b < nc; ++b)
                         outs_pair[a * nc + b] = ws + cross_off[cats[a]][cats[b]];
                 }
-                rc = index_cat_pairs<F>(rec.p, n, nc, Kc, runc, outs_self, outs_pair, st);
+                rc = index_cat_pairs<F>(nullptr, dd, cc, dfc, n, nc, Kc, runc, outs_self, outs_pair,
+                                        st);
                 if (rc) return rc;
                 cats_fused = true;
-                if (sparse_idx >= 0 && blk[sparse_idx].csc_indptr &&
-                    blk[sparse_idx].csc_indices && blk[sparse_idx].csc_data &&
-                    index_cat_sparse_fits<F>(nc, Kc, blk[sparse_idx].ncols)) {
+                if (want_cs) {
                     const tm_block_desc& S = blk[sparse_idx];
                     F* outs[8];
                     for (int a = 0; a < nc; ++a) {
@@ -380,7 +393,8 @@ int split_blocks(const tm_block_desc* blk, int nb, int64_t n, const F* d, const 
                         const int hi = cats[a] < sparse_idx ? sparse_idx : cats[a];
                         outs[a] = ws + cross_off[lo][hi];
                     }
-                    rc = index_cat_sparse<F>(rec.p, nc, Kc, runp,
+                    rc = index_cat_sparse<F>(need_rec ? rec.p : nullptr, dd,
+                                             use_packed ? S.csc_cat_codes : nullptr, nc, Kc, runp,
                                              static_cast<const F*>(S.csc_data), S.csc_indices,
                                              S.csc_indptr, S.ncols,
                                              (int)(S.csc_row_blocks > 1 ? S.csc_row_blocks : 1),

@@ -32,6 +32,7 @@
 
 namespace tmb {
 
+constexpr int IDX_MAX_CATS_DECL = 7;
 template <typename F>
 struct RowRec;
 template <>
@@ -91,6 +92,38 @@ __device__ __forceinline__ RowRec<F> load_rec(const RowRec<F>* __restrict__ rec,
     return r;
 }
 
+// Where a CSC-driven kernel takes the weight and the categorical codes of a non-zero's row from:
+//   records   rec[k] = {d, codes}: one 32-byte gather per non-zero (k_pack_records per call);
+//   packed    pk[e] = the codes of non-zero e's row, bit-packed into 64 bits in CSC order (built
+//             ONCE per matrix, like the cached CSR: streamed, coalesced) + a 4/8-byte gather of
+//             d[k].  No per-call packing pass, a quarter of the gathered bytes, and with the
+//             row-blocked CSC order the gather window (block_rows * sizeof F) sits in L2.
+struct CodeSrc {
+    const void* rec;
+    const void* d;
+    const unsigned long long* pk;
+    int shift[IDX_MAX_CATS_DECL];
+    unsigned mask[IDX_MAX_CATS_DECL];   // (1 << width) - 1 = the "missing" marker
+};
+
+template <typename F, int NC, bool PK>
+__device__ __forceinline__ void fetch_row(const CodeSrc& src, int e, int k, F& dk, int (&key)[NC]) {
+    if (PK) {
+        dk = __ldg(static_cast<const F*>(src.d) + k);
+        const unsigned long long pk = __ldg(src.pk + e);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            const unsigned v = (unsigned)(pk >> src.shift[c]) & src.mask[c];
+            key[c] = (v == src.mask[c] || dk == F(0)) ? -1 : (int)v;
+        }
+    } else {
+        const RowRec<F> r = load_rec<F>(static_cast<const RowRec<F>*>(src.rec), k);
+        dk = r.d;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) key[c] = r.c[c];
+    }
+}
+
 // Sum `val` over maximal runs of consecutive lanes with equal keys; true on the first lane of a
 // run, whose val then holds the run total (same helper as in categorical.cu).
 template <typename F, typename KeyT>
@@ -146,9 +179,12 @@ __device__ __forceinline__ void pair_add(const PairParams& prm, F* smem, int t, 
     }
 }
 
-template <typename F, int NC, int U>
+// DIRECT: the codes and d are read from their own arrays (coalesced, 4 (NC + 1) bytes per row)
+// instead of from packed 32-byte records
+template <typename F, int NC, int U, bool DIRECT>
 __global__ void __launch_bounds__(PAIRS_THREADS, 1)
-k_cat_pairs(const RowRec<F>* __restrict__ rec, int64_t n, const PairParams prm) {
+k_cat_pairs(const RowRec<F>* __restrict__ rec, const F* __restrict__ dvec, const PackParams src,
+            int64_t n, const PairParams prm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     F* smem = reinterpret_cast<F*>(smem_raw);
     for (int i = threadIdx.x; i < prm.smem_elems; i += blockDim.x) smem[i] = F(0);
@@ -161,7 +197,18 @@ k_cat_pairs(const RowRec<F>* __restrict__ rec, int64_t n, const PairParams prm) 
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int64_t k = base + u * 32 + lane;
-            if (k < n) {
+            if (k < n && DIRECT) {
+                r[u].d = dvec[k];
+#pragma unroll
+                for (int c = 0; c < rec_max_cats<F>(); ++c) r[u].c[c] = -1;
+                if (r[u].d != F(0)) {
+#pragma unroll
+                    for (int c = 0; c < NC; ++c) {
+                        const int v = __ldg(src.codes[c] + k) - src.drop_first[c];
+                        r[u].c[c] = v < 0 ? -1 : v;
+                    }
+                }
+            } else if (k < n) {
                 r[u] = load_rec<F>(rec, k);
             } else {
                 r[u].d = F(0);
@@ -250,11 +297,11 @@ struct CatSparseParams {
 // ncu (profiles/ncu_step_r1c_summary.csv): 3.6 ms at the benchmark shape, latency-bound on the
 // record gathers — 8.7 GB of DRAM reads, i.e. one 64-byte access per non-zero; the row-blocked
 // variant below keeps them in L2.
-template <typename F, int NC, int U>
+template <typename F, int NC, int U, bool PK>
 __global__ void __launch_bounds__(CS_THREADS)
 k_cat_sparse_csc(const F* __restrict__ data, const int32_t* __restrict__ row_idx,
-                 const int32_t* __restrict__ indptr, int p_s,
-                 const RowRec<F>* __restrict__ rec, const CatSparseParams prm) {
+                 const int32_t* __restrict__ indptr, int p_s, const CodeSrc src,
+                 const CatSparseParams prm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     F* smem = reinterpret_cast<F*>(smem_raw);
     const int lane = threadIdx.x & 31;
@@ -265,7 +312,8 @@ k_cat_sparse_csc(const F* __restrict__ data, const int32_t* __restrict__ row_idx
         __syncthreads();
         const int e0 = indptr[j], e1 = indptr[j + 1];
         for (int eb = e0 + wib * (32 * U); eb < e1; eb += NW * (32 * U)) {
-            RowRec<F> r[U];
+            F dk[U];
+            int keys[U][NC];
             F a[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
@@ -277,19 +325,19 @@ k_cat_sparse_csc(const F* __restrict__ data, const int32_t* __restrict__ row_idx
                     a[u] = data[e];
                 }
                 if (k >= 0) {
-                    r[u] = load_rec<F>(rec, k);
+                    fetch_row<F, NC, PK>(src, e, k, dk[u], keys[u]);
                 } else {
-                    r[u].d = F(0);
+                    dk[u] = F(0);
 #pragma unroll
-                    for (int c = 0; c < rec_max_cats<F>(); ++c) r[u].c[c] = -1;
+                    for (int c = 0; c < NC; ++c) keys[u][c] = -1;
                 }
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const F val0 = r[u].d * a[u];
+                const F val0 = dk[u] * a[u];
 #pragma unroll
                 for (int c = 0; c < NC; ++c) {
-                    int key = r[u].c[c];
+                    int key = keys[u][c];
                     if (prm.mode[c] == CS_PRIV) {
                         if (key >= 0) smem[prm.off[c] + key * CS_THREADS + threadIdx.x] += val0;
                         continue;
@@ -358,11 +406,11 @@ struct ColOwnerParams {
     int n_row_blocks;
 };
 
-template <typename F, int NC>
+template <typename F, int NC, bool PK>
 __global__ void __launch_bounds__(CO_THREADS)
 k_cat_sparse_cols(const F* __restrict__ data, const int32_t* __restrict__ row_idx,
-                  const int32_t* __restrict__ indptr, int p_s,
-                  const RowRec<F>* __restrict__ rec, const ColOwnerParams prm) {
+                  const int32_t* __restrict__ indptr, int p_s, const CodeSrc src,
+                  const ColOwnerParams prm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     F* smem = reinterpret_cast<F*>(smem_raw);
     const int lane = threadIdx.x & 31;
@@ -379,20 +427,20 @@ k_cat_sparse_cols(const F* __restrict__ data, const int32_t* __restrict__ row_id
             // warp-uniform trip count (run_reduce needs whole warps)
             for (int eb = e0 + (threadIdx.x & ~31); eb < e1; eb += CO_THREADS) {
                 const int e = eb + lane;
-                RowRec<F> r;
+                F dk = F(0);
+                int keys[NC];
                 F a = F(0);
                 if (e < e1) {
                     a = data[e];
-                    r = load_rec<F>(rec, row_idx[e]);
+                    fetch_row<F, NC, PK>(src, e, row_idx[e], dk, keys);
                 } else {
-                    r.d = F(0);
 #pragma unroll
-                    for (int c = 0; c < rec_max_cats<F>(); ++c) r.c[c] = -1;
+                    for (int c = 0; c < NC; ++c) keys[c] = -1;
                 }
-                const F val0 = r.d * a;
+                const F val0 = dk * a;
 #pragma unroll
                 for (int c = 0; c < NC; ++c) {
-                    int key = r.c[c];
+                    int key = keys[c];
                     F val = val0;
                     bool head = true;
                     if (prm.runs[c]) head = run_reduce<F, int>(key, val, lane);
@@ -485,24 +533,41 @@ template int index_pack_records<double>(const double*, int64_t, int, const int32
 constexpr size_t IDX_SMEM_BUDGET = 200 * 1024;
 
 template <typename F, int NC>
-static int launch_pairs(const RowRec<F>* rec, int64_t n, const PairParams& prm, cudaStream_t st) {
+static int launch_pairs(const RowRec<F>* rec, const F* d, const PackParams& src, int64_t n,
+                        const PairParams& prm, cudaStream_t st) {
     constexpr int U = 2;
     const size_t smem = sizeof(F) * (size_t)prm.smem_elems;
-    // per device and cheap: set on every launch rather than cached in a process-wide static
-    TM_CUDA(cudaFuncSetAttribute(k_cat_pairs<F, NC, U>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)IDX_SMEM_BUDGET));
     const int g = grid_for(n, PAIRS_THREADS * U, sm_count());
-    k_cat_pairs<F, NC, U><<<g, PAIRS_THREADS, smem, st>>>(rec, n, prm);
+    // per device and cheap: set on every launch rather than cached in a process-wide static
+    if (rec) {
+        TM_CUDA(cudaFuncSetAttribute(k_cat_pairs<F, NC, U, false>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)IDX_SMEM_BUDGET));
+        k_cat_pairs<F, NC, U, false><<<g, PAIRS_THREADS, smem, st>>>(rec, d, src, n, prm);
+    } else {
+        TM_CUDA(cudaFuncSetAttribute(k_cat_pairs<F, NC, U, true>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)IDX_SMEM_BUDGET));
+        k_cat_pairs<F, NC, U, true><<<g, PAIRS_THREADS, smem, st>>>(rec, d, src, n, prm);
+    }
     TM_LAUNCHED();
     return 0;
 }
 
 // outs_self[c]: K_c values; outs_pair[i * n_cat + j] (i < j): K_i x K_j row-major.  Overwrites.
+// rec_v != NULL: read the 32-byte row records; NULL: read d and the code vectors directly.
 template <typename F>
-int index_cat_pairs(const void* rec_v, int64_t n, int n_cat, const int64_t* K, const int32_t* runs,
-                    F* const* outs_self, F* const* outs_pair, cudaStream_t st) {
+int index_cat_pairs(const void* rec_v, const F* d, const int32_t* const* codes,
+                    const int32_t* drop_first, int64_t n, int n_cat, const int64_t* K,
+                    const int32_t* runs, F* const* outs_self, F* const* outs_pair,
+                    cudaStream_t st) {
     const RowRec<F>* rec = static_cast<const RowRec<F>*>(rec_v);
+    PackParams src;
+    memset(&src, 0, sizeof(src));
+    for (int c = 0; c < n_cat && c < 7; ++c) {
+        src.codes[c] = codes[c];
+        src.drop_first[c] = drop_first[c];
+    }
     PairParams prm;
     memset(&prm, 0, sizeof(prm));
     int64_t size[IDX_MAX_TARGETS];
@@ -568,33 +633,44 @@ int index_cat_pairs(const void* rec_v, int64_t n, int n_cat, const int64_t* K, c
     }
     prm.smem_elems = (int)used;
     switch (n_cat) {
-        case 1: return launch_pairs<F, 1>(rec, n, prm, st);
-        case 2: return launch_pairs<F, 2>(rec, n, prm, st);
-        case 3: return launch_pairs<F, 3>(rec, n, prm, st);
-        case 4: return launch_pairs<F, 4>(rec, n, prm, st);
-        case 5: return launch_pairs<F, 5>(rec, n, prm, st);
-        case 6: return launch_pairs<F, 6>(rec, n, prm, st);
-        default: return launch_pairs<F, rec_max_cats<F>()>(rec, n, prm, st);
+        case 1: return launch_pairs<F, 1>(rec, d, src, n, prm, st);
+        case 2: return launch_pairs<F, 2>(rec, d, src, n, prm, st);
+        case 3: return launch_pairs<F, 3>(rec, d, src, n, prm, st);
+        case 4: return launch_pairs<F, 4>(rec, d, src, n, prm, st);
+        case 5: return launch_pairs<F, 5>(rec, d, src, n, prm, st);
+        case 6: return launch_pairs<F, 6>(rec, d, src, n, prm, st);
+        default: return launch_pairs<F, rec_max_cats<F>()>(rec, d, src, n, prm, st);
     }
 }
-template int index_cat_pairs<float>(const void*, int64_t, int, const int64_t*, const int32_t*,
+template int index_cat_pairs<float>(const void*, const float*, const int32_t* const*,
+                                    const int32_t*, int64_t, int, const int64_t*, const int32_t*,
                                     float* const*, float* const*, cudaStream_t);
-template int index_cat_pairs<double>(const void*, int64_t, int, const int64_t*, const int32_t*,
+template int index_cat_pairs<double>(const void*, const double*, const int32_t* const*,
+                                     const int32_t*, int64_t, int, const int64_t*, const int32_t*,
                                      double* const*, double* const*, cudaStream_t);
 
 constexpr size_t CS_SMEM_BUDGET = 72 * 1024;  // three CTAs of 256 threads per SM
 
 template <typename F, int NC>
 static int launch_cat_sparse(const F* data, const int32_t* row_idx, const int32_t* indptr,
-                             int p_s, const RowRec<F>* rec, const CatSparseParams& prm,
+                             int p_s, const CodeSrc& src, const CatSparseParams& prm,
                              cudaStream_t st) {
     constexpr int U = 2;
-    TM_CUDA(cudaFuncSetAttribute(k_cat_sparse_csc<F, NC, U>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)CS_SMEM_BUDGET));
     const size_t smem = sizeof(F) * (size_t)(prm.smem_elems > 0 ? prm.smem_elems : 1);
     const int g = p_s < sm_count() * 12 ? p_s : sm_count() * 12;
-    k_cat_sparse_csc<F, NC, U><<<g, CS_THREADS, smem, st>>>(data, row_idx, indptr, p_s, rec, prm);
+    if (src.pk) {
+        TM_CUDA(cudaFuncSetAttribute(k_cat_sparse_csc<F, NC, U, true>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)CS_SMEM_BUDGET));
+        k_cat_sparse_csc<F, NC, U, true><<<g, CS_THREADS, smem, st>>>(data, row_idx, indptr, p_s,
+                                                                      src, prm);
+    } else {
+        TM_CUDA(cudaFuncSetAttribute(k_cat_sparse_csc<F, NC, U, false>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)CS_SMEM_BUDGET));
+        k_cat_sparse_csc<F, NC, U, false><<<g, CS_THREADS, smem, st>>>(data, row_idx, indptr, p_s,
+                                                                       src, prm);
+    }
     TM_LAUNCHED();
     return 0;
 }
@@ -649,17 +725,21 @@ template bool index_cat_sparse_fits<double>(int, const int64_t*, int64_t);
 
 template <typename F, int NC>
 static int launch_cat_sparse_cols(const F* data, const int32_t* row_idx, const int32_t* indptr,
-                                  int p_s, const RowRec<F>* rec, const ColOwnerParams& prm, int grid,
+                                  int p_s, const CodeSrc& rec, const ColOwnerParams& prm, int grid,
                                   cudaStream_t st) {
     const size_t smem = sizeof(F) * (size_t)prm.slot * (size_t)prm.cols_per_cta;
-    k_cat_sparse_cols<F, NC><<<grid, CO_THREADS, smem > 0 ? smem : 16, st>>>(data, row_idx, indptr,
-                                                                          p_s, rec, prm);
+    if (rec.pk)
+        k_cat_sparse_cols<F, NC, true><<<grid, CO_THREADS, smem > 0 ? smem : 16, st>>>(
+            data, row_idx, indptr, p_s, rec, prm);
+    else
+        k_cat_sparse_cols<F, NC, false><<<grid, CO_THREADS, smem > 0 ? smem : 16, st>>>(
+            data, row_idx, indptr, p_s, rec, prm);
     TM_LAUNCHED();
     return 0;
 }
 
 template <typename F>
-static int cat_sparse_cols(const RowRec<F>* rec, int n_cat, const int64_t* K, const int32_t* runs,
+static int cat_sparse_cols(const CodeSrc& rec, int n_cat, const int64_t* K, const int32_t* runs,
                            const F* csc_data, const int32_t* csc_row, const int32_t* csc_indptr,
                            int64_t p_s, int n_row_blocks, F* const* outs, cudaStream_t st) {
     ColOwnerParams prm;
@@ -711,11 +791,40 @@ static int cat_sparse_cols(const RowRec<F>* rec, int n_cat, const int64_t* K, co
 
 // outs[c]: K_c x p_s row-major, overwritten.  n_row_blocks > 1: the CSC arrays are row-blocked
 // (blocks of TM_CSC_ROW_BLOCK rows, block slowest, then column, then row).
+int index_pack_width(int64_t ncols) {
+    int w = 1;
+    while ((1ll << w) <= ncols) ++w;   // values 0 .. ncols-1, marker 2^w - 1 = missing
+    return w;
+}
+bool index_pack_fits(int n_cat, const int64_t* K) {
+    int bits = 0;
+    for (int c = 0; c < n_cat; ++c) bits += index_pack_width(K[c]);
+    return n_cat >= 1 && n_cat <= IDX_MAX_CATS && bits <= 64;
+}
+
+// rec_v: the 32-byte row records, or NULL when `packed` (codes of every CSC non-zero's row,
+// bit-packed block after block from bit 0, widths index_pack_width(K_c)) and `d` are given.
 template <typename F>
-int index_cat_sparse(const void* rec_v, int n_cat, const int64_t* K, const int32_t* runs,
-                     const F* csc_data, const int32_t* csc_row, const int32_t* csc_indptr,
-                     int64_t p_s, int n_row_blocks, F* const* outs, cudaStream_t st) {
-    const RowRec<F>* rec = static_cast<const RowRec<F>*>(rec_v);
+int index_cat_sparse(const void* rec_v, const F* d, const uint64_t* packed, int n_cat,
+                     const int64_t* K, const int32_t* runs, const F* csc_data,
+                     const int32_t* csc_row, const int32_t* csc_indptr, int64_t p_s,
+                     int n_row_blocks, F* const* outs, cudaStream_t st) {
+    CodeSrc rec;
+    memset(&rec, 0, sizeof(rec));
+    rec.rec = rec_v;
+    if (!rec_v) {
+        if (!packed || !d || !index_pack_fits(n_cat, K))
+            return fail("index_cat_sparse: neither row records nor packed codes");
+        rec.d = d;
+        rec.pk = reinterpret_cast<const unsigned long long*>(packed);
+        int sh = 0;
+        for (int c = 0; c < n_cat; ++c) {
+            const int w = index_pack_width(K[c]);
+            rec.shift[c] = sh;
+            rec.mask[c] = w >= 32 ? 0xffffffffu : ((1u << w) - 1u);
+            sh += w;
+        }
+    }
     if (n_row_blocks > 1)
         return cat_sparse_cols<F>(rec, n_cat, K, runs, csc_data, csc_row, csc_indptr, p_s,
                                   n_row_blocks, outs, st);
@@ -738,11 +847,12 @@ int index_cat_sparse(const void* rec_v, int n_cat, const int64_t* K, const int32
                                                            rec, prm, st);
     }
 }
-template int index_cat_sparse<float>(const void*, int, const int64_t*, const int32_t*, const float*,
-                                     const int32_t*, const int32_t*, int64_t, int, float* const*,
-                                     cudaStream_t);
-template int index_cat_sparse<double>(const void*, int, const int64_t*, const int32_t*,
-                                      const double*, const int32_t*, const int32_t*, int64_t, int,
+template int index_cat_sparse<float>(const void*, const float*, const uint64_t*, int,
+                                     const int64_t*, const int32_t*, const float*, const int32_t*,
+                                     const int32_t*, int64_t, int, float* const*, cudaStream_t);
+template int index_cat_sparse<double>(const void*, const double*, const uint64_t*, int,
+                                      const int64_t*, const int32_t*, const double*,
+                                      const int32_t*, const int32_t*, int64_t, int,
                                       double* const*, cudaStream_t);
 
 }  // namespace tmb

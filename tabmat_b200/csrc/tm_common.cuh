@@ -198,14 +198,22 @@ size_t index_record_bytes(int64_t n);
 template <typename F>
 int index_pack_records(const F* d, int64_t n, int n_cat, const int32_t* const* codes,
                        const int32_t* drop_first, void* rec, cudaStream_t st);
+// rec == NULL: d and the code vectors are read directly (no packing pass)
 template <typename F>
-int index_cat_pairs(const void* rec, int64_t n, int n_cat, const int64_t* K, const int32_t* runs,
-                    F* const* outs_self, F* const* outs_pair, cudaStream_t st);
+int index_cat_pairs(const void* rec, const F* d, const int32_t* const* codes,
+                    const int32_t* drop_first, int64_t n, int n_cat, const int64_t* K,
+                    const int32_t* runs, F* const* outs_self, F* const* outs_pair,
+                    cudaStream_t st);
 template <typename F>
 bool index_cat_sparse_fits(int n_cat, const int64_t* K, int64_t p_s);
+// bit-packed codes of the CSC non-zeros' rows (tm_block_desc.csc_cat_codes): field widths
+int index_pack_width(int64_t ncols);
+bool index_pack_fits(int n_cat, const int64_t* K);
+// rec == NULL: `packed` + `d` replace the row records
 template <typename F>
-int index_cat_sparse(const void* rec, int n_cat, const int64_t* K, const int32_t* runs,
-                     const F* csc_data, const int32_t* csc_row, const int32_t* csc_indptr,
-                     int64_t p_s, int n_row_blocks, F* const* outs, cudaStream_t st);
+int index_cat_sparse(const void* rec, const F* d, const uint64_t* packed, int n_cat,
+                     const int64_t* K, const int32_t* runs, const F* csc_data,
+                     const int32_t* csc_row, const int32_t* csc_indptr, int64_t p_s,
+                     int n_row_blocks, F* const* outs, cudaStream_t st);
 
 }  // namespace tmb

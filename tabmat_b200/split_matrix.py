@@ -277,19 +277,25 @@ class SplitMatrix(MatrixBase):
                 dsc.csr_indices, dsc.csr_indptr = c.indices.data_ptr(), c.indptr.data_ptr()
                 dsc.csr_row = c.row.data_ptr()
                 block_rows = int(os.environ.get("TABMAT_B200_CSC_ROW_BLOCK", CSC_ROW_BLOCK))
-                if (os.environ.get("TABMAT_B200_CSC_ROW_BLOCKS") == "1" and c.nnz
+                has_cat = any(isinstance(m, CategoricalMatrix) for m in self.matrices)
+                if (os.environ.get("TABMAT_B200_CSC_ROW_BLOCKS", "1") != "0" and c.nnz and has_cat
                         and mat.shape[0] > block_rows + block_rows // 2):
-                    # opt-in: row-blocked CSC + the column-owner kernel (k_cat_sparse_cols): the
-                    # record gathers stay inside a moving window of block_rows * 32 bytes.
-                    # Measured on B200 at n = 4e7: index pass 6.9 ms vs 7.6 ms with the plain
-                    # CSC order; costs one more copy of the non-zeros, so it stays opt-in.
+                    # row-blocked CSC + the column-owner kernel (k_cat_sparse_cols): the per-row
+                    # gathers of the categorical x sparse kernel stay inside a moving window of
+                    # block_rows rows that sits in L2.  One more copy of the non-zeros, built once
+                    # (TABMAT_B200_CSC_ROW_BLOCKS=0 keeps the plain CSC order).
                     bd, br, bp, nblk = mat._row_blocked_csc(block_rows)
                     dsc.csc_data, dsc.csc_indices = bd.data_ptr(), br.data_ptr()
                     dsc.csc_indptr, dsc.csc_row_blocks = bp.data_ptr(), nblk
+                    csc_rows = br
                 else:
                     cc = mat._csc
                     dsc.csc_data, dsc.csc_indices = cc.data.data_ptr(), cc.indices.data_ptr()
                     dsc.csc_indptr, dsc.csc_row_blocks = cc.indptr.data_ptr(), 0
+                    csc_rows = cc.indices
+                pk = self._packed_cat_codes(csc_rows, tdtype) if has_cat and c.nnz else None
+                if pk is not None:
+                    dsc.csc_cat_codes = pk.data_ptr()
             elif isinstance(mat, CategoricalMatrix):
                 ok = _dev.torch_dtype(mat.dtype) == tdtype
                 dsc.kind, dsc.data, dsc.drop_first = 2, mat._codes.data_ptr(), int(mat.drop_first)
@@ -310,6 +316,35 @@ class SplitMatrix(MatrixBase):
             plan = (descs, int(lib.tm_split_workspace_elems(descs, len(self.matrices))))
         cache[key] = plan
         return plan
+
+    def _packed_cat_codes(self, csc_rows: torch.Tensor, tdtype) -> Optional[torch.Tensor]:
+        """For every non-zero of the sparse block's CSC copy (in ITS order) the categorical
+        codes of the non-zero's row, bit-packed into one int64 (tm_block_desc.csc_cat_codes):
+        built once per matrix and cached, like the reference's cached CSR
+        (sparse_matrix.py:133-143).  None when the codes need more than 64 bits."""
+        if os.environ.get("TABMAT_B200_CSC_PACKED") == "0":
+            return None
+        cats = [m for m in self.matrices if isinstance(m, CategoricalMatrix)]
+        widths = [max(1, int(m.shape[1]).bit_length()) for m in cats]
+        if not cats or len(cats) > 7 or sum(widths) > 64 or any(m.shape[1] <= 0 for m in cats):
+            return None
+        cache = self.__dict__.setdefault("_packed_codes_cache", {})
+        key = csc_rows.data_ptr()
+        if key not in cache:
+            rows64 = csc_rows.to(torch.int64)
+            pk = torch.zeros(rows64.numel(), dtype=torch.int64, device=rows64.device)
+            shift = 0
+            for m, w in zip(cats, widths):
+                c = m._codes.index_select(0, rows64).to(torch.int64) - int(m.drop_first)
+                marker = (1 << w) - 1
+                c = torch.where(c < 0, torch.full_like(c, marker), c)
+                if shift + w == 64:   # the top field reaches the sign bit of the int64 carrier
+                    c = torch.where(c >= (1 << (w - 1)), c - (1 << w), c)
+                pk |= c << shift
+                shift += w
+                del c
+            cache[key] = (pk, csc_rows)   # keep the row array alive: its address is the key
+        return cache[key][0]
 
     def _sandwich_blocks_dev(self, d_t: torch.Tensor, rows_t) -> Optional[torch.Tensor]:
         """Flat workspace with every self / cross block (layout: csrc/split.cu), or None."""

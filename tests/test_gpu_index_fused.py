@@ -123,3 +123,28 @@ def test_row_blocked_csc_path(suf, levels, monkeypatch):
         ref = (F * dd[:, None]).T @ F
         cases.assert_close(X.sandwich(d, r), ref, dt, f"row-blocked csc {levels}")
         cases.assert_close(S.sandwich(d, r), ref, dt, f"row-blocked csc, sorted rows {levels}")
+
+
+@pytest.mark.parametrize("suf", ["f32", "f64"])
+@pytest.mark.parametrize("blocked", [False, True])
+def test_row_record_path_without_packed_codes(suf, blocked, monkeypatch):
+    """TABMAT_B200_CSC_PACKED=0: no bit-packed codes in the plan, so categorical x sparse goes
+    through the per-call 32-byte row records (the layout for code sets wider than 64 bits)."""
+    import tabmat_b200 as tm
+    from tabmat_b200 import split_matrix
+
+    monkeypatch.setenv("TABMAT_B200_CSC_PACKED", "0")
+    if blocked:
+        monkeypatch.setattr(split_matrix, "CSC_ROW_BLOCK", 1000)
+    dt = cases.DTYPES[suf]
+    n = 6007
+    X, full, d, rng = _build(dt, n, (10, 50, 200, 1000, 2000), seed=5)
+    plan = X._native_plan(tm._dev.torch_dtype(dt))
+    assert plan is not None and not plan[0][1].csc_cat_codes
+    assert (plan[0][1].csc_row_blocks == 7) == blocked
+    ref = (full * d.astype(np.float64)[:, None]).T @ full
+    cases.assert_close(X.sandwich(d), ref, dt, "row records")
+    monkeypatch.delenv("TABMAT_B200_CSC_PACKED")
+    Y, full2, d2, _ = _build(dt, n, (10, 50, 200, 1000, 2000), seed=5)
+    assert Y._native_plan(tm._dev.torch_dtype(dt))[0][1].csc_cat_codes
+    cases.assert_close(Y.sandwich(d2), ref, dt, "packed codes")
