@@ -358,6 +358,21 @@ int tm_split_sandwich_blocks_f32(const tm_block_desc* blocks, int n_blocks, int6
 int tm_split_sandwich_blocks_f64(const tm_block_desc* blocks, int n_blocks, int64_t n,
                                  const double* d, const int32_t* rows, int64_t n_rows,
                                  double* workspace, tm_stream_t stream);
+/* Fused IRLS pass (callers of matrix_base.py:15-77 make two calls, sandwich(d) for the Hessian
+ * and transpose_matvec(v) for the score, i.e. two passes over X): as tm_split_sandwich_blocks_*,
+ * and in the same pass over the dense block dense_vec[c] = sum_k v[k] * X_dense[k, c] over `rows`
+ * (ncols of the dense block; fp32/fp64 FMAs, never TF32).  The dense block is the only one whose
+ * transpose_matvec costs a pass over ~all of the matrix bytes; the sparse and categorical parts
+ * of X^T v are tm_csc_rmatvec / tm_cat_transpose_matvec calls.  No dense block: dense_vec is
+ * not touched. */
+int tm_split_sandwich_rmatvec_blocks_f32(const tm_block_desc* blocks, int n_blocks, int64_t n,
+                                         const float* d, const float* v, const int32_t* rows,
+                                         int64_t n_rows, float* workspace, float* dense_vec,
+                                         tm_stream_t stream);
+int tm_split_sandwich_rmatvec_blocks_f64(const tm_block_desc* blocks, int n_blocks, int64_t n,
+                                         const double* d, const double* v, const int32_t* rows,
+                                         int64_t n_rows, double* workspace, double* dense_vec,
+                                         tm_stream_t stream);
 /* Place the workspace into the p x p float64 result (split_matrix.py:336-354); `ld` = p.
  * Separate from the block computation so that a row-sharded caller can allreduce the flat
  * workspace in between.  A column whose entry in its block's `col_index` is negative is
@@ -406,6 +421,20 @@ int tm_permute_scatter_f32(const float* src, const int32_t* perm, int64_t n, flo
                            int accumulate, tm_stream_t stream);
 int tm_permute_scatter_f64(const double* src, const int32_t* perm, int64_t n, double* dst,
                            int accumulate, tm_stream_t stream);
+
+/* ---- StandardizedMatrix.sandwich epilogue (reference: standardized_mat.py:123-172) ---- */
+/* out[i,j] = term1[i,j] * mult[i] * mult[j] + dm[i] * shift[j] + shift[i] * dm[j]
+ *            + shift[i] * shift[j] * sum_d,   dm[i] = d_mat[i] * mult[i]   (m x m, overwrites).
+ * term1 = the inner matrix' sandwich restricted like the call: float64 when term1_f64 != 0 (a
+ * SplitMatrix), else the entry point's dtype; `diag` != 0: term1 is a categorical block's
+ * diagonal (m values).  d_mat = inner.transpose_matvec(d); mult may be NULL (no scaling);
+ * sum_d points to a DEVICE scalar (sum of d over the rows), so nothing synchronises. */
+int tm_std_sandwich_combine_f32(const void* term1, int term1_f64, int diag, const float* dmat,
+                                const float* shift, const float* mult, const float* sum_d,
+                                int64_t m, float* out, tm_stream_t stream);
+int tm_std_sandwich_combine_f64(const void* term1, int term1_f64, int diag, const double* dmat,
+                                const double* shift, const double* mult, const double* sum_d,
+                                int64_t m, double* out, tm_stream_t stream);
 
 /* ---- SplitMatrix assembly (reference: split_matrix.py:336-354, the numpy scatter) ---- */
 /* out[ri[a]*ld + ci[b]] = blk[a*nb + b]  (and, when mirror != 0, out[ci[b]*ld + ri[a]] too).

@@ -12,6 +12,7 @@ from ._lib import TabmatB200Error, launch_count, reset_launch_count  # noqa: F40
 from .categorical_matrix import CategoricalMatrix
 from .constructor import from_csc, from_df, from_pandas
 from .dense_matrix import DenseMatrix
+from .irls import irls_step
 from .matrix_base import MatrixBase
 from .row_order import RowSortedMatrix
 from .sparse_matrix import SparseMatrix
@@ -33,4 +34,5 @@ __all__ = [
     "from_csc",
     "from_df",
     "from_pandas",
+    "irls_step",
 ]

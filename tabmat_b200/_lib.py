@@ -65,11 +65,13 @@ _SIGS = {
     "tm_cat_sparse_sandwich": [P, I, I, N, P, P, P, P, P, I, I, P, I, P, I, P, P],
     "tm_dense_cross_sandwich": [P, I, I, P, P, I, N, P, P, P, P, P, P, P, I, P, P],
     "tm_split_sandwich_blocks": [P, N, I, P, P, I, P, P],
+    "tm_split_sandwich_rmatvec_blocks": [P, N, I, P, P, P, I, P, P, P],
     "tm_split_sandwich_assemble": [P, N, P, P, I, P],
     "tm_split_sandwich_blocks_part": [P, N, I, P, P, I, P, N, P],
     "tm_split_sandwich_assemble_part": [P, N, P, P, I, N, P],
     "tm_scatter_block": [P, I, I, P, P, P, I, N, P],
     "tm_scatter_diag": [P, I, P, P, I, P],
+    "tm_std_sandwich_combine": [P, N, N, P, P, P, P, I, P, P],
     "tm_permute_gather": [P, P, I, P, N, P],
     "tm_permute_scatter": [P, P, I, P, N, P],
 }

@@ -228,9 +228,63 @@ int permute(const F* src, const int32_t* perm, int64_t n, F* dst, int gather, in
     return 0;
 }
 
+// ---- StandardizedMatrix.sandwich epilogue (standardized_mat.py:123-172) in one kernel ------
+//   out[i, j] = term1[i, j] * mult[i] * mult[j] + dm[i] * shift[j] + shift[i] * dm[j]
+//               + shift[i] * shift[j] * sum_d,        dm[i] = d_mat[i] * mult[i]
+// term1 = the inner matrix' sandwich (float64 for a SplitMatrix, else F; a categorical's diagonal
+// when `diag`), d_mat = inner.transpose_matvec(d), sum_d a DEVICE scalar (no host sync).
+template <typename TI, typename F>
+__global__ void k_std_combine(const TI* __restrict__ term1, int diag, const F* __restrict__ dmat,
+                              const F* __restrict__ shift, const F* __restrict__ mult,
+                              const F* __restrict__ sum_d, int64_t m, F* __restrict__ out) {
+    const int64_t total = m * m;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const F sd = *sum_d;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+        const int64_t i = t / m, j = t - i * m;
+        const F mi = mult ? mult[i] : F(1), mj = mult ? mult[j] : F(1);
+        const F si = shift[i], sj = shift[j];
+        F r = dmat[i] * mi * sj + si * (dmat[j] * mj) + si * sj * sd;
+        if (diag) {
+            if (i == j) r += (F)term1[i] * mi * mj;
+        } else {
+            r += (F)term1[t] * (mi * mj);
+        }
+        out[t] = r;
+    }
+}
+
+template <typename F>
+int std_combine(const void* term1, int term1_f64, int diag, const F* dmat, const F* shift,
+                const F* mult, const F* sum_d, int64_t m, F* out, cudaStream_t st) {
+    if (m <= 0) return 0;
+    const int g = grid_for(m * m, 256 * 2, sm_count() * 8);
+    if (term1_f64)
+        k_std_combine<double, F><<<g, 256, 0, st>>>(static_cast<const double*>(term1), diag, dmat,
+                                                   shift, mult, sum_d, m, out);
+    else
+        k_std_combine<F, F><<<g, 256, 0, st>>>(static_cast<const F*>(term1), diag, dmat, shift,
+                                              mult, sum_d, m, out);
+    TM_LAUNCHED();
+    return 0;
+}
+
 }  // namespace tmb
 
 extern "C" {
+
+int tm_std_sandwich_combine_f32(const void* term1, int term1_f64, int diag, const float* dmat,
+                                const float* shift, const float* mult, const float* sum_d,
+                                int64_t m, float* out, tm_stream_t stream) {
+    return tmb::std_combine<float>(term1, term1_f64, diag, dmat, shift, mult, sum_d, m, out,
+                                   tmb::as_stream(stream));
+}
+int tm_std_sandwich_combine_f64(const void* term1, int term1_f64, int diag, const double* dmat,
+                                const double* shift, const double* mult, const double* sum_d,
+                                int64_t m, double* out, tm_stream_t stream) {
+    return tmb::std_combine<double>(term1, 1, diag, dmat, shift, mult, sum_d, m, out,
+                                    tmb::as_stream(stream));
+}
 
 int tm_permute_gather_f32(const float* src, const int32_t* perm, int64_t n, float* dst,
                           int accumulate, tm_stream_t stream) {

@@ -79,6 +79,10 @@ struct Params {
     // vector REDs of dense x sparse and dense x many-level categoricals (split_fused.cu does the
     // same from a second pass over X)
     int f_order;      // X is column-major: the TMA box lands K-major (SWIZZLE_128B) in the stage
+    // fused IRLS pass: vec_out[c] += sum_k v[k] * X[k, c] in full fp32 on the CUDA cores of the
+    // scale warps (v is staged by TMA next to d); has_v = 0: plain sandwich
+    int has_v;
+    float* vec_out;
     int sc_ncat;                       // <= TC_SCATTER_MAX_CATS
     const int32_t* sc_codes[TC_SCATTER_MAX_CATS];
     float* sc_tab[TC_SCATTER_MAX_CATS];
@@ -283,7 +287,8 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
 // loads are issued before the math.  Lanes with c >= P write nothing to S (those rows stay
 // zero) and zeros to T (tcgen05.st is warp-collective).
 __device__ __forceinline__ void scale_col4(uint32_t R, int P, uint32_t dsm, uint32_t Sp,
-                                           uint32_t t_addr, int c, int kb, int ks) {
+                                           uint32_t t_addr, int c, int kb, int ks, uint32_t vsm,
+                                           float& gacc) {
     // R, dsm, Sp: 32-bit shared addresses of the raw stage, its d vector and the S tile
     float x[4][4];
     const bool ok = c < P;
@@ -308,6 +313,13 @@ __device__ __forceinline__ void scale_col4(uint32_t R, int P, uint32_t dsm, uint
         if (ok) sts_u32x4(Sp + tile_off + kmajor_chunk_off(row, (uint32_t)k4), a);
         tmem_st_x4(t_addr + (uint32_t)(4 * k4), to_tf32(dv.x * x[u][0]), to_tf32(dv.y * x[u][1]),
                    to_tf32(dv.z * x[u][2]), to_tf32(dv.w * x[u][3]));
+        if (vsm) {  // X^T v rides along in fp32 (not TF32: it is the score of an IRLS step)
+            const float4 vv = lds_f32x4(vsm + 16u * (uint32_t)k4);
+            gacc = fmaf(vv.x, x[u][0], gacc);
+            gacc = fmaf(vv.y, x[u][1], gacc);
+            gacc = fmaf(vv.z, x[u][2], gacc);
+            gacc = fmaf(vv.w, x[u][3], gacc);
+        }
     }
 }
 
@@ -317,7 +329,8 @@ __device__ __forceinline__ void scale_col4(uint32_t R, int P, uint32_t dsm, uint
 // (SWIZZLE_128B) so that the 32 lanes of a warp, one column each, read a chunk without bank
 // conflicts.  No transpose is needed: a lane reads its 4 consecutive k as one LDS.128.
 __device__ __forceinline__ void scale_col4_f(uint32_t R, int P, uint32_t dsm, uint32_t Sp,
-                                             uint32_t t_addr, int c, int kb, int ks) {
+                                             uint32_t t_addr, int c, int kb, int ks, uint32_t vsm,
+                                             float& gacc) {
     const bool ok = c < P;
     const uint32_t tile_off = (uint32_t)(c >> 7) * TILE_BYTES;
     const uint32_t row = (uint32_t)c & 127u;
@@ -338,6 +351,13 @@ __device__ __forceinline__ void scale_col4_f(uint32_t R, int P, uint32_t dsm, ui
         if (ok) sts_u32x4(Sp + tile_off + kmajor_chunk_off(row, (uint32_t)k4), a);
         tmem_st_x4(t_addr + (uint32_t)(4 * k4), to_tf32(dv.x * x[u].x), to_tf32(dv.y * x[u].y),
                    to_tf32(dv.z * x[u].z), to_tf32(dv.w * x[u].w));
+        if (vsm) {
+            const float4 vv = lds_f32x4(vsm + 16u * (uint32_t)k4);
+            gacc = fmaf(vv.x, x[u].x, gacc);
+            gacc = fmaf(vv.y, x[u].y, gacc);
+            gacc = fmaf(vv.z, x[u].z, gacc);
+            gacc = fmaf(vv.w, x[u].w, gacc);
+        }
     }
 }
 
@@ -347,6 +367,7 @@ struct TmapSet {
     CUtensorMap x;
     CUtensorMap d;
     CUtensorMap codes[8];
+    CUtensorMap v;
 };
 
 // bring-up timeline: cycle stamps of CTA 0's first TL_ITERS iterations (prm.dbg only)
@@ -439,7 +460,8 @@ k_dense_syrk_tc(const __grid_constant__ TmapSet tmaps, const Params prm) {
         if (lane == 0) {
             int s = 0;
             uint32_t ph = 0;
-            const uint32_t tx = (uint32_t)(BK * P * 4) + 128u * (1u + (uint32_t)prm.oh_ncat);
+            const uint32_t tx = (uint32_t)(BK * P * 4) +
+                                128u * (1u + (uint32_t)prm.oh_ncat + (prm.has_v ? 1u : 0u));
             for (int it = 0; it < my_count; ++it, ++s) {
                 if (s == SR) {
                     s = 0;
@@ -458,6 +480,7 @@ k_dense_syrk_tc(const __grid_constant__ TmapSet tmaps, const Params prm) {
                 tma_load_1d(aux, &tmaps.d, &full[s], (int)k0);
                 for (int c = 0; c < prm.oh_ncat; ++c)
                     tma_load_1d(aux + 128u * (uint32_t)(c + 1), &tmaps.codes[c], &full[s], (int)k0);
+                if (prm.has_v) tma_load_1d(aux + 128u * 9u, &tmaps.v, &full[s], (int)k0);
             }
         }
     } else if (warp == 1) {
@@ -691,6 +714,7 @@ k_dense_syrk_tc(const __grid_constant__ TmapSet tmaps, const Params prm) {
         const int h = w >> 2;
         const int my_col = (prm.mtiles == 2 ? h * 128 : 0) + q * 32 + lane;
         const uint32_t oper_sa = smem_u32(Oper), rring_sa = smem_u32(Rring);
+        float gacc = 0.f;   // this thread's share of (X^T v)[my_col]
         int s = 0, b = 0;
         uint32_t ph = 0, phb = 0;
         for (int it = 0; it < my_count; ++it, ++s, ++b) {
@@ -735,18 +759,19 @@ k_dense_syrk_tc(const __grid_constant__ TmapSet tmaps, const Params prm) {
             {
                 const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + t_col0 +
                                         (uint32_t)(b * prm.mtiles + (my_col >> 7)) * 32;
+                const uint32_t vsm = prm.has_v ? dsm + 128u * 9u : 0u;
                 if (prm.f_order) {
                     if (prm.mtiles == 1) {
-                        scale_col4_f(R, P, dsm, Sp, t_addr, my_col, h, 2);
+                        scale_col4_f(R, P, dsm, Sp, t_addr, my_col, h, 2, vsm, gacc);
                     } else {
-                        scale_col4_f(R, P, dsm, Sp, t_addr, my_col, 0, 1);
-                        scale_col4_f(R, P, dsm, Sp, t_addr, my_col, 4, 1);
+                        scale_col4_f(R, P, dsm, Sp, t_addr, my_col, 0, 1, vsm, gacc);
+                        scale_col4_f(R, P, dsm, Sp, t_addr, my_col, 4, 1, vsm, gacc);
                     }
                 } else if (prm.mtiles == 1) {
-                    scale_col4(R, P, dsm, Sp, t_addr, my_col, h, 2);
+                    scale_col4(R, P, dsm, Sp, t_addr, my_col, h, 2, vsm, gacc);
                 } else {
-                    scale_col4(R, P, dsm, Sp, t_addr, my_col, 0, 1);
-                    scale_col4(R, P, dsm, Sp, t_addr, my_col, 4, 1);
+                    scale_col4(R, P, dsm, Sp, t_addr, my_col, 0, 1, vsm, gacc);
+                    scale_col4(R, P, dsm, Sp, t_addr, my_col, 4, 1, vsm, gacc);
                 }
             }
             if (t == 0) tl_stamp(prm, it, 6);
@@ -762,6 +787,7 @@ k_dense_syrk_tc(const __grid_constant__ TmapSet tmaps, const Params prm) {
             if (t == 0) tl_stamp(prm, it, 3);
         }
 
+        if (prm.has_v && my_col < P && my_count > 0) atomicAdd(&prm.vec_out[my_col], gacc);
         // epilogue: TMEM -> registers -> RED into `out` (transposed: lanes = output columns)
         mbar_wait(done, 0);
         tcgen05_fence_after();
@@ -898,7 +924,7 @@ static int launch_tc(const tc::TmapSet& tmaps, const tc::Params& prm, unsigned g
 
 int dense_sandwich_tc_f32(const float* X, int64_t n, int64_t p, int c_order, const float* d,
                           float* out, cudaStream_t st, const TcOneHot* oh, bool share_sm,
-                          const FusedCrossParams* scatter) {
+                          const FusedCrossParams* scatter, const float* v, float* vec_out) {
     using namespace tc;
     PFN_encodeTiled enc = get_encode();
     if (!enc) return fail("cuTensorMapEncodeTiled not available");
@@ -947,6 +973,18 @@ int dense_sandwich_tc_f32(const float* X, int64_t n, int64_t p, int c_order, con
     }
     if (!encode_1d(&tmaps.d, d, CU_TENSOR_MAP_DATA_TYPE_FLOAT32))
         return fail("cuTensorMapEncodeTiled failed (d)");
+    Scratch v_al((v && (reinterpret_cast<uintptr_t>(v) & 15) != 0) ? sizeof(float) * (size_t)n : 0, st);
+    if (v_al.err != cudaSuccess) return fail_cuda(v_al.err, "scratch");
+    if (v) {
+        if (!vec_out) return fail("dense_tc: v without vec_out");
+        if ((reinterpret_cast<uintptr_t>(v) & 15) != 0) {
+            TM_CUDA(cudaMemcpyAsync(v_al.p, v, sizeof(float) * (size_t)n, cudaMemcpyDeviceToDevice, st));
+            v = v_al.as<float>();
+        }
+        if (!encode_1d(&tmaps.v, v, CU_TENSOR_MAP_DATA_TYPE_FLOAT32))
+            return fail("cuTensorMapEncodeTiled failed (v)");
+        TM_CUDA(cudaMemsetAsync(vec_out, 0, sizeof(float) * (size_t)p, st));
+    }
     if (oh) {
         for (int c = 0; c < oh->ncat && c < 8; ++c) {
             if ((reinterpret_cast<uintptr_t>(oh->codes[c]) & 15) != 0)
@@ -991,7 +1029,9 @@ int dense_sandwich_tc_f32(const float* X, int64_t n, int64_t p, int c_order, con
     const int half = prm.mtiles * TILE_BYTES;
     prm.f_order = c_order ? 0 : 1;
     prm.aux_off = (int)((BK * p * 4 + 127) / 128 * 128);
-    prm.r_bytes = prm.aux_off + 128 + 8 * 128;
+    prm.r_bytes = prm.aux_off + 128 + 8 * 128 + 128;   // X tile | d | 8 code vectors | v
+    prm.has_v = v ? 1 : 0;
+    prm.vec_out = vec_out;
     if (prm.f_order) prm.r_bytes = (prm.r_bytes + 1023) / 1024 * 1024;  // swizzle atom = 8 x 128 B
     int scw = 0;
     if (scatter && (scatter->n_cat > 0 || scatter->out_sparse)) {

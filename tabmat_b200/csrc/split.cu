@@ -117,9 +117,16 @@ static inline int64_t n_rows_or_all(const int32_t* rows, int64_t n_rows, int64_t
     return rows ? n_rows : n;
 }
 
+TM_SHIM(dense_rmatvec, float, f32)
+TM_SHIM(dense_rmatvec, double, f64)
+
+// `v` / `dense_vec` (fused IRLS pass, both or neither): dense_vec[c] = sum_k v[k] X_dense[k, c]
+// over `rows`, computed by the same pass over the dense block as its sandwich (the tcgen05
+// kernel's scale warps, fp32 FMAs) or, where that kernel does not apply, by the GEMV kernel.
 template <typename F>
 int split_blocks(const tm_block_desc* blk, int nb, int64_t n, const F* d, const int32_t* rows,
-                 int64_t n_rows, F* ws, tm_stream_t stream, int part = 0) {
+                 int64_t n_rows, F* ws, tm_stream_t stream, int part = 0, const F* v = nullptr,
+                 F* dense_vec = nullptr) {
     F* tag = nullptr;
     if (nb <= 0) return 0;
     if (nb > 64) return fail("tm_split_sandwich: more than 64 blocks");
@@ -238,12 +245,20 @@ int split_blocks(const tm_block_desc* blk, int nb, int64_t n, const F* d, const 
         const tm_block_desc& D = blk[dense_idx];
         pass_mark(PASS_TENSOR, 0, st);
         Scratch dm(rows ? sizeof(float) * (size_t)n : 0, st);
+        Scratch vm(rows && v && tc_ok ? sizeof(float) * (size_t)n : 0, st);
         if (dm.err != cudaSuccess) return fail_cuda(dm.err, "scratch");
+        if (vm.err != cudaSuccess) return fail_cuda(vm.err, "scratch");
         const float* dd = reinterpret_cast<const float*>(d);
+        const float* vv = reinterpret_cast<const float*>(v);
         if (rows) {
             int rc = masked_weights<float>(dd, n, rows, n_rows, dm.as<float>(), st);
             if (rc) return rc;
             dd = dm.as<float>();
+            if (vv && tc_ok) {
+                rc = masked_weights<float>(vv, n, rows, n_rows, vm.as<float>(), st);
+                if (rc) return rc;
+                vv = vm.as<float>();
+            }
         }
         if (tc_ok) {
             Scratch tmp(sizeof(float) * (size_t)(oh_slots > 0 ? oh_slots : 1) * (size_t)D.ncols, st);
@@ -261,7 +276,8 @@ int split_blocks(const tm_block_desc* blk, int nb, int64_t n, const F* d, const 
             int rc = dense_sandwich_tc_f32(static_cast<const float*>(D.data), n, D.ncols, 1, dd,
                                            reinterpret_cast<float*>(ws + self_off[dense_idx]), st,
                                            oh.ncat ? &oh : nullptr, share_sm,
-                                           scatter_in_tc ? &fc : nullptr);
+                                           scatter_in_tc ? &fc : nullptr, vv,
+                                           reinterpret_cast<float*>(dense_vec));
             if (rc) return rc;
             if (scatter_in_tc) {
                 rc = cross_finish<float>(D.ncols, sp.c, sp.K,
@@ -477,6 +493,12 @@ int split_blocks(const tm_block_desc* blk, int nb, int64_t n, const F* d, const 
     //   5  main: I, then side: T | main: S
     // TABMAT_B200_SIDE_STREAM=0 forces 3.
     cudaStream_t main_st = as_stream(stream);
+    if (v && dense_vec && dense_idx >= 0 && n_dense == 1 && !tc_ok && part != 1) {
+        const tm_block_desc& D = blk[dense_idx];
+        int rcv = dense_rmatvec(tag, static_cast<const F*>(D.data), n, D.ncols, (int)D.c_order, v,
+                                rows, n_rows, (const int32_t*)nullptr, (int64_t)0, dense_vec, stream);
+        if (rcv) return rcv;
+    }
     cudaStream_t s1 = side_stream(0), s2 = side_stream(1);
     int sched = g_split_sched;
     if (!s1 || !s2) sched = 3;
@@ -748,6 +770,22 @@ int tm_split_sandwich_blocks_f64(const tm_block_desc* blocks, int n_blocks, int6
                                  const double* d, const int32_t* rows, int64_t n_rows,
                                  double* workspace, tm_stream_t stream) {
     return tmb::split_blocks<double>(blocks, n_blocks, n, d, rows, n_rows, workspace, stream);
+}
+int tm_split_sandwich_rmatvec_blocks_f32(const tm_block_desc* blocks, int n_blocks, int64_t n,
+                                         const float* d, const float* v, const int32_t* rows,
+                                         int64_t n_rows, float* workspace, float* dense_vec,
+                                         tm_stream_t stream) {
+    if (!v || !dense_vec) return tmb::fail("tm_split_sandwich_rmatvec_blocks: v and dense_vec are required");
+    return tmb::split_blocks<float>(blocks, n_blocks, n, d, rows, n_rows, workspace, stream, 0, v,
+                                    dense_vec);
+}
+int tm_split_sandwich_rmatvec_blocks_f64(const tm_block_desc* blocks, int n_blocks, int64_t n,
+                                         const double* d, const double* v, const int32_t* rows,
+                                         int64_t n_rows, double* workspace, double* dense_vec,
+                                         tm_stream_t stream) {
+    if (!v || !dense_vec) return tmb::fail("tm_split_sandwich_rmatvec_blocks: v and dense_vec are required");
+    return tmb::split_blocks<double>(blocks, n_blocks, n, d, rows, n_rows, workspace, stream, 0, v,
+                                     dense_vec);
 }
 int tm_split_sandwich_blocks_part_f32(const tm_block_desc* blocks, int n_blocks, int64_t n,
                                       const float* d, const int32_t* rows, int64_t n_rows,

@@ -151,7 +151,8 @@ int cat_dense_gather_f32(const float* X, int64_t p, const float* d, const int32_
                          cudaStream_t st);
 int dense_sandwich_tc_f32(const float* X, int64_t n, int64_t p, int c_order, const float* d,
                           float* out, cudaStream_t st, const TcOneHot* oh = nullptr,
-                          bool share_sm = false, const FusedCrossParams* scatter = nullptr);
+                          bool share_sm = false, const FusedCrossParams* scatter = nullptr,
+                          const float* v = nullptr, float* vec_out = nullptr);
 // does the tcgen05 kernel take the scatter work of `n_cat` many-level blocks along (p <= 128)?
 bool dense_tc_scatter_eligible(int64_t p, int n_cat);
 bool dense_tc_eligible(int64_t n, int64_t p, int c_order, const void* X);

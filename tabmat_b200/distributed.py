@@ -139,6 +139,22 @@ class RowShardedMatrix:
             return self._allreduce(part.to(self.reduce_dtype)).to(part.dtype)
         return self._allreduce(part)
 
+    def sandwich_and_transpose_matvec(self, d_local, v_local, rows=None, cols=None):
+        """Replicated ``(X.T diag(d) X, X.T v)`` of one IRLS step: the local fused pass
+        (``SplitMatrix.sandwich_and_transpose_matvec``) and ONE allreduce of
+        [flat block workspace | X.T v] (the length-p vector rides in the same payload)."""
+        local_rows = shard_rows(rows, self.lo, self.hi)
+        if hasattr(self.local, "_sandwich_rmatvec_blocks_dev"):
+            from . import _dev
+
+            res = self.local._sandwich_rmatvec_blocks_dev(d_local, v_local, _dev.idx32(local_rows))
+            if res is not None:
+                buf, elems = res
+                self._allreduce(buf)
+                return (self.local._assemble_dev(buf[:elems], cols),
+                        self.local._rmatvec_assemble_dev(buf[elems:], cols))
+        return self.sandwich(d_local, rows, cols), self.transpose_matvec(v_local, rows, cols)
+
     def sandwich_into(self, d_local, out, rows=None, dst: Optional[int] = 0):
         """``sandwich`` with host buffers: ``d_local`` (this rank's slice, host or device) in,
         the p x p float64 result into the host array ``out`` on rank ``dst`` (every rank when
@@ -182,4 +198,100 @@ class RowShardedMatrix:
         return self.local.matvec(v, cols)
 
     def _get_col_means(self, weights_local) -> torch.Tensor:
+        """Weighted column means (matrix_base.py:118-120); ``weights`` sums to 1 over ALL rows."""
         return self.transpose_matvec(weights_local)
+
+    def _get_col_stds(self, weights_local, col_means) -> torch.Tensor:
+        """sqrt(sum_k w_k (x_kj - mean_j)^2) over all shards: the local sums of squares are
+        additive, so the local stds are squared, summed over the ranks and rooted again
+        (dense_matrix.py:180-187 / sparse_matrix.py:305-315 per shard)."""
+        local = self.local._get_col_stds(weights_local, col_means)
+        if not isinstance(local, torch.Tensor):
+            local = torch.as_tensor(local)
+        return torch.sqrt(self._allreduce(local * local))
+
+    def _global_sum(self, x_local: torch.Tensor, rows=None) -> torch.Tensor:
+        """sum of x over the (restricted) rows of every shard, as a 1-element tensor."""
+        local_rows = shard_rows(rows, self.lo, self.hi)
+        if local_rows is None:
+            part = x_local.sum().reshape(1)
+        else:
+            idx = torch.as_tensor(local_rows, dtype=torch.int64, device=x_local.device)
+            part = x_local.index_select(0, idx).sum().reshape(1)
+        return self._allreduce(part)
+
+    def standardize(self, weights_local, center_predictors: bool, scale_predictors: bool):
+        """(RowShardedStandardizedMatrix, column means, column stds): matrix_base.py:128-167 over
+        the row shards.  The moments are length-p allreduces; the shift / scale vectors are then
+        identical on every rank and the rank-1 corrections of the standardized sandwich are
+        applied AFTER the collective (standardized_mat.py:123-172)."""
+        col_means = self._get_col_means(weights_local)
+        if scale_predictors:
+            col_stds = self._get_col_stds(weights_local, col_means)
+            # matrix_base.py:248-258: 1 / std, 1 where |std| < 1e-7
+            mult = torch.where(col_stds.abs() < 1e-7, torch.ones_like(col_stds), 1.0 / col_stds)
+            shifter = -col_means * mult if center_predictors else torch.zeros_like(col_means)
+        else:
+            col_stds, mult = None, None
+            shifter = -col_means if center_predictors else torch.zeros_like(col_means)
+        out_means = col_means if center_predictors else torch.zeros_like(col_means)
+        return RowShardedStandardizedMatrix(self, shifter, mult), out_means, col_stds
+
+
+class RowShardedStandardizedMatrix:
+    """``StandardizedMatrix`` (standardized_mat.py:17-230) over a :class:`RowShardedMatrix`:
+    ``(X + 1 shift^T) diag(mult)`` with X sharded by rows.  Vectors of length n are local
+    slices, ``shift`` / ``mult`` are replicated CUDA tensors of length p."""
+
+    def __init__(self, mat: RowShardedMatrix, shift: torch.Tensor, mult: Optional[torch.Tensor]):
+        self.mat = mat
+        self.shift = shift
+        self.mult = mult
+        self.shape = mat.shape
+        self.dtype = mat.dtype
+
+    def _sel(self, t, cols):
+        if t is None or cols is None:
+            return t
+        return t.index_select(0, torch.as_tensor(np.asarray(cols), dtype=torch.int64,
+                                                 device=t.device))
+
+    def sandwich(self, d_local, rows=None, cols=None) -> torch.Tensor:
+        """Replicated standardized sandwich: ONE allreduce of [block workspace | X.T d] for a
+        SplitMatrix (the inner sandwich and inner.T @ d come from the same pass and the same
+        payload), a 1-element allreduce for sum(d), then the rank-1 epilogue kernel."""
+        from . import _dev
+        from ._lib import check, fn
+
+        term1, d_mat = self.mat.sandwich_and_transpose_matvec(d_local, d_local, rows, cols)
+        tdt = d_local.dtype
+        sum_d = self.mat._global_sum(d_local, rows).to(tdt)
+        shift = self._sel(self.shift, cols).to(tdt).contiguous()
+        mult = None if self.mult is None else self._sel(self.mult, cols).to(tdt).contiguous()
+        diag = term1.dim() == 1
+        if term1.dtype not in (tdt, torch.float64):
+            term1 = term1.to(tdt)
+        m = int(shift.numel())
+        res = torch.empty((m, m), dtype=tdt, device=d_local.device)
+        check(fn("tm_std_sandwich_combine", _dev.suffix(tdt))(
+            _dev.ptr(term1.contiguous()), int(term1.dtype == torch.float64), int(diag),
+            _dev.ptr(d_mat.to(tdt).contiguous()), _dev.ptr(shift), _dev.ptr(mult),
+            _dev.ptr(sum_d), m, _dev.ptr(res), _dev.stream_ptr()))
+        return res
+
+    def matvec(self, v, cols=None) -> torch.Tensor:
+        """This rank's rows of (X[:, cols] * mult[cols]) @ v[cols] + shift[cols] . v[cols]
+        (standardized_mat.py:69-109); no collective."""
+        vv = v if self.mult is None else v * self.mult.to(v.dtype)
+        res = self.mat.matvec(vv, cols)
+        sv = self._sel(self.shift.to(v.dtype), cols)
+        return res + (sv * self._sel(v, cols)).sum()
+
+    def transpose_matvec(self, v_local, rows=None, cols=None) -> torch.Tensor:
+        """Replicated mult[cols] * X[rows, cols].T v[rows] + shift[cols] * sum(v[rows])
+        (standardized_mat.py:178-230)."""
+        res = self.mat.transpose_matvec(v_local, rows, cols)
+        total = self.mat._global_sum(v_local, rows).to(res.dtype)
+        if self.mult is not None:
+            res = res * self._sel(self.mult, cols).to(res.dtype)
+        return res + self._sel(self.shift, cols).to(res.dtype) * total

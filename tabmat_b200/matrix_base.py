@@ -33,6 +33,13 @@ class MatrixBase(ABC):
     def sandwich(self, d, rows=None, cols=None):
         """(self[rows, cols].T * d[rows]) @ self[rows, cols]."""
 
+    def sandwich_and_transpose_matvec(self, d, v, rows=None, cols=None):
+        """``(X[rows, cols].T @ diag(d[rows]) @ X[rows, cols],  X[rows, cols].T @ v[rows])`` — the
+        Hessian and the score of one IRLS step.  The reference's callers make the two calls
+        separately (matrix_base.py:15-77: ``sandwich`` and ``transpose_matvec``); classes that
+        can compute both in ONE pass over the matrix override this (``SplitMatrix``)."""
+        return self.sandwich(d, rows, cols), self.transpose_matvec(v, rows, cols)
+
     def __matmul__(self, other):
         return self.matvec(other)
 

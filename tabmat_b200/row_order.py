@@ -158,6 +158,28 @@ class RowSortedMatrix(MatrixBase):
         out = self.mat._sandwich_dev(self._gather(d_t), self._rows_in(rows), cols)
         return _dev.ret(out, host)
 
+    def sandwich_and_transpose_matvec(self, d, v, rows=None, cols=None):
+        """Fused IRLS pass (see ``SplitMatrix.sandwich_and_transpose_matvec``); ``d`` and ``v``
+        in the caller's row order."""
+        if not _dev.is_dev(d):
+            d = np.asarray(d)
+        if not _dev.is_dev(v):
+            v = np.asarray(v)
+        check_sandwich_compatible(self, d)
+        check_matvec_dimensions(self, v, transpose=True)
+        d_t, host = _vec_in(d)
+        v_t, _ = _vec_in(v)
+        H, g = self.mat._sandwich_rmatvec_dev(self._gather(d_t), self._gather(v_t),
+                                              self._rows_in(rows), cols)
+        return _dev.ret(H, host), _dev.ret(g, host)
+
+    def _sandwich_rmatvec_blocks_dev(self, d_t, v_t, rows_t):
+        return self.mat._sandwich_rmatvec_blocks_dev(self._gather(d_t), self._gather(v_t),
+                                                     self._rows_in(rows_t))
+
+    def _rmatvec_assemble_dev(self, vec, cols=None):
+        return self.mat._rmatvec_assemble_dev(vec, cols)
+
     def sandwich_into(self, d, out, rows=None, reduce=None):
         """Host-buffer form of :meth:`sandwich` (see ``SplitMatrix.sandwich_into``): ``d`` from
         host or device memory in the caller's row order, the result into the host array ``out``."""

@@ -358,6 +358,78 @@ class SplitMatrix(MatrixBase):
             _dev.length(rows_t), _dev.ptr(ws), _dev.stream_ptr()))
         return ws
 
+    # ---- fused IRLS pass: Hessian and score from one pass over the dense block -------------
+    def sandwich_and_transpose_matvec(self, d, v, rows=None, cols=None):
+        """``(X.T diag(d) X, X.T v)`` restricted to ``rows`` / ``cols`` — what a glum-style IRLS
+        step needs (Hessian with ``d`` = the working weights, score / right-hand side with
+        ``v``).  The reference's callers make two calls (``sandwich``, split_matrix.py:324-356,
+        and ``transpose_matvec``, :422-460), i.e. two passes over X; here the dense block — the
+        bulk of the bytes — is read ONCE: its share of ``X.T v`` is accumulated by the tcgen05
+        kernel's scale warps (fp32 FMAs, not TF32) while they stage the tile for the MMAs
+        (``tm_split_sandwich_rmatvec_blocks``).  The sparse and categorical shares are their own
+        small HBM-bound kernels.  Host in -> host out, device in -> device out."""
+        if not _dev.is_dev(d):
+            d = np.asarray(d)
+        if not _dev.is_dev(v):
+            v = np.asarray(v)
+        check_sandwich_compatible(self, d)
+        check_matvec_dimensions(self, v, transpose=True)
+        d_t, host = _vec_in(d)
+        v_t, _ = _vec_in(v)
+        H, g = self._sandwich_rmatvec_dev(d_t, v_t, _dev.idx32(rows), cols)
+        return _dev.ret(H, host), _dev.ret(g, host)
+
+    def _sandwich_rmatvec_blocks_dev(self, d_t, v_t, rows_t):
+        """(flat block workspace, X.T v in block order as one flat vector) or None."""
+        plan = self._native_plan(d_t.dtype)
+        if plan is None or v_t.dtype != d_t.dtype or v_t.dim() != 1:
+            return None
+        descs, elems = plan
+        p = self.shape[1]
+        # one buffer = [workspace | X.T v block after block]: a row-sharded caller reduces it
+        # with ONE collective
+        buf = torch.empty(elems + p, dtype=d_t.dtype, device=d_t.device)
+        ws, vec = buf[:elems], buf[elems:]
+        offs = np.concatenate([[0], np.cumsum([m.shape[1] for m in self.matrices])]).astype(int)
+        dense = [b for b, m in enumerate(self.matrices) if isinstance(m, DenseMatrix)]
+        dvec = vec[offs[dense[0]]:offs[dense[0] + 1]] if len(dense) == 1 else vec[:0]
+        if len(dense) == 1 and (dvec.data_ptr() % 16):   # keep the RED target vector aligned
+            dvec = torch.empty(dvec.numel(), dtype=d_t.dtype, device=d_t.device)
+        check(fn("tm_split_sandwich_rmatvec_blocks", _dev.suffix(d_t.dtype))(
+            descs, len(self.matrices), self.shape[0], _dev.ptr(d_t), _dev.ptr(v_t),
+            _dev.ptr(rows_t), _dev.length(rows_t), _dev.ptr(ws),
+            _dev.ptr(dvec) if len(dense) == 1 else None, _dev.stream_ptr()))
+        for b, m in enumerate(self.matrices):
+            part = vec[offs[b]:offs[b + 1]]
+            if len(dense) == 1 and b == dense[0]:
+                if dvec.data_ptr() != part.data_ptr():
+                    part.copy_(dvec)
+                continue
+            part.copy_(m.transpose_matvec(v_t, rows=rows_t))
+        return buf, elems
+
+    def _rmatvec_assemble_dev(self, vec: torch.Tensor, cols=None) -> torch.Tensor:
+        """X.T v from block order into column order (optionally only ``cols``)."""
+        out = torch.empty(self.shape[1], dtype=vec.dtype, device=vec.device)
+        o = 0
+        for idx_t, m in zip(self._dev_indices(), self.matrices):
+            out[idx_t] = vec[o:o + m.shape[1]]
+            o += m.shape[1]
+        if cols is not None:
+            out = out.index_select(0, _dev.idx32(cols).to(torch.int64))
+        return out
+
+    def _sandwich_rmatvec_dev(self, d_t, v_t, rows_t, cols):
+        res = None
+        if cols is None or self._cols_on_native_path(cols):
+            res = self._sandwich_rmatvec_blocks_dev(d_t, v_t, rows_t)
+        if res is None:
+            tdt = _dev.torch_dtype(np.result_type(self.dtype, _dev.np_dtype(v_t.dtype)))
+            g = self.transpose_matvec(v_t.to(tdt), rows=rows_t, cols=cols)
+            return self._sandwich_dev(d_t, rows_t, cols), g
+        buf, elems = res
+        return self._assemble_dev(buf[:elems], cols), self._rmatvec_assemble_dev(buf[elems:], cols)
+
     def _assemble_dev(self, ws: torch.Tensor, cols=None) -> torch.Tensor:
         """Place the flat block workspace into the float64 result.  With ``cols`` (sorted,
         unique column ids, split.pyx:157-209) only the selected rows / columns are placed: the

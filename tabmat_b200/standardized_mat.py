@@ -14,6 +14,7 @@ import torch
 from scipy import sparse as sps
 
 from . import _dev
+from ._lib import check, fn
 from .dense_matrix import DenseMatrix, _accumulate_out
 from .matrix_base import MatrixBase, _vec_in
 from .sparse_matrix import SparseMatrix
@@ -129,32 +130,32 @@ class StandardizedMatrix:
         if isinstance(self.mat, CategoricalMatrix):
             term1, _ = self.mat._sandwich_diag(d_t, rows_t, cols_t)
             term1_is_diag = True
+            d_mat = self.mat.transpose_matvec(d_t, rows_t, cols_t).to(tdt)
         else:
-            term1 = self.mat.sandwich(d_t, rows_t, cols_t)
+            # the inner sandwich and inner.T @ d come from ONE pass where the inner matrix can
+            # do that (SplitMatrix: tm_split_sandwich_rmatvec_blocks); two calls otherwise, like
+            # the reference (standardized_mat.py:141-147)
+            term1, d_mat = self.mat.sandwich_and_transpose_matvec(d_t, d_t, rows_t, cols_t)
+            d_mat = d_mat.to(tdt)
             term1_is_diag = False
-        d_mat = self.mat.transpose_matvec(d_t, rows_t, cols_t).to(tdt)
         shift = self._shift_t(tdt)
         mult = self._mult_t(tdt)
-        limited_shift = shift if cols_l is None else shift[cols_l]
+        limited_shift = (shift if cols_l is None else shift[cols_l]).contiguous()
         limited_mult = None
         if mult is not None:
-            limited_mult = mult if cols_l is None else mult[cols_l]
-            d_mat = d_mat * limited_mult
-        sum_d = d_t.sum() if rows_t is None else d_t[rows_t.to(torch.int64)].sum()
-        res = (torch.outer(d_mat, limited_shift) + torch.outer(limited_shift, d_mat)
-               + torch.outer(limited_shift, limited_shift) * sum_d)
-        if term1_is_diag:
-            to_add = term1.to(tdt)
-            if limited_mult is not None:
-                to_add = to_add * limited_mult**2
-            res.diagonal().add_(to_add)
-        else:
-            to_add = term1.to(res.dtype) if term1.dtype != res.dtype else term1
-            if limited_mult is not None:
-                to_add = to_add * torch.outer(limited_mult, limited_mult).to(to_add.dtype)
-            # the reference adds in place into the rank-1 sum, so the result keeps ITS dtype
-            # (f32 even over a SplitMatrix)
-            res += to_add.to(res.dtype)
+            limited_mult = (mult if cols_l is None else mult[cols_l]).contiguous()
+        sum_d = (d_t.sum() if rows_t is None else d_t[rows_t.to(torch.int64)].sum()).reshape(1)
+        if term1.dtype not in (tdt, torch.float64):
+            term1 = term1.to(tdt)
+        term1 = term1.contiguous()
+        m = int(limited_shift.numel())
+        # the reference adds in place into the rank-1 sum, so the result keeps ITS dtype (f32
+        # even over a SplitMatrix); one kernel instead of five eager ones
+        res = torch.empty((m, m), dtype=tdt, device=d_t.device)
+        check(fn("tm_std_sandwich_combine", _dev.suffix(tdt))(
+            _dev.ptr(term1), int(term1.dtype == torch.float64), int(term1_is_diag),
+            _dev.ptr(d_mat.contiguous()), _dev.ptr(limited_shift), _dev.ptr(limited_mult),
+            _dev.ptr(sum_d), m, _dev.ptr(res), _dev.stream_ptr()))
         return _dev.ret(res, host)
 
     def unstandardize(self) -> MatrixBase:

@@ -66,6 +66,19 @@ def main():
             check(f"{order}: transpose_matvec", tmv, full.transpose_matvec(v, rows=rows))
             check(f"{order}: matvec", mv, full.matvec(beta)[lo:hi])
             print(f"{order}: {world} ranks vs 1 GPU, normwise sandwich error {e1:.3e}", flush=True)
+        # fused IRLS pass and the row-sharded standardized sandwich against one GPU
+        Hs, gs = S.sandwich_and_transpose_matvec(dl, torch.from_numpy(v[lo:hi]).to(dev), rows=rows)
+        w = np.full(n, 1.0 / n, dtype=np.float32)
+        Z, _, _ = S.standardize(torch.from_numpy(w[lo:hi]).to(dev), True, True)
+        zs = Z.sandwich(dl, rows=rows).cpu().numpy()
+        ztm = Z.transpose_matvec(torch.from_numpy(v[lo:hi]).to(dev)).cpu().numpy()
+        if rank == 0:
+            Hf, gf = full.sandwich_and_transpose_matvec(s["d"], v, rows)
+            check(f"{order}: fused Hessian", Hs.cpu().numpy(), Hf)
+            check(f"{order}: fused score", gs.cpu().numpy(), gf)
+            Zf, _, _ = full.standardize(w, True, True)
+            check(f"{order}: standardized sandwich", zs, Zf.sandwich(s["d"], rows), tol=5e-3)
+            check(f"{order}: standardized transpose_matvec", ztm, Zf.transpose_matvec(v))
         dist.barrier()
     ok = torch.tensor([0 if fails else 1], device=dev)
     dist.all_reduce(ok, op=dist.ReduceOp.MIN)

@@ -43,6 +43,9 @@ class _HostShard:
         M = self._sel(None, cols)
         return M @ (v if cols is None else v[torch.from_numpy(np.asarray(cols, dtype=np.int64))])
 
+    def _get_col_stds(self, weights, col_means):
+        return torch.sqrt(((self.X - col_means) ** 2 * weights[:, None]).sum(0))
+
 
 def _worker(rank, world, port, n, p, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -84,6 +87,27 @@ def _worker(rank, world, port, n, p, q):
             np.testing.assert_allclose(
                 res[f"mv{pack}"],
                 full.matvec(torch.from_numpy(np.arange(p, dtype=np.float64))).numpy()[lo:hi])
+        # row-sharded standardize: moments by allreduce, corrections after the collective
+        w = np.abs(rng.standard_normal(n))
+        w /= w.sum()
+        S = RowShardedMatrix(_HostShard(X[lo:hi]), n)
+        for center, scale in ((True, True), (True, False), (False, True)):
+            Z, means, stds = S.standardize(torch.from_numpy(w[lo:hi]), center, scale)
+            mu = w @ X
+            sd = np.sqrt(w @ (X - mu) ** 2)
+            np.testing.assert_allclose(means.numpy(), mu if center else 0 * mu, atol=1e-12)
+            if scale:
+                np.testing.assert_allclose(stds.numpy(), sd, rtol=1e-10)
+            mult = 1 / sd if scale else np.ones(p)
+            Xs = (X - (mu if center else 0)) * mult
+            np.testing.assert_allclose(
+                Z.transpose_matvec(torch.from_numpy(v[lo:hi]), rows, cols).numpy(),
+                Xs[rows][:, cols].T @ v[rows], rtol=1e-9, atol=1e-9)
+            beta = np.arange(1, p + 1, dtype=np.float64)
+            np.testing.assert_allclose(Z.matvec(torch.from_numpy(beta)).numpy(), (Xs @ beta)[lo:hi],
+                                       rtol=1e-9, atol=1e-9)
+            np.testing.assert_allclose(Z.matvec(torch.from_numpy(beta), cols).numpy(),
+                                       (Xs[:, cols] @ beta[cols])[lo:hi], rtol=1e-9, atol=1e-9)
         q.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
         q.put((rank, repr(e)))
