@@ -190,6 +190,16 @@ int tm_cat_transpose_matvec_f64(const int32_t* codes, int64_t n, const double* v
                                 int64_t n_cols, int64_t n_cat_cols, int drop_first, double* out,
                                 tm_stream_t stream);
 
+/* multiply_complex / subset_categorical_complex, categorical.pyx:221-315: the CSR form of
+ * diag(d) @ X for a categorical block, built on the device.  Row i owns one entry (column
+ * codes[i] - drop_first, value d[i]) when codes[i] >= drop_first, none otherwise.
+ * indptr[n + 1] is always written; indices / data (capacity n; data may be NULL = structure
+ * only, d may be NULL = ones) receive the nnz = indptr[n] compacted entries. */
+int tm_cat_to_csr_f32(const int32_t* codes, int64_t n, int drop_first, const float* d,
+                      float* data, int32_t* indices, int32_t* indptr, tm_stream_t stream);
+int tm_cat_to_csr_f64(const int32_t* codes, int64_t n, int drop_first, const double* d,
+                      double* data, int32_t* indices, int32_t* indptr, tm_stream_t stream);
+
 /* matvec_{fast,complex}, categorical.pyx:128-180.
  * out[i] += v[c], c = codes[i]-drop_first, c >= 0 and c in cols.  ACCUMULATES (length n). */
 int tm_cat_matvec_f32(const int32_t* codes, int64_t n, const float* v, const int32_t* cols,

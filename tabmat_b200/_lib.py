@@ -60,6 +60,7 @@ _SIGS = {
     "tm_cat_sandwich": [P, I, P, P, I, I, N, P, P],
     "tm_cat_transpose_matvec": [P, I, P, P, I, P, I, I, N, P, P],
     "tm_cat_matvec": [P, I, P, P, I, I, N, P, P],
+    "tm_cat_to_csr": [P, I, N, P, P, P, P, P],
     "tm_cat_dense_sandwich": [P, I, I, N, P, P, I, N, P, I, P, I, P, P],
     "tm_cat_cat_sandwich": [P, P, I, I, I, N, N, P, P, I, P, P],
     "tm_cat_sparse_sandwich": [P, I, I, N, P, P, P, P, P, I, I, P, I, P, I, P, P],

@@ -24,6 +24,7 @@ import torch
 from scipy import sparse as sps
 
 from . import _dev
+from ._lib import check, fn
 from .dense_matrix import DenseMatrix, _accumulate_out
 from .ext import categorical as ext_cat
 from .ext import split as ext_split
@@ -373,23 +374,51 @@ class CategoricalMatrix(MatrixBase):
 
     # ---- conversions / indexing ------------------------------------------------------
     def getcol(self, i: int) -> SparseMatrix:
+        """Column i as an (n x 1) SparseMatrix of ones, built on the device
+        (categorical_matrix.py:674-688)."""
         i %= self.shape[1]  # wrap-around indexing
         i_corr = i + 1 if self.drop_first else i
-        col_i = sps.csc_matrix((self.indices == i_corr).astype(int)[:, None])
-        return SparseMatrix(col_i, column_names=[self.column_names[i]],
-                            term_names=[self.term_names[i]])
+        # codes == i_corr -> 0 (kept, column 0), everything else -> -1 (dropped)
+        hit = torch.where(self._codes == i_corr, 0, -1).to(torch.int32)
+        data, indices, indptr = self._device_csr_of(hit, 0, None, _dev.torch_dtype(self.dtype))
+        return SparseMatrix.from_device_csr(data, indices, indptr, (self.shape[0], 1),
+                                            column_names=[self.column_names[i]],
+                                            term_names=[self.term_names[i]])
+
+    @staticmethod
+    def _device_csr_of(codes: torch.Tensor, drop_first: int, d: Optional[torch.Tensor],
+                       tdt: torch.dtype):
+        """(data, indices, indptr) of diag(d) @ onehot(codes) in HBM via ``tm_cat_to_csr``
+        (multiply_complex / subset_categorical_complex, categorical.pyx:221-315)."""
+        n = int(codes.numel())
+        dev = codes.device
+        indptr = torch.empty(n + 1, dtype=torch.int32, device=dev)
+        indices = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+        data = torch.empty(max(n, 1), dtype=tdt, device=dev)
+        check(fn("tm_cat_to_csr", _dev.suffix(tdt))(
+            _dev.ptr(codes), n, int(drop_first), None if d is None else _dev.ptr(d),
+            _dev.ptr(data), _dev.ptr(indices), _dev.ptr(indptr), _dev.stream_ptr()))
+        nnz = int(indptr[-1].item())
+        return data[:nnz], indices[:nnz], indptr
+
+    def _to_sparse_dev(self, d: Optional[torch.Tensor] = None, tdt=None) -> SparseMatrix:
+        tdt = _dev.torch_dtype(self.dtype) if tdt is None else tdt
+        data, indices, indptr = self._device_csr_of(self._codes, int(self.drop_first), d, tdt)
+        return SparseMatrix.from_device_csr(data, indices, indptr, self.shape,
+                                            column_names=self.column_names,
+                                            term_names=self.term_names)
 
     def tocsr(self) -> sps.csr_matrix:
-        idx = self.indices
-        cols = idx - int(self.drop_first)
-        keep = cols >= 0
-        indptr = np.concatenate([[0], np.cumsum(keep)]).astype(np.int64)
-        return sps.csr_matrix((np.ones(int(keep.sum()), dtype=int), cols[keep].astype(np.int32),
-                               indptr), shape=self.shape)
+        """Host scipy CSR of ones (categorical_matrix.py:690-721); the structure is built on the
+        device and copied out once."""
+        _, indices, indptr = self._device_csr_of(self._codes, int(self.drop_first), None,
+                                                 torch.float32)
+        ind = _dev.to_host(indices)
+        return sps.csr_matrix((np.ones(len(ind), dtype=int), ind, _dev.to_host(indptr)),
+                              shape=self.shape)
 
     def to_sparse_matrix(self):
-        return SparseMatrix(self.tocsr(), column_names=self.column_names,
-                            term_names=self.term_names)
+        return self._to_sparse_dev()
 
     def toarray(self) -> np.ndarray:
         return self.tocsr().toarray()
@@ -431,15 +460,18 @@ class CategoricalMatrix(MatrixBase):
 
     def multiply(self, other) -> SparseMatrix:
         """diag(other) @ X as a SparseMatrix (categorical_matrix.py:840-876)."""
-        other = np.asarray(other) if not _dev.is_dev(other) else _dev.to_host(other)
+        if not _dev.is_dev(other):
+            other = np.asarray(other)
         if self.shape[0] != other.shape[0]:
             raise ValueError(
                 f"Shapes do not match. Expected length of {self.shape[0]}. Got {len(other)}."
             )
-        csr = self.tocsr().astype(other.dtype)
-        keep = (self.indices - int(self.drop_first)) >= 0
-        csr.data = np.squeeze(other)[keep].astype(other.dtype)
-        return SparseMatrix(csr, column_names=self.column_names, term_names=self.term_names)
+        o_t, _ = _vec_in(other if _dev.is_dev(other) else np.squeeze(other))
+        o_t = o_t.reshape(-1)
+        if o_t.dtype not in (torch.float32, torch.float64):
+            o_t = o_t.to(torch.float64)
+        # device-side multiply_complex (categorical.pyx:221-272): no host round trip of the codes
+        return self._to_sparse_dev(o_t.contiguous(), o_t.dtype)
 
     def __repr__(self):
         return f"{self.__class__.__name__}\nCategories: {self.categories}"

@@ -6,6 +6,8 @@
 // cat_split_helpers-tmpl.cpp:4-151, categorical_matrix.py:825-838 (cat x sparse).
 #include <cstdlib>
 
+#include <cub/device/device_scan.cuh>
+
 #include "tm_common.cuh"
 
 namespace tmb {
@@ -552,6 +554,55 @@ __global__ void k_cat_sparse(const int32_t* __restrict__ codes, const F* __restr
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// CSR form of a categorical block on the device: multiply_complex / subset_categorical_complex
+// (categorical.pyx:221-315) without the host round trip.  flags -> exclusive scan (CUB) ->
+// compaction; row i owns at most one entry (column codes[i] - drop_first, value d[i] or 1).
+// ---------------------------------------------------------------------------------------
+__global__ void k_cat_flags(const int32_t* __restrict__ codes, int64_t n, int drop_first,
+                            int32_t* __restrict__ flags) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += stride)
+        flags[i] = (i < n && codes[i] >= drop_first) ? 1 : 0;
+}
+template <typename F>
+__global__ void k_cat_compact(const int32_t* __restrict__ codes, int64_t n, int drop_first,
+                              const F* __restrict__ d, const int32_t* __restrict__ indptr,
+                              F* __restrict__ data, int32_t* __restrict__ indices) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int c = codes[i] - drop_first;
+        if (c < 0) continue;
+        const int32_t pos = indptr[i];
+        indices[pos] = c;
+        if (data) data[pos] = d ? d[i] : F(1);
+    }
+}
+
+template <typename F>
+int cat_to_csr(const int32_t* codes, int64_t n, int drop_first, const F* d, F* data,
+               int32_t* indices, int32_t* indptr, cudaStream_t st) {
+    if (n < 0 || n >= 0x7fffffffLL) return fail("tm_cat_to_csr: n out of range");
+    Scratch flags(sizeof(int32_t) * (size_t)(n + 1), st);
+    if (flags.err != cudaSuccess) return fail_cuda(flags.err, "scratch");
+    const int g = grid_for(n + 1, 256 * 4, sm_count() * 16);
+    k_cat_flags<<<g, 256, 0, st>>>(codes, n, drop_first, flags.as<int32_t>());
+    TM_LAUNCHED();
+    size_t tmp_bytes = 0;
+    TM_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, flags.as<int32_t>(), indptr,
+                                          (int)(n + 1), st));
+    Scratch tmp(tmp_bytes, st);
+    if (tmp.err != cudaSuccess) return fail_cuda(tmp.err, "scratch");
+    TM_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, flags.as<int32_t>(), indptr,
+                                          (int)(n + 1), st));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (n > 0) {
+        k_cat_compact<F><<<g, 256, 0, st>>>(codes, n, drop_first, d, indptr, data, indices);
+        TM_LAUNCHED();
+    }
+    return 0;
+}
+
 // ---- host wrappers ---------------------------------------------------------------------
 template <typename F>
 int cat_sandwich(const int32_t* codes, int64_t n, const F* d, const int32_t* rows, int64_t n_rows,
@@ -721,6 +772,11 @@ extern "C" {
                                       tm_stream_t stream) {                                       \
         return tmb::cat_transpose_matvec<F>(codes, n, v, rows, n_rows, cols, n_cols, K,            \
                                            drop_first, out, tmb::as_stream(stream));               \
+    }                                                                                             \
+    int tm_cat_to_csr_##SUF(const int32_t* codes, int64_t n, int drop_first, const F* d, F* data, \
+                            int32_t* indices, int32_t* indptr, tm_stream_t stream) {              \
+        return tmb::cat_to_csr<F>(codes, n, drop_first, d, data, indices, indptr,                  \
+                                 tmb::as_stream(stream));                                          \
     }                                                                                             \
     int tm_cat_matvec_##SUF(const int32_t* codes, int64_t n, const F* v, const int32_t* cols,     \
                             int64_t n_cols, int64_t K, int drop_first, F* out,                    \

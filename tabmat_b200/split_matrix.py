@@ -210,6 +210,32 @@ class SplitMatrix(MatrixBase):
             self._indices_dev = [_dev.to_dev(idx) for idx in self.indices]
         return self._indices_dev
 
+    def _block_order(self):
+        """(int32 CUDA tensor: column position of every block column, blocks concatenated;
+        block offsets).  One ``tm_permute_gather`` / ``tm_permute_scatter`` with it moves a
+        length-p vector between column order and block order for ALL blocks at once (the
+        reference indexes per block with numpy, split_matrix.py:391-417, :448-460)."""
+        cached = self.__dict__.get("_block_order_cache")
+        if cached is None:
+            perm = _dev.to_dev(np.concatenate(self.indices).astype(np.int32))
+            offs = np.concatenate([[0], np.cumsum([len(i) for i in self.indices])]).astype(int)
+            cached = self.__dict__["_block_order_cache"] = (perm, offs)
+        return cached
+
+    def _to_block_order(self, v_t: torch.Tensor) -> torch.Tensor:
+        perm, _ = self._block_order()
+        out = torch.empty_like(v_t)
+        check(fn("tm_permute_gather", _dev.suffix(v_t.dtype))(
+            _dev.ptr(v_t), _dev.ptr(perm), v_t.numel(), _dev.ptr(out), 0, _dev.stream_ptr()))
+        return out
+
+    def _from_block_order(self, vb_t: torch.Tensor) -> torch.Tensor:
+        perm, _ = self._block_order()
+        out = torch.empty_like(vb_t)
+        check(fn("tm_permute_scatter", _dev.suffix(vb_t.dtype))(
+            _dev.ptr(vb_t), _dev.ptr(perm), vb_t.numel(), _dev.ptr(out), 0, _dev.stream_ptr()))
+        return out
+
     def _split_col_subsets(self, cols):
         """(positions of each block's columns in the output, block-local column ids, n_cols);
         see split_matrix.py:269-291."""
@@ -410,11 +436,7 @@ class SplitMatrix(MatrixBase):
 
     def _rmatvec_assemble_dev(self, vec: torch.Tensor, cols=None) -> torch.Tensor:
         """X.T v from block order into column order (optionally only ``cols``)."""
-        out = torch.empty(self.shape[1], dtype=vec.dtype, device=vec.device)
-        o = 0
-        for idx_t, m in zip(self._dev_indices(), self.matrices):
-            out[idx_t] = vec[o:o + m.shape[1]]
-            o += m.shape[1]
+        out = self._from_block_order(vec.contiguous())
         if cols is not None:
             out = out.index_select(0, _dev.idx32(cols).to(torch.int64))
         return out
@@ -724,10 +746,14 @@ class SplitMatrix(MatrixBase):
         else:
             acc = torch.zeros(out_shape, dtype=tdt, device=v_t.device)
         sub_t = [None if s is None else _dev.idx32(s) for s in subset_cols]
-        for sub, idx_t, mat in zip(sub_t, self._dev_indices(), self.matrices):
+        # v in block order for all blocks with one gather kernel (1-d float vectors)
+        one_gather = v_t.dim() == 1 and v_t.dtype in (torch.float32, torch.float64)
+        if one_gather:
+            vb, offs = self._to_block_order(v_t.contiguous()), self._block_order()[1]
+        for b, (sub, idx_t, mat) in enumerate(zip(sub_t, self._dev_indices(), self.matrices)):
             if sub is not None and sub.numel() == 0:
                 continue
-            in_vec = v_t.index_select(0, idx_t)
+            in_vec = vb[offs[b]:offs[b + 1]] if one_gather else v_t.index_select(0, idx_t)
             if in_vec.dtype != _dev.torch_dtype(mat.dtype) and not isinstance(mat, CategoricalMatrix):
                 # mixed-dtype split: compute the block in its own dtype, add into acc
                 acc += mat.matvec(in_vec, sub).to(tdt)
@@ -755,6 +781,18 @@ class SplitMatrix(MatrixBase):
         if v_t.dtype != tdt:
             v_t = v_t.to(tdt)
         rows_t = _dev.idx32(rows)
+        if cols is None and v_t.dim() == 1:
+            # every block writes its slice of a block-ordered vector; ONE scatter kernel puts it
+            # into column order
+            offs = self._block_order()[1]
+            parts = [mat.transpose_matvec(v_t, rows=rows_t).to(tdt) if mat.shape[1] else
+                     torch.empty(0, dtype=tdt, device=v_t.device) for mat in self.matrices]
+            res = self._from_block_order(torch.cat(parts)) if len(parts) > 1 else \
+                self._from_block_order(parts[0].contiguous())
+            assert res.numel() == offs[-1]
+            if out is None:
+                return _dev.ret(res, host)
+            return _accumulate_out(out, res, None)
         res = torch.zeros([n_cols] + list(v_t.shape[1:]), dtype=tdt, device=v_t.device)
         if cols is None:
             pos_t = self._dev_indices()
