@@ -190,6 +190,20 @@ int tm_cat_transpose_matvec_f64(const int32_t* codes, int64_t n, const double* v
                                 int64_t n_cols, int64_t n_cat_cols, int drop_first, double* out,
                                 tm_stream_t stream);
 
+/* Deterministic form of the categorical histogram (transpose_matvec_fast/_complex,
+ * categorical.pyx:23-126, and sandwich_categorical, :183-218): out[c] (+)= sum over the rows of
+ * category c of w[k] (* row_w[k] when row_w != NULL), added in a fixed order, so the result is
+ * bit-identical from run to run (the reference made this operation deterministic on purpose,
+ * CHANGELOG.rst:134; the default kernels here add with atomics in arrival order).  perm = the
+ * rows with a valid category ordered by category (stable), segptr[K + 1] = the category
+ * offsets into perm.  accumulate = 0 overwrites out. */
+int tm_cat_segment_sum_f32(const float* w, const float* row_w, const int32_t* perm,
+                           const int32_t* segptr, int64_t K, float* out, int accumulate,
+                           tm_stream_t stream);
+int tm_cat_segment_sum_f64(const double* w, const double* row_w, const int32_t* perm,
+                           const int32_t* segptr, int64_t K, double* out, int accumulate,
+                           tm_stream_t stream);
+
 /* multiply_complex / subset_categorical_complex, categorical.pyx:221-315: the CSR form of
  * diag(d) @ X for a categorical block, built on the device.  Row i owns one entry (column
  * codes[i] - drop_first, value d[i]) when codes[i] >= drop_first, none otherwise.

@@ -8,7 +8,13 @@ hand-written CUDA kernels through the C-ABI in ``include/tabmat_b200.h``.
 There is no CPU fallback.
 """
 
-from ._lib import TabmatB200Error, launch_count, reset_launch_count  # noqa: F401
+from ._lib import (  # noqa: F401
+    TabmatB200Error,
+    deterministic,
+    launch_count,
+    reset_launch_count,
+    set_deterministic,
+)
 from .categorical_matrix import CategoricalMatrix
 from .constructor import from_csc, from_df, from_pandas
 from .dense_matrix import DenseMatrix
@@ -35,4 +41,5 @@ __all__ = [
     "from_df",
     "from_pandas",
     "irls_step",
+    "set_deterministic",
 ]

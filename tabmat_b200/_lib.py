@@ -61,6 +61,7 @@ _SIGS = {
     "tm_cat_transpose_matvec": [P, I, P, P, I, P, I, I, N, P, P],
     "tm_cat_matvec": [P, I, P, P, I, I, N, P, P],
     "tm_cat_to_csr": [P, I, N, P, P, P, P, P],
+    "tm_cat_segment_sum": [P, P, P, P, I, P, N, P],
     "tm_cat_dense_sandwich": [P, I, I, N, P, P, I, N, P, I, P, I, P, P],
     "tm_cat_cat_sandwich": [P, P, I, I, I, N, N, P, P, I, P, P],
     "tm_cat_sparse_sandwich": [P, I, I, N, P, P, P, P, P, I, I, P, I, P, I, P, P],
@@ -140,6 +141,24 @@ if os.environ.get("TABMAT_B200_CROSS_RUNS"):
 # TABMAT_B200_DENSE_F32_MODE: 0 auto (tcgen05 when eligible) | 1 CUDA-core only | 2 force tcgen05
 if os.environ.get("TABMAT_B200_DENSE_F32_MODE"):
     lib.tm_set_dense_f32_mode(int(os.environ["TABMAT_B200_DENSE_F32_MODE"]))
+
+
+#: opt-in deterministic mode (set_deterministic): categorical transpose_matvec / sandwich add in
+#: a fixed order (tm_cat_segment_sum) instead of with atomics; TABMAT_B200_DETERMINISTIC=1
+_DETERMINISTIC = os.environ.get("TABMAT_B200_DETERMINISTIC") == "1"
+
+
+def set_deterministic(on: bool) -> None:
+    """Bit-reproducible categorical ``transpose_matvec`` / ``sandwich`` (the operations the
+    reference made deterministic, CHANGELOG.rst:134).  Every other kernel adds partial sums with
+    float atomics / REDs in arrival order and stays run-to-run reproducible only to rounding
+    (DESIGN.md "Numerics")."""
+    global _DETERMINISTIC
+    _DETERMINISTIC = bool(on)
+
+
+def deterministic() -> bool:
+    return _DETERMINISTIC
 
 
 class TabmatB200Error(RuntimeError):

@@ -23,7 +23,7 @@ import numpy as np
 import torch
 from scipy import sparse as sps
 
-from . import _dev
+from . import _dev, _lib
 from ._lib import check, fn
 from .dense_matrix import DenseMatrix, _accumulate_out
 from .ext import categorical as ext_cat
@@ -291,6 +291,22 @@ class CategoricalMatrix(MatrixBase):
             vec_t = vec_t.to(self._tdtype)
         rows_t = None if is_unrestricted(rows, self.shape[0]) else _dev.idx32(rows)
         cols_t = self._restrict_cols(cols)
+        if _lib.deterministic() and self.shape[0] < 2**31 - 1:
+            res = self._segment_sum(vec_t, rows_t)
+            if cols_t is not None:   # columns outside the restriction contribute nothing
+                keep = torch.zeros_like(res)
+                keep[cols_t.to(torch.int64)] = 1
+                res = res * keep
+            if not out_is_none:
+                if _dev.is_dev(out) and out.dtype == res.dtype:
+                    out += res
+                    return out
+                return _accumulate_out(out, res, None)
+            if res.dtype != self._tdtype:
+                res = res.to(self._tdtype)
+            if cols is not None:
+                res = res.index_select(0, _dev.idx32(cols).to(torch.int64))
+            return _dev.ret(res, host)
         if not out_is_none and _dev.is_dev(out) and out.dtype == vec_t.dtype:
             ext_cat.transpose_matvec(self._codes, vec_t, self.shape[1], rows_t, cols_t, out,
                                      self.drop_first)
@@ -307,6 +323,20 @@ class CategoricalMatrix(MatrixBase):
             res = res.index_select(0, _dev.idx32(cols).to(torch.int64))
         return _dev.ret(res, host)
 
+    def _segment_sum(self, w_t: torch.Tensor, rows_t) -> torch.Tensor:
+        """Fixed-order weighted histogram of the codes (``tm_cat_segment_sum``): the
+        deterministic form of transpose_matvec / sandwich."""
+        perm, segptr, _ = self._sorted_perm()
+        row_w = None
+        if rows_t is not None:
+            row_w = torch.zeros(self.shape[0], dtype=w_t.dtype, device=w_t.device)
+            row_w[rows_t.to(torch.int64)] = 1
+        out = torch.empty(self.shape[1], dtype=w_t.dtype, device=w_t.device)
+        check(fn("tm_cat_segment_sum", _dev.suffix(w_t.dtype))(
+            _dev.ptr(w_t.contiguous()), _dev.ptr(row_w), _dev.ptr(perm), _dev.ptr(segptr),
+            self.shape[1], _dev.ptr(out), 0, _dev.stream_ptr()))
+        return out
+
     def sandwich(self, d, rows=None, cols=None):
         """Diagonal sandwich, returned as ``scipy.sparse.dia_matrix`` for host input
         (categorical_matrix.py:618-653) or as the 1-D diagonal CUDA tensor for device input."""
@@ -321,8 +351,11 @@ class CategoricalMatrix(MatrixBase):
         check_sandwich_compatible(self, d)
         d_t, host = _vec_in(d)
         rows_t = _dev.idx32(rows)
-        res_diag = ext_cat.sandwich_categorical(self._codes, d_t, rows_t, self.shape[1],
-                                                self.drop_first)
+        if _lib.deterministic() and self.shape[0] < 2**31 - 1:
+            res_diag = self._segment_sum(d_t, rows_t)
+        else:
+            res_diag = ext_cat.sandwich_categorical(self._codes, d_t, rows_t, self.shape[1],
+                                                    self.drop_first)
         if cols is not None and len(cols) < self.shape[1]:
             res_diag = res_diag.index_select(0, _dev.idx32(cols).to(torch.int64))
         return res_diag, host

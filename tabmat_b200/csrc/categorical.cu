@@ -603,6 +603,46 @@ int cat_to_csr(const int32_t* codes, int64_t n, int drop_first, const F* d, F* d
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------
+// Deterministic weighted histogram (opt-in, tm_set_deterministic): out[c] (+)= sum of w[k] over
+// the rows of category c, added in a FIXED order — the rows of a category come from the cached
+// sorted permutation (perm / segptr, like the sorted-gather kernel), one warp per category, lane
+// l adds entries l, l+32, ... in sequence, then a fixed butterfly.  Bit-identical from run to
+// run, unlike the atomic kernels above (the reference made categorical transpose_matvec
+// deterministic on purpose, CHANGELOG.rst:134).  Gathers 4-8 bytes per row: slower, opt-in.
+// `row_w` (nullable) = 0/1 row mask folded in as a factor.
+// ---------------------------------------------------------------------------------------
+template <typename F>
+__global__ void __launch_bounds__(256)
+k_cat_segment_sum(const F* __restrict__ w, const F* __restrict__ row_w,
+                  const int32_t* __restrict__ perm, const int32_t* __restrict__ segptr, int K,
+                  F* __restrict__ out, int accumulate) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int nwarps = (int)(((int64_t)gridDim.x * blockDim.x) >> 5);
+    for (int c = warp; c < K; c += nwarps) {
+        const int e0 = segptr[c], e1 = segptr[c + 1];
+        F s = F(0);
+        for (int e = e0 + lane; e < e1; e += 32) {
+            const int k = perm[e];
+            s += row_w ? w[k] * row_w[k] : w[k];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) out[c] = accumulate ? out[c] + s : s;
+    }
+}
+
+template <typename F>
+int cat_segment_sum(const F* w, const F* row_w, const int32_t* perm, const int32_t* segptr,
+                    int64_t K, F* out, int accumulate, cudaStream_t st) {
+    if (K <= 0) return 0;
+    const int g = grid_for(K * 32, 256, sm_count() * 8);
+    k_cat_segment_sum<F><<<g, 256, 0, st>>>(w, row_w, perm, segptr, (int)K, out, accumulate);
+    TM_LAUNCHED();
+    return 0;
+}
+
 // ---- host wrappers ---------------------------------------------------------------------
 template <typename F>
 int cat_sandwich(const int32_t* codes, int64_t n, const F* d, const int32_t* rows, int64_t n_rows,
@@ -772,6 +812,12 @@ extern "C" {
                                       tm_stream_t stream) {                                       \
         return tmb::cat_transpose_matvec<F>(codes, n, v, rows, n_rows, cols, n_cols, K,            \
                                            drop_first, out, tmb::as_stream(stream));               \
+    }                                                                                             \
+    int tm_cat_segment_sum_##SUF(const F* w, const F* row_w, const int32_t* perm,                 \
+                                 const int32_t* segptr, int64_t K, F* out, int accumulate,        \
+                                 tm_stream_t stream) {                                            \
+        return tmb::cat_segment_sum<F>(w, row_w, perm, segptr, K, out, accumulate,                 \
+                                      tmb::as_stream(stream));                                     \
     }                                                                                             \
     int tm_cat_to_csr_##SUF(const int32_t* codes, int64_t n, int drop_first, const F* d, F* data, \
                             int32_t* indices, int32_t* indptr, tm_stream_t stream) {              \

@@ -18,6 +18,8 @@
 #include <cstdlib>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "tm_common.cuh"
 
 namespace tmb {
@@ -105,7 +107,15 @@ static bool g_profile = false;
 static int g_prof_calls = 0;
 static cudaEvent_t g_pass_ev[PROF_RING][PASS_COUNT][2];
 static bool g_pass_used[PROF_RING][PASS_COUNT];
+// NVTX range per pass (visible in Nsight Systems / ncu --nvtx; a no-op without a tool attached)
+static const char* const kPassName[PASS_COUNT] = {"tabmat_b200:tensor_pass",
+                                                  "tabmat_b200:scatter_pass",
+                                                  "tabmat_b200:index_pass"};
 static void pass_mark(int pass, int which, cudaStream_t st) {
+    if (which == 0)
+        nvtxRangePushA(kPassName[pass]);
+    else
+        nvtxRangePop();
     if (!g_profile) return;
     const int slot = g_prof_calls % PROF_RING;
     if (!g_pass_ev[slot][pass][which]) cudaEventCreate(&g_pass_ev[slot][pass][which]);

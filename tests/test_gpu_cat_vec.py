@@ -62,3 +62,42 @@ def test_cat_vec_misaligned_views_fall_back():
     got = ecat.sandwich_categorical(codes, d, None, K, False).cpu().numpy()
     ref = np.bincount(codes.cpu().numpy(), weights=d.cpu().numpy().astype(np.float64), minlength=K)
     cases.assert_close(got, ref, np.float32, "misaligned cat sandwich")
+
+
+@pytest.mark.parametrize("suf", ["f32", "f64"])
+def test_deterministic_mode_is_bit_reproducible(suf):
+    """tabmat_b200.set_deterministic(True): categorical transpose_matvec / sandwich add in a fixed
+    order (tm_cat_segment_sum) — bit-identical across runs (the reference made this operation
+    deterministic, CHANGELOG.rst:134) and equal to numpy within rounding."""
+    import tabmat_b200 as tm
+
+    dt = cases.DTYPES[suf]
+    n, K = 300_001, 500
+    rng = np.random.default_rng(9)
+    codes = rng.integers(-1, K, size=n).astype(np.int32)
+    C = tm.CategoricalMatrix(codes, categories=np.arange(K), dtype=dt, drop_first=True,
+                             cat_missing_method="zero")
+    v = (rng.standard_normal(n) * 10.0 ** rng.integers(-3, 4, size=n)).astype(dt)
+    rows = np.sort(rng.choice(n, size=n // 2, replace=False)).astype(np.int32)
+    cols = np.arange(0, K - 1, 3, dtype=np.int32)
+    col = codes - 1
+    try:
+        tm.set_deterministic(True)
+        a = [C.transpose_matvec(v) for _ in range(4)]
+        assert all(np.array_equal(a[0], x) for x in a[1:]), "not bit-reproducible"
+        ok = col >= 0
+        ref = np.bincount(col[ok], weights=v[ok].astype(np.float64), minlength=K - 1)
+        cases.assert_close(a[0], ref, dt, "deterministic transpose_matvec")
+        m = np.zeros(n, dtype=bool)
+        m[rows] = True
+        ref_r = np.bincount(col[ok & m], weights=v[ok & m].astype(np.float64), minlength=K - 1)
+        cases.assert_close(C.transpose_matvec(v, rows=rows), ref_r, dt, "deterministic, rows")
+        cases.assert_close(C.transpose_matvec(v, rows=rows, cols=cols), ref_r[cols], dt,
+                           "deterministic, rows + cols")
+        d = np.abs(v)
+        s = [np.asarray(C.sandwich(d).diagonal()) for _ in range(3)]
+        assert np.array_equal(s[0], s[1]) and np.array_equal(s[0], s[2])
+        cases.assert_close(s[0], np.bincount(col[ok], weights=d[ok].astype(np.float64), minlength=K - 1),
+                           dt, "deterministic sandwich")
+    finally:
+        tm.set_deterministic(False)
