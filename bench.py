@@ -781,10 +781,26 @@ def main():
     d_host = torch.empty(n_local, dtype=tdt).pin_memory()
     d_host.copy_(d)
     e2e_note = ""
-    if wl.key in ("c5", "c4"):
+    shared = None
+    if wl.key in ("c5", "c4") and world > 1 and os.environ.get("TABMAT_B200_E2E_SHARED", "1") != "0":
+        # The p x p result is one object per job.  Every rank places its own 1/N row band of it
+        # after the allreduce and copies the band into ONE page-locked host buffer shared by the
+        # ranks (/dev/shm + cudaHostRegister): N PCIe links carry the 8 p^2 bytes instead of one.
+        from tabmat_b200.distributed import SharedHostResult
+
+        shared = SharedHostResult.for_group(p)
+
+        def e2e_step():
+            S.sandwich_into_shared(d_host, shared)
+
+        d2h = p * p * 8
+        e2e_note = ("d (each rank's shard) from pinned host memory every step; the p x p float64 "
+                    f"result lands in one pinned host buffer shared by the {world} ranks, each "
+                    "rank copying its own row band over its own PCIe link (a 1-element allreduce "
+                    "after the copies is the completion fence)")
+    elif wl.key in ("c5", "c4"):
         out_host = torch.empty((p, p), dtype=torch.float64).pin_memory()
-        # The p x p result is one object per job: with N > 1 ranks it is reduced to rank 0 and
-        # read to the host there (dst=0), instead of N redundant device->host copies.
+        # one rank; or TABMAT_B200_E2E_SHARED=0: reduce to rank 0 and one copy from there
         e2e_dst = 0 if world > 1 else None
 
         def e2e_step():
@@ -811,6 +827,8 @@ def main():
         e2e_step()
     e2e_ms = timed_loop(e2e_step, args.steps)
 
+    if shared is not None:
+        shared.close(unlink=rank == 0)
     fl = torch.tensor([float(flops_local), float(nnz_local)], device=device, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(fl)
@@ -955,7 +973,8 @@ def main():
             "vs_baseline": None, "dtype": wl.dtype, "data": "synthetic",
             "config": config,
             "e2e": {"value": e2e_value, "unit": unit, "ms_per_step": e2e_step_ms,
-                    "h2d_bytes_per_step": int(n_local * fsize), "d2h_bytes_per_step": int(d2h),
+                    "h2d_bytes_per_step": int(wl.n * fsize), "d2h_bytes_per_step": int(d2h),
+                    "h2d_bytes_per_step_per_gpu": int(n_local * fsize),
                     "note": e2e_note},
             "gpu_launches": int(launches),
             "clocks": clocks,

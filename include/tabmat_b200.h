@@ -410,6 +410,16 @@ int tm_split_sandwich_assemble_f64(const tm_block_desc* blocks, int n_blocks,
                                    const double* workspace, double* out, int64_t ld,
                                    tm_stream_t stream);
 
+/* Rows [row0, row1) of the result only, written to out_band (row1 - row0 rows of `ld` values):
+ * in a row-sharded job every rank places its own band after the allreduce of the workspace and
+ * copies it to the host over its own PCIe link (N links instead of one). */
+int tm_split_sandwich_assemble_band_f32(const tm_block_desc* blocks, int n_blocks,
+                                        const float* workspace, double* out_band, int64_t ld,
+                                        int64_t row0, int64_t row1, tm_stream_t stream);
+int tm_split_sandwich_assemble_band_f64(const tm_block_desc* blocks, int n_blocks,
+                                        const double* workspace, double* out_band, int64_t ld,
+                                        int64_t row0, int64_t row1, tm_stream_t stream);
+
 /* Two-phase form of the two calls above, for callers that want the result in HOST memory:
  * `part` 1 = the blocks without a dense operand (categorical / sparse self and cross blocks),
  * 2 = the blocks with one, 0 = all.  After blocks_part(1) + assemble_part(1) the finished

@@ -890,6 +890,9 @@ bool dense_tc_eligible(int64_t n, int64_t p, int c_order, const void* X) {
     if (p < 8 || p > 256) return false;
     // TMA: the pitch of the outer dimension must be a multiple of 16 bytes
     if (c_order ? (p % 4) != 0 : (n % 4) != 0) return false;
+    static const bool f_off =
+        getenv("TABMAT_B200_TC_FORDER") && atoi(getenv("TABMAT_B200_TC_FORDER")) == 0;
+    if (!c_order && f_off) return false;
     if ((reinterpret_cast<uintptr_t>(X) & 15) != 0) return false;
     if (n < 1 || n > 0x7fffffffLL) return false;
     if (tc::device_cc_major() != 10) return false;

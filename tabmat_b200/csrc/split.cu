@@ -15,6 +15,8 @@
 //                         where (a, b) is the kernel's native orientation:
 //                           categorical x dense / sparse x dense / categorical x sparse /
 //                           categorical_i x categorical_j (i < j)
+#include <climits>
+#include <cstdint>
 #include <cstdlib>
 #include <vector>
 
@@ -383,7 +385,10 @@ int split_blocks(const tm_block_desc* blk, int nb, int64_t n, const F* d, const 
                 getenv("TABMAT_B200_CSC_PACKED") && atoi(getenv("TABMAT_B200_CSC_PACKED")) == 0;
             const bool use_packed = want_cs && !packed_off && blk[sparse_idx].csc_cat_codes &&
                                     index_pack_fits(nc, Kc);
-            const bool need_rec = want_cs && !use_packed;
+            // TABMAT_B200_PAIRS_DIRECT=0: the pairs kernel reads the packed row records too
+            static const bool pairs_direct_off = getenv("TABMAT_B200_PAIRS_DIRECT") &&
+                                                 atoi(getenv("TABMAT_B200_PAIRS_DIRECT")) == 0;
+            const bool need_rec = (want_cs && !use_packed) || (ok && pairs_direct_off);
             Scratch rec(need_rec ? index_record_bytes<F>(n) : 0, st);
             Scratch dmi(ok && rows ? sizeof(F) * (size_t)n : 0, st);
             if (rec.err != cudaSuccess) return fail_cuda(rec.err, "scratch");
@@ -407,8 +412,8 @@ int split_blocks(const tm_block_desc* blk, int nb, int64_t n, const F* d, const 
                     for (int b = a + 1; b < nc; ++b)
                         outs_pair[a * nc + b] = ws + cross_off[cats[a]][cats[b]];
                 }
-                rc = index_cat_pairs<F>(nullptr, dd, cc, dfc, n, nc, Kc, runc, outs_self, outs_pair,
-                                        st);
+                rc = index_cat_pairs<F>(pairs_direct_off ? rec.p : nullptr, dd, cc, dfc, n, nc, Kc,
+                                        runc, outs_self, outs_pair, st);
                 if (rc) return rc;
                 cats_fused = true;
                 if (want_cs) {
@@ -419,7 +424,7 @@ int split_blocks(const tm_block_desc* blk, int nb, int64_t n, const F* d, const 
                         const int hi = cats[a] < sparse_idx ? sparse_idx : cats[a];
                         outs[a] = ws + cross_off[lo][hi];
                     }
-                    rc = index_cat_sparse<F>(need_rec ? rec.p : nullptr, dd,
+                    rc = index_cat_sparse<F>(use_packed ? nullptr : rec.p, dd,
                                              use_packed ? S.csc_cat_codes : nullptr, nc, Kc, runp,
                                              static_cast<const F*>(S.csc_data), S.csc_indices,
                                              S.csc_indptr, S.ncols,
@@ -605,9 +610,12 @@ struct AsmJobs {
     int n_jobs;
 };
 
+// row0 / row1: only destination rows in [row0, row1) are written, at out + (row - row0) * ld —
+// a row band of the result (each rank of a row-sharded job places and copies out its own band)
 template <typename F>
 __global__ void __launch_bounds__(256)
-k_assemble_all(const AsmJobs jobs, double* __restrict__ out, int64_t ld) {
+k_assemble_all(const AsmJobs jobs, double* __restrict__ out, int64_t ld, int64_t row0,
+               int64_t row1) {
     __shared__ F tile[32][33];
     const int t = blockIdx.x;
     int q = 0;
@@ -624,32 +632,34 @@ k_assemble_all(const AsmJobs jobs, double* __restrict__ out, int64_t ld) {
     if (kind == 2) {  // diagonal block: na == nb, src = the diagonal
         for (int i = ty; i < 32; i += 8) {
             const int64_t a = a0 + i, b = b0 + tx;
-            if (a < na && b < nb && ri[a] >= 0 && ri[b] >= 0)
-                out[ri[a] * ld + ri[b]] = a == b ? (double)src[a] : 0.0;
+            if (a < na && b < nb && ri[a] >= row0 && ri[a] < row1 && ri[b] >= 0)
+                out[(ri[a] - row0) * ld + ri[b]] = a == b ? (double)src[a] : 0.0;
         }
         return;
     }
-    // a negative destination = the column is not in the caller's `cols` selection
+    // a negative destination = the column is not in the caller's `cols` selection (row0 >= 0)
     for (int i = ty; i < 32; i += 8) {
         const int64_t a = a0 + i, b = b0 + tx;
         if (a < na && b < nb) {
             const F v = src[a * nb + b];
             tile[i][tx] = v;
-            if (ri[a] >= 0 && ci[b] >= 0) out[ri[a] * ld + ci[b]] = (double)v;
+            if (ri[a] >= row0 && ri[a] < row1 && ci[b] >= 0)
+                out[(ri[a] - row0) * ld + ci[b]] = (double)v;
         }
     }
     if (kind != 1) return;
     __syncthreads();
     for (int i = ty; i < 32; i += 8) {
         const int64_t b = b0 + i, a = a0 + tx;
-        if (a < na && b < nb && ri[a] >= 0 && ci[b] >= 0)
-            out[ci[b] * ld + ri[a]] = (double)tile[tx][i];
+        if (a < na && b < nb && ri[a] >= 0 && ci[b] >= row0 && ci[b] < row1)
+            out[(ci[b] - row0) * ld + ri[a]] = (double)tile[tx][i];
     }
 }
 
 template <typename F>
 int split_assemble(const tm_block_desc* blk, int nb, const F* ws, double* out, int64_t ld,
-                   tm_stream_t stream, int part = 0) {
+                   tm_stream_t stream, int part = 0, int64_t row0 = 0,
+                   int64_t row1 = INT64_MAX) {
     F* tag = nullptr;
     int64_t off = 0;
     // part 1: blocks without a dense operand; part 2: blocks with one; 0: all
@@ -658,7 +668,10 @@ int split_assemble(const tm_block_desc* blk, int nb, const F* ws, double* out, i
         !(getenv("TABMAT_B200_ASSEMBLE_FUSED") && atoi(getenv("TABMAT_B200_ASSEMBLE_FUSED")) == 0);
     bool all_indexed = true;
     for (int i = 0; i < nb; ++i) all_indexed &= blk[i].col_index != nullptr;
-    if (one_launch && all_indexed && nb * (nb + 1) / 2 <= ASM_MAX_JOBS) {
+    const bool band = row0 > 0 || row1 != INT64_MAX;
+    if (band && !(all_indexed && nb * (nb + 1) / 2 <= ASM_MAX_JOBS))
+        return fail("tm_split_sandwich_assemble_band: needs col_index on every block, <= 10 blocks");
+    if ((one_launch || band) && all_indexed && nb * (nb + 1) / 2 <= ASM_MAX_JOBS) {
         AsmJobs jobs;
         memset(&jobs, 0, sizeof(jobs));
         int nj = 0;
@@ -691,10 +704,12 @@ int split_assemble(const tm_block_desc* blk, int nb, const F* ws, double* out, i
         jobs.n_jobs = nj;
         if (nj == 0 || tiles == 0) return 0;
         if (tiles < (int64_t)kMaxGridX) {
-            k_assemble_all<F><<<(unsigned)tiles, 256, 0, as_stream(stream)>>>(jobs, out, ld);
+            k_assemble_all<F><<<(unsigned)tiles, 256, 0, as_stream(stream)>>>(jobs, out, ld, row0,
+                                                                              row1);
             TM_LAUNCHED();
             return 0;
         }
+        if (band) return fail("tm_split_sandwich_assemble_band: result too large");
         off = 0;  // absurdly large: fall through to the per-block launches
     }
     for (int i = 0; i < nb; ++i) {
@@ -816,6 +831,20 @@ int tm_split_sandwich_assemble_part_f64(const tm_block_desc* blocks, int n_block
                                         const double* workspace, double* out, int64_t ld, int part,
                                         tm_stream_t stream) {
     return tmb::split_assemble<double>(blocks, n_blocks, workspace, out, ld, stream, part);
+}
+int tm_split_sandwich_assemble_band_f32(const tm_block_desc* blocks, int n_blocks,
+                                        const float* workspace, double* out_band, int64_t ld,
+                                        int64_t row0, int64_t row1, tm_stream_t stream) {
+    if (row0 < 0 || row1 < row0) return tmb::fail("tm_split_sandwich_assemble_band: bad row range");
+    return tmb::split_assemble<float>(blocks, n_blocks, workspace, out_band, ld, stream, 0, row0,
+                                      row1);
+}
+int tm_split_sandwich_assemble_band_f64(const tm_block_desc* blocks, int n_blocks,
+                                        const double* workspace, double* out_band, int64_t ld,
+                                        int64_t row0, int64_t row1, tm_stream_t stream) {
+    if (row0 < 0 || row1 < row0) return tmb::fail("tm_split_sandwich_assemble_band: bad row range");
+    return tmb::split_assemble<double>(blocks, n_blocks, workspace, out_band, ld, stream, 0, row0,
+                                       row1);
 }
 int tm_memcpy2d_to_host(void* dst_host, int64_t dst_pitch, const void* src_dev, int64_t src_pitch,
                         int64_t width_bytes, int64_t height, tm_stream_t stream) {

@@ -67,6 +67,56 @@ def unpack_lower(v: torch.Tensor, p: int, dtype: torch.dtype) -> torch.Tensor:
     return out
 
 
+class SharedHostResult:
+    """One p x p float64 result buffer in host memory shared by the ranks of a node: a file in
+    /dev/shm mapped by every rank and page-locked for CUDA (``cudaHostRegister``), so that every
+    rank can copy ITS row band of a row-sharded sandwich straight to the host over its own PCIe
+    link (``RowShardedMatrix.sandwich_into_shared``) and the consumer — any rank, or another
+    process on the node — reads the whole matrix from ``.array``."""
+
+    def __init__(self, p: int, name: str, create: bool):
+        import os
+
+        self.p = int(p)
+        self.path = os.path.join("/dev/shm", name)
+        nbytes = self.p * self.p * 8
+        if create:
+            with open(self.path, "wb") as f:
+                f.truncate(nbytes)
+        self.array = np.memmap(self.path, dtype=np.float64, mode="r+", shape=(self.p, self.p))
+        self._registered = False
+        if torch.cuda.is_available():
+            rc = torch.cuda.cudart().cudaHostRegister(self.array.ctypes.data, nbytes, 0)
+            self._registered = int(rc) == 0
+
+    @classmethod
+    def for_group(cls, p: int, group=None, tag: str = "tabmat_b200_result"):
+        """Collective: rank 0 creates the buffer, the others map it."""
+        import os
+
+        rank = dist.get_rank(group) if dist.is_initialized() else 0
+        name = f"{tag}_{os.environ.get('MASTER_PORT', '0')}_{p}"
+        if rank == 0:
+            buf = cls(p, name, create=True)
+        if dist.is_initialized():
+            dist.barrier(group)
+        if rank != 0:
+            buf = cls(p, name, create=False)
+        return buf
+
+    def close(self, unlink: bool = False):
+        import os
+
+        if self._registered:
+            torch.cuda.cudart().cudaHostUnregister(self.array.ctypes.data)
+            self._registered = False
+        if unlink:
+            try:
+                os.unlink(self.path)
+            except OSError:
+                pass
+
+
 class RowShardedMatrix:
     """A matrix whose rows are sharded over the ranks of a process group.
 
@@ -187,6 +237,42 @@ class RowShardedMatrix:
         check(lib.tm_memcpy2d_to_host(ptr, p * 8, res.data_ptr(), p * 8, p * 8, p,
                                       _dev.stream_ptr()))
         return out
+
+    def sandwich_into_shared(self, d_local, shared: SharedHostResult, rows=None):
+        """Row-sharded ``sandwich`` with the result delivered to a host buffer shared by the
+        ranks: local blocks, one allreduce of the flat block workspace, then every rank places
+        rows ``[r * p / N, (r + 1) * p / N)`` of the p x p float64 result and copies that band to
+        ``shared`` over its own PCIe link — N links instead of the single 8 p^2-byte copy of
+        ``sandwich_into(dst=0)``.  A one-element allreduce enqueued after the copy is the
+        completion fence: once it has completed on a rank's stream, every band is in place.
+        Asynchronous on the current stream.  SplitMatrix-like locals only."""
+        from . import _dev
+        from ._lib import check, lib
+
+        if not hasattr(self.local, "_assemble_band_dev"):
+            raise TypeError("sandwich_into_shared needs a SplitMatrix / RowSortedMatrix shard")
+        if not _dev.is_dev(d_local):
+            src = d_local if isinstance(d_local, torch.Tensor) else torch.from_numpy(d_local)
+            d_dev = torch.empty(src.shape, dtype=src.dtype, device=_dev.require_cuda())
+            d_dev.copy_(src, non_blocking=True)
+            d_local = d_dev
+        local_rows = shard_rows(rows, self.lo, self.hi)
+        ws = self.local._sandwich_blocks_dev(d_local, _dev.idx32(local_rows))
+        if ws is None:
+            raise TypeError("the local shard has no native block plan (mixed dtypes?)")
+        self._allreduce(ws)
+        p = self.shape[1]
+        r0, r1 = shard_bounds(p, self.world_size, self.rank)
+        band = self.local._assemble_band_dev(ws, r0, r1)
+        if r1 > r0:
+            dst = shared.array.ctypes.data + r0 * p * 8
+            check(lib.tm_memcpy2d_to_host(dst, p * 8, band.data_ptr(), p * 8, p * 8, r1 - r0,
+                                          _dev.stream_ptr()))
+        fence = getattr(self, "_fence", None)
+        if fence is None:
+            fence = self._fence = torch.zeros(1, dtype=torch.float32, device=ws.device)
+        self._allreduce(fence)
+        return shared.array
 
     def transpose_matvec(self, v_local, rows=None, cols=None) -> torch.Tensor:
         """Replicated X[rows, cols].T @ v[rows] (length-p allreduce)."""

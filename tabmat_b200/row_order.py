@@ -199,6 +199,9 @@ class RowSortedMatrix(MatrixBase):
     def _assemble_dev(self, ws: torch.Tensor, cols=None) -> torch.Tensor:
         return self.mat._assemble_dev(ws, cols)
 
+    def _assemble_band_dev(self, ws: torch.Tensor, row0: int, row1: int) -> torch.Tensor:
+        return self.mat._assemble_band_dev(ws, row0, row1)
+
     def transpose_matvec(self, v, rows=None, cols=None, out=None):
         """X[rows, cols].T @ v[rows] (split_matrix.py:419-460)."""
         if not _dev.is_dev(v):

@@ -479,6 +479,17 @@ class SplitMatrix(MatrixBase):
         del keep
         return out
 
+    def _assemble_band_dev(self, ws: torch.Tensor, row0: int, row1: int) -> torch.Tensor:
+        """Rows [row0, row1) of the float64 result from the flat block workspace."""
+        descs, _ = self._native_plan(ws.dtype)
+        p = self.shape[1]
+        out = torch.empty((max(row1 - row0, 0), p), dtype=torch.float64, device=ws.device)
+        if out.numel():
+            check(fn("tm_split_sandwich_assemble_band", _dev.suffix(ws.dtype))(
+                descs, len(self.matrices), _dev.ptr(ws), _dev.ptr(out), p, row0, row1,
+                _dev.stream_ptr()))
+        return out
+
     # ---- result straight into host memory, copy overlapped with the dense-operand passes ----
     def _column_runs(self):
         """[(start, stop, is_dense)]: maximal runs of consecutive result columns that belong to

@@ -66,6 +66,17 @@ def main():
             check(f"{order}: transpose_matvec", tmv, full.transpose_matvec(v, rows=rows))
             check(f"{order}: matvec", mv, full.matvec(beta)[lo:hi])
             print(f"{order}: {world} ranks vs 1 GPU, normwise sandwich error {e1:.3e}", flush=True)
+        # result delivered band by band into a host buffer shared by the ranks
+        from tabmat_b200.distributed import SharedHostResult
+
+        shared = SharedHostResult.for_group(bench.P_TOTAL, tag=f"tm_test_{order}")
+        S.sandwich_into_shared(s["d"][lo:hi], shared)
+        torch.cuda.synchronize()
+        dist.barrier()
+        if rank == 0:
+            check(f"{order}: sandwich_into_shared", np.array(shared.array), ref)
+        dist.barrier()
+        shared.close(unlink=rank == 0)
         # fused IRLS pass and the row-sharded standardized sandwich against one GPU
         Hs, gs = S.sandwich_and_transpose_matvec(dl, torch.from_numpy(v[lo:hi]).to(dev), rows=rows)
         w = np.full(n, 1.0 / n, dtype=np.float32)
