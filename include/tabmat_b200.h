@@ -46,7 +46,17 @@ void tm_reset_launch_count(void);
 /* 1 if the tcgen05 (TMEM/TMA) dense path can run on the current device (cc 10.x). */
 int tm_has_tcgen05(void);
 /* Select the dense f32 sandwich implementation: 0 = auto (tcgen05 when eligible),
- * 1 = force the CUDA-core kernel, 2 = force tcgen05 (error when not eligible). */
+ * 1 = force the CUDA-core kernel, 2 = force tcgen05 (error when not eligible),
+ * 3 = fp32-accurate: "3xTF32" on the tensor cores where the tcgen05 path applies (every operand
+ * split into hi = tf32(a) and lo = tf32(a - hi), products hi*hi + hi*lo + lo*hi), the CUDA-core
+ * kernel elsewhere.
+ * NUMERICS: modes 0 and 2 round both operands of the dense f32 block (X and d*X) to TF32
+ * (10-bit mantissa) before the MMA and accumulate in fp32: normwise error ~1e-4 of the largest
+ * entry (inside BASELINE's 1e-3 fp32 tolerance, tests/test_gpu_baseline_configs.py prints it),
+ * but small differences of large entries (centred moments of columns with a big mean) lose
+ * ~3 digits against the reference's full-precision fp32 FMAs (dense_helpers-tmpl.cpp:97).
+ * Mode 3 restores fp32-level accuracy at a third of the tensor throughput; mode 1 is exact
+ * fp32.  Also settable with TABMAT_B200_DENSE_F32_MODE. */
 void tm_set_dense_f32_mode(int mode);
 /* Fused dense-operand cross pass (tm_dense_cross_sandwich_*, tm_split_sandwich_blocks_*):
  * 0 / 1 = run-aggregating kernel (default), 2 = the one-row-per-visit kernel. */

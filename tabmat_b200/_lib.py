@@ -139,7 +139,8 @@ lib.tm_set_cross_runs_mode.restype = None
 # 1 always | 2 never
 if os.environ.get("TABMAT_B200_CROSS_RUNS"):
     lib.tm_set_cross_runs_mode(int(os.environ["TABMAT_B200_CROSS_RUNS"]))
-# TABMAT_B200_DENSE_F32_MODE: 0 auto (tcgen05 when eligible) | 1 CUDA-core only | 2 force tcgen05
+# TABMAT_B200_DENSE_F32_MODE: 0 auto (tcgen05 TF32 when eligible) | 1 CUDA-core only (exact fp32)
+# | 2 force tcgen05 | 3 fp32-accurate 3xTF32 on the tensor cores
 if os.environ.get("TABMAT_B200_DENSE_F32_MODE"):
     lib.tm_set_dense_f32_mode(int(os.environ["TABMAT_B200_DENSE_F32_MODE"]))
 

@@ -83,6 +83,11 @@ struct Params {
     // scale warps (v is staged by TMA next to d); has_v = 0: plain sandwich
     int has_v;
     float* vec_out;
+    // 1: one TF32 MMA pass per stage.  3: "3xTF32" - every fp32 operand is split into
+    // hi = tf32(a) and lo = tf32(a - hi) and the products hi*hi + hi*lo + lo*hi are accumulated
+    // (three operand slots per raw stage), which restores fp32-level accuracy at a third of the
+    // tensor throughput (tm_set_dense_f32_mode(3))
+    int nsub;
     int sc_ncat;                       // <= TC_SCATTER_MAX_CATS
     const int32_t* sc_codes[TC_SCATTER_MAX_CATS];
     float* sc_tab[TC_SCATTER_MAX_CATS];
@@ -243,6 +248,12 @@ __device__ __forceinline__ void red_add_v4(float* p, float4 v) {
                  : "memory");
 }
 
+// operand of sub-pass `sub` of the 3xTF32 scheme: want_lo selects tf32(a - tf32(a))
+__device__ __forceinline__ uint32_t tf32_part(float a, bool want_lo) {
+    const uint32_t hi = to_tf32(a);
+    return want_lo ? to_tf32(a - __uint_as_float(hi)) : hi;
+}
+
 // UMMA shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
 //   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 | [32,46) stride byte offset >> 4
 //   [46,48) version = 1 (Blackwell) | [61,64) layout type (2 = SWIZZLE_128B)
@@ -288,8 +299,9 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
 // zero) and zeros to T (tcgen05.st is warp-collective).
 __device__ __forceinline__ void scale_col4(uint32_t R, int P, uint32_t dsm, uint32_t Sp,
                                            uint32_t t_addr, int c, int kb, int ks, uint32_t vsm,
-                                           float& gacc) {
+                                           float& gacc, int sub = 0) {
     // R, dsm, Sp: 32-bit shared addresses of the raw stage, its d vector and the S tile
+    const bool s_lo = sub == 1, t_lo = sub == 2;   // 3xTF32 sub-pass: which operand is the residual
     float x[4][4];
     const bool ok = c < P;
     const uint32_t r0 = R + (uint32_t)c * 4u;
@@ -306,13 +318,14 @@ __device__ __forceinline__ void scale_col4(uint32_t R, int P, uint32_t dsm, uint
         const int k4 = kb + u * ks;
         const float4 dv = lds_f32x4(dsm + 16u * (uint32_t)k4);
         uint4 a;
-        a.x = to_tf32(x[u][0]);
-        a.y = to_tf32(x[u][1]);
-        a.z = to_tf32(x[u][2]);
-        a.w = to_tf32(x[u][3]);
+        a.x = tf32_part(x[u][0], s_lo);
+        a.y = tf32_part(x[u][1], s_lo);
+        a.z = tf32_part(x[u][2], s_lo);
+        a.w = tf32_part(x[u][3], s_lo);
         if (ok) sts_u32x4(Sp + tile_off + kmajor_chunk_off(row, (uint32_t)k4), a);
-        tmem_st_x4(t_addr + (uint32_t)(4 * k4), to_tf32(dv.x * x[u][0]), to_tf32(dv.y * x[u][1]),
-                   to_tf32(dv.z * x[u][2]), to_tf32(dv.w * x[u][3]));
+        tmem_st_x4(t_addr + (uint32_t)(4 * k4), tf32_part(dv.x * x[u][0], t_lo),
+                   tf32_part(dv.y * x[u][1], t_lo), tf32_part(dv.z * x[u][2], t_lo),
+                   tf32_part(dv.w * x[u][3], t_lo));
         if (vsm) {  // X^T v rides along in fp32 (not TF32: it is the score of an IRLS step)
             const float4 vv = lds_f32x4(vsm + 16u * (uint32_t)k4);
             gacc = fmaf(vv.x, x[u][0], gacc);
@@ -330,8 +343,9 @@ __device__ __forceinline__ void scale_col4(uint32_t R, int P, uint32_t dsm, uint
 // conflicts.  No transpose is needed: a lane reads its 4 consecutive k as one LDS.128.
 __device__ __forceinline__ void scale_col4_f(uint32_t R, int P, uint32_t dsm, uint32_t Sp,
                                              uint32_t t_addr, int c, int kb, int ks, uint32_t vsm,
-                                             float& gacc) {
+                                             float& gacc, int sub = 0) {
     const bool ok = c < P;
+    const bool s_lo = sub == 1, t_lo = sub == 2;
     const uint32_t tile_off = (uint32_t)(c >> 7) * TILE_BYTES;
     const uint32_t row = (uint32_t)c & 127u;
     float4 x[4];
@@ -344,13 +358,14 @@ __device__ __forceinline__ void scale_col4_f(uint32_t R, int P, uint32_t dsm, ui
         const int k4 = kb + u * ks;
         const float4 dv = lds_f32x4(dsm + 16u * (uint32_t)k4);
         uint4 a;
-        a.x = to_tf32(x[u].x);
-        a.y = to_tf32(x[u].y);
-        a.z = to_tf32(x[u].z);
-        a.w = to_tf32(x[u].w);
+        a.x = tf32_part(x[u].x, s_lo);
+        a.y = tf32_part(x[u].y, s_lo);
+        a.z = tf32_part(x[u].z, s_lo);
+        a.w = tf32_part(x[u].w, s_lo);
         if (ok) sts_u32x4(Sp + tile_off + kmajor_chunk_off(row, (uint32_t)k4), a);
-        tmem_st_x4(t_addr + (uint32_t)(4 * k4), to_tf32(dv.x * x[u].x), to_tf32(dv.y * x[u].y),
-                   to_tf32(dv.z * x[u].z), to_tf32(dv.w * x[u].w));
+        tmem_st_x4(t_addr + (uint32_t)(4 * k4), tf32_part(dv.x * x[u].x, t_lo),
+                   tf32_part(dv.y * x[u].y, t_lo), tf32_part(dv.z * x[u].z, t_lo),
+                   tf32_part(dv.w * x[u].w, t_lo));
         if (vsm) {
             const float4 vv = lds_f32x4(vsm + 16u * (uint32_t)k4);
             gacc = fmaf(vv.x, x[u].x, gacc);
@@ -499,9 +514,10 @@ k_dense_syrk_tc(const __grid_constant__ TmapSet tmaps, const Params prm) {
         const int n1 = n_total > 256 ? 256 : n_total;
         const int n2 = n_total - n1;
         const uint32_t idesc1 = make_idesc(128, n1), idesc2 = make_idesc(128, n2 > 0 ? n2 : 16);
-        int b = 0;
+        int b = 0, sub = 0;
         uint32_t phb = 0;
-        for (int it = 0; it < my_count; ++it, ++b) {
+        const int total_it = my_count * prm.nsub;   // operand slots: nsub per raw stage
+        for (int it = 0; it < total_it; ++it, ++b) {
             if (b == SB) {
                 b = 0;
                 phb ^= 1;
@@ -512,6 +528,9 @@ k_dense_syrk_tc(const __grid_constant__ TmapSet tmaps, const Params prm) {
                 tl_stamp(prm, it, 4);
                 const uint64_t dS = desc0 + (uint64_t)((uint32_t)b * slot16);
                 const uint32_t Ta = tmem_base + t_col0 + (uint32_t)(b * prm.mtiles) * 32;
+                // 3xTF32 sub-pass 1 multiplies hi(d x) with the RESIDUAL of X: the one-hot
+                // columns (exact 0 / 1, no residual) must not be added a second time
+                const bool skip_oh = sub == 1;
                 if (prm.mtiles == 1) {
 #pragma unroll
                     for (int ks = 0; ks < BK / 8; ++ks) {
@@ -522,6 +541,8 @@ k_dense_syrk_tc(const __grid_constant__ TmapSet tmaps, const Params prm) {
                             const uint32_t acc2 = (it > 0 || ks > 1) ? 1u : 0u;
                             tcgen05_mma_tf32_ts(tmem_base + (uint32_t)(ks & 1) * 128, Ta + ks * 8,
                                                 db, idesc, acc2);
+                        } else if (skip_oh) {
+                            tcgen05_mma_tf32_ts(tmem_base, Ta + ks * 8, db, idesc, acc);
                         } else {
                             tcgen05_mma_tf32_ts(tmem_base, Ta + ks * 8, db, idesc1, acc);
                             if (n2 > 0)
@@ -544,6 +565,7 @@ k_dense_syrk_tc(const __grid_constant__ TmapSet tmaps, const Params prm) {
                 tl_stamp(prm, it, 5);
             }
             __syncwarp();
+            if (++sub == prm.nsub) sub = 0;
         }
         if (elect_one()) tcgen05_commit(done);
         __syncwarp();
@@ -717,23 +739,24 @@ k_dense_syrk_tc(const __grid_constant__ TmapSet tmaps, const Params prm) {
         float gacc = 0.f;   // this thread's share of (X^T v)[my_col]
         int s = 0, b = 0;
         uint32_t ph = 0, phb = 0;
-        for (int it = 0; it < my_count; ++it, ++s, ++b) {
+        for (int it = 0; it < my_count; ++it, ++s) {
             if (s == SR) {
                 s = 0;
                 ph ^= 1;
             }
+            if (lane == 0) mbar_wait(&full[s], ph);
+            __syncwarp();
+            if (t == 0) tl_stamp(prm, it, 2);
+          for (int sub = 0; sub < prm.nsub; ++sub, ++b) {   // 3xTF32: three operand slots per stage
             if (b == SB) {
                 b = 0;
                 phb ^= 1;
             }
             // one lane polls, the warp follows through __syncwarp
-            if (lane == 0) mbar_wait(&emptyB[b], phb ^ 1);  // MMAs of iteration it-SB left slot b
+            if (lane == 0) mbar_wait(&emptyB[b], phb ^ 1);  // MMAs of slot use it-SB left slot b
             __syncwarp();
             if (t == 0) tl_stamp(prm, it, 1);
             const uint32_t Sp = oper_sa + (uint32_t)b * slot_bytes;
-            if (lane == 0) mbar_wait(&full[s], ph);
-            __syncwarp();
-            if (t == 0) tl_stamp(prm, it, 2);
             const uint32_t stage = rring_sa + (uint32_t)s * (uint32_t)prm.r_bytes;
             const uint32_t dsm = stage + (uint32_t)prm.aux_off;
             if (prm.oh_groups) {
@@ -759,19 +782,19 @@ k_dense_syrk_tc(const __grid_constant__ TmapSet tmaps, const Params prm) {
             {
                 const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + t_col0 +
                                         (uint32_t)(b * prm.mtiles + (my_col >> 7)) * 32;
-                const uint32_t vsm = prm.has_v ? dsm + 128u * 9u : 0u;
+                const uint32_t vsm = (prm.has_v && sub == 0) ? dsm + 128u * 9u : 0u;
                 if (prm.f_order) {
                     if (prm.mtiles == 1) {
-                        scale_col4_f(R, P, dsm, Sp, t_addr, my_col, h, 2, vsm, gacc);
+                        scale_col4_f(R, P, dsm, Sp, t_addr, my_col, h, 2, vsm, gacc, sub);
                     } else {
-                        scale_col4_f(R, P, dsm, Sp, t_addr, my_col, 0, 1, vsm, gacc);
-                        scale_col4_f(R, P, dsm, Sp, t_addr, my_col, 4, 1, vsm, gacc);
+                        scale_col4_f(R, P, dsm, Sp, t_addr, my_col, 0, 1, vsm, gacc, sub);
+                        scale_col4_f(R, P, dsm, Sp, t_addr, my_col, 4, 1, vsm, gacc, sub);
                     }
                 } else if (prm.mtiles == 1) {
-                    scale_col4(R, P, dsm, Sp, t_addr, my_col, h, 2, vsm, gacc);
+                    scale_col4(R, P, dsm, Sp, t_addr, my_col, h, 2, vsm, gacc, sub);
                 } else {
-                    scale_col4(R, P, dsm, Sp, t_addr, my_col, 0, 1, vsm, gacc);
-                    scale_col4(R, P, dsm, Sp, t_addr, my_col, 4, 1, vsm, gacc);
+                    scale_col4(R, P, dsm, Sp, t_addr, my_col, 0, 1, vsm, gacc, sub);
+                    scale_col4(R, P, dsm, Sp, t_addr, my_col, 4, 1, vsm, gacc, sub);
                 }
             }
             if (t == 0) tl_stamp(prm, it, 6);
@@ -781,10 +804,11 @@ k_dense_syrk_tc(const __grid_constant__ TmapSet tmaps, const Params prm) {
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) {
-                mbar_arrive(&emptyR[s]);   // the raw stage can be refilled
+                if (sub == prm.nsub - 1) mbar_arrive(&emptyR[s]);   // the raw stage can be refilled
                 mbar_arrive(&scaled[b]);   // the operands are ready for the MMA warp
             }
             if (t == 0) tl_stamp(prm, it, 3);
+          }
         }
 
         if (prm.has_v && my_col < P && my_count > 0) atomicAdd(&prm.vec_out[my_col], gacc);
@@ -1035,6 +1059,7 @@ int dense_sandwich_tc_f32(const float* X, int64_t n, int64_t p, int c_order, con
     prm.r_bytes = prm.aux_off + 128 + 8 * 128 + 128;   // X tile | d | 8 code vectors | v
     prm.has_v = v ? 1 : 0;
     prm.vec_out = vec_out;
+    prm.nsub = g_dense_f32_mode == 3 ? 3 : 1;
     if (prm.f_order) prm.r_bytes = (prm.r_bytes + 1023) / 1024 * 1024;  // swizzle atom = 8 x 128 B
     int scw = 0;
     if (scatter && (scatter->n_cat > 0 || scatter->out_sparse)) {

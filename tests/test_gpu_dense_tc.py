@@ -169,3 +169,66 @@ def test_tcgen05_syrk_column_selection(order, frac, force_mode):
     if frac >= 0.2:
         force_mode(2)   # must be accepted: the selection is eligible for the tensor path
         run_cuda("dense_sandwich", dict(X=X, d=d, rows=None, cols=cols))
+
+
+@pytest.mark.parametrize("order", ["C", "F"])
+@pytest.mark.parametrize("n,p", [(50_000, 64), (20_000, 256), (4099 * 4, 128)])
+def test_tf32x3_restores_fp32_accuracy(n, p, order, force_mode):
+    """tm_set_dense_f32_mode(3): hi/lo operand split, three MMAs per product.  On an
+    ill-conditioned X (columns with a large common offset, so X^T D X has big entries whose small
+    differences matter) single-pass TF32 loses ~3 digits; 3xTF32 must be as accurate as the fp32
+    CUDA-core kernel (the reference's f32 kernels use full-precision FMAs).  The three errors are
+    printed: this is the record of the TF32 margin."""
+    from tests.gpu_runner import run_cuda
+
+    rng = np.random.default_rng(n + p)
+    X = (30.0 + rng.standard_normal((n, p))).astype(np.float32)
+    if order == "F":
+        X = np.asfortranarray(X)
+    d = rng.random(n).astype(np.float32)
+    Xd = X.astype(np.float64)
+    ref = Xd.T @ (d.astype(np.float64)[:, None] * Xd)
+    # what matters downstream: the centred second moments = small differences of big entries
+    mu = (d.astype(np.float64) @ Xd) / d.sum()
+    cen = ref - d.sum() * np.outer(mu, mu)
+    err = {}
+    for mode, name in ((2, "tf32"), (3, "tf32x3"), (1, "fp32 cuda cores")):
+        force_mode(mode)
+        got = run_cuda("dense_sandwich", dict(X=X, d=d, rows=None, cols=None)).astype(np.float64)
+        err[name] = (np.abs(got - ref).max() / np.abs(ref).max(),
+                     np.abs((got - d.sum() * np.outer(mu, mu)) - cen).max() / np.abs(cen).max())
+    print(f"\nn={n} p={p} {order}: normwise / centred-moment error  " +
+          "  ".join(f"{k}: {a:.2e} / {b:.2e}" for k, (a, b) in err.items()))
+    assert err["tf32"][0] <= 1e-3
+    assert err["tf32x3"][0] <= 2e-6 and err["tf32x3"][0] <= 20 * max(err["fp32 cuda cores"][0], 1e-7)
+    assert err["tf32x3"][1] <= 50 * max(err["fp32 cuda cores"][1], 1e-6)
+
+
+def test_tf32x3_with_onehot_blocks_in_a_split_matrix(force_mode):
+    """Mode 3 through the fused SplitMatrix pass: the one-hot columns are exact 0/1 and must be
+    added in two of the three sub-passes only."""
+    import scipy.sparse as sps
+
+    import tabmat_b200 as tm
+
+    rng = np.random.default_rng(8)
+    n = 20_000
+    X = (10.0 + rng.standard_normal((n, 32))).astype(np.float32)
+    c1 = rng.integers(0, 12, size=n).astype(np.int32)
+    c2 = rng.integers(0, 500, size=n).astype(np.int32)
+    A = sps.random(n, 40, density=0.05, random_state=rng, format="csc").astype(np.float32)
+    S = tm.SplitMatrix([tm.DenseMatrix(X), tm.SparseMatrix(A),
+                        tm.CategoricalMatrix(c1, categories=np.arange(12), dtype=np.float32),
+                        tm.CategoricalMatrix(c2, categories=np.arange(500), dtype=np.float32)])
+    full = np.hstack([X, A.toarray(), np.eye(12)[c1], np.eye(500)[c2]]).astype(np.float64)
+    d = rng.random(n).astype(np.float32)
+    ref = (full * d.astype(np.float64)[:, None]).T @ full
+    errs = {}
+    for mode in (0, 3):
+        force_mode(mode)
+        got = S.sandwich(d)
+        errs[mode] = np.abs(got - ref).max() / np.abs(ref).max()
+        blk = np.abs(got[72:84, :32] - ref[72:84, :32]).max() / np.abs(ref[72:84, :32]).max()
+        errs[(mode, "onehot x dense")] = blk
+    print("\nsplit f32, tf32 vs tf32x3:", {str(k): f"{v:.2e}" for k, v in errs.items()})
+    assert errs[0] <= 1e-3 and errs[3] <= 5e-6 and errs[(3, "onehot x dense")] <= 5e-6
