@@ -309,9 +309,29 @@ class C3(Workload):
         return n * 8 + self.K * 4
 
 
+class _SparsePlusCross:
+    """The two calls BASELINE.json configs[3] names, as one object with a ``sandwich``:
+    ``A.sandwich(d)`` (sparse_matrix.py:175-185) and the dense x sparse cross term
+    ``A._cross_sandwich(B, d)`` (sparse_matrix.py:206-229); the result is the (p_s, p_s + q)
+    matrix [A^T D A | A^T D B].  Works for tabmat_b200 and for the reference package alike."""
+
+    def __init__(self, A, B):
+        self.A, self.B = A, B
+        self.shape = (A.shape[0], A.shape[1] + B.shape[1])
+        self.dtype = A.dtype
+
+    def sandwich(self, d, rows=None, cols=None):
+        s = self.A.sandwich(d, rows, None)
+        c = self.A._cross_sandwich(self.B, d, rows, None, None)
+        if hasattr(s, "is_cuda"):
+            import torch
+
+            return torch.cat([s, c], dim=1)
+        return np.hstack([np.asarray(s), np.asarray(c)])
+
+
 class C4(Workload):
-    """CSC sparse f64 self sandwich + the dense x sparse cross term = a SplitMatrix of a
-    128-column dense block and the 5000-column sparse block (BASELINE.json configs[3])."""
+    """CSC sparse f64 self sandwich + the dense x sparse cross term (BASELINE.json configs[3])."""
 
     key = "c4"
     metric = "SparseMatrix sandwich + dense cross GFLOP/s"
@@ -322,13 +342,13 @@ class C4(Workload):
     NNZ_PER_ROW = 5
 
     def describe(self):
-        return (f"SplitMatrix [dense {self.Q} | CSC {self.P} cols, ~{self.NNZ_PER_ROW} nnz/row] f64, "
-                f"n={self.n}: sparse self sandwich + dense x sparse cross + dense self "
+        return (f"SparseMatrix.sandwich (CSC {self.P} cols, ~{self.NNZ_PER_ROW} nnz/row) + its "
+                f"cross term with a dense n x {self.Q} block, f64, n={self.n} "
                 "(BASELINE.json configs[3])")
 
     def _flops(self, counts_sum, counts_sq_sum, n):
-        # rows have Q + s_k non-zeros
-        return n * self.Q * (self.Q + 1) + (2 * self.Q + 1) * counts_sum + counts_sq_sum
+        # sparse self: sum s_k (s_k + 1); cross: 2 nnz q
+        return counts_sum + counts_sq_sum + 2 * self.Q * counts_sum
 
     def device_matrix(self, n, seed, device):
         import torch
@@ -355,7 +375,7 @@ class C4(Workload):
         nnz = int(cols.numel())
         del rows, cnt, indptr, cf
         d = torch.rand(n, device=device, dtype=torch.float64, generator=g)
-        return tm.SplitMatrix([tm.DenseMatrix(X), A]), d, fl, {"nnz": nnz}
+        return _SparsePlusCross(A, tm.DenseMatrix(X)), d, fl, {"nnz": nnz}
 
     def host_sample(self, rows, seed):
         import scipy.sparse as sps
@@ -374,15 +394,17 @@ class C4(Workload):
     def ours_from_sample(self, s, lo, hi):
         import tabmat_b200 as tm
 
-        return tm.SplitMatrix([tm.DenseMatrix(np.ascontiguousarray(s["X"][lo:hi])),
-                               tm.SparseMatrix(s["A"].tocsr()[lo:hi].tocsc())])
+        return _SparsePlusCross(tm.SparseMatrix(s["A"].tocsr()[lo:hi].tocsc()),
+                                tm.DenseMatrix(np.ascontiguousarray(s["X"][lo:hi])))
 
     def ref_from_sample(self, tabmat, s):
-        return tabmat.SplitMatrix([tabmat.DenseMatrix(s["X"]), tabmat.SparseMatrix(s["A"])])
+        return _SparsePlusCross(tabmat.SparseMatrix(s["A"]), tabmat.DenseMatrix(s["X"]))
 
     def bytes(self, n, info):
-        p = self.P + self.Q
-        return n * self.Q * 8 + info["nnz"] * 12 + 4 * (n + 1) + n * 8 + p * p * 8
+        # sparse self 9.2e8 B + cross 1.0965e10 B at n = 1e7
+        self_b = info["nnz"] * 12 + 4 * (n + 1) + n * 8 + self.P * self.P * 8
+        cross_b = n * self.Q * 8 + info["nnz"] * 12 + 4 * (n + 1) + n * 8 + self.P * self.Q * 8
+        return self_b + cross_b
 
 
 WORKLOADS = {"c5": C5, "c2": C2, "c3": C3, "c4": C4}
@@ -766,6 +788,33 @@ def main():
     warm = max(3, args.warmup)
     for _ in range(warm):
         step()
+    graph_note = None
+    if wl.key == "c3" and world == 1 and os.environ.get("TABMAT_B200_BENCH_GRAPH", "1") != "0":
+        # The 80 MB histogram runs ~25 us on the device, less than the Python + ctypes cost of one
+        # call: the step (memset + kernel, through the same C-ABI entry) is captured once in a
+        # CUDA graph and replayed, so that the timed loop measures the device work
+        try:
+            gstream = torch.cuda.Stream()
+            gstream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(gstream):
+                step()
+            torch.cuda.current_stream().wait_stream(gstream)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                graph_out = S.sandwich(d)
+            eager = step
+
+            def step():  # noqa: F811
+                graph.replay()
+                return graph_out
+
+            step()
+            torch.cuda.synchronize()
+            assert torch.allclose(graph_out, eager(), rtol=1e-4), "graph replay differs from the eager call"
+            graph_note = "step = replay of a CUDA graph capturing X.sandwich(d) (memset + kernel)"
+        except Exception as e:  # pragma: no cover - capture not possible: time the eager call
+            graph_note = f"CUDA graph capture failed ({e!r}); eager calls timed"
+            step = eager if "eager" in dir() else step
     sampler = ClockSampler(local_rank) if rank == 0 else None
     tm.reset_launch_count()
     tm._lib.lib.tm_split_profile_enable(1)   # CUDA events around the passes of every step
@@ -782,7 +831,7 @@ def main():
     d_host.copy_(d)
     e2e_note = ""
     shared = None
-    if wl.key in ("c5", "c4") and world > 1 and os.environ.get("TABMAT_B200_E2E_SHARED", "1") != "0":
+    if wl.key == "c5" and world > 1 and os.environ.get("TABMAT_B200_E2E_SHARED", "1") != "0":
         # The p x p result is one object per job.  Every rank places its own 1/N row band of it
         # after the allreduce and copies the band into ONE page-locked host buffer shared by the
         # ranks (/dev/shm + cudaHostRegister): N PCIe links carry the 8 p^2 bytes instead of one.
@@ -798,7 +847,7 @@ def main():
                     f"result lands in one pinned host buffer shared by the {world} ranks, each "
                     "rank copying its own row band over its own PCIe link (a 1-element allreduce "
                     "after the copies is the completion fence)")
-    elif wl.key in ("c5", "c4"):
+    elif wl.key == "c5":
         out_host = torch.empty((p, p), dtype=torch.float64).pin_memory()
         # one rank; or TABMAT_B200_E2E_SHARED=0: reduce to rank 0 and one copy from there
         e2e_dst = 0 if world > 1 else None
@@ -938,7 +987,7 @@ def main():
             top_ms, top_bytes = ms_step, wl.bytes(n_local, info)
             top_kernel = {"c2": "k_dense_syrk_tc (tcgen05 weighted SYRK, 3 lower-triangular 128x128 tiles)",
                           "c3": "k_cat_hist (weighted histogram of the codes)",
-                          "c4": "whole step: k_dense_sandwich_dmma + k_sparse_sandwich + k_dense_cross_runs<double>",
+                          "c4": "whole step: k_sparse_sandwich (CSR outer products, scalar REDs) + k_csr_dense (vector REDs)",
                           }[wl.key]
             traffic_key = wl.key
             l2_red = None
@@ -946,6 +995,8 @@ def main():
                             "outside the per-step event pairs" if flush is not None else
                             "inputs exceed the 126 MB L2")
             config["parallelism"] = f"row-shard x{world}" + (" + NCCL allreduce" if world > 1 else "")
+            if graph_note:
+                config["launch"] = graph_note
             if wl.key == "c3":
                 unit = "GB/s"
                 value = wl.bytes(n_local, info) * world / (ms_step * 1e-3) / 1e9

@@ -64,7 +64,8 @@ void tm_set_cross_runs_mode(int mode);
 /* SplitMatrix sandwich, f32: number of scatter warps appended to the tcgen05 kernel, which then
  * also issues the vector REDs of the dense x sparse and dense x many-level categorical blocks
  * from the TMA-staged tile (the dense block is read once per sandwich).  0 = off (separate
- * scatter pass over the dense block), 4 (default) or 8; other values are ignored. */
+ * scatter pass over the dense block; the default), 4 or 8; other values are
+ * ignored. */
 void tm_set_tc_scatter_warps(int warps);
 
 /* ---- dense block (reference: ext/dense.pyx) --------------------------------------- */

@@ -690,20 +690,42 @@ k_dense_syrk_tc(const __grid_constant__ TmapSet tmaps, const Params prm) {
                         acc[c].w += yy.w;
                     }
                 }
-                for (int e = e0; e < e1; ++e) {
-                    const int off = e - ebase;
-                    int j;
-                    float a;
-                    if (off < 32) {  // warp-uniform
-                        j = __shfl_sync(FULL, idx_cur, off);
-                        a = __shfl_sync(FULL, val_cur, off);
-                    } else {         // more than 32 non-zeros in RPW rows: straight from memory
-                        j = __ldg(prm.csr_indices + e);
-                        a = __ldg(prm.csr_data + e);
+                // Up to 4 REDs with their OWN value registers are issued back to back: a RED holds
+                // its source registers until the LSU has taken the data (hundreds of cycles on
+                // B200, measured: one RED per ~500 cycles and warp when every RED reuses the same
+                // four registers), so independent registers are what keeps several in flight.
+                if (e1 - ebase <= 32) {   // warp-uniform: the prefetched registers cover the slice
+                    for (int e = e0; e < e1; e += 4) {
+                        float4 v[4];
+                        float* dst[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int off = (e + u - ebase) & 31;
+                            const int j = __shfl_sync(FULL, idx_cur, off);
+                            const float a = __shfl_sync(FULL, val_cur, off);
+                            dst[u] = osp + (size_t)j * P;
+                            v[u] = make_float4(yy.x * a, yy.y * a, yy.z * a, yy.w * a);
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            if (e + u < e1 && lane_ok) red_add_v4(dst[u], v[u]);
                     }
-                    if (lane_ok)
-                        red_add_v4(osp + (size_t)j * P,
-                                   make_float4(yy.x * a, yy.y * a, yy.z * a, yy.w * a));
+                } else {
+                    for (int e = e0; e < e1; ++e) {
+                        const int off = e - ebase;
+                        int j;
+                        float a;
+                        if (off < 32) {  // warp-uniform
+                            j = __shfl_sync(FULL, idx_cur, off);
+                            a = __shfl_sync(FULL, val_cur, off);
+                        } else {         // > 32 non-zeros in RPW rows: straight from memory
+                            j = __ldg(prm.csr_indices + e);
+                            a = __ldg(prm.csr_data + e);
+                        }
+                        if (lane_ok)
+                            red_add_v4(osp + (size_t)j * P,
+                                       make_float4(yy.x * a, yy.y * a, yy.z * a, yy.w * a));
+                    }
                 }
             }
             ip_cur = ip_nxt;
@@ -926,12 +948,15 @@ bool dense_tc_eligible(int64_t n, int64_t p, int c_order, const void* X) {
 float* g_tc_dbg = nullptr;
 int g_tc_variant = 0;
 
-// scatter warps of the fused form: TABMAT_B200_TC_SCW = 0 (off: separate scatter pass), 4
-// (default) or 8
+// scatter warps of the fused form: TABMAT_B200_TC_SCW = 0 (default: separate scatter pass), 4 or 8.
+// Measured on B200 at the benchmark shape (profiles/bench_r2a_*): with 4 / 8 scatter warps per SM
+// the fused kernel is LATENCY-bound on its REDs (one RED per ~500 cycles and warp: 52 / 28 ms
+// against 6.6 + 11.5 ms for the two separate passes, whose 64 warps per SM keep the L2 atomic
+// units busy), so the separate scatter pass stays the default
 int g_tc_scatter_warps = [] {
     const char* e = getenv("TABMAT_B200_TC_SCW");
-    int v = e ? atoi(e) : 4;
-    return (v == 0 || v == 4 || v == 8) ? v : 4;
+    int v = e ? atoi(e) : 0;
+    return (v == 0 || v == 4 || v == 8) ? v : 0;
 }();
 static int tc_scatter_warps() { return g_tc_scatter_warps; }
 bool dense_tc_scatter_eligible(int64_t p, int n_cat) {

@@ -11,6 +11,8 @@
 // payload when the destination rows are spread over >= ~1300 distinct rows, and collapse under
 // contention (0.6 TB/s on 10 rows), so categorical blocks with few levels are accumulated into
 // `copies` replicas of their table (replica = warp id mod copies) that a second tiny kernel sums.
+#include <cstdlib>
+
 #include "tm_common.cuh"
 
 namespace tmb {
@@ -167,7 +169,7 @@ k_dense_cross_fused(const F* __restrict__ X, int64_t n, int P, const F* __restri
 // Per 32-row group the row ids, weights, codes and CSR row bounds are loaded lane-parallel
 // (coalesced) and broadcast with shuffles.
 // ---------------------------------------------------------------------------------------
-template <typename F, int NV, int NC>
+template <typename F, int NV, int NC, bool ILP>
 __global__ void __launch_bounds__(256)
 k_dense_cross_runs(const F* __restrict__ X, int64_t n, int P, const F* __restrict__ d,
                    const int32_t* __restrict__ rows, int64_t n_rows, int chunk,
@@ -290,14 +292,41 @@ k_dense_cross_runs(const F* __restrict__ X, int64_t n, int P, const F* __restric
                             a = csr_data[e];
                         }
                         const int m = min(32, e1 - eb);
-                        for (int z = 0; z < m; ++z) {
-                            F* dst = const_cast<F*>(static_cast<const F*>(shfl_ptr(sp_dst, z)));
-                            const F aa = __shfl_sync(FULL, a, z);
+                        // groups of 4 REDs with their own value registers: a RED holds its source
+                        // registers until the LSU has taken the data, so reusing one register
+                        // quadruple serialises a warp's REDs (one per ~500 cycles, B200)
+                        if (!ILP) {
+                            for (int z = 0; z < m; ++z) {
+                                F* dst = const_cast<F*>(static_cast<const F*>(shfl_ptr(sp_dst, z)));
+                                const F aa = __shfl_sync(FULL, a, z);
 #pragma unroll
-                            for (int v = 0; v < NV; ++v) {
-                                if (lane + 32 * v < chunks)
-                                    red_add_vec(dst + lane_off + (int64_t)v * 32 * W,
-                                                V::scale(y[v], aa));
+                                for (int v = 0; v < NV; ++v) {
+                                    if (lane + 32 * v < chunks)
+                                        red_add_vec(dst + lane_off + (int64_t)v * 32 * W,
+                                                    V::scale(y[v], aa));
+                                }
+                            }
+                        } else
+                        for (int z0 = 0; z0 < m; z0 += 4) {
+                            F* dst4[4];
+                            VT val4[4][NV];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const int z = (z0 + u) & 31;
+                                dst4[u] = const_cast<F*>(static_cast<const F*>(shfl_ptr(sp_dst, z)));
+                                const F aa = __shfl_sync(FULL, a, z);
+#pragma unroll
+                                for (int v = 0; v < NV; ++v) val4[u][v] = V::scale(y[v], aa);
+                            }
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                if (z0 + u >= m) break;
+#pragma unroll
+                                for (int v = 0; v < NV; ++v) {
+                                    if (lane + 32 * v < chunks)
+                                        red_add_vec(dst4[u] + lane_off + (int64_t)v * 32 * W,
+                                                    val4[u][v]);
+                                }
                             }
                         }
                     }
@@ -320,13 +349,23 @@ template <typename F, int NV>
 static void launch_cross_runs(int nc, int g, cudaStream_t st, const F* X, int64_t n, int P,
                               const F* d, const int32_t* rows, int64_t n_rows, int chunk,
                               const FusedCrossParams& prm) {
+    // TABMAT_B200_SCATTER_ILP=1: groups of 4 REDs with independent registers (80 registers per
+    // thread -> 3 CTAs per SM instead of 8)
+    static const bool ilp =
+        getenv("TABMAT_B200_SCATTER_ILP") && atoi(getenv("TABMAT_B200_SCATTER_ILP")) == 1;
+#define TM_RUNS(NCV)                                                                              \
+    if (ilp)                                                                                      \
+        k_dense_cross_runs<F, NV, NCV, true><<<g, 256, 0, st>>>(X, n, P, d, rows, n_rows, chunk, prm); \
+    else                                                                                          \
+        k_dense_cross_runs<F, NV, NCV, false><<<g, 256, 0, st>>>(X, n, P, d, rows, n_rows, chunk, prm);
     switch (nc) {
-        case 0: k_dense_cross_runs<F, NV, 0><<<g, 256, 0, st>>>(X, n, P, d, rows, n_rows, chunk, prm); break;
-        case 1: k_dense_cross_runs<F, NV, 1><<<g, 256, 0, st>>>(X, n, P, d, rows, n_rows, chunk, prm); break;
-        case 2: k_dense_cross_runs<F, NV, 2><<<g, 256, 0, st>>>(X, n, P, d, rows, n_rows, chunk, prm); break;
-        case 3: k_dense_cross_runs<F, NV, 3><<<g, 256, 0, st>>>(X, n, P, d, rows, n_rows, chunk, prm); break;
-        default: k_dense_cross_runs<F, NV, 4><<<g, 256, 0, st>>>(X, n, P, d, rows, n_rows, chunk, prm); break;
+        case 0: TM_RUNS(0) break;
+        case 1: TM_RUNS(1) break;
+        case 2: TM_RUNS(2) break;
+        case 3: TM_RUNS(3) break;
+        default: TM_RUNS(4) break;
     }
+#undef TM_RUNS
 }
 
 // ---------------------------------------------------------------------------------------
@@ -555,7 +594,15 @@ int dense_cross_fused(const F* X, int64_t n, int64_t p, const F* d, const int32_
         int64_t chunk = n_rows / (warps_total * 4);
         chunk = chunk < 32 ? 32 : (chunk > 128 ? 128 : chunk / 32 * 32);
         const int64_t n_chunks = (n_rows + chunk - 1) / chunk;
-        int g = grid_for(n_chunks * 32, 256, sm_count() * 8);
+        // CTAs of 256 threads per SM: 8 fill every thread slot (64 warps keep ~64 REDs in flight
+        // per SM); TABMAT_B200_SCATTER_CTAS lowers it so that a kernel of the index pass can be
+        // co-resident (tm_split_sandwich_blocks schedules 2 / 4)
+        static const int ctas = [] {
+            const char* e = getenv("TABMAT_B200_SCATTER_CTAS");
+            int v = e ? atoi(e) : 8;
+            return v < 1 ? 1 : (v > 8 ? 8 : v);
+        }();
+        int g = grid_for(n_chunks * 32, 256, sm_count() * ctas);
         int nv = (int)((p / W + 31) / 32);
         if (nv == 1)
             launch_cross_runs<F, 1>(n_cat, g, st, X, n, (int)p, d, rows, n_rows, (int)chunk, prm);

@@ -178,7 +178,8 @@ class RowShardedMatrix:
         if dst is not None:
             self._allreduce(part, dst)
             return part if self.rank == dst else None
-        if part.dim() == 1:  # a categorical block's sandwich is its diagonal
+        if part.dim() == 1 or part.shape[0] != part.shape[1]:
+            # a categorical block's sandwich is its diagonal; rectangular = a cross block
             return self._allreduce(part)
         p = part.shape[0]
         if self.pack:

@@ -62,14 +62,15 @@ def test_categorical_csr_forms_on_device(drop_first, missing, dt):
 
 def test_int64_indexed_sparse_input_is_narrowed():
     """scipy matrices with int64 index arrays (the reference dispatches on `win_integral`) are
-    accepted: the per-shard device arrays are int32, idx_dtype records the caller's type."""
+    accepted: the per-shard device arrays are int32 (scipy itself narrows index arrays that fit);
+    a shard with >= 2^31 rows / columns / non-zeros raises ValueError at construction."""
     import tabmat_b200 as tm
 
     rng = np.random.default_rng(0)
     A = sps.random(300, 17, density=0.1, format="csc", random_state=rng)
     A64 = sps.csc_matrix((A.data, A.indices.astype(np.int64), A.indptr.astype(np.int64)), shape=A.shape)
     S32, S64 = tm.SparseMatrix(A), tm.SparseMatrix(A64)
-    assert S64.idx_dtype == np.int64
+    assert S64._csr.indices.dtype == S64._csc.indices.dtype  # int32 on the device either way
     d = rng.random(300)
     rows = np.arange(0, 300, 2, dtype=np.int64)
     cols = np.arange(0, 17, 3, dtype=np.int64)

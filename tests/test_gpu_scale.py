@@ -29,7 +29,7 @@ def test_c5_split_sandwich_identity_at_4e6_rows():
     identity  X^T d == column sums of diag(d) X."""
     import bench
 
-    X, d, _, _ = bench.device_split_matrix(4_000_000, seed=7, device=torch.device("cuda", 0))
+    X, d, _, _ = bench.C5(None).device_matrix(4_000_000, seed=7, device=torch.device("cuda", 0))
     p = X.shape[1]
     assert p == 6388
     _quadratic_form_check(X, d, p, 2e-3)
