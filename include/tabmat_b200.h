@@ -63,9 +63,10 @@ void tm_set_dense_f32_mode(int mode);
 void tm_set_cross_runs_mode(int mode);
 /* SplitMatrix sandwich, f32: number of scatter warps appended to the tcgen05 kernel, which then
  * also issues the vector REDs of the dense x sparse and dense x many-level categorical blocks
- * from the TMA-staged tile (the dense block is read once per sandwich).  0 = off (separate
- * scatter pass over the dense block; the default), 4 or 8; other values are
- * ignored. */
+ * from the TMA-staged tile (the dense block is read once per sandwich).  -1 = auto (default:
+ * 4 warps when only the run-aggregated categorical REDs ride along, i.e. dense x sparse is
+ * computed by the gather kernel; none otherwise), 0 = never, 4 or 8 = always;
+ * other values are ignored. */
 void tm_set_tc_scatter_warps(int warps);
 
 /* ---- dense block (reference: ext/dense.pyx) --------------------------------------- */
@@ -164,6 +165,21 @@ int tm_csc_rmatvec_f64(const double* csc_data, const int32_t* csc_indices,
                        const int32_t* csc_indptr, int64_t n, int64_t p, const double* v,
                        const int32_t* rows, int64_t n_rows, const int32_t* cols, int64_t n_cols,
                        double* out, int accumulate, tm_stream_t stream);
+
+/* csr_dense_sandwich (sparse.pyx:211-260), unrestricted, gather form: out = A^T diag(d) B for
+ * a ROW-MAJOR B (n x q, q a multiple of 4 (f32) / 2 (f64), q <= 256 / 128) from a row-blocked CSC
+ * copy of A: non-zeros ordered by (row block, column, row), bptr = n_blocks * p_sparse + 1
+ * offsets, brow = global row ids.  Blocks should be small enough that block_rows * q * sizeof F
+ * stays in L2 (<= 32 MB).  One vector RED per (row block, column) run instead of one per
+ * non-zero; a `rows` restriction is expressed through d (zero weight outside).
+ * Overwrites out (p_sparse x q). */
+int tm_csc_dense_gather_sandwich_f32(const float* bdata, const int32_t* brow, const int32_t* bptr,
+                                     int64_t p_sparse, int64_t n_blocks, const float* B, int64_t q,
+                                     const float* d, float* out, tm_stream_t stream);
+int tm_csc_dense_gather_sandwich_f64(const double* bdata, const int32_t* brow,
+                                     const int32_t* bptr, int64_t p_sparse, int64_t n_blocks,
+                                     const double* B, int64_t q, const double* d, double* out,
+                                     tm_stream_t stream);
 
 /* transpose_square_dot_weights (sparse), sparse.pyx:262-282.
  * out[j] = sum_{nz (i,j)} w[i] * X[i,j]^2.  Overwrites out (p). */
@@ -359,6 +375,16 @@ typedef struct tm_block_desc {
      * Built once per matrix (like the reference's cached CSR, sparse_matrix.py:133-143): the
      * categorical x sparse kernel then streams the codes and gathers only d[row]. */
     const uint64_t* csc_cat_codes;
+    /* sparse, optional: a second row-blocked CSC copy (same layout as csc_* with
+     * csc_row_blocks > 1) whose blocks are small enough that a block of the DENSE operand stays
+     * in L2 (block_rows * ncols_dense * sizeof F <= 32 MB): enables the gather form of the
+     * dense x sparse block (one vector RED per (row block, column) run instead of one per
+     * non-zero).  gcsc_row_blocks = number of row blocks B; gcsc_indptr has B * ncols + 1
+     * offsets. */
+    const void* gcsc_data;
+    const int32_t* gcsc_indices;
+    const int32_t* gcsc_indptr;
+    int64_t gcsc_row_blocks;
 } tm_block_desc;
 
 #define TM_CSC_ROW_BLOCK (1 << 20)

@@ -54,6 +54,7 @@ _SIGS = {
     "tm_dense_sq_dot_weights": [P, I, I, N, P, P, P, P],
     "tm_sparse_sandwich": [P, P, P, P, I, I, I, P, P, I, P, I, P, P],
     "tm_csr_dense_sandwich": [P, P, P, I, I, P, I, N, P, P, I, P, I, P, I, P, P],
+    "tm_csc_dense_gather_sandwich": [P, P, P, I, I, P, I, P, P, P],
     "tm_csr_matvec": [P, P, P, I, I, P, P, I, P, I, P, N, P],
     "tm_csc_rmatvec": [P, P, P, I, I, P, P, I, P, I, P, N, P],
     "tm_csc_sq_dot_weights": [P, P, P, I, I, P, P, P],
@@ -103,7 +104,9 @@ class BlockDesc(C.Structure):
                 ("nnz", C.c_int64), ("col_index", C.c_void_p), ("cat_perm", C.c_void_p),
                 ("cat_segptr", C.c_void_p), ("cat_nvalid", C.c_int64), ("csc_data", C.c_void_p),
                 ("csc_indices", C.c_void_p), ("csc_indptr", C.c_void_p), ("csc_row_blocks", C.c_int64),
-                ("csc_cat_codes", C.c_void_p)]
+                ("csc_cat_codes", C.c_void_p), ("gcsc_data", C.c_void_p),
+                ("gcsc_indices", C.c_void_p), ("gcsc_indptr", C.c_void_p),
+                ("gcsc_row_blocks", C.c_int64)]
 
 #: rows per block of the row-blocked CSC copy (TM_CSC_ROW_BLOCK in include/tabmat_b200.h)
 CSC_ROW_BLOCK = 1 << 20

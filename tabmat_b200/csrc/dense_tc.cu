@@ -955,12 +955,18 @@ int g_tc_variant = 0;
 // units busy), so the separate scatter pass stays the default
 int g_tc_scatter_warps = [] {
     const char* e = getenv("TABMAT_B200_TC_SCW");
-    int v = e ? atoi(e) : 0;
-    return (v == 0 || v == 4 || v == 8) ? v : 0;
+    int v = e ? atoi(e) : -1;
+    return (v == 0 || v == 4 || v == 8) ? v : -1;
 }();
-static int tc_scatter_warps() { return g_tc_scatter_warps; }
-bool dense_tc_scatter_eligible(int64_t p, int n_cat) {
-    return tc_scatter_warps() > 0 && p <= 128 && n_cat <= TC_SCATTER_MAX_CATS;
+// -1 = auto: 4 scatter warps when they only carry the run-aggregated categorical REDs (a few per
+// row tile: far below one RED per 500 cycles and warp), none when the per-non-zero REDs of
+// dense x sparse would ride along too (latency-bound, see above)
+static int tc_scatter_warps(bool with_sparse) {
+    if (g_tc_scatter_warps >= 0) return g_tc_scatter_warps;
+    return with_sparse ? 0 : 4;
+}
+bool dense_tc_scatter_eligible(int64_t p, int n_cat, bool with_sparse) {
+    return tc_scatter_warps(with_sparse) > 0 && p <= 128 && n_cat <= TC_SCATTER_MAX_CATS;
 }
 
 template <int MB, int SCW>
@@ -1088,9 +1094,9 @@ int dense_sandwich_tc_f32(const float* X, int64_t n, int64_t p, int c_order, con
     if (prm.f_order) prm.r_bytes = (prm.r_bytes + 1023) / 1024 * 1024;  // swizzle atom = 8 x 128 B
     int scw = 0;
     if (scatter && (scatter->n_cat > 0 || scatter->out_sparse)) {
-        if (!dense_tc_scatter_eligible(p, scatter->n_cat))
+        if (!dense_tc_scatter_eligible(p, scatter->n_cat, scatter->out_sparse != nullptr))
             return fail("dense_tc: scatter work not eligible for the fused form");
-        scw = tc_scatter_warps();
+        scw = tc_scatter_warps(scatter->out_sparse != nullptr);
         prm.sc_ncat = scatter->n_cat;
         for (int c = 0; c < scatter->n_cat; ++c) {
             prm.sc_codes[c] = scatter->codes[c];
@@ -1181,7 +1187,7 @@ int tm_has_tcgen05(void) {
 }
 void tm_set_dense_f32_mode(int mode) { tmb::g_dense_f32_mode = mode; }
 void tm_set_tc_scatter_warps(int warps) {
-    if (warps == 0 || warps == 4 || warps == 8) tmb::g_tc_scatter_warps = warps;
+    if (warps == -1 || warps == 0 || warps == 4 || warps == 8) tmb::g_tc_scatter_warps = warps;
 }
 /* test hook (not part of the public header): device buffer of >= 65536 + 3*128*128 floats */
 void tm_debug_set_tc_buffer(float* buf) { tmb::g_tc_dbg = buf; }

@@ -16,6 +16,7 @@
 //                           categorical x dense / sparse x dense / categorical x sparse /
 //                           categorical_i x categorical_j (i < j)
 #include <climits>
+#include <cstring>
 #include <cstdint>
 #include <cstdlib>
 #include <vector>
@@ -208,14 +209,24 @@ int split_blocks(const tm_block_desc* blk, int nb, int64_t n, const F* d, const 
             }
     }
     const bool have_tensor = tc_ok || any_gather;
+    // dense x sparse by row-blocked gather instead of one RED per non-zero (TABMAT_B200_DXS:
+    // "gather" (default when the matrix carries the blocked copy) | "red")
+    static const bool gather_env_off = getenv("TABMAT_B200_DXS") && !strcmp(getenv("TABMAT_B200_DXS"), "red");
+    const bool sparse_by_gather = fuse && !gather_env_off && sparse_idx >= 0 &&
+                                  blk[sparse_idx].nnz > 0 && blk[sparse_idx].gcsc_data &&
+                                  blk[sparse_idx].gcsc_indices && blk[sparse_idx].gcsc_indptr &&
+                                  blk[sparse_idx].gcsc_row_blocks > 0;
+
     // fused form: the scatter work (dense x many-level categoricals, dense x sparse) rides along
     // the tcgen05 kernel as extra warps reading the TMA-staged tile, so X is read once
     int n_scatter_cats = 0;
     for (int i = 0; i < nb; ++i)
         if (blk[i].kind == KIND_CAT && !on_tensor[i]) ++n_scatter_cats;
+    const bool sparse_for_tc = sparse_idx >= 0 && blk[sparse_idx].nnz > 0 && !sparse_by_gather;
     const bool scatter_in_tc =
-        tc_ok && fuse && dense_tc_scatter_eligible(blk[dense_idx].ncols, n_scatter_cats) &&
-        (n_scatter_cats > 0 || (sparse_idx >= 0 && blk[sparse_idx].nnz > 0));
+        tc_ok && fuse &&
+        dense_tc_scatter_eligible(blk[dense_idx].ncols, n_scatter_cats, sparse_for_tc) &&
+        (n_scatter_cats > 0 || sparse_for_tc);
 
     // destinations and sources of the scatter work (shared by the fused tensor pass and the
     // stand-alone scatter pass)
@@ -279,10 +290,12 @@ int split_blocks(const tm_block_desc* blk, int nb, int64_t n, const F* d, const 
             FusedCrossParams fc;
             CrossScratch fscr;
             if (scatter_in_tc) {
+                const bool sp_here = !sparse_by_gather;   // else the gather kernel owns that block
                 int rc = cross_prepare<float>(
                     D.ncols, sp.c, sp.codes, sp.K, sp.df, reinterpret_cast<float* const*>(sp.outs),
-                    reinterpret_cast<const float*>(sp.sdata), sp.sind, sp.sptr, sp.ps,
-                    reinterpret_cast<float*>(sp.out_s), fc, fscr, st);
+                    sp_here ? reinterpret_cast<const float*>(sp.sdata) : nullptr,
+                    sp_here ? sp.sind : nullptr, sp_here ? sp.sptr : nullptr, sp_here ? sp.ps : 0,
+                    sp_here ? reinterpret_cast<float*>(sp.out_s) : nullptr, fc, fscr, st);
                 if (rc) return rc;
             }
             int rc = dense_sandwich_tc_f32(static_cast<const float*>(D.data), n, D.ncols, 1, dd,
@@ -330,12 +343,37 @@ int split_blocks(const tm_block_desc* blk, int nb, int64_t n, const F* d, const 
             TM_CUDA(cudaMemsetAsync(ws + cross_off[a][b], 0,
                                     sizeof(F) * (size_t)(blk[a].ncols * blk[b].ncols), st));
         }
-        if (scatter_in_tc) return 0;  // done by the scatter warps of the tcgen05 kernel
+        if (scatter_in_tc && !sparse_by_gather) return 0;  // done by the tcgen05 kernel's scatter warps
         if (sp.c > 0 || sp.out_s) {
             pass_mark(PASS_SCATTER, 0, st);
-            int rc = dense_cross_fused<F>(static_cast<const F*>(D.data), n, D.ncols, d, rows,
+            int rc = 0;
+            if (sparse_by_gather) {
+                // dense x sparse: row-blocked gather (one RED per (row block, column) run)
+                const tm_block_desc& S = blk[sparse_idx];
+                Scratch dmg(rows ? sizeof(F) * (size_t)n : 0, st);
+                if (dmg.err != cudaSuccess) return fail_cuda(dmg.err, "scratch");
+                const F* dd = d;
+                if (rows) {
+                    rc = masked_weights<F>(d, n, rows, n_rows, dmg.as<F>(), st);
+                    if (rc) return rc;
+                    dd = dmg.as<F>();
+                }
+                rc = csc_dense_gather<F>(static_cast<const F*>(D.data), D.ncols, dd,
+                                         static_cast<const F*>(S.gcsc_data), S.gcsc_indices,
+                                         S.gcsc_indptr, S.ncols, S.gcsc_row_blocks, sp.out_s, st);
+                if (rc) return rc;
+                // dense x many-level categoricals: the scatter warps of the tcgen05 kernel when it
+                // runs in its fused form, else the RED kernel without a sparse operand
+                if (sp.c > 0 && !scatter_in_tc)
+                    rc = dense_cross_fused<F>(static_cast<const F*>(D.data), n, D.ncols, d, rows,
+                                              n_rows, sp.c, sp.codes, sp.K, sp.df, sp.outs,
+                                              (const F*)nullptr, nullptr, nullptr, 0, (F*)nullptr,
+                                              /*runs=*/1, st);
+            } else {
+                rc = dense_cross_fused<F>(static_cast<const F*>(D.data), n, D.ncols, d, rows,
                                           n_rows, sp.c, sp.codes, sp.K, sp.df, sp.outs, sp.sdata,
                                           sp.sind, sp.sptr, sp.ps, sp.out_s, /*runs=*/1, st);
+            }
             if (rc) return rc;
             pass_mark(PASS_SCATTER, 1, st);
         }

@@ -484,6 +484,145 @@ int cat_dense_gather_f32(const float* X, int64_t p, const float* d, const int32_
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------
+// dense x sparse by ROW-BLOCKED GATHER (the alternative to one vector RED per non-zero):
+//   out[j, :] = sum over the non-zeros (k, j) of column j of  A[k, j] * d[k] * X[k, :]
+// The L2 atomic units cap the RED form at 1.9e11 sector-ops/s (16 per non-zero at 128 fp32
+// columns: 11.5 ms at the benchmark shape); the L2 read path is about twice as wide.  Here the
+// non-zeros are stored ordered by (row block, column, row) — a second row-blocked CSC copy,
+// built once per matrix, with blocks of `block_rows` rows chosen so that a block of X
+// (block_rows * P * sizeof F <= 32 MB) stays in the 126 MB L2.  A warp owns a fixed set of
+// columns, walks the row blocks in order, gathers the 512-byte X rows of a (block, column) run
+// with coalesced 16-byte loads, sums them in registers and issues ONE vector RED per run
+// (~65 non-zeros at the benchmark shape: 65x fewer REDs).  All CTAs are resident and every warp
+// has the same number of columns, so the whole grid sweeps the row blocks together; a soft
+// barrier (per-block arrival counters, bounded spin: a hint, never needed for correctness)
+// keeps any CTA from running more than `lag` blocks ahead, so the gather window stays in L2.
+// ---------------------------------------------------------------------------------------
+constexpr int GD_THREADS = 128;
+
+template <typename F, int NV>
+__global__ void __launch_bounds__(GD_THREADS)
+k_csc_dense_gather(const F* __restrict__ X, int P, const F* __restrict__ d,
+                   const F* __restrict__ bdata, const int32_t* __restrict__ brow,
+                   const int32_t* __restrict__ bptr, int p_s, int n_blocks, int cols_per_warp,
+                   F* __restrict__ out, unsigned* __restrict__ progress, int lag) {
+    using V = Vec<F>;
+    using VT = typename V::T;
+    constexpr int W = V::W;
+    constexpr int U = 8;   // X rows in flight per warp
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int gw = (int)(((int64_t)blockIdx.x * GD_THREADS + threadIdx.x) >> 5);
+    const int chunks = P / W;
+    const int j0 = gw * cols_per_warp;
+    const int j1 = min(p_s, j0 + cols_per_warp);
+    for (int b = 0; b < n_blocks; ++b) {
+        if (b >= lag) {
+            if (threadIdx.x == 0) {
+                const volatile unsigned* pr = progress + (b - lag);
+                for (int spin = 0; spin < 4096 && *pr < gridDim.x; ++spin) __nanosleep(64);
+            }
+            __syncthreads();
+        }
+        const int32_t* ptr = bptr + (int64_t)b * p_s;
+        for (int j = j0; j < j1; ++j) {
+            const int e0 = ptr[j], e1 = ptr[j + 1];
+            if (e0 == e1) continue;
+            VT acc[NV];
+#pragma unroll
+            for (int v = 0; v < NV; ++v) acc[v] = V::zero();
+            for (int eb = e0; eb < e1; eb += 32) {
+                const int e = eb + lane;
+                int k_l = 0;
+                F w_l = F(0);
+                if (e < e1) {
+                    k_l = __ldg(brow + e);
+                    w_l = __ldg(bdata + e) * __ldg(d + k_l);
+                }
+                const int cnt = min(32, e1 - eb);
+                for (int z0 = 0; z0 < cnt; z0 += U) {
+                    VT x[U][NV];
+                    F w[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const int z = (z0 + u) & 31;   // lanes past cnt carry weight 0, row 0
+                        const int k = __shfl_sync(FULL, k_l, z);
+                        w[u] = __shfl_sync(FULL, w_l, z);
+                        const VT* xr = reinterpret_cast<const VT*>(X + (int64_t)k * P);
+#pragma unroll
+                        for (int v = 0; v < NV; ++v) {
+                            const int ch = lane + 32 * v;
+                            x[u][v] = ch < chunks ? __ldg(xr + ch) : V::zero();
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        if (z0 + u >= cnt) break;
+#pragma unroll
+                        for (int v = 0; v < NV; ++v) acc[v] = V::add(acc[v], V::scale(x[u][v], w[u]));
+                    }
+                }
+            }
+            F* dst = out + (int64_t)j * P + (int64_t)lane * W;
+#pragma unroll
+            for (int v = 0; v < NV; ++v)
+                if (lane + 32 * v < chunks) red_add_vec(dst + (int64_t)v * 32 * W, acc[v]);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) atomicAdd(progress + b, 1u);
+    }
+}
+
+// out (p_s x p) is overwritten.  bdata / brow / bptr: row-blocked CSC (n_blocks * p_s + 1 offsets).
+template <typename F>
+int csc_dense_gather(const F* X, int64_t p, const F* d, const F* bdata, const int32_t* brow,
+                     const int32_t* bptr, int64_t p_s, int64_t n_blocks, F* out, cudaStream_t st) {
+    constexpr int W = Vec<F>::W;
+    if (p <= 0 || p % W != 0 || p > 64 * W) return fail("csc_dense_gather: unsupported dense width");
+    if (p_s <= 0 || n_blocks <= 0) return 0;
+    TM_CUDA(cudaMemsetAsync(out, 0, sizeof(F) * (size_t)(p_s * p), st));
+    Scratch prog(sizeof(unsigned) * (size_t)n_blocks, st);
+    if (prog.err != cudaSuccess) return fail_cuda(prog.err, "scratch");
+    TM_CUDA(cudaMemsetAsync(prog.p, 0, sizeof(unsigned) * (size_t)n_blocks, st));
+    const int nv = (int)((p / W + 31) / 32);
+    // one resident wave, the same number of columns for every warp
+    int per_sm = 0;
+    if (nv == 1)
+        TM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_csc_dense_gather<F, 1>,
+                                                              GD_THREADS, 0));
+    else
+        TM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_csc_dense_gather<F, 2>,
+                                                              GD_THREADS, 0));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 4) per_sm = 4;
+    const int64_t max_warps = (int64_t)sm_count() * per_sm * (GD_THREADS / 32);
+    const int cpw = (int)((p_s + max_warps - 1) / max_warps);
+    const int64_t warps = (p_s + cpw - 1) / cpw;
+    const int grid = (int)((warps + GD_THREADS / 32 - 1) / (GD_THREADS / 32));
+    static const int lag = [] {
+        const char* e = getenv("TABMAT_B200_GATHER_LAG");
+        int v = e ? atoi(e) : 2;
+        return v < 1 ? 1 : v;
+    }();
+    if (nv == 1)
+        k_csc_dense_gather<F, 1><<<grid, GD_THREADS, 0, st>>>(
+            X, (int)p, d, bdata, brow, bptr, (int)p_s, (int)n_blocks, cpw, out,
+            prog.as<unsigned>(), lag);
+    else
+        k_csc_dense_gather<F, 2><<<grid, GD_THREADS, 0, st>>>(
+            X, (int)p, d, bdata, brow, bptr, (int)p_s, (int)n_blocks, cpw, out,
+            prog.as<unsigned>(), lag);
+    TM_LAUNCHED();
+    return 0;
+}
+template int csc_dense_gather<float>(const float*, int64_t, const float*, const float*,
+                                     const int32_t*, const int32_t*, int64_t, int64_t, float*,
+                                     cudaStream_t);
+template int csc_dense_gather<double>(const double*, int64_t, const double*, const double*,
+                                      const int32_t*, const int32_t*, int64_t, int64_t, double*,
+                                      cudaStream_t);
+
 // out[r, :] = sum over replicas of tab[(rep*K + r), :]
 template <typename F>
 __global__ void k_sum_replicas(const F* __restrict__ tab, int K, int copies, int64_t P,
@@ -638,6 +777,20 @@ template int dense_cross_fused<double>(const double*, int64_t, int64_t, const do
 extern "C" {
 
 void tm_set_cross_runs_mode(int mode) { tmb::g_cross_runs_mode = mode; }
+
+int tm_csc_dense_gather_sandwich_f32(const float* bdata, const int32_t* brow, const int32_t* bptr,
+                                     int64_t p_sparse, int64_t n_blocks, const float* B, int64_t q,
+                                     const float* d, float* out, tm_stream_t stream) {
+    return tmb::csc_dense_gather<float>(B, q, d, bdata, brow, bptr, p_sparse, n_blocks, out,
+                                        tmb::as_stream(stream));
+}
+int tm_csc_dense_gather_sandwich_f64(const double* bdata, const int32_t* brow,
+                                     const int32_t* bptr, int64_t p_sparse, int64_t n_blocks,
+                                     const double* B, int64_t q, const double* d, double* out,
+                                     tm_stream_t stream) {
+    return tmb::csc_dense_gather<double>(B, q, d, bdata, brow, bptr, p_sparse, n_blocks, out,
+                                         tmb::as_stream(stream));
+}
 
 int tm_dense_cross_sandwich_f32(const float* X, int64_t n, int64_t p, const float* d,
                                 const int32_t* rows, int64_t n_rows, int n_cat,

@@ -154,7 +154,7 @@ int dense_sandwich_tc_f32(const float* X, int64_t n, int64_t p, int c_order, con
                           bool share_sm = false, const FusedCrossParams* scatter = nullptr,
                           const float* v = nullptr, float* vec_out = nullptr);
 // does the tcgen05 kernel take the scatter work of `n_cat` many-level blocks along (p <= 128)?
-bool dense_tc_scatter_eligible(int64_t p, int n_cat);
+bool dense_tc_scatter_eligible(int64_t p, int n_cat, bool with_sparse);
 bool dense_tc_eligible(int64_t n, int64_t p, int c_order, const void* X);
 
 // ---- fused dense-operand cross blocks (split_fused.cu) ---------------------------------
@@ -168,6 +168,10 @@ int dense_cross_fused(const F* X, int64_t n, int64_t p, const F* d, const int32_
                       const int32_t* csr_indices, const int32_t* csr_indptr, int64_t p_sparse,
                       F* out_sparse, int runs, cudaStream_t st);
 extern int g_cross_runs_mode;
+// dense x sparse by row-blocked gather (split_fused.cu): out (p_s x p) overwritten
+template <typename F>
+int csc_dense_gather(const F* X, int64_t p, const F* d, const F* bdata, const int32_t* brow,
+                     const int32_t* bptr, int64_t p_s, int64_t n_blocks, F* out, cudaStream_t st);
 // The two halves of dense_cross_fused around the kernel launch: zero-fill the destinations,
 // set up the replicated tables of few-level blocks (scratch handed back through `scr`, the
 // caller owns it until cross_finish has been enqueued), and sum the replicas afterwards.

@@ -117,8 +117,9 @@ class SparseMatrix(MatrixBase):
         with ``n_blocks * ncols + 1`` offsets — the row-blocked CSC copy that keeps the per-row
         gathers of the categorical x sparse kernel inside the L2 (built once and cached, like
         the reference's cached CSR, sparse_matrix.py:133-143)."""
-        cached = self.__dict__.get("_bcsc")
-        if cached is None or cached[4] != block_rows:
+        cache = self.__dict__.setdefault("_bcsc", {})
+        cached = cache.get(block_rows)
+        if cached is None:
             c = self._csr
             n, p = self._shape
             n_blocks = max(1, -(-n // block_rows))
@@ -130,7 +131,7 @@ class SparseMatrix(MatrixBase):
             ptr[1:] = torch.cumsum(counts, 0)
             cached = (c.data[order].contiguous(), c.row[order].contiguous(),
                       ptr.to(torch.int32).contiguous(), n_blocks, block_rows)
-            self.__dict__["_bcsc"] = cached
+            cache[block_rows] = cached
         return cached[:4]
 
     def _init_names(self, column_names, term_names):
@@ -300,7 +301,44 @@ class SparseMatrix(MatrixBase):
         d_t, host = _vec_in(d)
         rows_t, L_t = setup_restrictions(self.shape, rows, L_cols)
         R_t = _dev.idx32(R_cols)
-        return _dev.ret(csr_dense_sandwich(self._csr, B_t, d_t, rows_t, L_t, R_t), host)
+        res = self._sandwich_dense_gather(B_t, d_t, rows_t, L_t, R_t)
+        if res is None:
+            res = csr_dense_sandwich(self._csr, B_t, d_t, rows_t, L_t, R_t)
+        return _dev.ret(res, host)
+
+    def _sandwich_dense_gather(self, B_t, d_t, rows_t, L_t, R_t):
+        """Gather form of the sparse x dense cross sandwich (``tm_csc_dense_gather_sandwich``):
+        large matrices, row-major B, no column restriction.  One vector RED per (row block,
+        column) run of a row-blocked CSC copy (built once and cached, like the reference's cached
+        CSR) instead of one per non-zero.  None = not applicable."""
+        import os
+
+        from ._lib import check, fn
+
+        if os.environ.get("TABMAT_B200_DXS") == "red" or L_t is not None or R_t is not None:
+            return None
+        n, p = self._shape
+        q = int(B_t.shape[1]) if B_t.dim() == 2 else 0
+        fsize = B_t.element_size()
+        width = 16 // fsize
+        if (not B_t.is_contiguous() or q <= 0 or q % width or q > 64 * width
+                or B_t.data_ptr() % 16 or not self._csr.nnz):
+            return None
+        cap = int(os.environ.get("TABMAT_B200_GATHER_MB", "32")) * (1 << 20)
+        rows_blk = 1 << (max(1024, cap // (q * fsize)).bit_length() - 1)
+        if n <= rows_blk + rows_blk // 2:
+            return None
+        bd, br, bp, nblk = self._row_blocked_csc(rows_blk)
+        dd = d_t
+        if rows_t is not None:   # the restriction becomes a zero weight outside `rows`
+            dd = torch.zeros_like(d_t)
+            idx = rows_t.to(torch.int64)
+            dd[idx] = d_t[idx]
+        out = torch.empty((p, q), dtype=B_t.dtype, device=B_t.device)
+        check(fn("tm_csc_dense_gather_sandwich", _dev.suffix(B_t.dtype))(
+            _dev.ptr(bd), _dev.ptr(br), _dev.ptr(bp), p, nblk, _dev.ptr(B_t), q,
+            _dev.ptr(dd.contiguous()), _dev.ptr(out), _dev.stream_ptr()))
+        return out
 
     def _matvec_helper(self, vec, rows, cols, out, transpose: bool):
         if not _dev.is_dev(vec):

@@ -322,6 +322,13 @@ class SplitMatrix(MatrixBase):
                 pk = self._packed_cat_codes(csc_rows, tdtype) if has_cat and c.nnz else None
                 if pk is not None:
                     dsc.csc_cat_codes = pk.data_ptr()
+                # second row-blocked copy for the gather form of dense x sparse: blocks small
+                # enough that a block of the dense operand (rows x ncols x sizeof) stays in L2
+                gb = self._gather_block_rows(tdtype)
+                if gb and c.nnz and mat.shape[0] > gb + gb // 2:
+                    gd, gr, gp, gnblk = mat._row_blocked_csc(gb)
+                    dsc.gcsc_data, dsc.gcsc_indices = gd.data_ptr(), gr.data_ptr()
+                    dsc.gcsc_indptr, dsc.gcsc_row_blocks = gp.data_ptr(), gnblk
             elif isinstance(mat, CategoricalMatrix):
                 ok = _dev.torch_dtype(mat.dtype) == tdtype
                 dsc.kind, dsc.data, dsc.drop_first = 2, mat._codes.data_ptr(), int(mat.drop_first)
@@ -342,6 +349,26 @@ class SplitMatrix(MatrixBase):
             plan = (descs, int(lib.tm_split_workspace_elems(descs, len(self.matrices))))
         cache[key] = plan
         return plan
+
+    def _gather_block_rows(self, tdtype) -> int:
+        """Rows per block of the row-blocked CSC copy that feeds the gather form of the
+        dense x sparse block (csrc/split_fused.cu: k_csc_dense_gather): the largest power of two
+        with rows * (dense width) * sizeof <= 32 MB, so that a block of the dense operand stays in
+        the 126 MB L2 while three blocks are in flight.  0 = do not build it (no single row-major
+        dense block of a supported width, or TABMAT_B200_DXS=red)."""
+        if os.environ.get("TABMAT_B200_DXS") == "red":
+            return 0
+        dense = [m for m in self.matrices if isinstance(m, DenseMatrix)]
+        if len(dense) != 1 or dense[0]._array.dtype != tdtype or not dense[0]._array.is_contiguous():
+            return 0
+        fsize = 4 if tdtype == torch.float32 else 8
+        q = dense[0].shape[1]
+        width = 16 // fsize
+        if q <= 0 or q % width or q > 64 * width:
+            return 0
+        cap = int(os.environ.get("TABMAT_B200_GATHER_MB", "32")) * (1 << 20)
+        rows = max(1024, cap // (q * fsize))
+        return 1 << (rows.bit_length() - 1)
 
     def _packed_cat_codes(self, csc_rows: torch.Tensor, tdtype) -> Optional[torch.Tensor]:
         """For every non-zero of the sparse block's CSC copy (in ITS order) the categorical

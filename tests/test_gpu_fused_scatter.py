@@ -83,7 +83,7 @@ def test_fused_scatter_matches_dense_recomputation(case, scw):
             err = np.abs(got - sep).max() / np.abs(ref).max()
             assert err < 1e-4, err
     finally:
-        lib.tm_set_tc_scatter_warps(4)
+        lib.tm_set_tc_scatter_warps(-1)
 
 
 def test_fused_scatter_counts_are_exact():
@@ -134,3 +134,68 @@ def test_cols_selection_on_the_native_path(frac, monkeypatch):
         for got, what in ((a, "native"), (b, "native, sorted rows"), (c, "per-pair")):
             assert got.shape == ref.shape
             cases.assert_close(got, ref, np.float32, f"cols {what}")
+
+
+@pytest.mark.parametrize("suf", ["f32", "f64"])
+@pytest.mark.parametrize("case", [(6007, 128, 300, 0.01, (10, 50, 200, 1000, 2000)),
+                                  (5000, 32, 40, 0.05, ()), (4099, 64, 50, 0.5, (12, 300))],
+                         ids=lambda c: f"n{c[0]}p{c[1]}s{c[2]}")
+def test_dense_x_sparse_by_row_blocked_gather(suf, case, monkeypatch):
+    """The gather form of the dense x sparse block (k_csc_dense_gather: one RED per (row block,
+    column) run from a second row-blocked CSC copy): shrink the block so that a small matrix
+    spans several row blocks; against float64 recomputation and against the RED form, plain and
+    row-sorted, with a row restriction; and the stand-alone entry behind sandwich_dense."""
+    import tabmat_b200 as tm
+
+    n, pd, ps, dens, levels = case
+    dt = cases.DTYPES[suf]
+    X, full, d, rng = _build(n, pd, ps, dens, levels, seed=n + 1)
+    if dt == np.float64:
+        X = X.astype(np.float64)
+        d = d.astype(np.float64)
+    monkeypatch.setattr(type(X), "_gather_block_rows", lambda self, tdt: 512)
+    plan = X._native_plan(tm._dev.torch_dtype(dt))
+    assert plan is not None and plan[0][1].gcsc_row_blocks == -(-n // 512)
+    rows = np.sort(rng.choice(n, size=n // 3, replace=False)).astype(np.int32)
+    S = tm.RowSortedMatrix.from_split(X)
+    Y, _, _, _ = _build(n, pd, ps, dens, levels, seed=n + 1)   # same data, RED form
+    if dt == np.float64:
+        Y = Y.astype(np.float64)
+    monkeypatch.setattr(type(Y), "_gather_block_rows", lambda self, tdt: 0)
+    for r in (None, rows):
+        F = full if r is None else full[r]
+        dd = d.astype(np.float64) if r is None else d.astype(np.float64)[r]
+        ref = (F * dd[:, None]).T @ F
+        cases.assert_close(X.sandwich(d, r), ref, dt, "gather form")
+        cases.assert_close(S.sandwich(d, r), ref, dt, "gather form, sorted rows")
+    assert not Y._native_plan(tm._dev.torch_dtype(dt))[0][1].gcsc_row_blocks
+    cases.assert_close(Y.sandwich(d), (full * d.astype(np.float64)[:, None]).T @ full, dt, "RED form")
+
+
+@pytest.mark.parametrize("suf", ["f32", "f64"])
+def test_sparse_sandwich_dense_gather_entry(suf, monkeypatch):
+    """SparseMatrix.sandwich_dense (sparse.pyx:211-260) through the gather entry point
+    (TABMAT_B200_GATHER_MB shrunk so that 40k rows span many blocks) == the RED kernel == f64."""
+    import tabmat_b200 as tm
+
+    dt = cases.DTYPES[suf]
+    rng = np.random.default_rng(12)
+    n, p, q = 40_000, 300, 32
+    A = sps.random(n, p, density=0.01, random_state=rng, format="csc").astype(dt)
+    B = rng.standard_normal((n, q)).astype(dt)
+    d = rng.random(n).astype(dt)
+    rows = np.sort(rng.choice(n, size=n // 2, replace=False)).astype(np.int32)
+    S = tm.SparseMatrix(A)
+    monkeypatch.setenv("TABMAT_B200_GATHER_MB", "0")   # -> blocks of 1024 rows
+    tm.reset_launch_count()
+    for r in (None, rows):
+        Ad = A.toarray().astype(np.float64)
+        Ar, Br, dr = (Ad, B, d) if r is None else (Ad[r], B[r], d[r])
+        ref = Ar.T @ (dr.astype(np.float64)[:, None] * Br.astype(np.float64))
+        got = S.sandwich_dense(B, d, r, None, None)
+        cases.assert_close(got, ref, dt, "gather sandwich_dense")
+    assert 1024 in S.__dict__["_bcsc"]
+    monkeypatch.setenv("TABMAT_B200_DXS", "red")
+    cases.assert_close(S.sandwich_dense(B, d, None, None, None),
+                       A.toarray().astype(np.float64).T @ (d.astype(np.float64)[:, None] * B.astype(np.float64)),
+                       dt, "RED sandwich_dense")
