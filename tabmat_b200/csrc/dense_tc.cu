@@ -297,11 +297,12 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
 // the MMAs), the d-scaled values to this lane's TMEM lane of the T operand (M side).  All 16
 // loads are issued before the math.  Lanes with c >= P write nothing to S (those rows stay
 // zero) and zeros to T (tcgen05.st is warp-collective).
+template <int SUB>
 __device__ __forceinline__ void scale_col4(uint32_t R, int P, uint32_t dsm, uint32_t Sp,
                                            uint32_t t_addr, int c, int kb, int ks, uint32_t vsm,
-                                           float& gacc, int sub = 0) {
+                                           float& gacc) {
     // R, dsm, Sp: 32-bit shared addresses of the raw stage, its d vector and the S tile
-    const bool s_lo = sub == 1, t_lo = sub == 2;   // 3xTF32 sub-pass: which operand is the residual
+    constexpr bool s_lo = SUB == 1, t_lo = SUB == 2;   // 3xTF32 sub-pass: which operand is the residual
     float x[4][4];
     const bool ok = c < P;
     const uint32_t r0 = R + (uint32_t)c * 4u;
@@ -341,11 +342,12 @@ __device__ __forceinline__ void scale_col4(uint32_t R, int P, uint32_t dsm, uint
 // 128-byte row of 32 k-values per X column, 16-byte chunks XOR-swizzled by the TMA unit
 // (SWIZZLE_128B) so that the 32 lanes of a warp, one column each, read a chunk without bank
 // conflicts.  No transpose is needed: a lane reads its 4 consecutive k as one LDS.128.
+template <int SUB>
 __device__ __forceinline__ void scale_col4_f(uint32_t R, int P, uint32_t dsm, uint32_t Sp,
                                              uint32_t t_addr, int c, int kb, int ks, uint32_t vsm,
-                                             float& gacc, int sub = 0) {
+                                             float& gacc) {
     const bool ok = c < P;
-    const bool s_lo = sub == 1, t_lo = sub == 2;
+    constexpr bool s_lo = SUB == 1, t_lo = SUB == 2;
     const uint32_t tile_off = (uint32_t)(c >> 7) * TILE_BYTES;
     const uint32_t row = (uint32_t)c & 127u;
     float4 x[4];
@@ -376,6 +378,26 @@ __device__ __forceinline__ void scale_col4_f(uint32_t R, int P, uint32_t dsm, ui
     }
 }
 
+// one operand slot of a raw stage: sub-pass SUB of the 3xTF32 scheme (0 = the plain TF32 pass)
+template <int SUB>
+__device__ __forceinline__ void scale_stage(bool f_order, int mtiles, uint32_t R, int P, uint32_t dsm,
+                                            uint32_t Sp, uint32_t t_addr, int my_col, int h,
+                                            uint32_t vsm, float& gacc) {
+    if (f_order) {
+        if (mtiles == 1) {
+            scale_col4_f<SUB>(R, P, dsm, Sp, t_addr, my_col, h, 2, vsm, gacc);
+        } else {
+            scale_col4_f<SUB>(R, P, dsm, Sp, t_addr, my_col, 0, 1, vsm, gacc);
+            scale_col4_f<SUB>(R, P, dsm, Sp, t_addr, my_col, 4, 1, vsm, gacc);
+        }
+    } else if (mtiles == 1) {
+        scale_col4<SUB>(R, P, dsm, Sp, t_addr, my_col, h, 2, vsm, gacc);
+    } else {
+        scale_col4<SUB>(R, P, dsm, Sp, t_addr, my_col, 0, 1, vsm, gacc);
+        scale_col4<SUB>(R, P, dsm, Sp, t_addr, my_col, 4, 1, vsm, gacc);
+    }
+}
+
 // tensor maps of one launch: the X tile, the weight vector d and the one-hot code vectors
 // (1-d maps, 32 elements per stage; out-of-range rows read as zero)
 struct TmapSet {
@@ -397,7 +419,10 @@ __device__ __forceinline__ void tl_stamp(const Params& prm, int it, int e) {
 // min-blocks 2 only caps the registers (<= 102/thread) so that the L2-atomic-bound scatter
 // kernels of a SplitMatrix sandwich can share the SM with this kernel's one resident CTA
 // SCW = number of scatter warps appended after the scale warps (0: plain SYRK + one-hot kernel)
-template <int MIN_BLOCKS, int SCW>
+// NSUB = operand slots per raw stage: 1 (TF32) or 3 (3xTF32, tm_set_dense_f32_mode(3)); a
+// template parameter because the scale warps are the throughput-critical part of the pipeline
+// and the plain path must not pay for the residual arithmetic
+template <int MIN_BLOCKS, int SCW, int NSUB>
 __global__ void __launch_bounds__(NUM_THREADS + 32 * SCW, MIN_BLOCKS)
 k_dense_syrk_tc(const __grid_constant__ TmapSet tmaps, const Params prm) {
     extern __shared__ uint8_t smem_raw[];
@@ -516,7 +541,7 @@ k_dense_syrk_tc(const __grid_constant__ TmapSet tmaps, const Params prm) {
         const uint32_t idesc1 = make_idesc(128, n1), idesc2 = make_idesc(128, n2 > 0 ? n2 : 16);
         int b = 0, sub = 0;
         uint32_t phb = 0;
-        const int total_it = my_count * prm.nsub;   // operand slots: nsub per raw stage
+        const int total_it = my_count * NSUB;   // operand slots: NSUB per raw stage
         for (int it = 0; it < total_it; ++it, ++b) {
             if (b == SB) {
                 b = 0;
@@ -530,7 +555,7 @@ k_dense_syrk_tc(const __grid_constant__ TmapSet tmaps, const Params prm) {
                 const uint32_t Ta = tmem_base + t_col0 + (uint32_t)(b * prm.mtiles) * 32;
                 // 3xTF32 sub-pass 1 multiplies hi(d x) with the RESIDUAL of X: the one-hot
                 // columns (exact 0 / 1, no residual) must not be added a second time
-                const bool skip_oh = sub == 1;
+                const bool skip_oh = NSUB > 1 && sub == 1;
                 if (prm.mtiles == 1) {
 #pragma unroll
                     for (int ks = 0; ks < BK / 8; ++ks) {
@@ -565,7 +590,7 @@ k_dense_syrk_tc(const __grid_constant__ TmapSet tmaps, const Params prm) {
                 tl_stamp(prm, it, 5);
             }
             __syncwarp();
-            if (++sub == prm.nsub) sub = 0;
+            if (++sub == NSUB) sub = 0;
         }
         if (elect_one()) tcgen05_commit(done);
         __syncwarp();
@@ -690,42 +715,22 @@ k_dense_syrk_tc(const __grid_constant__ TmapSet tmaps, const Params prm) {
                         acc[c].w += yy.w;
                     }
                 }
-                // Up to 4 REDs with their OWN value registers are issued back to back: a RED holds
-                // its source registers until the LSU has taken the data (hundreds of cycles on
-                // B200, measured: one RED per ~500 cycles and warp when every RED reuses the same
-                // four registers), so independent registers are what keeps several in flight.
-                if (e1 - ebase <= 32) {   // warp-uniform: the prefetched registers cover the slice
-                    for (int e = e0; e < e1; e += 4) {
-                        float4 v[4];
-                        float* dst[4];
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const int off = (e + u - ebase) & 31;
-                            const int j = __shfl_sync(FULL, idx_cur, off);
-                            const float a = __shfl_sync(FULL, val_cur, off);
-                            dst[u] = osp + (size_t)j * P;
-                            v[u] = make_float4(yy.x * a, yy.y * a, yy.z * a, yy.w * a);
-                        }
-#pragma unroll
-                        for (int u = 0; u < 4; ++u)
-                            if (e + u < e1 && lane_ok) red_add_v4(dst[u], v[u]);
+                // (groups of 4 REDs with independent value registers were measured: no gain — a
+                // warp's REDs are serialised by the memory pipeline, ~500 cycles each on B200)
+                for (int e = e0; e < e1; ++e) {
+                    const int off = e - ebase;
+                    int j;
+                    float a;
+                    if (off < 32) {  // warp-uniform
+                        j = __shfl_sync(FULL, idx_cur, off);
+                        a = __shfl_sync(FULL, val_cur, off);
+                    } else {         // more than 32 non-zeros in RPW rows: straight from memory
+                        j = __ldg(prm.csr_indices + e);
+                        a = __ldg(prm.csr_data + e);
                     }
-                } else {
-                    for (int e = e0; e < e1; ++e) {
-                        const int off = e - ebase;
-                        int j;
-                        float a;
-                        if (off < 32) {  // warp-uniform
-                            j = __shfl_sync(FULL, idx_cur, off);
-                            a = __shfl_sync(FULL, val_cur, off);
-                        } else {         // > 32 non-zeros in RPW rows: straight from memory
-                            j = __ldg(prm.csr_indices + e);
-                            a = __ldg(prm.csr_data + e);
-                        }
-                        if (lane_ok)
-                            red_add_v4(osp + (size_t)j * P,
-                                       make_float4(yy.x * a, yy.y * a, yy.z * a, yy.w * a));
-                    }
+                    if (lane_ok)
+                        red_add_v4(osp + (size_t)j * P,
+                                   make_float4(yy.x * a, yy.y * a, yy.z * a, yy.w * a));
                 }
             }
             ip_cur = ip_nxt;
@@ -769,7 +774,7 @@ k_dense_syrk_tc(const __grid_constant__ TmapSet tmaps, const Params prm) {
             if (lane == 0) mbar_wait(&full[s], ph);
             __syncwarp();
             if (t == 0) tl_stamp(prm, it, 2);
-          for (int sub = 0; sub < prm.nsub; ++sub, ++b) {   // 3xTF32: three operand slots per stage
+          for (int sub = 0; sub < NSUB; ++sub, ++b) {   // 3xTF32: three operand slots per stage
             if (b == SB) {
                 b = 0;
                 phb ^= 1;
@@ -805,19 +810,12 @@ k_dense_syrk_tc(const __grid_constant__ TmapSet tmaps, const Params prm) {
                 const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + t_col0 +
                                         (uint32_t)(b * prm.mtiles + (my_col >> 7)) * 32;
                 const uint32_t vsm = (prm.has_v && sub == 0) ? dsm + 128u * 9u : 0u;
-                if (prm.f_order) {
-                    if (prm.mtiles == 1) {
-                        scale_col4_f(R, P, dsm, Sp, t_addr, my_col, h, 2, vsm, gacc, sub);
-                    } else {
-                        scale_col4_f(R, P, dsm, Sp, t_addr, my_col, 0, 1, vsm, gacc, sub);
-                        scale_col4_f(R, P, dsm, Sp, t_addr, my_col, 4, 1, vsm, gacc, sub);
-                    }
-                } else if (prm.mtiles == 1) {
-                    scale_col4(R, P, dsm, Sp, t_addr, my_col, h, 2, vsm, gacc, sub);
-                } else {
-                    scale_col4(R, P, dsm, Sp, t_addr, my_col, 0, 1, vsm, gacc, sub);
-                    scale_col4(R, P, dsm, Sp, t_addr, my_col, 4, 1, vsm, gacc, sub);
-                }
+                if (NSUB == 1 || sub == 0)
+                    scale_stage<0>(prm.f_order, prm.mtiles, R, P, dsm, Sp, t_addr, my_col, h, vsm, gacc);
+                else if (sub == 1)
+                    scale_stage<1>(prm.f_order, prm.mtiles, R, P, dsm, Sp, t_addr, my_col, h, 0u, gacc);
+                else
+                    scale_stage<2>(prm.f_order, prm.mtiles, R, P, dsm, Sp, t_addr, my_col, h, 0u, gacc);
             }
             if (t == 0) tl_stamp(prm, it, 6);
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
@@ -826,7 +824,7 @@ k_dense_syrk_tc(const __grid_constant__ TmapSet tmaps, const Params prm) {
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) {
-                if (sub == prm.nsub - 1) mbar_arrive(&emptyR[s]);   // the raw stage can be refilled
+                if (sub == NSUB - 1) mbar_arrive(&emptyR[s]);   // the raw stage can be refilled
                 mbar_arrive(&scaled[b]);   // the operands are ready for the MMA warp
             }
             if (t == 0) tl_stamp(prm, it, 3);
@@ -969,13 +967,13 @@ bool dense_tc_scatter_eligible(int64_t p, int n_cat, bool with_sparse) {
     return tc_scatter_warps(with_sparse) > 0 && p <= 128 && n_cat <= TC_SCATTER_MAX_CATS;
 }
 
-template <int MB, int SCW>
+template <int MB, int SCW, int NSUB>
 static int launch_tc(const tc::TmapSet& tmaps, const tc::Params& prm, unsigned grid, size_t smem,
                      cudaStream_t st) {
     // per device and cheap: set on every launch rather than cached in a process-wide static
-    TM_CUDA(cudaFuncSetAttribute(tc::k_dense_syrk_tc<MB, SCW>,
+    TM_CUDA(cudaFuncSetAttribute(tc::k_dense_syrk_tc<MB, SCW, NSUB>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    tc::k_dense_syrk_tc<MB, SCW><<<grid, tc::NUM_THREADS + 32 * SCW, smem, st>>>(tmaps, prm);
+    tc::k_dense_syrk_tc<MB, SCW, NSUB><<<grid, tc::NUM_THREADS + 32 * SCW, smem, st>>>(tmaps, prm);
     TM_LAUNCHED();
     return 0;
 }
@@ -1134,14 +1132,22 @@ int dense_sandwich_tc_f32(const float* X, int64_t n, int64_t p, int c_order, con
     TM_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)(p * p), st));
     long long grid = prm.num_row_tiles < sm_count() ? prm.num_row_tiles : sm_count();
     int rc;
-    if (scw == 8)
-        rc = launch_tc<1, 8>(tmaps, prm, (unsigned)grid, smem, st);
-    else if (scw == 4)
-        rc = launch_tc<1, 4>(tmaps, prm, (unsigned)grid, smem, st);
-    else if (share_sm)
-        rc = launch_tc<2, 0>(tmaps, prm, (unsigned)grid, smem, st);
-    else
-        rc = launch_tc<1, 0>(tmaps, prm, (unsigned)grid, smem, st);
+    if (prm.nsub == 3) {
+        if (scw == 8)
+            rc = launch_tc<1, 8, 3>(tmaps, prm, (unsigned)grid, smem, st);
+        else if (scw == 4)
+            rc = launch_tc<1, 4, 3>(tmaps, prm, (unsigned)grid, smem, st);
+        else
+            rc = launch_tc<1, 0, 3>(tmaps, prm, (unsigned)grid, smem, st);
+    } else if (scw == 8) {
+        rc = launch_tc<1, 8, 1>(tmaps, prm, (unsigned)grid, smem, st);
+    } else if (scw == 4) {
+        rc = launch_tc<1, 4, 1>(tmaps, prm, (unsigned)grid, smem, st);
+    } else if (share_sm) {
+        rc = launch_tc<2, 0, 1>(tmaps, prm, (unsigned)grid, smem, st);
+    } else {
+        rc = launch_tc<1, 0, 1>(tmaps, prm, (unsigned)grid, smem, st);
+    }
     if (rc) return rc;
     return symmetrize_from_upper<float>(out, p, st);
 }

@@ -35,7 +35,7 @@ def test_version_and_error_string():
 def test_block_descriptor_layout_matches_the_library():
     from tabmat_b200 import _lib
 
-    assert _lib.lib.tm_sizeof_block_desc() == ctypes.sizeof(_lib.BlockDesc) == 136
+    assert _lib.lib.tm_sizeof_block_desc() == ctypes.sizeof(_lib.BlockDesc) == 168
     descs = (_lib.BlockDesc * 2)()
     descs[0].kind, descs[0].ncols = 0, 5          # dense 5 columns
     descs[1].kind, descs[1].ncols = 2, 3          # categorical 3 columns

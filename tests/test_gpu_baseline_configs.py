@@ -96,19 +96,21 @@ def test_c4_sparse_f64_self_and_cross_vs_reference():
     s = wl.host_sample(ROWS, seed=23)
     ref = _reference(wl, s)
     X = wl.ours_from_sample(s, 0, ROWS)
-    got = X.sandwich(s["d"])
-    q = wl.Q
+    got = X.sandwich(s["d"])          # [A^T D A | A^T D B], the two calls configs[3] names
+    P = wl.P
     n_all, _ = _errs(got, ref)
-    n_self, _ = _errs(got[q:, q:], ref[q:, q:])
-    n_cross, _ = _errs(got[q:, :q], ref[q:, :q])
+    n_self, _ = _errs(got[:, :P], ref[:, :P])
+    n_cross, _ = _errs(got[:, P:], ref[:, P:])
     _record("c4", normwise=n_all, sparse_self=n_self, dense_x_sparse=n_cross, tol=1e-5, rows=ROWS)
     assert max(n_all, n_self, n_cross) <= 1e-5
-    # the stand-alone SparseMatrix entry points (sparse.pyx:17-77, :211-260) on the same arrays
+    # the same two blocks inside a SplitMatrix [dense | sparse] (fused split path, f64)
     import tabmat_b200 as tm
 
-    A = tm.SparseMatrix(s["A"])
-    n2, _ = _errs(A.sandwich(s["d"]), ref[q:, q:])
-    n3, _ = _errs(A._cross_sandwich(tm.DenseMatrix(s["X"]), s["d"], None, None, None), ref[q:, :q])
+    S = tm.SplitMatrix([tm.DenseMatrix(s["X"]), tm.SparseMatrix(s["A"])])
+    H = S.sandwich(s["d"])
+    q = wl.Q
+    n2, _ = _errs(H[q:, q:], ref[:, :P])
+    n3, _ = _errs(H[q:, :q], ref[:, P:])
     assert max(n2, n3) <= 1e-5
 
 

@@ -41,7 +41,10 @@ case "$mode" in
     timeout -s KILL ${T:-900} python tools/bench_blocks.py "$@" > gpurun_out/bench_blocks_$TAG.log 2>&1
     echo "blocks rc=$?"; cut -c1-600 gpurun_out/bench_blocks_$TAG.log ;;
   launches)
-    timeout -s KILL ${T:-900} ncu --metrics gpu__time_duration.sum --clock-control none -c ${C:-400} --csv \
+    # only this library's kernels (namespaces tmb:: / tmb::tc::), so that the construction of the
+    # matrix (torch sort / index kernels) does not fill the launch list
+    timeout -s KILL ${T:-900} ncu --metrics gpu__time_duration.sum --clock-control none \
+      --kernel-name-base demangled -k "regex:tmb::" -c ${C:-400} --csv \
       --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline "$@" \
       > gpurun_out/launches_$TAG.log 2>&1
     echo "launches rc=$?"; tail -2 gpurun_out/launches_$TAG.log | cut -c1-300 ;;
