@@ -88,6 +88,13 @@ struct Params {
     // (three operand slots per raw stage), which restores fp32-level accuracy at a third of the
     // tensor throughput (tm_set_dense_f32_mode(3))
     int nsub;
+    // column panels.  Legacy (panel == 0): the kernel's P columns are columns 0..P-1 of X and one
+    // TMA box brings a whole row tile.  panel == 1 (p > 256): the kernel works on TWO 128-column
+    // panels of a wider X - panel A = columns a0..a0+wa-1 (local columns 0..127), panel B =
+    // b0..b0+wb-1 (local columns 128..255), one TMA box each - and writes the output tiles
+    // selected by tile_mask (bit 0: A x A, bit 1: B x A, bit 2: B x B) at their global position
+    // in the ldo x ldo result.  The host loops over panel pairs.
+    int panel, a0, b0, wa, wb, ldo, tile_mask;
     int sc_ncat;                       // <= TC_SCATTER_MAX_CATS
     const int32_t* sc_codes[TC_SCATTER_MAX_CATS];
     float* sc_tab[TC_SCATTER_MAX_CATS];
@@ -298,15 +305,13 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
 // loads are issued before the math.  Lanes with c >= P write nothing to S (those rows stay
 // zero) and zeros to T (tcgen05.st is warp-collective).
 template <int SUB>
-__device__ __forceinline__ void scale_col4(uint32_t R, int P, uint32_t dsm, uint32_t Sp,
-                                           uint32_t t_addr, int c, int kb, int ks, uint32_t vsm,
-                                           float& gacc) {
-    // R, dsm, Sp: 32-bit shared addresses of the raw stage, its d vector and the S tile
+__device__ __forceinline__ void scale_col4(uint32_t r0, uint32_t pitch, bool ok, uint32_t dsm,
+                                           uint32_t Sp, uint32_t t_addr, int c, int kb, int ks,
+                                           uint32_t vsm, float& gacc) {
+    // r0: shared address of element (row 0, column c) of the raw stage, pitch: bytes per row;
+    // dsm, Sp: shared addresses of the stage's d vector and of the S tile
     constexpr bool s_lo = SUB == 1, t_lo = SUB == 2;   // 3xTF32 sub-pass: which operand is the residual
     float x[4][4];
-    const bool ok = c < P;
-    const uint32_t r0 = R + (uint32_t)c * 4u;
-    const uint32_t pitch = (uint32_t)P * 4u;
 #pragma unroll
     for (int u = 0; u < 4; ++u)
 #pragma unroll
@@ -343,10 +348,9 @@ __device__ __forceinline__ void scale_col4(uint32_t R, int P, uint32_t dsm, uint
 // (SWIZZLE_128B) so that the 32 lanes of a warp, one column each, read a chunk without bank
 // conflicts.  No transpose is needed: a lane reads its 4 consecutive k as one LDS.128.
 template <int SUB>
-__device__ __forceinline__ void scale_col4_f(uint32_t R, int P, uint32_t dsm, uint32_t Sp,
+__device__ __forceinline__ void scale_col4_f(uint32_t R, bool ok, uint32_t dsm, uint32_t Sp,
                                              uint32_t t_addr, int c, int kb, int ks, uint32_t vsm,
                                              float& gacc) {
-    const bool ok = c < P;
     constexpr bool s_lo = SUB == 1, t_lo = SUB == 2;
     const uint32_t tile_off = (uint32_t)(c >> 7) * TILE_BYTES;
     const uint32_t row = (uint32_t)c & 127u;
@@ -380,21 +384,22 @@ __device__ __forceinline__ void scale_col4_f(uint32_t R, int P, uint32_t dsm, ui
 
 // one operand slot of a raw stage: sub-pass SUB of the 3xTF32 scheme (0 = the plain TF32 pass)
 template <int SUB>
-__device__ __forceinline__ void scale_stage(bool f_order, int mtiles, uint32_t R, int P, uint32_t dsm,
-                                            uint32_t Sp, uint32_t t_addr, int my_col, int h,
-                                            uint32_t vsm, float& gacc) {
+__device__ __forceinline__ void scale_stage(bool f_order, int mtiles, uint32_t R, uint32_t col_off,
+                                            uint32_t pitch, bool ok, uint32_t dsm, uint32_t Sp,
+                                            uint32_t t_addr, int my_col, int h, uint32_t vsm,
+                                            float& gacc) {
     if (f_order) {
         if (mtiles == 1) {
-            scale_col4_f<SUB>(R, P, dsm, Sp, t_addr, my_col, h, 2, vsm, gacc);
+            scale_col4_f<SUB>(R, ok, dsm, Sp, t_addr, my_col, h, 2, vsm, gacc);
         } else {
-            scale_col4_f<SUB>(R, P, dsm, Sp, t_addr, my_col, 0, 1, vsm, gacc);
-            scale_col4_f<SUB>(R, P, dsm, Sp, t_addr, my_col, 4, 1, vsm, gacc);
+            scale_col4_f<SUB>(R, ok, dsm, Sp, t_addr, my_col, 0, 1, vsm, gacc);
+            scale_col4_f<SUB>(R, ok, dsm, Sp, t_addr, my_col, 4, 1, vsm, gacc);
         }
     } else if (mtiles == 1) {
-        scale_col4<SUB>(R, P, dsm, Sp, t_addr, my_col, h, 2, vsm, gacc);
+        scale_col4<SUB>(R + col_off, pitch, ok, dsm, Sp, t_addr, my_col, h, 2, vsm, gacc);
     } else {
-        scale_col4<SUB>(R, P, dsm, Sp, t_addr, my_col, 0, 1, vsm, gacc);
-        scale_col4<SUB>(R, P, dsm, Sp, t_addr, my_col, 4, 1, vsm, gacc);
+        scale_col4<SUB>(R + col_off, pitch, ok, dsm, Sp, t_addr, my_col, 0, 1, vsm, gacc);
+        scale_col4<SUB>(R + col_off, pitch, ok, dsm, Sp, t_addr, my_col, 4, 1, vsm, gacc);
     }
 }
 
@@ -405,6 +410,7 @@ struct TmapSet {
     CUtensorMap d;
     CUtensorMap codes[8];
     CUtensorMap v;
+    CUtensorMap xb;   // panel mode: the box of panel B (its own width)
 };
 
 // bring-up timeline: cycle stamps of CTA 0's first TL_ITERS iterations (prm.dbg only)
@@ -500,7 +506,7 @@ k_dense_syrk_tc(const __grid_constant__ TmapSet tmaps, const Params prm) {
         if (lane == 0) {
             int s = 0;
             uint32_t ph = 0;
-            const uint32_t tx = (uint32_t)(BK * P * 4) +
+            const uint32_t tx = (uint32_t)(BK * (prm.panel ? prm.wa + prm.wb : P) * 4) +
                                 128u * (1u + (uint32_t)prm.oh_ncat + (prm.has_v ? 1u : 0u));
             for (int it = 0; it < my_count; ++it, ++s) {
                 if (s == SR) {
@@ -513,7 +519,15 @@ k_dense_syrk_tc(const __grid_constant__ TmapSet tmaps, const Params prm) {
                 uint8_t* stage = Rring + (size_t)s * prm.r_bytes;
                 const uint32_t aux = smem_u32(stage) + (uint32_t)prm.aux_off;
                 mbar_expect_tx(&full[s], tx);
-                if (prm.f_order)
+                if (prm.panel) {   // one box per 128-column panel, at its global column offset
+                    if (prm.f_order) {
+                        tma_load_2d(stage, &tmaps.x, &full[s], (int)k0, prm.a0);
+                        if (prm.wb) tma_load_2d(stage + TILE_BYTES, &tmaps.xb, &full[s], (int)k0, prm.b0);
+                    } else {
+                        tma_load_2d(stage, &tmaps.x, &full[s], prm.a0, (int)k0);
+                        if (prm.wb) tma_load_2d(stage + TILE_BYTES, &tmaps.xb, &full[s], prm.b0, (int)k0);
+                    }
+                } else if (prm.f_order)
                     tma_load_2d(stage, &tmaps.x, &full[s], (int)k0, 0);   // (k, column) coordinates
                 else
                     tma_load_2d(stage, &tmaps.x, &full[s], 0, (int)k0);
@@ -581,9 +595,12 @@ k_dense_syrk_tc(const __grid_constant__ TmapSet tmaps, const Params prm) {
                         const uint32_t acc = (it > 0 || ks > 0) ? 1u : 0u;
                         const uint64_t d0 = dS + (uint64_t)(ks * 2);
                         const uint64_t d1 = d0 + (uint64_t)(TILE_BYTES / 16);
-                        tcgen05_mma_tf32_ts(tmem_base, Ta + ks * 8, d0, idesc, acc);             // (0,0)
-                        tcgen05_mma_tf32_ts(tmem_base + 128, Ta + 32 + ks * 8, d0, idesc, acc);  // (1,0)
-                        tcgen05_mma_tf32_ts(tmem_base + 256, Ta + 32 + ks * 8, d1, idesc, acc);  // (1,1)
+                        if (prm.tile_mask & 1)
+                            tcgen05_mma_tf32_ts(tmem_base, Ta + ks * 8, d0, idesc, acc);             // (0,0)
+                        if (prm.tile_mask & 2)
+                            tcgen05_mma_tf32_ts(tmem_base + 128, Ta + 32 + ks * 8, d0, idesc, acc);  // (1,0)
+                        if (prm.tile_mask & 4)
+                            tcgen05_mma_tf32_ts(tmem_base + 256, Ta + 32 + ks * 8, d1, idesc, acc);  // (1,1)
                     }
                 }
                 tcgen05_commit(&emptyB[b]);
@@ -763,6 +780,19 @@ k_dense_syrk_tc(const __grid_constant__ TmapSet tmaps, const Params prm) {
         const int h = w >> 2;
         const int my_col = (prm.mtiles == 2 ? h * 128 : 0) + q * 32 + lane;
         const uint32_t oper_sa = smem_u32(Oper), rring_sa = smem_u32(Rring);
+        // where this thread's column sits in a raw stage (row-major X)
+        uint32_t col_off, col_pitch;
+        bool col_ok;
+        if (prm.panel) {
+            const bool in_b = my_col >= 128;
+            col_ok = in_b ? (my_col - 128) < prm.wb : my_col < prm.wa;
+            col_pitch = (uint32_t)(in_b ? prm.wb : prm.wa) * 4u;
+            col_off = in_b ? (uint32_t)TILE_BYTES + (uint32_t)(my_col - 128) * 4u : (uint32_t)my_col * 4u;
+        } else {
+            col_ok = my_col < P;
+            col_pitch = (uint32_t)P * 4u;
+            col_off = (uint32_t)my_col * 4u;
+        }
         float gacc = 0.f;   // this thread's share of (X^T v)[my_col]
         int s = 0, b = 0;
         uint32_t ph = 0, phb = 0;
@@ -811,11 +841,14 @@ k_dense_syrk_tc(const __grid_constant__ TmapSet tmaps, const Params prm) {
                                         (uint32_t)(b * prm.mtiles + (my_col >> 7)) * 32;
                 const uint32_t vsm = (prm.has_v && sub == 0) ? dsm + 128u * 9u : 0u;
                 if (NSUB == 1 || sub == 0)
-                    scale_stage<0>(prm.f_order, prm.mtiles, R, P, dsm, Sp, t_addr, my_col, h, vsm, gacc);
+                    scale_stage<0>(prm.f_order, prm.mtiles, R, col_off, col_pitch, col_ok, dsm, Sp,
+                                   t_addr, my_col, h, vsm, gacc);
                 else if (sub == 1)
-                    scale_stage<1>(prm.f_order, prm.mtiles, R, P, dsm, Sp, t_addr, my_col, h, 0u, gacc);
+                    scale_stage<1>(prm.f_order, prm.mtiles, R, col_off, col_pitch, col_ok, dsm, Sp,
+                                   t_addr, my_col, h, 0u, gacc);
                 else
-                    scale_stage<2>(prm.f_order, prm.mtiles, R, P, dsm, Sp, t_addr, my_col, h, 0u, gacc);
+                    scale_stage<2>(prm.f_order, prm.mtiles, R, col_off, col_pitch, col_ok, dsm, Sp,
+                                   t_addr, my_col, h, 0u, gacc);
             }
             if (t == 0) tl_stamp(prm, it, 6);
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
@@ -837,10 +870,18 @@ k_dense_syrk_tc(const __grid_constant__ TmapSet tmaps, const Params prm) {
         tcgen05_fence_after();
         const int chalf = (warp - 2) >> 2;    // which half of the column chunks this warp drains
         if (my_count > 0) {
+            // local column -> global column of the result (legacy: identity)
+            auto gcol = [&](int c) -> int {
+                if (!prm.panel) return c < P ? c : -1;
+                if (c < 128) return c < prm.wa ? prm.a0 + c : -1;
+                return (c - 128) < prm.wb ? prm.b0 + (c - 128) : -1;
+            };
+            const int ldo = prm.panel ? prm.ldo : P;
             int tile = 0;
             for (int mt = 0; mt < prm.mtiles; ++mt) {
                 for (int nt = 0; nt <= mt; ++nt, ++tile) {
-                    const int C = mt * 128 + q * 32 + lane;  // output column (= X column of A)
+                    if (prm.mtiles == 2 && !((prm.tile_mask >> tile) & 1)) continue;
+                    const int C = gcol(mt * 128 + q * 32 + lane);  // output column (= X column of A)
 #pragma unroll 1
                     for (int cc = 0; cc < (prm.dual_acc ? 4 : 2); ++cc) {
                         // dual_acc: the second accumulator tile (TMEM columns 128..255) holds the
@@ -859,9 +900,9 @@ k_dense_syrk_tc(const __grid_constant__ TmapSet tmaps, const Params prm) {
                         }
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
-                            const int Rr = nt * 128 + n0 + j;  // output row (= X column of B)
-                            if (Rr < P && C < P && C >= Rr)
-                                atomicAdd(&prm.out[(size_t)Rr * P + C], __uint_as_float(v[j]));
+                            const int Rr = gcol(nt * 128 + n0 + j);  // output row (= X column of B)
+                            if (Rr >= 0 && C >= Rr)
+                                atomicAdd(&prm.out[(size_t)Rr * ldo + C], __uint_as_float(v[j]));
                         }
                     }
                 }
@@ -931,7 +972,13 @@ static int device_cc_major() {
 }  // namespace tc
 
 bool dense_tc_eligible(int64_t n, int64_t p, int c_order, const void* X) {
-    if (p < 8 || p > 256) return false;
+    // p > 256 runs as passes over pairs of 128-column panels (TABMAT_B200_TC_MAX_P caps it)
+    static const int64_t max_p = [] {
+        const char* e = getenv("TABMAT_B200_TC_MAX_P");
+        int64_t v = e ? atoll(e) : 2048;
+        return v < 8 ? 8 : v;
+    }();
+    if (p < 8 || p > max_p) return false;
     // TMA: the pitch of the outer dimension must be a multiple of 16 bytes
     if (c_order ? (p % 4) != 0 : (n % 4) != 0) return false;
     static const bool f_off =
@@ -978,9 +1025,54 @@ static int launch_tc(const tc::TmapSet& tmaps, const tc::Params& prm, unsigned g
     return 0;
 }
 
+// one launch on two 128-column panels of a wider matrix (p > 256); see tc::Params::panel
+struct PanelSpec {
+    int a0, wa, b0, wb, mask;
+    int64_t p_full;
+};
+
+static int dense_sandwich_tc_launch(const float* X, int64_t n, int64_t p, int c_order, const float* d,
+                                    float* out, cudaStream_t st, const TcOneHot* oh, bool share_sm,
+                                    const FusedCrossParams* scatter, const float* v, float* vec_out,
+                                    const PanelSpec* ps);
+
 int dense_sandwich_tc_f32(const float* X, int64_t n, int64_t p, int c_order, const float* d,
                           float* out, cudaStream_t st, const TcOneHot* oh, bool share_sm,
                           const FusedCrossParams* scatter, const float* v, float* vec_out) {
+    if (p <= 256)
+        return dense_sandwich_tc_launch(X, n, p, c_order, d, out, st, oh, share_sm, scatter, v,
+                                        vec_out, nullptr);
+    // p > 256: 128-column panels.  Panel pairs (2m, 2m+1) give the three tiles of their 256 x 256
+    // diagonal block in one pass; every remaining cross tile (I, J), J < I, is one pass over the
+    // two panels that issues only that tile's MMAs.  Every pass streams 256 columns of X, so the
+    // traffic grows with the number of passes (6 for p = 512, 28 for p = 1024) - still an order
+    // of magnitude below the CUDA-core kernel, whose cost grows with p^2.
+    if (oh || scatter || v) return fail("dense_tc: p > 256 is a plain SYRK");
+    TM_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)(p * p), st));
+    const int np = (int)((p + 127) / 128);
+    auto width = [&](int I) { return (int)(I == np - 1 ? p - (int64_t)I * 128 : 128); };
+    for (int m = 0; 2 * m < np; ++m) {
+        const int A = 2 * m, B = 2 * m + 1;
+        PanelSpec ps{A * 128, width(A), B < np ? B * 128 : 0, B < np ? width(B) : 0, 7, p};
+        int rc = dense_sandwich_tc_launch(X, n, p, c_order, d, out, st, nullptr, false, nullptr,
+                                          nullptr, nullptr, &ps);
+        if (rc) return rc;
+    }
+    for (int I = 0; I < np; ++I)
+        for (int J = 0; J < I; ++J) {
+            if (J == I - 1 && (I & 1)) continue;   // inside a diagonal pair
+            PanelSpec ps{J * 128, width(J), I * 128, width(I), 2, p};
+            int rc = dense_sandwich_tc_launch(X, n, p, c_order, d, out, st, nullptr, false, nullptr,
+                                              nullptr, nullptr, &ps);
+            if (rc) return rc;
+        }
+    return symmetrize_from_upper<float>(out, p, st);
+}
+
+static int dense_sandwich_tc_launch(const float* X, int64_t n, int64_t p, int c_order, const float* d,
+                                    float* out, cudaStream_t st, const TcOneHot* oh, bool share_sm,
+                                    const FusedCrossParams* scatter, const float* v, float* vec_out,
+                                    const PanelSpec* ps) {
     using namespace tc;
     PFN_encodeTiled enc = get_encode();
     if (!enc) return fail("cuTensorMapEncodeTiled not available");
@@ -989,7 +1081,32 @@ int dense_sandwich_tc_f32(const float* X, int64_t n, int64_t p, int c_order, con
 
     TmapSet tmaps;
     memset(&tmaps, 0, sizeof(tmaps));
-    if (!c_order) {
+    const int64_t p_full = ps ? ps->p_full : p;
+    if (ps) {
+        p = ps->wb ? 128 + ps->wb : ps->wa;   // the kernel's local column count
+        auto enc_box = [&](CUtensorMap* m, int w) -> bool {
+            if (!c_order) {
+                cuuint64_t gdim[2] = {(cuuint64_t)n, (cuuint64_t)p_full};
+                cuuint64_t gstride[1] = {(cuuint64_t)n * sizeof(float)};
+                cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)w};
+                cuuint32_t estr[2] = {1, 1};
+                return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(X), gdim, gstride,
+                           box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+            }
+            cuuint64_t gdim[2] = {(cuuint64_t)p_full, (cuuint64_t)n};
+            cuuint64_t gstride[1] = {(cuuint64_t)p_full * sizeof(float)};
+            cuuint32_t box[2] = {(cuuint32_t)w, (cuuint32_t)BK};
+            cuuint32_t estr[2] = {1, 1};
+            return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(X), gdim, gstride, box,
+                       estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+        };
+        if (!enc_box(&tmaps.x, ps->wa)) return fail("cuTensorMapEncodeTiled failed (panel A)");
+        if (ps->wb && !enc_box(&tmaps.xb, ps->wb)) return fail("cuTensorMapEncodeTiled failed (panel B)");
+    } else if (!c_order) {
         // column-major X = (p x n) row-major: box of 32 consecutive rows (inner) x p columns
         cuuint64_t gdim[2] = {(cuuint64_t)n, (cuuint64_t)p};
         cuuint64_t gstride[1] = {(cuuint64_t)n * sizeof(float)};
@@ -1084,7 +1201,17 @@ int dense_sandwich_tc_f32(const float* X, int64_t n, int64_t p, int c_order, con
     }
     const int half = prm.mtiles * TILE_BYTES;
     prm.f_order = c_order ? 0 : 1;
+    prm.tile_mask = 7;
     prm.aux_off = (int)((BK * p * 4 + 127) / 128 * 128);
+    if (ps) {
+        prm.panel = 1;
+        prm.a0 = ps->a0, prm.wa = ps->wa, prm.b0 = ps->b0, prm.wb = ps->wb;
+        prm.ldo = (int)p_full;
+        prm.tile_mask = ps->mask;
+        // panel A box at 0, panel B box one tile (16 KB) further
+        prm.aux_off = ps->wb ? TILE_BYTES + (BK * ps->wb * 4 + 127) / 128 * 128
+                             : (BK * ps->wa * 4 + 127) / 128 * 128;
+    }
     prm.r_bytes = prm.aux_off + 128 + 8 * 128 + 128;   // X tile | d | 8 code vectors | v
     prm.has_v = v ? 1 : 0;
     prm.vec_out = vec_out;
@@ -1129,7 +1256,7 @@ int dense_sandwich_tc_f32(const float* X, int64_t n, int64_t p, int c_order, con
     prm.stagesR = stagesR;
     size_t smem = (size_t)stagesR * prm.r_bytes + fixed;
 
-    TM_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)(p * p), st));
+    if (!ps) TM_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)(p * p), st));
     long long grid = prm.num_row_tiles < sm_count() ? prm.num_row_tiles : sm_count();
     int rc;
     if (prm.nsub == 3) {
@@ -1149,6 +1276,7 @@ int dense_sandwich_tc_f32(const float* X, int64_t n, int64_t p, int c_order, con
         rc = launch_tc<1, 0, 1>(tmaps, prm, (unsigned)grid, smem, st);
     }
     if (rc) return rc;
+    if (ps) return 0;   // the caller mirrors the triangle once, after the last panel pass
     return symmetrize_from_upper<float>(out, p, st);
 }
 

@@ -237,3 +237,32 @@ def test_tf32x3_with_onehot_blocks_in_a_split_matrix(force_mode):
         errs[(mode, "onehot x dense")] = blk
     print("\nsplit f32, tf32 vs tf32x3:", {str(k): f"{v:.2e}" for k, v in errs.items()})
     assert errs[0] <= 1e-3 and errs[3] <= 5e-6 and errs[(3, "onehot x dense")] <= 5e-6
+
+
+@pytest.mark.parametrize("order", ["C", "F"])
+@pytest.mark.parametrize("n,p", [(5000, 260), (4100, 384), (3000, 512), (2500, 700), (36, 1028)])
+def test_tcgen05_syrk_wide_matrices_by_panels(n, p, order, force_mode):
+    """p > 256: passes over pairs of 128-column panels (diagonal pairs give three tiles, every
+    other cross tile is its own pass), ragged last panel, odd panel counts; C and F order
+    (dense_helpers-tmpl.cpp:266-308 handles any p in both orders)."""
+    from tests.gpu_runner import run_cuda
+
+    rng = np.random.default_rng(n + p)
+    X = rng.standard_normal((n, p)).astype(np.float32)
+    if order == "F":
+        X = np.asfortranarray(X)
+    d = rng.standard_normal(n).astype(np.float32)
+    rows = np.sort(rng.choice(n, size=max(1, n // 2), replace=False)).astype(np.int32)
+    cols = np.sort(rng.choice(p, size=p // 2, replace=False)).astype(np.int32)
+    Xd = X.astype(np.float64)
+    force_mode(2)
+    for r, c in ((None, None), (rows, None), (None, cols)):
+        got = run_cuda("dense_sandwich", dict(X=X, d=d, rows=r, cols=c))
+        Xs = Xd if c is None else Xd[:, c]
+        Xr, dr = (Xs, d) if r is None else (Xs[r], d[r])
+        ref = Xr.T @ (dr.astype(np.float64)[:, None] * Xr)
+        cases.assert_close(got, ref, np.float32, f"panels n={n} p={p} {order}")
+        assert np.array_equal(got, got.T)
+    force_mode(1)
+    core = run_cuda("dense_sandwich", dict(X=X, d=d, rows=None, cols=None))
+    cases.assert_close(core, Xd.T @ (d.astype(np.float64)[:, None] * Xd), np.float32, "cuda-core")
