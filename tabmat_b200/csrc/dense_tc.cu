@@ -1003,12 +1003,13 @@ int g_tc_scatter_warps = [] {
     int v = e ? atoi(e) : -1;
     return (v == 0 || v == 4 || v == 8) ? v : -1;
 }();
-// -1 = auto: 4 scatter warps when they only carry the run-aggregated categorical REDs (a few per
-// row tile: far below one RED per 500 cycles and warp), none when the per-non-zero REDs of
-// dense x sparse would ride along too (latency-bound, see above)
+// -1 = auto (= none, see below); 4 / 8 force the fused form
 static int tc_scatter_warps(bool with_sparse) {
-    if (g_tc_scatter_warps >= 0) return g_tc_scatter_warps;
-    return with_sparse ? 0 : 4;
+    (void)with_sparse;
+    // auto = none.  Measured (profiles/bench_r2c_*): even with only the run-aggregated categorical
+    // REDs the scatter warps slow the kernel 6.6 -> 30 ms - their per-tile global loads (codes,
+    // CSR slice) sit on the critical path of the raw-stage ring under a saturated memory system
+    return g_tc_scatter_warps >= 0 ? g_tc_scatter_warps : 0;
 }
 bool dense_tc_scatter_eligible(int64_t p, int n_cat, bool with_sparse) {
     return tc_scatter_warps(with_sparse) > 0 && p <= 128 && n_cat <= TC_SCATTER_MAX_CATS;

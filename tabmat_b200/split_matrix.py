@@ -356,7 +356,12 @@ class SplitMatrix(MatrixBase):
         with rows * (dense width) * sizeof <= 32 MB, so that a block of the dense operand stays in
         the 126 MB L2 while three blocks are in flight.  0 = do not build it (no single row-major
         dense block of a supported width, or TABMAT_B200_DXS=red)."""
-        if os.environ.get("TABMAT_B200_DXS") == "red":
+        # Measured at the benchmark shape (n = 4e7, 128 fp32 dense columns, ~3 non-zeros per row):
+        # gather 14.0-16.2 ms (16 / 32 / 64 MB blocks) against 11.5 ms for the RED form, so the
+        # split path keeps the REDs unless TABMAT_B200_DXS=gather; the stand-alone
+        # SparseMatrix.sandwich_dense (fp64, 5 non-zeros per row: 32 sector-ops per non-zero as
+        # REDs) is the case where the gather form wins (config C4: 8.4 ms vs 12.6 ms)
+        if os.environ.get("TABMAT_B200_DXS") != "gather":
             return 0
         dense = [m for m in self.matrices if isinstance(m, DenseMatrix)]
         if len(dense) != 1 or dense[0]._array.dtype != tdtype or not dense[0]._array.is_contiguous():
