@@ -876,6 +876,35 @@ def main():
         e2e_step()
     e2e_ms = timed_loop(e2e_step, args.steps)
 
+    # ---- fused IRLS pass, outside the timed region: Hessian + score from one
+    # pass over the dense block vs the reference's two calls
+    irls = None
+    if wl.key == "c5" and not os.environ.get("TABMAT_B200_BENCH_NO_IRLS"):
+        vvec = torch.randn(n_local, device=device, dtype=tdt)
+
+        def ev_time(fn, reps=3):
+            fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                fn()
+            e1.record()
+            e1.synchronize()
+            return e0.elapsed_time(e1) / reps
+
+        t_sand = ev_time(lambda: S.sandwich(d))
+        t_fused = ev_time(lambda: S.sandwich_and_transpose_matvec(d, vvec))
+        t_tmv = ev_time(lambda: S.transpose_matvec(vvec))
+        Hf, gf = S.sandwich_and_transpose_matvec(d, vvec)
+        gs = S.transpose_matvec(vvec)
+        irls = {"sandwich_ms": t_sand, "sandwich_and_transpose_matvec_ms": t_fused,
+                "separate_transpose_matvec_ms": t_tmv,
+                "fused_over_sandwich": t_fused / t_sand,
+                "score_fused_vs_separate_normwise": float(((gf - gs).abs().max() / gs.abs().max()).item()),
+                "note": "X.sandwich_and_transpose_matvec(d, v): Hessian and score of one IRLS step; the "
+                        "dense block's share of X^T v rides in the tcgen05 kernel's scale warps"}
+        del vvec, Hf, gf, gs
     if shared is not None:
         shared.close(unlink=rank == 0)
     fl = torch.tensor([float(flops_local), float(nnz_local)], device=device, dtype=torch.float64)
@@ -1043,6 +1072,8 @@ def main():
                 line["cpu_baseline"]["ms_extrapolated_to_full_n"] = cpu["ms_extrapolated_full"]
         if parity is not None:
             line["parity"] = parity
+        if irls is not None:
+            line["irls_step"] = irls
         if args.breakdown and bd is not None:
             for k, v in sorted(bd.items(), key=lambda kv: -kv[1]):
                 print(f"  {k:24s} {v:9.3f} ms", file=sys.stderr)
