@@ -425,30 +425,41 @@ k_cat_sparse_cols(const F* __restrict__ data, const int32_t* __restrict__ row_id
             F* tab = smem + (j - c0) * prm.slot;
             const int e0 = indptr[base + j], e1 = indptr[base + j + 1];
             // warp-uniform trip count (run_reduce needs whole warps)
-            for (int eb = e0 + (threadIdx.x & ~31); eb < e1; eb += CO_THREADS) {
-                const int e = eb + lane;
-                F dk = F(0);
-                int keys[NC];
-                F a = F(0);
-                if (e < e1) {
-                    a = data[e];
-                    fetch_row<F, NC, PK>(src, e, row_idx[e], dk, keys);
-                } else {
+            // two groups of CO_THREADS non-zeros per visit: the loads (and the dependent d
+            // gathers) of both are in flight before the first table update
+            constexpr int UC = 2;
+            for (int eb = e0 + (threadIdx.x & ~31); eb < e1; eb += UC * CO_THREADS) {
+                F dk[UC], a[UC];
+                int keys[UC][NC];
 #pragma unroll
-                    for (int c = 0; c < NC; ++c) keys[c] = -1;
+                for (int u = 0; u < UC; ++u) {
+                    const int e = eb + u * CO_THREADS + lane;
+                    dk[u] = F(0);
+                    a[u] = F(0);
+                    if (e < e1) {
+                        a[u] = data[e];
+                        fetch_row<F, NC, PK>(src, e, row_idx[e], dk[u], keys[u]);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < NC; ++c) keys[u][c] = -1;
+                    }
                 }
-                const F val0 = dk * a;
 #pragma unroll
-                for (int c = 0; c < NC; ++c) {
-                    int key = keys[c];
-                    F val = val0;
-                    bool head = true;
-                    if (prm.runs[c]) head = run_reduce<F, int>(key, val, lane);
-                    if (!head || key < 0) continue;
-                    if (prm.in_smem[c])
-                        atomicAdd(tab + prm.off[c] + (lane % prm.rep[c]) * prm.K[c] + key, val);
-                    else
-                        red_add(static_cast<F*>(prm.out[c]) + (int64_t)key * p_s + j, val);
+                for (int u = 0; u < UC; ++u) {
+                    if (eb + u * CO_THREADS >= e1) break;   // warp-uniform
+                    const F val0 = dk[u] * a[u];
+#pragma unroll
+                    for (int c = 0; c < NC; ++c) {
+                        int key = keys[u][c];
+                        F val = val0;
+                        bool head = true;
+                        if (prm.runs[c]) head = run_reduce<F, int>(key, val, lane);
+                        if (!head || key < 0) continue;
+                        if (prm.in_smem[c])
+                            atomicAdd(tab + prm.off[c] + (lane % prm.rep[c]) * prm.K[c] + key, val);
+                        else
+                            red_add(static_cast<F*>(prm.out[c]) + (int64_t)key * p_s + j, val);
+                    }
                 }
             }
         }
