@@ -292,10 +292,38 @@ class RowShardedMatrix:
         """sqrt(sum_k w_k (x_kj - mean_j)^2) over all shards: the local sums of squares are
         additive, so the local stds are squared, summed over the ranks and rooted again
         (dense_matrix.py:180-187 / sparse_matrix.py:305-315 per shard)."""
-        local = self.local._get_col_stds(weights_local, col_means)
-        if not isinstance(local, torch.Tensor):
-            local = torch.as_tensor(local)
-        return torch.sqrt(self._allreduce(local * local))
+        # Dense blocks use the centred form sum w (x - mean)^2 (dense.pyx:103-122), which IS
+        # additive over shards.  Sparse and categorical blocks use sum w x^2 - mean^2
+        # (sparse_matrix.py:305-315, categorical_matrix.py:655-672) with the GLOBAL mean: only
+        # the raw second moment is additive there (and a shard's share of it may well be below
+        # mean^2), so those columns are taken with a zero mean and the mean is subtracted once,
+        # after the allreduce.  One payload of 2p values.
+        def sq(x):
+            x = x if isinstance(x, torch.Tensor) else torch.as_tensor(x)
+            return x * x
+
+        centred = sq(self.local._get_col_stds(weights_local, col_means))
+        dense = self._dense_column_mask(centred.device)
+        if bool(dense.all()):
+            return torch.sqrt(self._allreduce(centred))
+        raw = sq(self.local._get_col_stds(weights_local, torch.zeros_like(col_means)))
+        both = self._allreduce(torch.stack([centred, raw]))
+        var = torch.where(dense, both[0], (both[1] - col_means * col_means).clamp_min(0))
+        return torch.sqrt(var)
+
+    def _dense_column_mask(self, device) -> torch.Tensor:
+        """True for the columns whose local ``_get_col_stds`` is the centred (additive) form."""
+        p = self.shape[1]
+        mat = getattr(self.local, "mat", self.local)   # RowSortedMatrix wraps a SplitMatrix
+        name = type(mat).__name__
+        if name in ("SparseMatrix", "CategoricalMatrix"):
+            return torch.zeros(p, dtype=torch.bool, device=device)
+        mask = torch.ones(p, dtype=torch.bool, device=device)
+        if name == "SplitMatrix":
+            for m, idx in zip(mat.matrices, mat.indices):
+                if type(m).__name__ != "DenseMatrix":
+                    mask[torch.as_tensor(np.asarray(idx), dtype=torch.int64, device=device)] = False
+        return mask
 
     def _global_sum(self, x_local: torch.Tensor, rows=None) -> torch.Tensor:
         """sum of x over the (restricted) rows of every shard, as a 1-element tensor."""

@@ -47,6 +47,15 @@ class _HostShard:
         return torch.sqrt(((self.X - col_means) ** 2 * weights[:, None]).sum(0))
 
 
+class SparseMatrix(_HostShard):
+    """Stand-in with the NON-additive std formula of the sparse / categorical blocks
+    (sqrt(max(0, sum w x^2 - mean^2)) with the global mean, sparse_matrix.py:305-315); the
+    class name is what RowShardedMatrix._dense_column_mask looks at."""
+
+    def _get_col_stds(self, weights, col_means):
+        return torch.sqrt(torch.clamp_min((self.X ** 2 * weights[:, None]).sum(0) - col_means ** 2, 0))
+
+
 def _worker(rank, world, port, n, p, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -90,6 +99,11 @@ def _worker(rank, world, port, n, p, q):
         # row-sharded standardize: moments by allreduce, corrections after the collective
         w = np.abs(rng.standard_normal(n))
         w /= w.sum()
+        Xoff = X + 3.0   # big means: a shard's second moment is far below mean^2
+        Ssp = RowShardedMatrix(SparseMatrix(Xoff[lo:hi]), n)
+        mu_off = torch.from_numpy(w @ Xoff)
+        np.testing.assert_allclose(Ssp._get_col_stds(torch.from_numpy(w[lo:hi]), mu_off).numpy(),
+                                   np.sqrt(w @ (Xoff - w @ Xoff) ** 2), rtol=1e-8)
         S = RowShardedMatrix(_HostShard(X[lo:hi]), n)
         for center, scale in ((True, True), (True, False), (False, True)):
             Z, means, stds = S.standardize(torch.from_numpy(w[lo:hi]), center, scale)
