@@ -456,6 +456,17 @@ int tm_split_sandwich_assemble_band_f64(const tm_block_desc* blocks, int n_block
                                         const double* workspace, double* out_band, int64_t ld,
                                         int64_t row0, int64_t row1, tm_stream_t stream);
 
+/* The same restricted to the blocks of `part` (1 = without a dense operand, 2 = with one; see
+ * the two-phase calls below): a rank of a row-sharded job overlaps the host copy of its band. */
+int tm_split_sandwich_assemble_part_band_f32(const tm_block_desc* blocks, int n_blocks,
+                                             const float* workspace, double* out_band, int64_t ld,
+                                             int part, int64_t row0, int64_t row1,
+                                             tm_stream_t stream);
+int tm_split_sandwich_assemble_part_band_f64(const tm_block_desc* blocks, int n_blocks,
+                                             const double* workspace, double* out_band, int64_t ld,
+                                             int part, int64_t row0, int64_t row1,
+                                             tm_stream_t stream);
+
 /* Two-phase form of the two calls above, for callers that want the result in HOST memory:
  * `part` 1 = the blocks without a dense operand (categorical / sparse self and cross blocks),
  * 2 = the blocks with one, 0 = all.  After blocks_part(1) + assemble_part(1) the finished

@@ -71,6 +71,7 @@ _SIGS = {
     "tm_split_sandwich_rmatvec_blocks": [P, N, I, P, P, P, I, P, P, P],
     "tm_split_sandwich_assemble": [P, N, P, P, I, P],
     "tm_split_sandwich_assemble_band": [P, N, P, P, I, I, I, P],
+    "tm_split_sandwich_assemble_part_band": [P, N, P, P, I, N, I, I, P],
     "tm_split_sandwich_blocks_part": [P, N, I, P, P, I, P, N, P],
     "tm_split_sandwich_assemble_part": [P, N, P, P, I, N, P],
     "tm_scatter_block": [P, I, I, P, P, P, I, N, P],

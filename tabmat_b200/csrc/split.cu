@@ -884,6 +884,22 @@ int tm_split_sandwich_assemble_band_f64(const tm_block_desc* blocks, int n_block
     return tmb::split_assemble<double>(blocks, n_blocks, workspace, out_band, ld, stream, 0, row0,
                                        row1);
 }
+int tm_split_sandwich_assemble_part_band_f32(const tm_block_desc* blocks, int n_blocks,
+                                             const float* workspace, double* out_band, int64_t ld,
+                                             int part, int64_t row0, int64_t row1,
+                                             tm_stream_t stream) {
+    if (row0 < 0 || row1 < row0) return tmb::fail("tm_split_sandwich_assemble_part_band: bad row range");
+    return tmb::split_assemble<float>(blocks, n_blocks, workspace, out_band, ld, stream, part, row0,
+                                      row1);
+}
+int tm_split_sandwich_assemble_part_band_f64(const tm_block_desc* blocks, int n_blocks,
+                                             const double* workspace, double* out_band, int64_t ld,
+                                             int part, int64_t row0, int64_t row1,
+                                             tm_stream_t stream) {
+    if (row0 < 0 || row1 < row0) return tmb::fail("tm_split_sandwich_assemble_part_band: bad row range");
+    return tmb::split_assemble<double>(blocks, n_blocks, workspace, out_band, ld, stream, part, row0,
+                                       row1);
+}
 int tm_memcpy2d_to_host(void* dst_host, int64_t dst_pitch, const void* src_dev, int64_t src_pitch,
                         int64_t width_bytes, int64_t height, tm_stream_t stream) {
     if (width_bytes <= 0 || height <= 0) return 0;

@@ -252,26 +252,22 @@ class RowShardedMatrix:
 
         if not hasattr(self.local, "_assemble_band_dev"):
             raise TypeError("sandwich_into_shared needs a SplitMatrix / RowSortedMatrix shard")
-        if not _dev.is_dev(d_local):
-            src = d_local if isinstance(d_local, torch.Tensor) else torch.from_numpy(d_local)
-            d_dev = torch.empty(src.shape, dtype=src.dtype, device=_dev.require_cuda())
-            d_dev.copy_(src, non_blocking=True)
-            d_local = d_dev
-        local_rows = shard_rows(rows, self.lo, self.hi)
-        ws = self.local._sandwich_blocks_dev(d_local, _dev.idx32(local_rows))
-        if ws is None:
-            raise TypeError("the local shard has no native block plan (mixed dtypes?)")
-        self._allreduce(ws)
         p = self.shape[1]
         r0, r1 = shard_bounds(p, self.world_size, self.rank)
-        band = self.local._assemble_band_dev(ws, r0, r1)
-        if r1 > r0:
-            dst = shared.array.ctypes.data + r0 * p * 8
-            check(lib.tm_memcpy2d_to_host(dst, p * 8, band.data_ptr(), p * 8, p * 8, r1 - r0,
-                                          _dev.stream_ptr()))
+
+        def reduce(ws):   # every rank keeps the sum: each one places its own band
+            if ws.numel():
+                self._allreduce(ws)
+            return True
+
+        # the two-phase path of SplitMatrix.sandwich_into, restricted to this rank's band: the
+        # blocks without the dense operand are reduced, placed and copied while the dense passes
+        # still run
+        self.local.sandwich_into(d_local, shared.array, shard_rows(rows, self.lo, self.hi),
+                                 reduce=reduce, band=(r0, r1))
         fence = getattr(self, "_fence", None)
         if fence is None:
-            fence = self._fence = torch.zeros(1, dtype=torch.float32, device=ws.device)
+            fence = self._fence = torch.zeros(1, dtype=torch.float32, device=_dev.require_cuda())
         self._allreduce(fence)
         return shared.array
 

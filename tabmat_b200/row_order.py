@@ -180,7 +180,7 @@ class RowSortedMatrix(MatrixBase):
     def _rmatvec_assemble_dev(self, vec, cols=None):
         return self.mat._rmatvec_assemble_dev(vec, cols)
 
-    def sandwich_into(self, d, out, rows=None, reduce=None):
+    def sandwich_into(self, d, out, rows=None, reduce=None, band=None):
         """Host-buffer form of :meth:`sandwich` (see ``SplitMatrix.sandwich_into``): ``d`` from
         host or device memory in the caller's row order, the result into the host array ``out``."""
         if _dev.is_dev(d):
@@ -190,7 +190,8 @@ class RowSortedMatrix(MatrixBase):
             d_t = torch.empty(src.shape, dtype=src.dtype, device=_dev.require_cuda())
             d_t.copy_(src, non_blocking=True)
         check_sandwich_compatible(self, d_t)
-        return self.mat._sandwich_into_dev(self._gather(d_t), self._rows_in(rows), out, reduce)
+        return self.mat._sandwich_into_dev(self._gather(d_t), self._rows_in(rows), out, reduce,
+                                           band)
 
     def _sandwich_blocks_dev(self, d_t: torch.Tensor, rows_t):
         """Flat block workspace (for the row-sharded allreduce, distributed.py)."""

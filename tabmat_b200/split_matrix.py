@@ -539,7 +539,7 @@ class SplitMatrix(MatrixBase):
             self.__dict__["_col_runs"] = runs
         return runs
 
-    def sandwich_into(self, d, out, rows=None, reduce=None):
+    def sandwich_into(self, d, out, rows=None, reduce=None, band=None):
         """``out[:] = X[rows].T @ diag(d[rows]) @ X[rows]`` for a HOST float64 ``out`` (p x p,
         C-contiguous numpy array or CPU tensor; pinned memory gives full PCIe speed).
 
@@ -558,12 +558,14 @@ class SplitMatrix(MatrixBase):
             d_t = torch.empty(src.shape, dtype=src.dtype, device=_dev.require_cuda())
             d_t.copy_(src, non_blocking=True)
         check_sandwich_compatible(self, d_t)
-        return self._sandwich_into_dev(d_t, _dev.idx32(rows), out, reduce)
+        return self._sandwich_into_dev(d_t, _dev.idx32(rows), out, reduce, band)
 
-    def _sandwich_into_dev(self, d_t: torch.Tensor, rows_t, out, reduce=None):
+    def _sandwich_into_dev(self, d_t: torch.Tensor, rows_t, out, reduce=None, band=None):
         """``reduce(ws_slice) -> bool`` (row-sharded callers): sum the slice of the flat block
         workspace over the ranks in place and tell whether this rank holds the result (and so
-        places and copies it)."""
+        places and copies it).  ``band = (r0, r1)``: this rank places and copies only rows
+        ``[r0, r1)`` of the result (into the same rows of ``out``, e.g. a host buffer shared by
+        the ranks); needs the two-phase path."""
         p = self.shape[1]
         if isinstance(out, torch.Tensor):
             ok = (not out.is_cuda) and out.dtype == torch.float64 and out.is_contiguous()
@@ -578,10 +580,25 @@ class SplitMatrix(MatrixBase):
         row_bytes = p * 8
         suf = _dev.suffix(d_t.dtype)
 
+        b0, b1 = (0, p) if band is None else (int(band[0]), int(band[1]))
+
         def copy2d(buf, r0, r1, c0, c1, stream):
-            o = (r0 * p + c0) * 8
-            check(lib.tm_memcpy2d_to_host(out_ptr + o, row_bytes, buf.data_ptr() + o, row_bytes,
+            """rows [r0, r1) x columns [c0, c1) of the result, clipped to this rank's band;
+            ``buf`` holds the band (its row 0 = result row b0)."""
+            r0, r1 = max(r0, b0), min(r1, b1)
+            if r1 <= r0:
+                return
+            check(lib.tm_memcpy2d_to_host(out_ptr + (r0 * p + c0) * 8, row_bytes,
+                                          buf.data_ptr() + ((r0 - b0) * p + c0) * 8, row_bytes,
                                           (c1 - c0) * 8, r1 - r0, stream))
+
+        def assemble(ws_t, buf, part):
+            if band is None:
+                check(fn("tm_split_sandwich_assemble_part", suf)(descs, nb, _dev.ptr(ws_t),
+                                                                _dev.ptr(buf), p, part, st))
+            elif b1 > b0:
+                check(fn("tm_split_sandwich_assemble_part_band", suf)(
+                    descs, nb, _dev.ptr(ws_t), _dev.ptr(buf), p, part, b0, b1, st))
 
         plan = self._native_plan(d_t.dtype)
         runs = self._column_runs()
@@ -591,6 +608,16 @@ class SplitMatrix(MatrixBase):
         # workspace to be one contiguous piece: true when the dense block comes first
         two_phase = (plan is not None and dense_runs and other_runs and len(runs) <= 6
                      and (reduce is None or isinstance(self.matrices[0], DenseMatrix)))
+        if not two_phase and band is not None:
+            # one phase, this rank's band only
+            ws = self._sandwich_blocks_dev(d_t, rows_t)
+            if ws is None:
+                raise TypeError("band output needs a native block plan (one dtype for all blocks)")
+            if reduce is not None and not reduce(ws):
+                return None
+            res = self._assemble_band_dev(ws, b0, b1)
+            copy2d(res, b0, b1, 0, p, st)
+            return out
         if not two_phase:
             if reduce is not None and plan is not None:
                 ws = self._sandwich_blocks_dev(d_t, rows_t)
@@ -619,9 +646,8 @@ class SplitMatrix(MatrixBase):
         buf = None
         cs = None
         if mine:
-            buf = torch.empty((p, p), dtype=torch.float64, device=d_t.device)
-            check(fn("tm_split_sandwich_assemble_part", suf)(descs, nb, _dev.ptr(ws),
-                                                            _dev.ptr(buf), p, 1, st))
+            buf = torch.empty((b1 - b0, p), dtype=torch.float64, device=d_t.device)
+            assemble(ws, buf, 1)
             cs = self.__dict__.get("_copy_stream")
             if cs is None:
                 cs = self.__dict__["_copy_stream"] = torch.cuda.Stream()
@@ -635,8 +661,7 @@ class SplitMatrix(MatrixBase):
             reduce(ws[:head])
         if not mine:
             return None
-        check(fn("tm_split_sandwich_assemble_part", suf)(descs, nb, _dev.ptr(ws), _dev.ptr(buf), p,
-                                                        2, st))
+        assemble(ws, buf, 2)
         for (r0, r1, _) in dense_runs:
             copy2d(buf, r0, r1, 0, p, st)
         for (r0, r1, _) in other_runs:
