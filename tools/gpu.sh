@@ -53,7 +53,12 @@ case "$mode" in
     timeout -s KILL ${T:-1200} ncu --set full --clock-control none --import-source on -k "regex:$rx" \
       -s ${S:-0} -c ${C:-4} -o gpurun_out/prof_$TAG -f python ${PROG:-bench.py --steps 1 --warmup 1 --no-cpu-baseline} "$@" \
       > gpurun_out/ncu_$TAG.log 2>&1
-    echo "ncu rc=$?"; tail -3 gpurun_out/ncu_$TAG.log | cut -c1-300; ls -la gpurun_out/prof_$TAG.ncu-rep ;;
+    echo "ncu rc=$?"; tail -3 gpurun_out/ncu_$TAG.log | cut -c1-300; ls -la gpurun_out/prof_$TAG.ncu-rep
+    # gpurun_out/ is capped at 64 MiB: keep the raw-metric CSV (every metric of every captured
+    # launch) and drop the report unless KEEP_REP=1
+    ncu -i gpurun_out/prof_$TAG.ncu-rep --page raw --csv > gpurun_out/ncu_${TAG}_raw.csv 2>/dev/null
+    if [ -z "${KEEP_REP:-}" ]; then rm -f gpurun_out/prof_$TAG.ncu-rep; fi
+    ls -la gpurun_out/ncu_${TAG}_raw.csv ;;
   sweep)
     var=$1; shift
     for v in "$@"; do
