@@ -501,7 +501,7 @@ int cat_dense_gather_f32(const float* X, int64_t p, const float* d, const int32_
 // ---------------------------------------------------------------------------------------
 constexpr int GD_THREADS = 128;
 
-template <typename F, int NV>
+template <typename F, int NV, int U>
 __global__ void __launch_bounds__(GD_THREADS)
 k_csc_dense_gather(const F* __restrict__ X, int P, const F* __restrict__ d,
                    const F* __restrict__ bdata, const int32_t* __restrict__ brow,
@@ -509,8 +509,7 @@ k_csc_dense_gather(const F* __restrict__ X, int P, const F* __restrict__ d,
                    F* __restrict__ out, unsigned* __restrict__ progress, int lag) {
     using V = Vec<F>;
     using VT = typename V::T;
-    constexpr int W = V::W;
-    constexpr int U = 8;   // X rows in flight per warp
+    constexpr int W = V::W;   // U = X rows in flight per warp
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int gw = (int)(((int64_t)blockIdx.x * GD_THREADS + threadIdx.x) >> 5);
@@ -586,16 +585,30 @@ int csc_dense_gather(const F* X, int64_t p, const F* d, const F* bdata, const in
     if (prog.err != cudaSuccess) return fail_cuda(prog.err, "scratch");
     TM_CUDA(cudaMemsetAsync(prog.p, 0, sizeof(unsigned) * (size_t)n_blocks, st));
     const int nv = (int)((p / W + 31) / 32);
+    // rows in flight per warp (TABMAT_B200_GATHER_U: 8 default, 16) and CTAs per SM
+    // (TABMAT_B200_GATHER_CTAS, default 4): the kernel is bound by L2 latency x bytes in flight
+    static const int u_rows = [] {
+        const char* e = getenv("TABMAT_B200_GATHER_U");
+        return (e && atoi(e) == 16) ? 16 : 8;
+    }();
+    static const int cta_cap = [] {
+        const char* e = getenv("TABMAT_B200_GATHER_CTAS");
+        int v = e ? atoi(e) : 4;
+        return v < 1 ? 1 : (v > 16 ? 16 : v);
+    }();
     // one resident wave, the same number of columns for every warp
     int per_sm = 0;
-    if (nv == 1)
-        TM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_csc_dense_gather<F, 1>,
+    if (nv == 1 && u_rows == 16)
+        TM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_csc_dense_gather<F, 1, 16>,
+                                                              GD_THREADS, 0));
+    else if (nv == 1)
+        TM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_csc_dense_gather<F, 1, 8>,
                                                               GD_THREADS, 0));
     else
-        TM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_csc_dense_gather<F, 2>,
+        TM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_csc_dense_gather<F, 2, 8>,
                                                               GD_THREADS, 0));
     if (per_sm < 1) per_sm = 1;
-    if (per_sm > 4) per_sm = 4;
+    if (per_sm > cta_cap) per_sm = cta_cap;
     const int64_t max_warps = (int64_t)sm_count() * per_sm * (GD_THREADS / 32);
     const int cpw = (int)((p_s + max_warps - 1) / max_warps);
     const int64_t warps = (p_s + cpw - 1) / cpw;
@@ -605,12 +618,16 @@ int csc_dense_gather(const F* X, int64_t p, const F* d, const F* bdata, const in
         int v = e ? atoi(e) : 2;
         return v < 1 ? 1 : v;
     }();
-    if (nv == 1)
-        k_csc_dense_gather<F, 1><<<grid, GD_THREADS, 0, st>>>(
+    if (nv == 1 && u_rows == 16)
+        k_csc_dense_gather<F, 1, 16><<<grid, GD_THREADS, 0, st>>>(
+            X, (int)p, d, bdata, brow, bptr, (int)p_s, (int)n_blocks, cpw, out,
+            prog.as<unsigned>(), lag);
+    else if (nv == 1)
+        k_csc_dense_gather<F, 1, 8><<<grid, GD_THREADS, 0, st>>>(
             X, (int)p, d, bdata, brow, bptr, (int)p_s, (int)n_blocks, cpw, out,
             prog.as<unsigned>(), lag);
     else
-        k_csc_dense_gather<F, 2><<<grid, GD_THREADS, 0, st>>>(
+        k_csc_dense_gather<F, 2, 8><<<grid, GD_THREADS, 0, st>>>(
             X, (int)p, d, bdata, brow, bptr, (int)p_s, (int)n_blocks, cpw, out,
             prog.as<unsigned>(), lag);
     TM_LAUNCHED();
