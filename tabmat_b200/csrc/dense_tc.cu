@@ -96,6 +96,9 @@ struct Params {
     // in the ldo x ldo result.  The host loops over panel pairs.
     int panel, a0, b0, wa, wb, ldo, tile_mask;
     int sc_ncat;                       // <= TC_SCATTER_MAX_CATS
+    int sc_staged;    // 1: the scatter blocks' code vectors are TMA-staged next to the one-hot
+                      // ones (slots oh_ncat .. oh_ncat + sc_ncat - 1 of the stage): the scatter
+                      // warps then touch no global memory except for their REDs
     const int32_t* sc_codes[TC_SCATTER_MAX_CATS];
     float* sc_tab[TC_SCATTER_MAX_CATS];
     int sc_K[TC_SCATTER_MAX_CATS];
@@ -304,10 +307,15 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
 // the MMAs), the d-scaled values to this lane's TMEM lane of the T operand (M side).  All 16
 // loads are issued before the math.  Lanes with c >= P write nothing to S (those rows stay
 // zero) and zeros to T (tcgen05.st is warp-collective).
-template <int SUB>
-__device__ __forceinline__ void scale_col4(uint32_t r0, uint32_t pitch, bool ok, uint32_t dsm,
+// PITCH: the row pitch of the raw stage in bytes as a compile-time constant (512 = 128 columns,
+// 1024 = 256 columns: the 16 row offsets of the transposing loads fold into the LDS immediates,
+// which takes ~a quarter of the scale warps' instructions away - they are what paces the kernel
+// at p = 256, ncu: issue slots 63 % busy, tensor pipe 47 %), or 0 = use `pitch_rt`
+template <int SUB, int PITCH>
+__device__ __forceinline__ void scale_col4(uint32_t r0, uint32_t pitch_rt, bool ok, uint32_t dsm,
                                            uint32_t Sp, uint32_t t_addr, int c, int kb, int ks,
                                            uint32_t vsm, float& gacc) {
+    const uint32_t pitch = PITCH ? (uint32_t)PITCH : pitch_rt;
     // r0: shared address of element (row 0, column c) of the raw stage, pitch: bytes per row;
     // dsm, Sp: shared addresses of the stage's d vector and of the S tile
     constexpr bool s_lo = SUB == 1, t_lo = SUB == 2;   // 3xTF32 sub-pass: which operand is the residual
@@ -396,10 +404,19 @@ __device__ __forceinline__ void scale_stage(bool f_order, int mtiles, uint32_t R
             scale_col4_f<SUB>(R, ok, dsm, Sp, t_addr, my_col, 4, 1, vsm, gacc);
         }
     } else if (mtiles == 1) {
-        scale_col4<SUB>(R + col_off, pitch, ok, dsm, Sp, t_addr, my_col, h, 2, vsm, gacc);
+        if (pitch == 512)
+            scale_col4<SUB, 512>(R + col_off, pitch, ok, dsm, Sp, t_addr, my_col, h, 2, vsm, gacc);
+        else
+            scale_col4<SUB, 0>(R + col_off, pitch, ok, dsm, Sp, t_addr, my_col, h, 2, vsm, gacc);
+    } else if (pitch == 1024) {
+        scale_col4<SUB, 1024>(R + col_off, pitch, ok, dsm, Sp, t_addr, my_col, 0, 1, vsm, gacc);
+        scale_col4<SUB, 1024>(R + col_off, pitch, ok, dsm, Sp, t_addr, my_col, 4, 1, vsm, gacc);
+    } else if (pitch == 512) {
+        scale_col4<SUB, 512>(R + col_off, pitch, ok, dsm, Sp, t_addr, my_col, 0, 1, vsm, gacc);
+        scale_col4<SUB, 512>(R + col_off, pitch, ok, dsm, Sp, t_addr, my_col, 4, 1, vsm, gacc);
     } else {
-        scale_col4<SUB>(R + col_off, pitch, ok, dsm, Sp, t_addr, my_col, 0, 1, vsm, gacc);
-        scale_col4<SUB>(R + col_off, pitch, ok, dsm, Sp, t_addr, my_col, 4, 1, vsm, gacc);
+        scale_col4<SUB, 0>(R + col_off, pitch, ok, dsm, Sp, t_addr, my_col, 0, 1, vsm, gacc);
+        scale_col4<SUB, 0>(R + col_off, pitch, ok, dsm, Sp, t_addr, my_col, 4, 1, vsm, gacc);
     }
 }
 
@@ -506,8 +523,9 @@ k_dense_syrk_tc(const __grid_constant__ TmapSet tmaps, const Params prm) {
         if (lane == 0) {
             int s = 0;
             uint32_t ph = 0;
+            const int n_codes = prm.oh_ncat + (prm.sc_staged ? prm.sc_ncat : 0);
             const uint32_t tx = (uint32_t)(BK * (prm.panel ? prm.wa + prm.wb : P) * 4) +
-                                128u * (1u + (uint32_t)prm.oh_ncat + (prm.has_v ? 1u : 0u));
+                                128u * (1u + (uint32_t)n_codes + (prm.has_v ? 1u : 0u));
             for (int it = 0; it < my_count; ++it, ++s) {
                 if (s == SR) {
                     s = 0;
@@ -532,7 +550,7 @@ k_dense_syrk_tc(const __grid_constant__ TmapSet tmaps, const Params prm) {
                 else
                     tma_load_2d(stage, &tmaps.x, &full[s], 0, (int)k0);
                 tma_load_1d(aux, &tmaps.d, &full[s], (int)k0);
-                for (int c = 0; c < prm.oh_ncat; ++c)
+                for (int c = 0; c < n_codes; ++c)
                     tma_load_1d(aux + 128u * (uint32_t)(c + 1), &tmaps.codes[c], &full[s], (int)k0);
                 if (prm.has_v) tma_load_1d(aux + 128u * 9u, &tmaps.v, &full[s], (int)k0);
             }
@@ -630,6 +648,92 @@ k_dense_syrk_tc(const __grid_constant__ TmapSet tmaps, const Params prm) {
         const int nc = prm.sc_ncat;
         const bool has_sp = prm.out_sparse != nullptr;
         const uint32_t rring_sa = smem_u32(Rring);
+        if (prm.sc_staged && !has_sp) {
+            // ---- categorical blocks only, codes staged by TMA: no global load anywhere in this
+            // warp, so nothing but the raw-stage ring paces it.  All lanes read the same d / code
+            // words (broadcast LDS), the run logic is warp-uniform and needs no shuffles.  Each
+            // block keeps TWO accumulator sets and flushes them alternately: a RED holds its
+            // source registers for hundreds of cycles, the other set takes the next run meanwhile.
+            float* tabs[NCM];
+            float4 accA[NCM], accB[NCM];
+            int curc[NCM];
+            bool useB[NCM];
+#pragma unroll
+            for (int c = 0; c < NCM; ++c) {
+                curc[c] = -1;
+                useB[c] = false;
+                accA[c] = accB[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+                tabs[c] = nullptr;
+                if (c < nc)
+                    tabs[c] = prm.sc_tab[c] +
+                              (size_t)((blockIdx.x * SCW + ws) % prm.sc_copies[c]) * (size_t)prm.sc_K[c] * P +
+                              lane * 4;
+            }
+            int s2 = 0;
+            uint32_t ph2 = 0;
+            for (int it = 0; it < my_count; ++it, ++s2) {
+                if (s2 == SR) {
+                    s2 = 0;
+                    ph2 ^= 1;
+                }
+                if (lane == 0) mbar_wait(&full[s2], ph2);
+                __syncwarp();
+                const uint32_t stage = rring_sa + (uint32_t)s2 * (uint32_t)prm.r_bytes;
+                const uint32_t aux = stage + (uint32_t)prm.aux_off;
+                float4 y[RPW];
+                float dq[RPW];
+                int cq[NCM][RPW];
+#pragma unroll
+                for (int q = 0; q < RPW; ++q) {
+                    y[q] = lane_ok ? lds_f32x4(stage + (uint32_t)(r0 + q) * (uint32_t)P * 4u + (uint32_t)lane * 16u)
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+                    dq[q] = lds_f32(aux + (uint32_t)(r0 + q) * 4u);
+                }
+#pragma unroll
+                for (int c = 0; c < NCM; ++c)
+#pragma unroll
+                    for (int q = 0; q < RPW; ++q)
+                        cq[c][q] = c < nc ? lds_s32(aux + 128u * (uint32_t)(1 + prm.oh_ncat + c) +
+                                                    (uint32_t)(r0 + q) * 4u) - prm.sc_df[c]
+                                          : -1;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&emptyR[s2]);  // the raw stage can be refilled
+#pragma unroll
+                for (int q = 0; q < RPW; ++q) {
+                    const float dk = dq[q];
+                    if (dk == 0.f) continue;  // also the rows past the end (TMA zero fill)
+                    const float4 yy = make_float4(y[q].x * dk, y[q].y * dk, y[q].z * dk, y[q].w * dk);
+#pragma unroll
+                    for (int c = 0; c < NCM; ++c) {
+                        if (c >= nc) continue;
+                        const int code = cq[c][q] < 0 ? -1 : cq[c][q];
+                        if (code != curc[c]) {  // warp-uniform: a run of block c ends here
+                            if (curc[c] >= 0 && lane_ok) {
+                                if (useB[c]) red_add_v4(tabs[c] + (size_t)curc[c] * P, accB[c]);
+                                else red_add_v4(tabs[c] + (size_t)curc[c] * P, accA[c]);
+                            }
+                            useB[c] = !useB[c];   // the next run accumulates in the other set
+                            if (useB[c]) accB[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            else accA[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            curc[c] = code;
+                        }
+                        if (code >= 0) {
+                            if (useB[c]) {
+                                accB[c].x += yy.x, accB[c].y += yy.y, accB[c].z += yy.z, accB[c].w += yy.w;
+                            } else {
+                                accA[c].x += yy.x, accA[c].y += yy.y, accA[c].z += yy.z, accA[c].w += yy.w;
+                            }
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < NCM; ++c)
+                if (c < nc && curc[c] >= 0 && lane_ok) {
+                    if (useB[c]) red_add_v4(tabs[c] + (size_t)curc[c] * P, accB[c]);
+                    else red_add_v4(tabs[c] + (size_t)curc[c] * P, accA[c]);
+                }
+        } else {
         float* tab[NCM];
         float4 acc[NCM];
         int cur[NCM];
@@ -760,6 +864,7 @@ k_dense_syrk_tc(const __grid_constant__ TmapSet tmaps, const Params prm) {
 #pragma unroll
         for (int c = 0; c < NCM; ++c)
             if (c < nc && cur[c] >= 0 && lane_ok) red_add_v4(tab[c] + (size_t)cur[c] * P, acc[c]);
+        }   // general (sparse + global-load) path
     } else {
         // ===== scale warps, then epilogue =====
         const int w = warp - 2;                // 0..7
@@ -1005,11 +1110,20 @@ int g_tc_scatter_warps = [] {
 }();
 // -1 = auto (= none, see below); 4 / 8 force the fused form
 static int tc_scatter_warps(bool with_sparse) {
-    (void)with_sparse;
-    // auto = none.  Measured (profiles/bench_r2c_*): even with only the run-aggregated categorical
-    // REDs the scatter warps slow the kernel 6.6 -> 30 ms - their per-tile global loads (codes,
-    // CSR slice) sit on the critical path of the raw-stage ring under a saturated memory system
-    return g_tc_scatter_warps >= 0 ? g_tc_scatter_warps : 0;
+    // auto: none when the per-non-zero REDs of dense x sparse would ride along (latency-bound,
+    // above).  With only the run-aggregated categorical REDs left (dense x sparse computed by
+    // the gather kernel) the first form still ran 30 ms instead of 6.6 (profiles/bench_r2c_*):
+    // its per-tile global loads of the codes sat on the critical path of the raw-stage ring; the
+    // codes are now staged by TMA (Params::sc_staged) and TABMAT_B200_TC_SCW_CATS picks the warp
+    // count for that form (default 4)
+    if (g_tc_scatter_warps >= 0) return g_tc_scatter_warps;
+    if (with_sparse) return 0;
+    static const int cats = [] {
+        const char* e = getenv("TABMAT_B200_TC_SCW_CATS");
+        int v = e ? atoi(e) : 4;
+        return (v == 0 || v == 4 || v == 8) ? v : 4;
+    }();
+    return cats;
 }
 bool dense_tc_scatter_eligible(int64_t p, int n_cat, bool with_sparse) {
     return tc_scatter_warps(with_sparse) > 0 && p <= 128 && n_cat <= TC_SCATTER_MAX_CATS;
@@ -1230,6 +1344,20 @@ static int dense_sandwich_tc_launch(const float* X, int64_t n, int64_t p, int c_
             prm.sc_K[c] = scatter->K[c];
             prm.sc_copies[c] = scatter->copies[c] > 0 ? scatter->copies[c] : 1;
             prm.sc_df[c] = scatter->drop_first[c];
+        }
+        // cats only: stage their code vectors by TMA after the one-hot ones when the 8 slots
+        // suffice and the vectors are 16-byte aligned
+        if (!scatter->out_sparse && prm.oh_ncat + scatter->n_cat <= 8) {
+            bool ok = true;
+            for (int c = 0; c < scatter->n_cat; ++c)
+                ok = ok && (reinterpret_cast<uintptr_t>(scatter->codes[c]) & 15) == 0;
+            if (ok) {
+                for (int c = 0; c < scatter->n_cat; ++c)
+                    if (!encode_1d(&tmaps.codes[prm.oh_ncat + c], scatter->codes[c],
+                                   CU_TENSOR_MAP_DATA_TYPE_INT32))
+                        return fail("cuTensorMapEncodeTiled failed (scatter codes)");
+                prm.sc_staged = 1;
+            }
         }
         prm.csr_data = static_cast<const float*>(scatter->csr_data);
         prm.csr_indices = scatter->csr_indices;

@@ -324,7 +324,7 @@ class SparseMatrix(MatrixBase):
         if (not B_t.is_contiguous() or q <= 0 or q % width or q > 64 * width
                 or B_t.data_ptr() % 16 or not self._csr.nnz):
             return None
-        cap = int(os.environ.get("TABMAT_B200_GATHER_MB", "32")) * (1 << 20)
+        cap = int(os.environ.get("TABMAT_B200_GATHER_MB", "64")) * (1 << 20)
         rows_blk = 1 << (max(1024, cap // (q * fsize)).bit_length() - 1)
         if n <= rows_blk + rows_blk // 2:
             return None

@@ -371,7 +371,7 @@ class SplitMatrix(MatrixBase):
         width = 16 // fsize
         if q <= 0 or q % width or q > 64 * width:
             return 0
-        cap = int(os.environ.get("TABMAT_B200_GATHER_MB", "32")) * (1 << 20)
+        cap = int(os.environ.get("TABMAT_B200_GATHER_MB", "64")) * (1 << 20)
         rows = max(1024, cap // (q * fsize))
         return 1 << (rows.bit_length() - 1)
 
