@@ -125,6 +125,15 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// Arrive WITHOUT release semantics.  The default (.release) makes the warp wait until its prior
+// memory operations are performed - including global REDs still in flight (~2000 cycles each
+// under load), which is what made the scatter warps of the fused form 4-8x slower than the MMA
+// pipeline (measured: 27.7 ms with 4 warps although they issued < 2 REDs per tile).  The only
+// ordering the raw-stage ring needs from a consumer is "my shared-memory READS of the stage are
+// done", which the callers guarantee by arriving after the loaded values have been used.
+__device__ __forceinline__ void mbar_arrive_relaxed(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t addr = smem_u32(bar);
     asm volatile(
@@ -696,8 +705,6 @@ k_dense_syrk_tc(const __grid_constant__ TmapSet tmaps, const Params prm) {
                         cq[c][q] = c < nc ? lds_s32(aux + 128u * (uint32_t)(1 + prm.oh_ncat + c) +
                                                     (uint32_t)(r0 + q) * 4u) - prm.sc_df[c]
                                           : -1;
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&emptyR[s2]);  // the raw stage can be refilled
 #pragma unroll
                 for (int q = 0; q < RPW; ++q) {
                     const float dk = dq[q];
@@ -726,6 +733,10 @@ k_dense_syrk_tc(const __grid_constant__ TmapSet tmaps, const Params prm) {
                         }
                     }
                 }
+                // every value read from the stage has been consumed: hand it back (relaxed: do
+                // not wait for the REDs above)
+                __syncwarp();
+                if (lane == 0) mbar_arrive_relaxed(&emptyR[s2]);
             }
 #pragma unroll
             for (int c = 0; c < NCM; ++c)
@@ -809,8 +820,6 @@ k_dense_syrk_tc(const __grid_constant__ TmapSet tmaps, const Params prm) {
                                : make_float4(0.f, 0.f, 0.f, 0.f);
                 dq[q] = lds_f32(stage + (uint32_t)prm.aux_off + (uint32_t)(r0 + q) * 4u);
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&emptyR[s]);  // the raw stage can be refilled
             const int ebase = __shfl_sync(FULL, ip_cur, 0);
 #pragma unroll
             for (int q = 0; q < RPW; ++q) {
@@ -854,6 +863,10 @@ k_dense_syrk_tc(const __grid_constant__ TmapSet tmaps, const Params prm) {
                                    make_float4(yy.x * a, yy.y * a, yy.z * a, yy.w * a));
                 }
             }
+            // the rows read from the stage have been consumed: hand it back (relaxed arrive: do
+            // not wait for the REDs above)
+            __syncwarp();
+            if (lane == 0) mbar_arrive_relaxed(&emptyR[s]);
             ip_cur = ip_nxt;
             ip_nxt = ip_nn;
             idx_cur = idx_nxt;
