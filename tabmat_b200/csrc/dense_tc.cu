@@ -148,6 +148,33 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
+// The same with a suspend-time hint: the waiting thread sleeps in hardware until the phase
+// completes (or the hint expires) instead of re-issuing TRYWAIT + BRA every few cycles.  ncu on
+// the fused form showed 4e8 executions of one such spin loop against 1e6 for the useful
+// instructions: the spinning scale warps were taking the issue slots of their scheduler away
+// from the scatter warp that shares it.  Used by the scale / scatter warps (many waiters); the
+// single MMA issuer and the producer keep the tight form.
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
+    uint32_t addr = smem_u32(bar);
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "WAIT_LOOP_S:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"
+        "@P1 bra DONE_S;\n\t"
+        "bra WAIT_LOOP_S;\n\t"
+        "DONE_S:\n\t"
+        "}" ::"r"(addr),
+        "r"(parity), "r"(20000u)
+        : "memory");
+}
+template <bool SLEEP>
+__device__ __forceinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity) {
+    if (SLEEP)
+        mbar_wait_sleep(bar, parity);
+    else
+        mbar_wait(bar, parity);
+}
 __device__ __forceinline__ void fence_barrier_init() {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
@@ -540,7 +567,7 @@ k_dense_syrk_tc(const __grid_constant__ TmapSet tmaps, const Params prm) {
                     s = 0;
                     ph ^= 1;
                 }
-                mbar_wait(&emptyR[s], ph ^ 1);
+                mbar_wait_t<(SCW > 0)>(&emptyR[s], ph ^ 1);
                 tl_stamp(prm, it, 0);
                 const long long k0 = ((long long)blockIdx.x + (long long)it * gridDim.x) * BK;
                 uint8_t* stage = Rring + (size_t)s * prm.r_bytes;
@@ -588,7 +615,7 @@ k_dense_syrk_tc(const __grid_constant__ TmapSet tmaps, const Params prm) {
                 b = 0;
                 phb ^= 1;
             }
-            mbar_wait(&scaled[b], phb);
+            mbar_wait_t<(SCW > 0)>(&scaled[b], phb);
             tcgen05_fence_after();
             if (elect_one()) {
                 tl_stamp(prm, it, 4);
@@ -685,7 +712,7 @@ k_dense_syrk_tc(const __grid_constant__ TmapSet tmaps, const Params prm) {
                     s2 = 0;
                     ph2 ^= 1;
                 }
-                if (lane == 0) mbar_wait(&full[s2], ph2);
+                if (lane == 0) mbar_wait_sleep(&full[s2], ph2);
                 __syncwarp();
                 const uint32_t stage = rring_sa + (uint32_t)s2 * (uint32_t)prm.r_bytes;
                 const uint32_t aux = stage + (uint32_t)prm.aux_off;
@@ -809,7 +836,7 @@ k_dense_syrk_tc(const __grid_constant__ TmapSet tmaps, const Params prm) {
             // prefetch: entries of tile it + 1 (its indptr was requested a tile ago), indptr of it + 2
             load_entries(it + 1, ip_nxt, idx_nxt, val_nxt, code_nxt);
             const int ip_nn = load_ip(it + 2);
-            if (lane == 0) mbar_wait(&full[s], ph);
+            if (lane == 0) mbar_wait_sleep(&full[s], ph);
             __syncwarp();
             const uint32_t stage = rring_sa + (uint32_t)s * (uint32_t)prm.r_bytes;
             float4 y[RPW];
@@ -919,7 +946,7 @@ k_dense_syrk_tc(const __grid_constant__ TmapSet tmaps, const Params prm) {
                 s = 0;
                 ph ^= 1;
             }
-            if (lane == 0) mbar_wait(&full[s], ph);
+            if (lane == 0) mbar_wait_t<(SCW > 0)>(&full[s], ph);
             __syncwarp();
             if (t == 0) tl_stamp(prm, it, 2);
           for (int sub = 0; sub < NSUB; ++sub, ++b) {   // 3xTF32: three operand slots per stage
@@ -928,7 +955,7 @@ k_dense_syrk_tc(const __grid_constant__ TmapSet tmaps, const Params prm) {
                 phb ^= 1;
             }
             // one lane polls, the warp follows through __syncwarp
-            if (lane == 0) mbar_wait(&emptyB[b], phb ^ 1);  // MMAs of slot use it-SB left slot b
+            if (lane == 0) mbar_wait_t<(SCW > 0)>(&emptyB[b], phb ^ 1);  // MMAs of slot use it-SB left slot b
             __syncwarp();
             if (t == 0) tl_stamp(prm, it, 1);
             const uint32_t Sp = oper_sa + (uint32_t)b * slot_bytes;
@@ -984,7 +1011,7 @@ k_dense_syrk_tc(const __grid_constant__ TmapSet tmaps, const Params prm) {
 
         if (prm.has_v && my_col < P && my_count > 0) atomicAdd(&prm.vec_out[my_col], gacc);
         // epilogue: TMEM -> registers -> RED into `out` (transposed: lanes = output columns)
-        mbar_wait(done, 0);
+        mbar_wait_t<(SCW > 0)>(done, 0);
         tcgen05_fence_after();
         const int chalf = (warp - 2) >> 2;    // which half of the column chunks this warp drains
         if (my_count > 0) {
