@@ -686,19 +686,21 @@ k_dense_syrk_tc(const __grid_constant__ TmapSet tmaps, const Params prm) {
         const uint32_t rring_sa = smem_u32(Rring);
         if (prm.sc_staged && !has_sp) {
             // ---- categorical blocks only, codes staged by TMA: no global load anywhere in this
-            // warp, so nothing but the raw-stage ring paces it.  All lanes read the same d / code
-            // words (broadcast LDS), the run logic is warp-uniform and needs no shuffles.  Each
-            // block keeps TWO accumulator sets and flushes them alternately: a RED holds its
-            // source registers for hundreds of cycles, the other set takes the next run meanwhile.
+            // warp.  A lone warp runs at one dependent instruction per ~5 cycles (ncu: the first
+            // form of this path executed ~680 branchy instructions per tile and needed ~6400
+            // cycles for them, 4x the MMA pipeline's tile period), so the code per tile is kept
+            // short and straight: all lanes read the same d / code words (broadcast LDS.128), the
+            // outer loop over the blocks skips the unused ones, the run logic is one warp-uniform
+            // compare per row, the adds are predicated FMAs.  A flush copies the sum to a second
+            // register set and REDs from there: the RED holds its source registers for hundreds
+            // of cycles, the accumulator itself is free at once.
             float* tabs[NCM];
-            float4 accA[NCM], accB[NCM];
+            float4 accs[NCM], outb[NCM];
             int curc[NCM];
-            bool useB[NCM];
 #pragma unroll
             for (int c = 0; c < NCM; ++c) {
                 curc[c] = -1;
-                useB[c] = false;
-                accA[c] = accB[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+                accs[c] = outb[c] = make_float4(0.f, 0.f, 0.f, 0.f);
                 tabs[c] = nullptr;
                 if (c < nc)
                     tabs[c] = prm.sc_tab[c] +
@@ -718,45 +720,44 @@ k_dense_syrk_tc(const __grid_constant__ TmapSet tmaps, const Params prm) {
                 const uint32_t aux = stage + (uint32_t)prm.aux_off;
                 float4 y[RPW];
                 float dq[RPW];
-                int cq[NCM][RPW];
 #pragma unroll
-                for (int q = 0; q < RPW; ++q) {
+                for (int q = 0; q < RPW; ++q)
                     y[q] = lane_ok ? lds_f32x4(stage + (uint32_t)(r0 + q) * (uint32_t)P * 4u + (uint32_t)lane * 16u)
                                    : make_float4(0.f, 0.f, 0.f, 0.f);
-                    dq[q] = lds_f32(aux + (uint32_t)(r0 + q) * 4u);
+#pragma unroll
+                for (int q4 = 0; q4 < RPW; q4 += 4) {
+                    const float4 dd = lds_f32x4(aux + (uint32_t)(r0 + q4) * 4u);
+                    dq[q4] = dd.x, dq[q4 + 1] = dd.y, dq[q4 + 2] = dd.z, dq[q4 + 3] = dd.w;
                 }
 #pragma unroll
-                for (int c = 0; c < NCM; ++c)
+                for (int c = 0; c < NCM; ++c) {
+                    if (c >= nc) continue;   // warp-uniform: unused blocks cost nothing
+                    int code[RPW];
+                    const uint32_t ca = aux + 128u * (uint32_t)(1 + prm.oh_ncat + c) + (uint32_t)r0 * 4u;
 #pragma unroll
-                    for (int q = 0; q < RPW; ++q)
-                        cq[c][q] = c < nc ? lds_s32(aux + 128u * (uint32_t)(1 + prm.oh_ncat + c) +
-                                                    (uint32_t)(r0 + q) * 4u) - prm.sc_df[c]
-                                          : -1;
+                    for (int q4 = 0; q4 < RPW; q4 += 4) {
+                        const float4 cc = lds_f32x4(ca + (uint32_t)q4 * 4u);   // 4 int32 codes
+                        code[q4] = __float_as_int(cc.x), code[q4 + 1] = __float_as_int(cc.y);
+                        code[q4 + 2] = __float_as_int(cc.z), code[q4 + 3] = __float_as_int(cc.w);
+                    }
+                    const int df = prm.sc_df[c];
 #pragma unroll
-                for (int q = 0; q < RPW; ++q) {
-                    const float dk = dq[q];
-                    if (dk == 0.f) continue;  // also the rows past the end (TMA zero fill)
-                    const float4 yy = make_float4(y[q].x * dk, y[q].y * dk, y[q].z * dk, y[q].w * dk);
-#pragma unroll
-                    for (int c = 0; c < NCM; ++c) {
-                        if (c >= nc) continue;
-                        const int code = cq[c][q] < 0 ? -1 : cq[c][q];
-                        if (code != curc[c]) {  // warp-uniform: a run of block c ends here
-                            if (curc[c] >= 0 && lane_ok) {
-                                if (useB[c]) red_add_v4(tabs[c] + (size_t)curc[c] * P, accB[c]);
-                                else red_add_v4(tabs[c] + (size_t)curc[c] * P, accA[c]);
-                            }
-                            useB[c] = !useB[c];   // the next run accumulates in the other set
-                            if (useB[c]) accB[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-                            else accA[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-                            curc[c] = code;
+                    for (int q = 0; q < RPW; ++q) {
+                        const float dk = dq[q];
+                        int cd = code[q] - df;
+                        cd = cd < 0 ? -1 : cd;
+                        cd = dk == 0.f ? curc[c] : cd;   // a zero-weight row never ends a run
+                        if (cd != curc[c]) {             // warp-uniform, rare on sorted rows
+                            outb[c] = accs[c];
+                            if (curc[c] >= 0 && lane_ok) red_add_v4(tabs[c] + (size_t)curc[c] * P, outb[c]);
+                            accs[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            curc[c] = cd;
                         }
-                        if (code >= 0) {
-                            if (useB[c]) {
-                                accB[c].x += yy.x, accB[c].y += yy.y, accB[c].z += yy.z, accB[c].w += yy.w;
-                            } else {
-                                accA[c].x += yy.x, accA[c].y += yy.y, accA[c].z += yy.z, accA[c].w += yy.w;
-                            }
+                        if (cd >= 0) {
+                            accs[c].x = fmaf(y[q].x, dk, accs[c].x);
+                            accs[c].y = fmaf(y[q].y, dk, accs[c].y);
+                            accs[c].z = fmaf(y[q].z, dk, accs[c].z);
+                            accs[c].w = fmaf(y[q].w, dk, accs[c].w);
                         }
                     }
                 }
@@ -767,10 +768,7 @@ k_dense_syrk_tc(const __grid_constant__ TmapSet tmaps, const Params prm) {
             }
 #pragma unroll
             for (int c = 0; c < NCM; ++c)
-                if (c < nc && curc[c] >= 0 && lane_ok) {
-                    if (useB[c]) red_add_v4(tabs[c] + (size_t)curc[c] * P, accB[c]);
-                    else red_add_v4(tabs[c] + (size_t)curc[c] * P, accA[c]);
-                }
+                if (c < nc && curc[c] >= 0 && lane_ok) red_add_v4(tabs[c] + (size_t)curc[c] * P, accs[c]);
         } else {
         float* tab[NCM];
         float4 acc[NCM];
