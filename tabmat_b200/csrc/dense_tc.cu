@@ -741,6 +741,31 @@ k_dense_syrk_tc(const __grid_constant__ TmapSet tmaps, const Params prm) {
                         code[q4 + 2] = __float_as_int(cc.z), code[q4 + 3] = __float_as_int(cc.w);
                     }
                     const int df = prm.sc_df[c];
+                    bool same = true;   // the whole slice carries one code (row-sorted storage)
+#pragma unroll
+                    for (int q = 1; q < RPW; ++q) same = same && code[q] == code[0];
+                    if (same) {
+                        // fast path: at most one flush, then 4 * RPW straight FMAs (rows with
+                        // weight 0 add 0)
+                        int cd = code[0] - df;
+                        cd = cd < 0 ? -1 : cd;
+                        if (cd != curc[c]) {
+                            outb[c] = accs[c];
+                            if (curc[c] >= 0 && lane_ok) red_add_v4(tabs[c] + (size_t)curc[c] * P, outb[c]);
+                            accs[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            curc[c] = cd;
+                        }
+                        if (cd >= 0) {
+#pragma unroll
+                            for (int q = 0; q < RPW; ++q) {
+                                accs[c].x = fmaf(y[q].x, dq[q], accs[c].x);
+                                accs[c].y = fmaf(y[q].y, dq[q], accs[c].y);
+                                accs[c].z = fmaf(y[q].z, dq[q], accs[c].z);
+                                accs[c].w = fmaf(y[q].w, dq[q], accs[c].w);
+                            }
+                        }
+                        continue;
+                    }
 #pragma unroll
                     for (int q = 0; q < RPW; ++q) {
                         const float dk = dq[q];
