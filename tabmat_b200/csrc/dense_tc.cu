@@ -134,6 +134,19 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_arrive_relaxed(uint64_t* bar) {
     asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// relaxed arrive that the hardware may not issue before `dep` exists: `dep` is computed from the
+// values loaded from the stage, so the arrive cannot overtake those shared-memory reads
+__device__ __forceinline__ void mbar_arrive_relaxed_after(uint64_t* bar, uint32_t dep) {
+    asm volatile(
+        "{\n\t"
+        ".reg .b32 t;\n\t"
+        "and.b32 t, %1, 0;\n\t"
+        "add.u32 t, t, %0;\n\t"
+        "mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [t];\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(dep)
+        : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t addr = smem_u32(bar);
     asm volatile(
@@ -729,17 +742,32 @@ k_dense_syrk_tc(const __grid_constant__ TmapSet tmaps, const Params prm) {
                     const float4 dd = lds_f32x4(aux + (uint32_t)(r0 + q4) * 4u);
                     dq[q4] = dd.x, dq[q4 + 1] = dd.y, dq[q4 + 2] = dd.z, dq[q4 + 3] = dd.w;
                 }
+                int codes[NCM][RPW];
+                uint32_t dep = 0;   // depends on every value loaded from the stage
 #pragma unroll
                 for (int c = 0; c < NCM; ++c) {
-                    if (c >= nc) continue;   // warp-uniform: unused blocks cost nothing
-                    int code[RPW];
                     const uint32_t ca = aux + 128u * (uint32_t)(1 + prm.oh_ncat + c) + (uint32_t)r0 * 4u;
 #pragma unroll
                     for (int q4 = 0; q4 < RPW; q4 += 4) {
-                        const float4 cc = lds_f32x4(ca + (uint32_t)q4 * 4u);   // 4 int32 codes
-                        code[q4] = __float_as_int(cc.x), code[q4 + 1] = __float_as_int(cc.y);
-                        code[q4 + 2] = __float_as_int(cc.z), code[q4 + 3] = __float_as_int(cc.w);
+                        if (c < nc) {
+                            const float4 cc = lds_f32x4(ca + (uint32_t)q4 * 4u);   // 4 int32 codes
+                            codes[c][q4] = __float_as_int(cc.x), codes[c][q4 + 1] = __float_as_int(cc.y);
+                            codes[c][q4 + 2] = __float_as_int(cc.z), codes[c][q4 + 3] = __float_as_int(cc.w);
+                            dep ^= (uint32_t)codes[c][q4 + 3];
+                        }
                     }
+                }
+#pragma unroll
+                for (int q = 0; q < RPW; ++q) dep ^= __float_as_uint(y[q].w) ^ __float_as_uint(dq[q]);
+                // all reads of the stage are in registers: hand it back at once (relaxed: the REDs
+                // of earlier tiles may still be in flight; the dependency keeps the arrive behind
+                // the loads)
+                __syncwarp();
+                if (lane == 0) mbar_arrive_relaxed_after(&emptyR[s2], dep);
+#pragma unroll
+                for (int c = 0; c < NCM; ++c) {
+                    if (c >= nc) continue;   // warp-uniform: unused blocks cost nothing
+                    int (&code)[RPW] = codes[c];
                     const int df = prm.sc_df[c];
                     bool same = true;   // the whole slice carries one code (row-sorted storage)
 #pragma unroll
@@ -786,10 +814,6 @@ k_dense_syrk_tc(const __grid_constant__ TmapSet tmaps, const Params prm) {
                         }
                     }
                 }
-                // every value read from the stage has been consumed: hand it back (relaxed: do
-                // not wait for the REDs above)
-                __syncwarp();
-                if (lane == 0) mbar_arrive_relaxed(&emptyR[s2]);
             }
 #pragma unroll
             for (int c = 0; c < NCM; ++c)
