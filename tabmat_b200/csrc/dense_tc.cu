@@ -96,8 +96,6 @@ struct Params {
     // in the ldo x ldo result.  The host loops over panel pairs.
     int panel, a0, b0, wa, wb, ldo, tile_mask;
     int sc_ncat;                       // <= TC_SCATTER_MAX_CATS
-    int sc_in_scale;  // 1 (needs sc_staged, no sparse work): the scale warps themselves keep the
-                      // categorical run sums (CatState), no scatter warps are launched
     int sc_staged;    // 1: the scatter blocks' code vectors are TMA-staged next to the one-hot
                       // ones (slots oh_ncat .. oh_ncat + sc_ncat - 1 of the stage): the scatter
                       // warps then touch no global memory except for their REDs
@@ -362,64 +360,10 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
 // 1024 = 256 columns: the 16 row offsets of the transposing loads fold into the LDS immediates,
 // which takes ~a quarter of the scale warps' instructions away - they are what paces the kernel
 // at p = 256, ncu: issue slots 63 % busy, tensor pipe 47 %), or 0 = use `pitch_rt`
-// dense x many-level categorical blocks INSIDE the scale warps (Params::sc_in_scale): a scale
-// thread owns one X column and already holds d[k] * X[k, column] for its rows of the stage, so
-// it can keep the running sum of a run of equal codes in a register and RED it when the code
-// changes (lanes = consecutive columns: one coalesced scalar RED per warp).  No extra warps and
-// - unlike scatter warps - no second read of the stage from shared memory, whose port is the
-// scarce resource of this kernel.  The codes are TMA-staged next to d.
-struct CatState {
-    float acc[TC_SCATTER_MAX_CATS];
-    int cur[TC_SCATTER_MAX_CATS];
-    float* tab[TC_SCATTER_MAX_CATS];   // table base + this thread's column (nullptr = column >= P)
-    int df[TC_SCATTER_MAX_CATS];
-    int P;
-    int n;
-};
-__device__ __forceinline__ void cat_flush(CatState& cs, int c) {
-    if (cs.cur[c] >= 0 && cs.tab[c]) atomicAdd(cs.tab[c] + (size_t)cs.cur[c] * cs.P, cs.acc[c]);
-    cs.acc[c] = 0.f;
-}
-// rows 4 * k4 .. 4 * k4 + 3 of the stage: weights dv, this thread's scaled values px
-__device__ __forceinline__ void cat_chunk(CatState& cs, uint32_t csm, int k4, const float4& dv,
-                                          float p0, float p1, float p2, float p3) {
-#pragma unroll
-    for (int c = 0; c < TC_SCATTER_MAX_CATS; ++c) {
-        if (c >= cs.n) continue;   // warp-uniform
-        const float4 cf = lds_f32x4(csm + 128u * (uint32_t)c + 16u * (uint32_t)k4);   // 4 codes
-        const int c0 = __float_as_int(cf.x), c1 = __float_as_int(cf.y), c2 = __float_as_int(cf.z),
-                  c3 = __float_as_int(cf.w);
-        if (c0 == c1 && c1 == c2 && c2 == c3) {   // one code for the chunk (row-sorted storage)
-            int cd = c0 - cs.df[c];
-            cd = cd < 0 ? -1 : cd;
-            if (cd != cs.cur[c]) {
-                cat_flush(cs, c);
-                cs.cur[c] = cd;
-            }
-            if (cd >= 0) cs.acc[c] += (p0 + p1) + (p2 + p3);
-            continue;
-        }
-        const int cc[4] = {c0, c1, c2, c3};
-        const float pp[4] = {p0, p1, p2, p3};
-        const float dd[4] = {dv.x, dv.y, dv.z, dv.w};
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            int cd = cc[i] - cs.df[c];
-            cd = cd < 0 ? -1 : cd;
-            cd = dd[i] == 0.f ? cs.cur[c] : cd;   // a zero-weight row never ends a run
-            if (cd != cs.cur[c]) {
-                cat_flush(cs, c);
-                cs.cur[c] = cd;
-            }
-            if (cd >= 0) cs.acc[c] += pp[i];
-        }
-    }
-}
-
 template <int SUB, int PITCH>
 __device__ __forceinline__ void scale_col4(uint32_t r0, uint32_t pitch_rt, bool ok, uint32_t dsm,
                                            uint32_t Sp, uint32_t t_addr, int c, int kb, int ks,
-                                           uint32_t vsm, float& gacc, uint32_t csm, CatState& cs) {
+                                           uint32_t vsm, float& gacc) {
     const uint32_t pitch = PITCH ? (uint32_t)PITCH : pitch_rt;
     // r0: shared address of element (row 0, column c) of the raw stage, pitch: bytes per row;
     // dsm, Sp: shared addresses of the stage's d vector and of the S tile
@@ -442,11 +386,9 @@ __device__ __forceinline__ void scale_col4(uint32_t r0, uint32_t pitch_rt, bool 
         a.z = tf32_part(x[u][2], s_lo);
         a.w = tf32_part(x[u][3], s_lo);
         if (ok) sts_u32x4(Sp + tile_off + kmajor_chunk_off(row, (uint32_t)k4), a);
-        const float p0 = dv.x * x[u][0], p1 = dv.y * x[u][1], p2 = dv.z * x[u][2],
-                    p3 = dv.w * x[u][3];
-        tmem_st_x4(t_addr + (uint32_t)(4 * k4), tf32_part(p0, t_lo), tf32_part(p1, t_lo),
-                   tf32_part(p2, t_lo), tf32_part(p3, t_lo));
-        if (SUB == 0 && csm) cat_chunk(cs, csm, k4, dv, p0, p1, p2, p3);
+        tmem_st_x4(t_addr + (uint32_t)(4 * k4), tf32_part(dv.x * x[u][0], t_lo),
+                   tf32_part(dv.y * x[u][1], t_lo), tf32_part(dv.z * x[u][2], t_lo),
+                   tf32_part(dv.w * x[u][3], t_lo));
         if (vsm) {  // X^T v rides along in fp32 (not TF32: it is the score of an IRLS step)
             const float4 vv = lds_f32x4(vsm + 16u * (uint32_t)k4);
             gacc = fmaf(vv.x, x[u][0], gacc);
@@ -502,7 +444,7 @@ template <int SUB>
 __device__ __forceinline__ void scale_stage(bool f_order, int mtiles, uint32_t R, uint32_t col_off,
                                             uint32_t pitch, bool ok, uint32_t dsm, uint32_t Sp,
                                             uint32_t t_addr, int my_col, int h, uint32_t vsm,
-                                            float& gacc, uint32_t csm, CatState& cs) {
+                                            float& gacc) {
     if (f_order) {
         if (mtiles == 1) {
             scale_col4_f<SUB>(R, ok, dsm, Sp, t_addr, my_col, h, 2, vsm, gacc);
@@ -512,18 +454,18 @@ __device__ __forceinline__ void scale_stage(bool f_order, int mtiles, uint32_t R
         }
     } else if (mtiles == 1) {
         if (pitch == 512)
-            scale_col4<SUB, 512>(R + col_off, pitch, ok, dsm, Sp, t_addr, my_col, h, 2, vsm, gacc, csm, cs);
+            scale_col4<SUB, 512>(R + col_off, pitch, ok, dsm, Sp, t_addr, my_col, h, 2, vsm, gacc);
         else
-            scale_col4<SUB, 0>(R + col_off, pitch, ok, dsm, Sp, t_addr, my_col, h, 2, vsm, gacc, csm, cs);
+            scale_col4<SUB, 0>(R + col_off, pitch, ok, dsm, Sp, t_addr, my_col, h, 2, vsm, gacc);
     } else if (pitch == 1024) {
-        scale_col4<SUB, 1024>(R + col_off, pitch, ok, dsm, Sp, t_addr, my_col, 0, 1, vsm, gacc, csm, cs);
-        scale_col4<SUB, 1024>(R + col_off, pitch, ok, dsm, Sp, t_addr, my_col, 4, 1, vsm, gacc, csm, cs);
+        scale_col4<SUB, 1024>(R + col_off, pitch, ok, dsm, Sp, t_addr, my_col, 0, 1, vsm, gacc);
+        scale_col4<SUB, 1024>(R + col_off, pitch, ok, dsm, Sp, t_addr, my_col, 4, 1, vsm, gacc);
     } else if (pitch == 512) {
-        scale_col4<SUB, 512>(R + col_off, pitch, ok, dsm, Sp, t_addr, my_col, 0, 1, vsm, gacc, csm, cs);
-        scale_col4<SUB, 512>(R + col_off, pitch, ok, dsm, Sp, t_addr, my_col, 4, 1, vsm, gacc, csm, cs);
+        scale_col4<SUB, 512>(R + col_off, pitch, ok, dsm, Sp, t_addr, my_col, 0, 1, vsm, gacc);
+        scale_col4<SUB, 512>(R + col_off, pitch, ok, dsm, Sp, t_addr, my_col, 4, 1, vsm, gacc);
     } else {
-        scale_col4<SUB, 0>(R + col_off, pitch, ok, dsm, Sp, t_addr, my_col, 0, 1, vsm, gacc, csm, cs);
-        scale_col4<SUB, 0>(R + col_off, pitch, ok, dsm, Sp, t_addr, my_col, 4, 1, vsm, gacc, csm, cs);
+        scale_col4<SUB, 0>(R + col_off, pitch, ok, dsm, Sp, t_addr, my_col, 0, 1, vsm, gacc);
+        scale_col4<SUB, 0>(R + col_off, pitch, ok, dsm, Sp, t_addr, my_col, 4, 1, vsm, gacc);
     }
 }
 
@@ -1044,19 +986,6 @@ k_dense_syrk_tc(const __grid_constant__ TmapSet tmaps, const Params prm) {
             col_off = (uint32_t)my_col * 4u;
         }
         float gacc = 0.f;   // this thread's share of (X^T v)[my_col]
-        CatState cs;
-        cs.n = prm.sc_in_scale ? prm.sc_ncat : 0;
-        cs.P = P;
-#pragma unroll
-        for (int c = 0; c < TC_SCATTER_MAX_CATS; ++c) {
-            cs.acc[c] = 0.f;
-            cs.cur[c] = -1;
-            cs.df[c] = c < cs.n ? prm.sc_df[c] : 0;
-            cs.tab[c] = (c < cs.n && my_col < P)
-                            ? prm.sc_tab[c] + (size_t)((blockIdx.x * NUM_SCALE_WARPS + w) % prm.sc_copies[c]) *
-                                                  (size_t)prm.sc_K[c] * P + my_col
-                            : nullptr;
-        }
         int s = 0, b = 0;
         uint32_t ph = 0, phb = 0;
         for (int it = 0; it < my_count; ++it, ++s) {
@@ -1103,17 +1032,15 @@ k_dense_syrk_tc(const __grid_constant__ TmapSet tmaps, const Params prm) {
                 const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + t_col0 +
                                         (uint32_t)(b * prm.mtiles + (my_col >> 7)) * 32;
                 const uint32_t vsm = (prm.has_v && sub == 0) ? dsm + 128u * 9u : 0u;
-                // staged code vectors of the scatter categoricals (slots after the one-hot ones)
-                const uint32_t csm = cs.n ? dsm + 128u * (uint32_t)(1 + prm.oh_ncat) : 0u;
                 if (NSUB == 1 || sub == 0)
                     scale_stage<0>(prm.f_order, prm.mtiles, R, col_off, col_pitch, col_ok, dsm, Sp,
-                                   t_addr, my_col, h, vsm, gacc, csm, cs);
+                                   t_addr, my_col, h, vsm, gacc);
                 else if (sub == 1)
                     scale_stage<1>(prm.f_order, prm.mtiles, R, col_off, col_pitch, col_ok, dsm, Sp,
-                                   t_addr, my_col, h, 0u, gacc, 0u, cs);
+                                   t_addr, my_col, h, 0u, gacc);
                 else
                     scale_stage<2>(prm.f_order, prm.mtiles, R, col_off, col_pitch, col_ok, dsm, Sp,
-                                   t_addr, my_col, h, 0u, gacc, 0u, cs);
+                                   t_addr, my_col, h, 0u, gacc);
             }
             if (t == 0) tl_stamp(prm, it, 6);
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
@@ -1130,9 +1057,6 @@ k_dense_syrk_tc(const __grid_constant__ TmapSet tmaps, const Params prm) {
         }
 
         if (prm.has_v && my_col < P && my_count > 0) atomicAdd(&prm.vec_out[my_col], gacc);
-#pragma unroll
-        for (int c = 0; c < TC_SCATTER_MAX_CATS; ++c)
-            if (c < cs.n) cat_flush(cs, c);
         // epilogue: TMEM -> registers -> RED into `out` (transposed: lanes = output columns)
         mbar_wait_t<(SCW > 0)>(done, 0);
         tcgen05_fence_after();
@@ -1520,13 +1444,6 @@ static int dense_sandwich_tc_launch(const float* X, int64_t n, int64_t p, int c_
                                    CU_TENSOR_MAP_DATA_TYPE_INT32))
                         return fail("cuTensorMapEncodeTiled failed (scatter codes)");
                 prm.sc_staged = 1;
-                // TABMAT_B200_TC_CATS_IN_SCALE=0: keep the run sums in separate scatter warps
-                static const bool in_scale_off = getenv("TABMAT_B200_TC_CATS_IN_SCALE") &&
-                                                 atoi(getenv("TABMAT_B200_TC_CATS_IN_SCALE")) == 0;
-                if (!in_scale_off && prm.mtiles == 1 && g_tc_scatter_warps < 0) {
-                    prm.sc_in_scale = 1;
-                    scw = 0;
-                }
             }
         }
         prm.csr_data = static_cast<const float*>(scatter->csr_data);
