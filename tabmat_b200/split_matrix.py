@@ -353,15 +353,17 @@ class SplitMatrix(MatrixBase):
     def _gather_block_rows(self, tdtype) -> int:
         """Rows per block of the row-blocked CSC copy that feeds the gather form of the
         dense x sparse block (csrc/split_fused.cu: k_csc_dense_gather): the largest power of two
-        with rows * (dense width) * sizeof <= 32 MB, so that a block of the dense operand stays in
-        the 126 MB L2 while three blocks are in flight.  0 = do not build it (no single row-major
+        with rows * (dense width) * sizeof <= 64 MB, so that a block of the dense operand stays in
+        the 126 MB L2 (128 MB blocks measured 3 % faster still: the window is not critical).  0 = do not build it (no single row-major
         dense block of a supported width, or TABMAT_B200_DXS=red)."""
-        # Measured at the benchmark shape (n = 4e7, 128 fp32 dense columns, ~3 non-zeros per row):
-        # gather 14.0-16.2 ms (16 / 32 / 64 MB blocks) against 11.5 ms for the RED form, so the
-        # split path keeps the REDs unless TABMAT_B200_DXS=gather; the stand-alone
-        # SparseMatrix.sandwich_dense (fp64, 5 non-zeros per row: 32 sector-ops per non-zero as
-        # REDs) is the case where the gather form wins (config C4: 8.4 ms vs 12.6 ms)
-        if os.environ.get("TABMAT_B200_DXS") != "gather":
+        # Measured at the benchmark shape (n = 4e7, 128 fp32 dense columns, ~3 non-zeros per row,
+        # profiles/bench_r2m_*): gather 7.4-7.6 ms + the categorical run sums in 4 scatter warps
+        # of the tcgen05 kernel (8.1 ms instead of 6.7) = 22.7 ms per step against 25.1 ms for
+        # the RED form (scatter pass 11.5 ms).  Default for that case (fp32, dense width <= 128,
+        # tcgen05 available); TABMAT_B200_DXS=red keeps the REDs, =gather forces the gather form
+        # elsewhere (fp64 / wider dense blocks: the categorical blocks then need their own pass).
+        mode = os.environ.get("TABMAT_B200_DXS", "auto")
+        if mode == "red":
             return 0
         dense = [m for m in self.matrices if isinstance(m, DenseMatrix)]
         if len(dense) != 1 or dense[0]._array.dtype != tdtype or not dense[0]._array.is_contiguous():
@@ -370,6 +372,9 @@ class SplitMatrix(MatrixBase):
         q = dense[0].shape[1]
         width = 16 // fsize
         if q <= 0 or q % width or q > 64 * width:
+            return 0
+        if mode != "gather" and not (tdtype == torch.float32 and 8 <= q <= 128
+                                     and lib.tm_has_tcgen05()):
             return 0
         cap = int(os.environ.get("TABMAT_B200_GATHER_MB", "64")) * (1 << 20)
         rows = max(1024, cap // (q * fsize))
