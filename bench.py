@@ -824,6 +824,7 @@ def main():
     tm._lib.lib.tm_split_profile_read(pass_arr)
     tm._lib.lib.tm_split_profile_enable(0)
     pass_ms = {"tensor": float(pass_arr[0]), "scatter": float(pass_arr[1]), "index": float(pass_arr[2])}
+    plan = int(tm._lib.lib.tm_split_last_plan())   # which forms the step used (see the header)
     clocks = sampler.stop() if sampler else None
 
     # ---- end to end through the public API: d from pinned host memory, result to pinned host
@@ -957,41 +958,46 @@ def main():
         if wl.key == "c5":
             n_oh = sum(1 for K in CAT_LEVELS if K <= 256)
             ps = SPARSE_BLOCKS * SPARSE_COLS
-            fused = pass_ms["scatter"] <= 0   # scatter warps inside the tcgen05 kernel
+            cats_in_tc, sparse_in_tc, gather = bool(plan & 2), bool(plan & 4), bool(plan & 8)
+            n_big = len(CAT_LEVELS) - n_oh
+            xb = P_DENSE * 4 + 4   # one dense row + its weight
             pass_bytes = {
-                # X + d + the few-level categoricals' codes in; dense self + their cross blocks out
-                "tensor": n_local * (P_DENSE * 4 + 4 + 4 * n_oh)
-                + 4 * (P_DENSE * P_DENSE + sum(K for K in CAT_LEVELS if K <= 256) * P_DENSE),
-                # X + d + many-level codes + CSR (data, indices, indptr) in; their cross blocks out
-                "scatter": n_local * (P_DENSE * 4 + 4 + 4 * (len(CAT_LEVELS) - n_oh)) + nnz_local * 8
-                + 4 * (n_local + 1) + 4 * (ps + sum(K for K in CAT_LEVELS if K > 256)) * P_DENSE,
-                # CSR + row ids + every code vector + d in; sparse self, cat x sparse, cat x cat out
+                # X + d + the codes of the categoricals it serves in; dense self + those cross
+                # blocks (+ the CSR arrays and the dense x sparse block in the fully fused form)
+                "tensor": n_local * (xb + 4 * (n_oh + (n_big if cats_in_tc else 0)))
+                + (nnz_local * 8 + 4 * (n_local + 1) + 4 * ps * P_DENSE if sparse_in_tc else 0)
+                + 4 * (P_DENSE * P_DENSE + sum(K for K in CAT_LEVELS if K <= 256 or cats_in_tc) * P_DENSE),
+                # gather form: X + d + the row-blocked CSC (value, row id) in, dense x sparse out;
+                # RED form: X + d + many-level codes + CSR in, their cross blocks out
+                "scatter": (n_local * xb + nnz_local * 8 + 4 * ps * P_DENSE) if gather else
+                (n_local * (xb + 4 * n_big) + nnz_local * 8 + 4 * (n_local + 1)
+                 + 4 * (ps + sum(K for K in CAT_LEVELS if K > 256)) * P_DENSE),
+                # CSC (value, row id, packed codes) + d + every code vector in; sparse self,
+                # cat x sparse, cat x cat out
                 "index": nnz_local * 12 + 4 * (n_local + 1) + n_local * (4 * len(CAT_LEVELS) + 4)
                 + 4 * (ps * ps + sum(CAT_LEVELS) * ps + sum(CAT_LEVELS)
                        + sum(a * b for i, a in enumerate(CAT_LEVELS) for b in CAT_LEVELS[i + 1:])),
             }
-            if fused:
-                # one pass over X does the work of both: X + d + all codes + CSR in, every block
-                # with the dense operand out
-                pass_bytes["tensor"] = (n_local * (P_DENSE * 4 + 4 + 4 * len(CAT_LEVELS)) + nnz_local * 8
-                                        + 4 * (n_local + 1)
-                                        + 4 * (P_DENSE * P_DENSE + (ps + sum(CAT_LEVELS)) * P_DENSE))
+            fused = sparse_in_tc
             kernel_names = {
-                "tensor": ("k_dense_syrk_tc, fused form (tcgen05 SYRK + one-hot MMAs + scatter warps: "
-                           "every block with the dense operand, X read once)") if fused else
-                          "k_dense_syrk_tc (tcgen05 SYRK + one-hot MMAs: dense self, dense x few-level cats)",
-                "scatter": "k_dense_cross_runs (dense x many-level cats + dense x sparse, vector RED)",
-                "index": "index pass (k_pack_records, k_cat_pairs, k_cat_sparse_*, k_sparse_sandwich)",
+                "tensor": "k_dense_syrk_tc (tcgen05 SYRK + one-hot MMAs"
+                          + (" + scatter warps: run sums of the many-level categoricals" if cats_in_tc else "")
+                          + (" + the vector REDs of dense x sparse" if sparse_in_tc else "") + ")",
+                "scatter": ("k_csc_dense_gather (dense x sparse by row-blocked gather, one RED per run)"
+                            if gather else
+                            "k_dense_cross_runs (dense x many-level cats + dense x sparse, vector RED)"),
+                "index": "index pass (k_cat_pairs, k_cat_sparse_cols, k_sparse_sandwich)",
             }
             live = {k: v for k, v in pass_ms.items() if v > 0}
             top = max(live, key=live.get)
             top_ms, top_bytes, top_kernel = live[top], pass_bytes[top], kernel_names[top]
-            traffic_key = ("tensor_fused" if fused else "tensor") if top == "tensor" else top
+            traffic_key = {"tensor": "tensor_cats" if cats_in_tc else "tensor",
+                           "scatter": "gather" if gather else "scatter", "index": "index"}[top]
             # L2 RED payload: one 512-byte row per sparse non-zero (+ per row and many-level
             # categorical in the caller's row order); measured L2 atomic peak 6.0 TB/s
             n_red_cat = 0 if sorted_rows else len(CAT_LEVELS) - n_oh
-            red_bytes = (n_local * n_red_cat + nnz_local) * P_DENSE * 4
-            red_ms = pass_ms["tensor"] if fused else pass_ms["scatter"]
+            red_bytes = (n_local * n_red_cat + (0 if gather else nnz_local)) * P_DENSE * 4
+            red_ms = pass_ms["tensor"] if (fused or (gather and cats_in_tc)) else pass_ms["scatter"]
             whole_bytes = split_bytes(n_local, nnz_local)
             config.update({
                 "nnz_sparse_total": nnz, "l2": "inputs (>20 GB per step) exceed the 126 MB L2",
@@ -999,23 +1005,32 @@ def main():
                 "row_order": (args.row_order if not sorted_rows else
                               "sorted by (cat2000, cat1000) at construction; d permuted inside "
                               "the timed region"),
-                "pass_schedule": ("serial: fused tensor+scatter pass, then index pass" if fused
-                                  else "serial (tensor, index, scatter)"),
+                "pass_schedule": "serial (tensor, index, scatter)",
+                "forms": {"cats_in_tcgen05_kernel": cats_in_tc, "sparse_in_tcgen05_kernel": sparse_in_tc,
+                          "dense_x_sparse": "gather" if gather else "red"},
                 "whole_step_hbm_gbs": whole_bytes / (ms_step * 1e-3) / 1e9,
                 "whole_step_hbm_frac": whole_bytes / (ms_step * 1e-3) / 1e9 / hbm_peak})
             line_extra["passes_ms"] = pass_ms
             line_extra["passes_hbm_frac"] = {
                 k: (pass_bytes[k] / (v * 1e-3) / 1e9 / hbm_peak if v > 0 else None)
                 for k, v in pass_ms.items()}
-            l2_red = {"payload_bytes": red_bytes,
-                      "achieved_TBs": red_bytes / (red_ms * 1e-3) / 1e12 if red_ms > 0 else None,
-                      "measured_peak_TBs": 6.0,
-                      "note": "the vector REDs of dense x sparse are bound by the L2 atomic units "
-                              "(1.9e11 sector-ops/s), not by HBM"}
+            l2_red = None
+            if not gather:
+                l2_red = {"payload_bytes": red_bytes,
+                          "achieved_TBs": red_bytes / (red_ms * 1e-3) / 1e12 if red_ms > 0 else None,
+                          "measured_peak_TBs": 6.0,
+                          "note": "the vector REDs of dense x sparse are bound by the L2 atomic "
+                                  "units (1.9e11 sector-ops/s), not by HBM"}
+            else:
+                # the gather form reads one 512-byte X row per non-zero through L2
+                line_extra["l2_gather"] = {
+                    "bytes": nnz_local * P_DENSE * 4,
+                    "achieved_TBs": nnz_local * P_DENSE * 4 / (pass_ms["scatter"] * 1e-3) / 1e12,
+                    "note": "k_csc_dense_gather: X rows gathered through L2, one RED per (row block, column) run"}
         else:
             top_ms, top_bytes = ms_step, wl.bytes(n_local, info)
             top_kernel = {"c2": "k_dense_syrk_tc (tcgen05 weighted SYRK, 3 lower-triangular 128x128 tiles)",
-                          "c3": "k_cat_hist (weighted histogram of the codes)",
+                          "c3": "k_cat_hist_vec (weighted histogram of the codes, 16-byte loads)",
                           "c4": "whole step: k_sparse_sandwich (CSR outer products, scalar REDs) + k_csr_dense (vector REDs)",
                           }[wl.key]
             traffic_key = wl.key

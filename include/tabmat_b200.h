@@ -397,6 +397,10 @@ int64_t tm_sizeof_block_desc(void);
  * categoricals and dense x sparse, caller's stream), index pass (all blocks without the dense
  * operand)}, averaged over the (at most 64 last) calls since tm_split_profile_enable(1); -1 for
  * a pass that did not run. */
+/* Which forms the last tm_split_sandwich_blocks_* call of this process used (measurement aid):
+ * bit 0 = the tcgen05 pass ran, bit 1 = the many-level categorical blocks were summed by its
+ * scatter warps, bit 2 = so was dense x sparse, bit 3 = dense x sparse by row-blocked gather. */
+int tm_split_last_plan(void);
 void tm_split_profile_enable(int on);
 int tm_split_profile_read(float* ms);
 

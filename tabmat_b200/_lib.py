@@ -86,7 +86,8 @@ EXPORTED = ["tm_version", "tm_last_error", "tm_launch_count", "tm_reset_launch_c
             "tm_has_tcgen05", "tm_set_dense_f32_mode", "tm_set_cross_runs_mode",
             "tm_set_tc_scatter_warps",
             "tm_split_workspace_elems", "tm_split_workspace_head_elems", "tm_memcpy2d_to_host",
-            "tm_dense_onehot_sandwich_f32", "tm_split_profile_enable", "tm_split_profile_read", "tm_sizeof_block_desc"]
+            "tm_dense_onehot_sandwich_f32", "tm_split_profile_enable", "tm_split_profile_read", "tm_sizeof_block_desc",
+            "tm_split_last_plan"]
 for _name, _args in _SIGS.items():
     for _suf in ("f32", "f64"):
         _fn = getattr(lib, f"{_name}_{_suf}")
@@ -118,6 +119,7 @@ lib.tm_dense_onehot_sandwich_f32.restype = c_int
 lib.tm_sizeof_block_desc.restype = c_i64
 if lib.tm_sizeof_block_desc() != C.sizeof(BlockDesc):  # pragma: no cover
     raise ImportError("tm_block_desc layout mismatch between libtabmat_b200.so and _lib.BlockDesc")
+lib.tm_split_last_plan.restype = c_int
 lib.tm_split_profile_enable.argtypes = [c_int]
 lib.tm_split_profile_enable.restype = None
 lib.tm_split_profile_read.argtypes = [C.c_void_p]

@@ -101,6 +101,10 @@ static int initial_sched() {
     return (sf && atoi(sf) == 1) ? 1 : 3;
 }
 static int g_split_sched = initial_sched();
+// which forms the last tm_split_sandwich_blocks_* call used (tm_split_last_plan): bit 0 = the
+// tcgen05 pass ran, bit 1 = categorical scatter work inside it, bit 2 = sparse scatter work inside
+// it, bit 3 = dense x sparse by gather
+static int g_last_plan = 0;
 
 // ---- optional pass-level timing (tm_split_profile_*): CUDA events on the stream each pass
 // is launched on; bench.py reads them after synchronising ---------------------------------
@@ -228,6 +232,8 @@ int split_blocks(const tm_block_desc* blk, int nb, int64_t n, const F* d, const 
         dense_tc_scatter_eligible(blk[dense_idx].ncols, n_scatter_cats, sparse_for_tc) &&
         (n_scatter_cats > 0 || sparse_for_tc);
 
+    g_last_plan = (tc_ok ? 1 : 0) | (scatter_in_tc && n_scatter_cats > 0 ? 2 : 0) |
+                  (scatter_in_tc && sparse_for_tc ? 4 : 0) | (sparse_by_gather ? 8 : 0);
     // destinations and sources of the scatter work (shared by the fused tensor pass and the
     // stand-alone scatter pass)
     struct ScatterPlan {
@@ -782,6 +788,7 @@ int split_assemble(const tm_block_desc* blk, int nb, const F* ws, double* out, i
 extern "C" {
 
 int64_t tm_sizeof_block_desc(void) { return (int64_t)sizeof(tm_block_desc); }
+int tm_split_last_plan(void) { return tmb::g_last_plan; }
 
 void tm_split_profile_enable(int on) {
     tmb::g_profile = on != 0;
