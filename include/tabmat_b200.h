@@ -61,12 +61,24 @@ void tm_set_dense_f32_mode(int mode);
 /* Fused dense-operand cross pass (tm_dense_cross_sandwich_*, tm_split_sandwich_blocks_*):
  * 0 / 1 = run-aggregating kernel (default), 2 = the one-row-per-visit kernel. */
 void tm_set_cross_runs_mode(int mode);
+/* Number of SMs the one-wave gather kernel of the dense x sparse block leaves free, so that a
+ * collective running on another stream (the allreduce of the blocks that are already finished,
+ * tabmat_b200/distributed.py) has somewhere to run.  0 = none (default). */
+void tm_set_sm_reserve(int sms);
 /* SplitMatrix sandwich, f32: number of scatter warps appended to the tcgen05 kernel, which then
- * also issues the vector REDs of the dense x sparse and dense x many-level categorical blocks
- * from the TMA-staged tile (the dense block is read once per sandwich).  -1 = auto (default; =
- * none: the fused form measured 28-52 ms against 18 ms for the two separate passes at the
- * benchmark shape), 0 = never, 4 or 8 = always; other values are ignored. */
+ * also computes the dense x many-level categorical blocks (run sums + vector REDs) - and, when
+ * forced, the per-non-zero REDs of the dense x sparse block - from the TMA-staged tile.
+ * -1 = auto (default: 4 warps when only categorical blocks are left to it, i.e. when the sparse
+ * block goes through the gather form; none otherwise - with the sparse REDs the fused form
+ * measured 28-52 ms against 18 ms for two passes), 0 = never, 4 or 8 = always;
+ * other values are ignored. */
 void tm_set_tc_scatter_warps(int warps);
+/* fp32 -> tf32 rounding of the tcgen05 operands (round to nearest, ties away, like the
+ * reference-free cvt.rna.tf32.f32): 0 = the cvt instruction (4 SASS instructions on sm_100a),
+ * 1 = integer add + mask (same values for finite inputs and infinities), 2 = integer add only
+ * (the tensor core ignores the low 13 bits of a tf32 operand), -1 = default
+ * (TABMAT_B200_TC_ROUND, else 1). */
+void tm_set_tc_round_mode(int mode);
 
 /* ---- dense block (reference: ext/dense.pyx) --------------------------------------- */
 /* dense_sandwich, dense.pyx:19-44 -> _dense{C,F}_sandwich, dense_helpers-tmpl.cpp:266-308.

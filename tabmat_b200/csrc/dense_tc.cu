@@ -88,6 +88,7 @@ struct Params {
     // (three operand slots per raw stage), which restores fp32-level accuracy at a third of the
     // tensor throughput (tm_set_dense_f32_mode(3))
     int nsub;
+    int round_mode;   // fp32 -> tf32 of the MMA operands: see to_tf32<RM>
     // column panels.  Legacy (panel == 0): the kernel's P columns are columns 0..P-1 of X and one
     // TMA box brings a whole row tile.  panel == 1 (p > 256): the kernel works on TWO 128-column
     // panels of a wider X - panel A = columns a0..a0+wa-1 (local columns 0..127), panel B =
@@ -295,9 +296,24 @@ __device__ __forceinline__ bool elect_one() {
         : "=r"(pred));
     return pred != 0;
 }
+// fp32 -> tf32, round to nearest, ties away from zero.  ptxas expands `cvt.rna.tf32.f32` into FOUR
+// instructions on sm_100a (FSETP |x| >= inf, VIADD 0x1000, SEL, LOP3 & 0xffffe000) and the scale
+// warps - which pace the kernel - do 32 conversions per thread and tile.  RM selects:
+//   0  the cvt instruction;
+//   1  (bits + 0x1000) & 0xffffe000: the same value for every finite x and for +-inf (the carry
+//      stops in bit 12, which the mask drops); a NaN stays a NaN unless its payload is all ones;
+//   2  bits + 0x1000 only: the tensor core ignores the low 13 bits of a tf32 operand, so the
+//      mask is redundant for an MMA operand (NOT for the residual of the 3xTF32 scheme).
+template <int RM = 0>
 __device__ __forceinline__ uint32_t to_tf32(float x) {
     uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    if (RM == 0) {
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    } else if (RM == 1) {
+        r = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
+    } else {
+        r = __float_as_uint(x) + 0x1000u;
+    }
     return r;
 }
 
@@ -308,9 +324,11 @@ __device__ __forceinline__ void red_add_v4(float* p, float4 v) {
 }
 
 // operand of sub-pass `sub` of the 3xTF32 scheme: want_lo selects tf32(a - tf32(a))
+template <int RM>
 __device__ __forceinline__ uint32_t tf32_part(float a, bool want_lo) {
-    const uint32_t hi = to_tf32(a);
-    return want_lo ? to_tf32(a - __uint_as_float(hi)) : hi;
+    if (!want_lo) return to_tf32<RM>(a);
+    const uint32_t hi = to_tf32 < RM == 2 ? 1 : RM > (a);
+    return to_tf32<RM>(a - __uint_as_float(hi));
 }
 
 // UMMA shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
@@ -360,7 +378,7 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
 // 1024 = 256 columns: the 16 row offsets of the transposing loads fold into the LDS immediates,
 // which takes ~a quarter of the scale warps' instructions away - they are what paces the kernel
 // at p = 256, ncu: issue slots 63 % busy, tensor pipe 47 %), or 0 = use `pitch_rt`
-template <int SUB, int PITCH>
+template <int SUB, int PITCH, int RM>
 __device__ __forceinline__ void scale_col4(uint32_t r0, uint32_t pitch_rt, bool ok, uint32_t dsm,
                                            uint32_t Sp, uint32_t t_addr, int c, int kb, int ks,
                                            uint32_t vsm, float& gacc) {
@@ -381,14 +399,14 @@ __device__ __forceinline__ void scale_col4(uint32_t r0, uint32_t pitch_rt, bool 
         const int k4 = kb + u * ks;
         const float4 dv = lds_f32x4(dsm + 16u * (uint32_t)k4);
         uint4 a;
-        a.x = tf32_part(x[u][0], s_lo);
-        a.y = tf32_part(x[u][1], s_lo);
-        a.z = tf32_part(x[u][2], s_lo);
-        a.w = tf32_part(x[u][3], s_lo);
+        a.x = tf32_part<RM>(x[u][0], s_lo);
+        a.y = tf32_part<RM>(x[u][1], s_lo);
+        a.z = tf32_part<RM>(x[u][2], s_lo);
+        a.w = tf32_part<RM>(x[u][3], s_lo);
         if (ok) sts_u32x4(Sp + tile_off + kmajor_chunk_off(row, (uint32_t)k4), a);
-        tmem_st_x4(t_addr + (uint32_t)(4 * k4), tf32_part(dv.x * x[u][0], t_lo),
-                   tf32_part(dv.y * x[u][1], t_lo), tf32_part(dv.z * x[u][2], t_lo),
-                   tf32_part(dv.w * x[u][3], t_lo));
+        tmem_st_x4(t_addr + (uint32_t)(4 * k4), tf32_part<RM>(dv.x * x[u][0], t_lo),
+                   tf32_part<RM>(dv.y * x[u][1], t_lo), tf32_part<RM>(dv.z * x[u][2], t_lo),
+                   tf32_part<RM>(dv.w * x[u][3], t_lo));
         if (vsm) {  // X^T v rides along in fp32 (not TF32: it is the score of an IRLS step)
             const float4 vv = lds_f32x4(vsm + 16u * (uint32_t)k4);
             gacc = fmaf(vv.x, x[u][0], gacc);
@@ -404,7 +422,7 @@ __device__ __forceinline__ void scale_col4(uint32_t r0, uint32_t pitch_rt, bool 
 // 128-byte row of 32 k-values per X column, 16-byte chunks XOR-swizzled by the TMA unit
 // (SWIZZLE_128B) so that the 32 lanes of a warp, one column each, read a chunk without bank
 // conflicts.  No transpose is needed: a lane reads its 4 consecutive k as one LDS.128.
-template <int SUB>
+template <int SUB, int RM>
 __device__ __forceinline__ void scale_col4_f(uint32_t R, bool ok, uint32_t dsm, uint32_t Sp,
                                              uint32_t t_addr, int c, int kb, int ks, uint32_t vsm,
                                              float& gacc) {
@@ -421,14 +439,14 @@ __device__ __forceinline__ void scale_col4_f(uint32_t R, bool ok, uint32_t dsm, 
         const int k4 = kb + u * ks;
         const float4 dv = lds_f32x4(dsm + 16u * (uint32_t)k4);
         uint4 a;
-        a.x = tf32_part(x[u].x, s_lo);
-        a.y = tf32_part(x[u].y, s_lo);
-        a.z = tf32_part(x[u].z, s_lo);
-        a.w = tf32_part(x[u].w, s_lo);
+        a.x = tf32_part<RM>(x[u].x, s_lo);
+        a.y = tf32_part<RM>(x[u].y, s_lo);
+        a.z = tf32_part<RM>(x[u].z, s_lo);
+        a.w = tf32_part<RM>(x[u].w, s_lo);
         if (ok) sts_u32x4(Sp + tile_off + kmajor_chunk_off(row, (uint32_t)k4), a);
-        tmem_st_x4(t_addr + (uint32_t)(4 * k4), tf32_part(dv.x * x[u].x, t_lo),
-                   tf32_part(dv.y * x[u].y, t_lo), tf32_part(dv.z * x[u].z, t_lo),
-                   tf32_part(dv.w * x[u].w, t_lo));
+        tmem_st_x4(t_addr + (uint32_t)(4 * k4), tf32_part<RM>(dv.x * x[u].x, t_lo),
+                   tf32_part<RM>(dv.y * x[u].y, t_lo), tf32_part<RM>(dv.z * x[u].z, t_lo),
+                   tf32_part<RM>(dv.w * x[u].w, t_lo));
         if (vsm) {
             const float4 vv = lds_f32x4(vsm + 16u * (uint32_t)k4);
             gacc = fmaf(vv.x, x[u].x, gacc);
@@ -440,33 +458,44 @@ __device__ __forceinline__ void scale_col4_f(uint32_t R, bool ok, uint32_t dsm, 
 }
 
 // one operand slot of a raw stage: sub-pass SUB of the 3xTF32 scheme (0 = the plain TF32 pass)
-template <int SUB>
+template <int SUB, int RM>
 __device__ __forceinline__ void scale_stage(bool f_order, int mtiles, uint32_t R, uint32_t col_off,
                                             uint32_t pitch, bool ok, uint32_t dsm, uint32_t Sp,
                                             uint32_t t_addr, int my_col, int h, uint32_t vsm,
                                             float& gacc) {
     if (f_order) {
         if (mtiles == 1) {
-            scale_col4_f<SUB>(R, ok, dsm, Sp, t_addr, my_col, h, 2, vsm, gacc);
+            scale_col4_f<SUB, RM>(R, ok, dsm, Sp, t_addr, my_col, h, 2, vsm, gacc);
         } else {
-            scale_col4_f<SUB>(R, ok, dsm, Sp, t_addr, my_col, 0, 1, vsm, gacc);
-            scale_col4_f<SUB>(R, ok, dsm, Sp, t_addr, my_col, 4, 1, vsm, gacc);
+            scale_col4_f<SUB, RM>(R, ok, dsm, Sp, t_addr, my_col, 0, 1, vsm, gacc);
+            scale_col4_f<SUB, RM>(R, ok, dsm, Sp, t_addr, my_col, 4, 1, vsm, gacc);
         }
     } else if (mtiles == 1) {
         if (pitch == 512)
-            scale_col4<SUB, 512>(R + col_off, pitch, ok, dsm, Sp, t_addr, my_col, h, 2, vsm, gacc);
+            scale_col4<SUB, 512, RM>(R + col_off, pitch, ok, dsm, Sp, t_addr, my_col, h, 2, vsm, gacc);
         else
-            scale_col4<SUB, 0>(R + col_off, pitch, ok, dsm, Sp, t_addr, my_col, h, 2, vsm, gacc);
+            scale_col4<SUB, 0, RM>(R + col_off, pitch, ok, dsm, Sp, t_addr, my_col, h, 2, vsm, gacc);
     } else if (pitch == 1024) {
-        scale_col4<SUB, 1024>(R + col_off, pitch, ok, dsm, Sp, t_addr, my_col, 0, 1, vsm, gacc);
-        scale_col4<SUB, 1024>(R + col_off, pitch, ok, dsm, Sp, t_addr, my_col, 4, 1, vsm, gacc);
+        scale_col4<SUB, 1024, RM>(R + col_off, pitch, ok, dsm, Sp, t_addr, my_col, 0, 1, vsm, gacc);
+        scale_col4<SUB, 1024, RM>(R + col_off, pitch, ok, dsm, Sp, t_addr, my_col, 4, 1, vsm, gacc);
     } else if (pitch == 512) {
-        scale_col4<SUB, 512>(R + col_off, pitch, ok, dsm, Sp, t_addr, my_col, 0, 1, vsm, gacc);
-        scale_col4<SUB, 512>(R + col_off, pitch, ok, dsm, Sp, t_addr, my_col, 4, 1, vsm, gacc);
+        scale_col4<SUB, 512, RM>(R + col_off, pitch, ok, dsm, Sp, t_addr, my_col, 0, 1, vsm, gacc);
+        scale_col4<SUB, 512, RM>(R + col_off, pitch, ok, dsm, Sp, t_addr, my_col, 4, 1, vsm, gacc);
     } else {
-        scale_col4<SUB, 0>(R + col_off, pitch, ok, dsm, Sp, t_addr, my_col, 0, 1, vsm, gacc);
-        scale_col4<SUB, 0>(R + col_off, pitch, ok, dsm, Sp, t_addr, my_col, 4, 1, vsm, gacc);
+        scale_col4<SUB, 0, RM>(R + col_off, pitch, ok, dsm, Sp, t_addr, my_col, 0, 1, vsm, gacc);
+        scale_col4<SUB, 0, RM>(R + col_off, pitch, ok, dsm, Sp, t_addr, my_col, 4, 1, vsm, gacc);
     }
+}
+
+// fp32 -> tf32 of the MMA operands (to_tf32<RM>): -1 = TABMAT_B200_TC_ROUND or the default
+int g_tc_round = -1;
+static int tc_round_mode() {
+    int rm = g_tc_round;
+    if (rm < 0) {
+        static const int env = getenv("TABMAT_B200_TC_ROUND") ? atoi(getenv("TABMAT_B200_TC_ROUND")) : 1;
+        rm = env;
+    }
+    return rm < 0 || rm > 2 ? 1 : rm;
 }
 
 // tensor maps of one launch: the X tile, the weight vector d and the one-hot code vectors
@@ -1032,15 +1061,25 @@ k_dense_syrk_tc(const __grid_constant__ TmapSet tmaps, const Params prm) {
                 const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + t_col0 +
                                         (uint32_t)(b * prm.mtiles + (my_col >> 7)) * 32;
                 const uint32_t vsm = (prm.has_v && sub == 0) ? dsm + 128u * 9u : 0u;
-                if (NSUB == 1 || sub == 0)
-                    scale_stage<0>(prm.f_order, prm.mtiles, R, col_off, col_pitch, col_ok, dsm, Sp,
-                                   t_addr, my_col, h, vsm, gacc);
+                if (NSUB == 1) {
+                    if (prm.round_mode == 2)
+                        scale_stage<0, 2>(prm.f_order, prm.mtiles, R, col_off, col_pitch, col_ok,
+                                          dsm, Sp, t_addr, my_col, h, vsm, gacc);
+                    else if (prm.round_mode == 1)
+                        scale_stage<0, 1>(prm.f_order, prm.mtiles, R, col_off, col_pitch, col_ok,
+                                          dsm, Sp, t_addr, my_col, h, vsm, gacc);
+                    else
+                        scale_stage<0, 0>(prm.f_order, prm.mtiles, R, col_off, col_pitch, col_ok,
+                                          dsm, Sp, t_addr, my_col, h, vsm, gacc);
+                } else if (sub == 0)
+                    scale_stage<0, 1>(prm.f_order, prm.mtiles, R, col_off, col_pitch, col_ok, dsm,
+                                      Sp, t_addr, my_col, h, vsm, gacc);
                 else if (sub == 1)
-                    scale_stage<1>(prm.f_order, prm.mtiles, R, col_off, col_pitch, col_ok, dsm, Sp,
-                                   t_addr, my_col, h, 0u, gacc);
+                    scale_stage<1, 1>(prm.f_order, prm.mtiles, R, col_off, col_pitch, col_ok, dsm,
+                                      Sp, t_addr, my_col, h, 0u, gacc);
                 else
-                    scale_stage<2>(prm.f_order, prm.mtiles, R, col_off, col_pitch, col_ok, dsm, Sp,
-                                   t_addr, my_col, h, 0u, gacc);
+                    scale_stage<2, 1>(prm.f_order, prm.mtiles, R, col_off, col_pitch, col_ok, dsm,
+                                      Sp, t_addr, my_col, h, 0u, gacc);
             }
             if (t == 0) tl_stamp(prm, it, 6);
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
@@ -1418,6 +1457,7 @@ static int dense_sandwich_tc_launch(const float* X, int64_t n, int64_t p, int c_
     prm.has_v = v ? 1 : 0;
     prm.vec_out = vec_out;
     prm.nsub = g_dense_f32_mode == 3 ? 3 : 1;
+    prm.round_mode = tc_round_mode();
     if (prm.f_order) prm.r_bytes = (prm.r_bytes + 1023) / 1024 * 1024;  // swizzle atom = 8 x 128 B
     int scw = 0;
     if (scatter && (scatter->n_cat > 0 || scatter->out_sparse)) {
@@ -1536,6 +1576,7 @@ int tm_has_tcgen05(void) {
     return tmb::tc::device_cc_major() == 10 && tmb::tc::get_encode() != nullptr ? 1 : 0;
 }
 void tm_set_dense_f32_mode(int mode) { tmb::g_dense_f32_mode = mode; }
+void tm_set_tc_round_mode(int mode) { tmb::tc::g_tc_round = mode; }
 void tm_set_tc_scatter_warps(int warps) {
     if (warps == -1 || warps == 0 || warps == 4 || warps == 8) tmb::g_tc_scatter_warps = warps;
 }

@@ -38,6 +38,51 @@ __global__ void k_sparse_sandwich(const F* __restrict__ data, const int32_t* __r
     }
 }
 
+// The same with the (packed lower-triangular) result table of a NARROW sparse block in shared
+// memory: m (m + 1) / 2 entries <= ~200 KB (m <= 319 in f32, 225 in f64).  One CTA per SM keeps
+// a private table, adds with shared-memory atomics (4x the L2 RED rate of the whole chip, no
+// contention collapse on the few popular columns) and flushes its non-zero entries with one RED
+// each.  Pays once nnz is well above SMs * table size (the flush); the host picks.
+constexpr int SS_THREADS = 1024;
+template <typename F>
+__global__ void __launch_bounds__(SS_THREADS)
+k_sparse_sandwich_smem(const F* __restrict__ data, const int32_t* __restrict__ indices,
+                       const int32_t* __restrict__ indptr, const int32_t* __restrict__ nz_row,
+                       int64_t nnz, const F* __restrict__ d, const uint8_t* __restrict__ row_mask,
+                       const int32_t* __restrict__ col_pos, int m, F* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char ss_raw[];
+    F* tab = reinterpret_cast<F*>(ss_raw);
+    const int tri = m * (m + 1) / 2;
+    for (int i = threadIdx.x; i < tri; i += SS_THREADS) tab[i] = F(0);
+    __syncthreads();
+    // a CTA takes contiguous pieces of the non-zeros: the inner walk over the row stays in L1
+    const int64_t stride = (int64_t)gridDim.x * SS_THREADS;
+    for (int64_t e = (int64_t)blockIdx.x * SS_THREADS + threadIdx.x; e < nnz; e += stride) {
+        const int k = nz_row[e];
+        if (row_mask && !row_mask[k]) continue;
+        const int ja = indices[e];
+        const int pa = col_pos ? col_pos[ja] : ja;
+        if (pa < 0) continue;
+        const F dk = d[k];
+        if (dk == F(0)) continue;
+        const F va = data[e] * dk;
+        F* trow = tab + pa * (pa + 1) / 2;
+        for (int b = indptr[k]; b <= e; ++b) {
+            const int jb = indices[b];
+            const int pb = col_pos ? col_pos[jb] : jb;
+            if (pb < 0) continue;
+            atomicAdd(&trow[pb], va * data[b]);
+        }
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < m * m; idx += SS_THREADS) {
+        const int pa = idx / m, pb = idx - pa * m;
+        if (pb > pa) continue;
+        const F v = tab[pa * (pa + 1) / 2 + pb];
+        if (v != F(0)) red_add(&out[idx], v);
+    }
+}
+
 // ---------------------------------------------------------------------------------------
 // sparse x dense cross sandwich.  One warp per row k: the lanes hold d_k * B[k, B_cols[.]]
 // in registers and, for every non-zero (k, j) with pos(j) >= 0, RED-add the scaled row into
@@ -157,10 +202,33 @@ int sparse_sandwich(const F* data, const int32_t* indices, const int32_t* indptr
         int rc = build_pos_map(cols, m, p, cpos.as<int32_t>(), st);
         if (rc) return rc;
     }
-    int g = grid_for(nnz, 256, sm_count() * 32);
-    k_sparse_sandwich<F><<<g, 256, 0, st>>>(data, indices, indptr, nz_row, nnz, d,
-                                            rows ? rmask.as<uint8_t>() : nullptr,
-                                            cols ? cpos.as<int32_t>() : nullptr, m, out);
+    // narrow block, many non-zeros: private shared-memory tables (TABMAT_B200_SPARSE_SMEM=0
+    // keeps the L2 RED form, =2 forces the tables whenever they fit)
+    const size_t tri_bytes = sizeof(F) * (size_t)(m * (m + 1) / 2);
+    const char* sm_env = getenv("TABMAT_B200_SPARSE_SMEM");
+    const int sm_mode = sm_env ? atoi(sm_env) : 1;
+    const bool in_smem = sm_mode != 0 && tri_bytes <= 200 * 1024 &&
+                         (sm_mode == 2 || nnz > (int64_t)sm_count() * (m * (m + 1) / 2));
+    if (in_smem) {
+        static bool attr_done[2][16] = {};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        bool& done = attr_done[sizeof(F) == 8][dev & 15];
+        if (!done) {
+            TM_CUDA(cudaFuncSetAttribute(k_sparse_sandwich_smem<F>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            done = true;
+        }
+        const int g = (int)std::min<int64_t>(sm_count(), (nnz + SS_THREADS - 1) / SS_THREADS);
+        k_sparse_sandwich_smem<F><<<g, SS_THREADS, tri_bytes, st>>>(
+            data, indices, indptr, nz_row, nnz, d, rows ? rmask.as<uint8_t>() : nullptr,
+            cols ? cpos.as<int32_t>() : nullptr, (int)m, out);
+    } else {
+        int g = grid_for(nnz, 256, sm_count() * 32);
+        k_sparse_sandwich<F><<<g, 256, 0, st>>>(data, indices, indptr, nz_row, nnz, d,
+                                                rows ? rmask.as<uint8_t>() : nullptr,
+                                                cols ? cpos.as<int32_t>() : nullptr, m, out);
+    }
     TM_LAUNCHED();
     return symmetrize_from_lower<F>(out, m, st);
 }

@@ -567,8 +567,17 @@ int split_blocks(const tm_block_desc* blk, int nb, int64_t n, const F* d, const 
         return rc1;
     }
     if (part == 2) {  // the rest
-        int rc2 = tensor_pass(main_st, false);
-        if (rc2 == 0) rc2 = scatter_pass(main_st);
+        // with SMs reserved for a collective that a row-sharded caller started after part 1
+        // (tm_set_sm_reserve), the gather form goes first: it can share the GPU, the persistent
+        // tcgen05 kernel cannot
+        int rc2 = 0;
+        if (sparse_by_gather && g_sm_reserve > 0) {
+            rc2 = scatter_pass(main_st);
+            if (rc2 == 0) rc2 = tensor_pass(main_st, false);
+        } else {
+            rc2 = tensor_pass(main_st, false);
+            if (rc2 == 0) rc2 = scatter_pass(main_st);
+        }
         return rc2;
     }
     if (!have_tensor && (sched == 0 || sched == 1)) sched = 3;

@@ -609,7 +609,11 @@ int csc_dense_gather(const F* X, int64_t p, const F* d, const F* bdata, const in
                                                               GD_THREADS, 0));
     if (per_sm < 1) per_sm = 1;
     if (per_sm > cta_cap) per_sm = cta_cap;
-    const int64_t max_warps = (int64_t)sm_count() * per_sm * (GD_THREADS / 32);
+    // SMs left free for a concurrent collective (tm_set_sm_reserve; row-sharded callers overlap
+    // the allreduce of the index blocks with this kernel)
+    int sms = sm_count() - g_sm_reserve;
+    if (sms < 8) sms = 8;
+    const int64_t max_warps = (int64_t)sms * per_sm * (GD_THREADS / 32);
     const int cpw = (int)((p_s + max_warps - 1) / max_warps);
     const int64_t warps = (p_s + cpw - 1) / cpw;
     const int grid = (int)((warps + GD_THREADS / 32 - 1) / (GD_THREADS / 32));
@@ -778,6 +782,7 @@ int dense_cross_fused(const F* X, int64_t n, int64_t p, const F* d, const int32_
 }
 
 int g_cross_runs_mode = 0;
+int g_sm_reserve = 0;
 
 template int dense_cross_fused<float>(const float*, int64_t, int64_t, const float*, const int32_t*,
                                       int64_t, int, const int32_t* const*, const int64_t*,
@@ -794,6 +799,7 @@ template int dense_cross_fused<double>(const double*, int64_t, int64_t, const do
 extern "C" {
 
 void tm_set_cross_runs_mode(int mode) { tmb::g_cross_runs_mode = mode; }
+void tm_set_sm_reserve(int sms) { tmb::g_sm_reserve = sms < 0 ? 0 : (sms > 64 ? 64 : sms); }
 
 int tm_csc_dense_gather_sandwich_f32(const float* bdata, const int32_t* brow, const int32_t* bptr,
                                      int64_t p_sparse, int64_t n_blocks, const float* B, int64_t q,

@@ -168,6 +168,7 @@ int dense_cross_fused(const F* X, int64_t n, int64_t p, const F* d, const int32_
                       const int32_t* csr_indices, const int32_t* csr_indptr, int64_t p_sparse,
                       F* out_sparse, int runs, cudaStream_t st);
 extern int g_cross_runs_mode;
+extern int g_sm_reserve;   // SMs the gather kernel leaves free (tm_set_sm_reserve)
 // dense x sparse by row-blocked gather (split_fused.cu): out (p_s x p) overwritten
 template <typename F>
 int csc_dense_gather(const F* X, int64_t p, const F* d, const F* bdata, const int32_t* brow,

@@ -142,6 +142,14 @@ class RowShardedMatrix:
         self.dtype = local.dtype
         self.pack = pack
         self.reduce_dtype = reduce_dtype
+        # TABMAT_B200_DIST_OVERLAP=1: start the allreduce of the index blocks while the
+        # dense-operand passes still run (sandwich of a SplitMatrix shard).  Off by default:
+        # measured slower (12.75 vs 11.55 ms at 2 GPUs, profiles/bench_r2r_*): the collective
+        # shares L2 and SMs with the L2-bound gather kernel, which goes from 3.8 to 5.0 ms
+        import os
+
+        self.overlap = os.environ.get("TABMAT_B200_DIST_OVERLAP", "0") == "1"
+        self.sm_reserve = int(os.environ.get("TABMAT_B200_DIST_SM_RESERVE", "8"))
 
     # -- collectives ---------------------------------------------------------------------
     def _allreduce(self, t: torch.Tensor, dst: Optional[int] = None) -> torch.Tensor:
@@ -165,6 +173,24 @@ class RowShardedMatrix:
             # entry once, block dtype) and assemble the p x p float64 after the collective
             from . import _dev
 
+            ws = None
+            if (self.world_size > 1 and dst is None and self.overlap
+                    and hasattr(self.local, "_sandwich_blocks_overlapped_dev")):
+                # the allreduce of the index blocks (95 % of the payload) runs while the
+                # dense-operand passes compute; a few SMs are left to the collective
+                from ._lib import lib
+
+                lib.tm_set_sm_reserve(self.sm_reserve)
+                try:
+                    ws = self.local._sandwich_blocks_overlapped_dev(
+                        d_local, _dev.idx32(local_rows),
+                        lambda t: dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group,
+                                                  async_op=True),
+                        self._allreduce)
+                finally:
+                    lib.tm_set_sm_reserve(0)
+                if ws is not None:
+                    return self.local._assemble_dev(ws, cols)
             ws = self.local._sandwich_blocks_dev(d_local, _dev.idx32(local_rows))
             if ws is not None:
                 self._allreduce(ws, dst)
@@ -263,8 +289,12 @@ class RowShardedMatrix:
         # the two-phase path of SplitMatrix.sandwich_into, restricted to this rank's band: the
         # blocks without the dense operand are reduced, placed and copied while the dense passes
         # still run
-        self.local.sandwich_into(d_local, shared.array, shard_rows(rows, self.lo, self.hi),
-                                 reduce=reduce, band=(r0, r1))
+        lib.tm_set_sm_reserve(self.sm_reserve if self.world_size > 1 and self.overlap else 0)
+        try:
+            self.local.sandwich_into(d_local, shared.array, shard_rows(rows, self.lo, self.hi),
+                                     reduce=reduce, band=(r0, r1))
+        finally:
+            lib.tm_set_sm_reserve(0)
         fence = getattr(self, "_fence", None)
         if fence is None:
             fence = self._fence = torch.zeros(1, dtype=torch.float32, device=_dev.require_cuda())

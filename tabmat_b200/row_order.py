@@ -197,6 +197,10 @@ class RowSortedMatrix(MatrixBase):
         """Flat block workspace (for the row-sharded allreduce, distributed.py)."""
         return self.mat._sandwich_blocks_dev(self._gather(d_t), self._rows_in(rows_t))
 
+    def _sandwich_blocks_overlapped_dev(self, d_t, rows_t, reduce_async, reduce):
+        return self.mat._sandwich_blocks_overlapped_dev(self._gather(d_t), self._rows_in(rows_t),
+                                                        reduce_async, reduce)
+
     def _assemble_dev(self, ws: torch.Tensor, cols=None) -> torch.Tensor:
         return self.mat._assemble_dev(ws, cols)
 

@@ -421,6 +421,32 @@ class SplitMatrix(MatrixBase):
             _dev.length(rows_t), _dev.ptr(ws), _dev.stream_ptr()))
         return ws
 
+    def _sandwich_blocks_overlapped_dev(self, d_t: torch.Tensor, rows_t, reduce_async, reduce):
+        """The flat block workspace of a ROW-SHARDED sandwich with the collective overlapped:
+        the blocks without the dense operand (95 % of the payload) are computed first and
+        ``reduce_async(ws_tail)`` starts their allreduce (it returns an object with ``wait()``);
+        the dense-operand passes run meanwhile (the gather kernel leaves SMs free for the
+        collective, ``tm_set_sm_reserve``); ``reduce(ws_head)`` then sums the small rest.  None
+        when the layout does not allow the two phases (the dense block must come first)."""
+        plan = self._native_plan(d_t.dtype)
+        if plan is None or not isinstance(self.matrices[0], DenseMatrix) or len(self.matrices) < 2:
+            return None
+        descs, elems = plan
+        nb = len(self.matrices)
+        head = int(lib.tm_split_workspace_head_elems(descs, nb))
+        ws = torch.empty(elems, dtype=d_t.dtype, device=d_t.device)
+        args = (descs, nb, self.shape[0], _dev.ptr(d_t), _dev.ptr(rows_t), _dev.length(rows_t),
+                _dev.ptr(ws))
+        suf = _dev.suffix(d_t.dtype)
+        st = _dev.stream_ptr()
+        check(fn("tm_split_sandwich_blocks_part", suf)(*args, 1, st))
+        work = reduce_async(ws[head:]) if elems > head else None
+        check(fn("tm_split_sandwich_blocks_part", suf)(*args, 2, st))
+        if work is not None:
+            work.wait()
+        reduce(ws[:head])
+        return ws
+
     # ---- fused IRLS pass: Hessian and score from one pass over the dense block -------------
     def sandwich_and_transpose_matvec(self, d, v, rows=None, cols=None):
         """``(X.T diag(d) X, X.T v)`` restricted to ``rows`` / ``cols`` — what a glum-style IRLS
@@ -597,13 +623,13 @@ class SplitMatrix(MatrixBase):
                                           buf.data_ptr() + ((r0 - b0) * p + c0) * 8, row_bytes,
                                           (c1 - c0) * 8, r1 - r0, stream))
 
-        def assemble(ws_t, buf, part):
+        def assemble(ws_t, buf, part, stream):
             if band is None:
                 check(fn("tm_split_sandwich_assemble_part", suf)(descs, nb, _dev.ptr(ws_t),
-                                                                _dev.ptr(buf), p, part, st))
+                                                                _dev.ptr(buf), p, part, stream))
             elif b1 > b0:
                 check(fn("tm_split_sandwich_assemble_part_band", suf)(
-                    descs, nb, _dev.ptr(ws_t), _dev.ptr(buf), p, part, b0, b1, st))
+                    descs, nb, _dev.ptr(ws_t), _dev.ptr(buf), p, part, b0, b1, stream))
 
         plan = self._native_plan(d_t.dtype)
         runs = self._column_runs()
@@ -652,7 +678,7 @@ class SplitMatrix(MatrixBase):
         cs = None
         if mine:
             buf = torch.empty((b1 - b0, p), dtype=torch.float64, device=d_t.device)
-            assemble(ws, buf, 1)
+            assemble(ws, buf, 1, st)
             cs = self.__dict__.get("_copy_stream")
             if cs is None:
                 cs = self.__dict__["_copy_stream"] = torch.cuda.Stream()
@@ -666,7 +692,7 @@ class SplitMatrix(MatrixBase):
             reduce(ws[:head])
         if not mine:
             return None
-        assemble(ws, buf, 2)
+        assemble(ws, buf, 2, st)
         for (r0, r1, _) in dense_runs:
             copy2d(buf, r0, r1, 0, p, st)
         for (r0, r1, _) in other_runs:

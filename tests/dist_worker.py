@@ -50,6 +50,9 @@ def main():
         dl = torch.from_numpy(s["d"][lo:hi]).to(dev)
         got = S.sandwich(dl).cpu().numpy()
         got_r = S.sandwich(dl, rows=rows).cpu().numpy()
+        S.overlap = False     # whole workspace reduced at the end (no allreduce/compute overlap)
+        got_plain = S.sandwich(dl).cpu().numpy()
+        S.overlap = True
         only0 = S.sandwich(dl, dst=0)
         assert (only0 is None) == (rank != 0)
         tmv = S.transpose_matvec(torch.from_numpy(v[lo:hi]).to(dev), rows=rows).cpu().numpy()
@@ -60,6 +63,7 @@ def main():
         if rank == 0:
             ref = full.sandwich(s["d"])
             e1 = check(f"{order}: sandwich", got, ref)
+            check(f"{order}: sandwich, no overlap", got_plain, ref)
             check(f"{order}: sandwich rows", got_r, full.sandwich(s["d"], rows=rows))
             check(f"{order}: sandwich dst=0", only0.cpu().numpy(), ref)
             check(f"{order}: sandwich_into", out_host, ref)

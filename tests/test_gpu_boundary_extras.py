@@ -104,3 +104,37 @@ def test_split_matvec_uses_block_order_gather(monkeypatch):
     cases.assert_close(out, 1 + full.T @ w, np.float64, "transpose_matvec accumulates into out")
     rows = np.arange(0, n, 3)
     cases.assert_close(S.transpose_matvec(w, rows=rows), full[rows].T @ w[rows], np.float64, "rows")
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("m", [7, 220])
+def test_sparse_self_sandwich_shared_memory_tables(dt, m, monkeypatch):
+    """The narrow-block form of the sparse self sandwich (k_sparse_sandwich_smem: packed lower
+    triangle in shared memory, one table per SM) == the L2 RED form == float64 recomputation
+    (sparse.pyx:17-78), with `rows` / `cols` restrictions, empty rows, zero weights."""
+    import scipy.sparse as sps
+
+    import tabmat_b200 as tm
+    from tests import cases
+
+    rng = np.random.default_rng(m)
+    n = 30_011
+    A = sps.random(n, m, density=min(0.9, 6.0 / m), random_state=rng, format="csc").astype(dt)
+    d = rng.standard_normal(n).astype(dt)
+    d[rng.random(n) < 0.1] = 0
+    rows = np.sort(rng.choice(n, size=n // 3, replace=False)).astype(np.int32)
+    cols = np.sort(rng.choice(m, size=max(2, m // 2), replace=False)).astype(np.int32)
+    S = tm.SparseMatrix(A)
+    Ad = A.toarray().astype(np.float64)
+    for r, c in ((None, None), (rows, None), (None, cols), (rows, cols)):
+        Ar = Ad if r is None else Ad[r]
+        dr = d.astype(np.float64) if r is None else d.astype(np.float64)[r]
+        Ar = Ar if c is None else Ar[:, c]
+        ref = Ar.T @ (dr[:, None] * Ar)
+        monkeypatch.setenv("TABMAT_B200_SPARSE_SMEM", "2")
+        got = S.sandwich(d, r, c)
+        monkeypatch.setenv("TABMAT_B200_SPARSE_SMEM", "0")
+        red = S.sandwich(d, r, c)
+        cases.assert_close(got, ref, dt, "shared-memory tables")
+        cases.assert_close(red, ref, dt, "L2 RED form")
+        assert np.array_equal(got, got.T)

@@ -266,3 +266,34 @@ def test_tcgen05_syrk_wide_matrices_by_panels(n, p, order, force_mode):
     force_mode(1)
     core = run_cuda("dense_sandwich", dict(X=X, d=d, rows=None, cols=None))
     cases.assert_close(core, Xd.T @ (d.astype(np.float64)[:, None] * Xd), np.float32, "cuda-core")
+
+
+def test_tf32_rounding_modes_agree():
+    """fp32 -> tf32 of the MMA operands: the cvt.rna.tf32.f32 instruction (mode 0), integer
+    add + mask (1) and integer add alone (2, the tensor core ignores the low 13 bits) give the
+    same sandwich up to the order of the atomic adds; X is offset so that a truncating
+    conversion (no rounding at all) would show as a bias of ~2e-4."""
+    import tabmat_b200 as tm
+
+    lib = tm._lib.lib
+    if not lib.tm_has_tcgen05():
+        pytest.skip("needs sm_100")
+    rng = np.random.default_rng(3)
+    n, p = 200_000, 128
+    X = (1.0 + rng.random((n, p))).astype(np.float32)
+    d = rng.random(n).astype(np.float32)
+    D = tm.DenseMatrix(X)
+    ref = (X.astype(np.float64) * d[:, None].astype(np.float64)).T @ X.astype(np.float64)
+    res = {}
+    try:
+        for mode in (0, 1, 2):
+            lib.tm_set_tc_round_mode(mode)
+            res[mode] = D.sandwich(d)
+    finally:
+        lib.tm_set_tc_round_mode(-1)
+    scale = np.abs(ref).max()
+    for mode in (1, 2):
+        assert np.abs(res[mode] - res[0]).max() / scale < 2e-6, mode
+    for mode in (0, 1, 2):
+        # unbiased rounding: far below the 2^-11 relative bias of a truncating conversion
+        assert abs((res[mode] - ref).mean()) / scale < 2e-5, mode
