@@ -76,8 +76,8 @@ void tm_set_tc_scatter_warps(int warps);
 /* fp32 -> tf32 rounding of the tcgen05 operands (round to nearest, ties away, like the
  * reference-free cvt.rna.tf32.f32): 0 = the cvt instruction (4 SASS instructions on sm_100a),
  * 1 = integer add + mask (same values for finite inputs and infinities), 2 = integer add only
- * (the tensor core ignores the low 13 bits of a tf32 operand), -1 = default
- * (TABMAT_B200_TC_ROUND, else 1). */
+ * (the tensor core ignores the low 13 bits of a tf32 operand; tested), -1 = default
+ * (TABMAT_B200_TC_ROUND, else 2). */
 void tm_set_tc_round_mode(int mode);
 
 /* ---- dense block (reference: ext/dense.pyx) --------------------------------------- */

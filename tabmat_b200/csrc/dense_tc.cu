@@ -42,9 +42,9 @@ namespace tc {
 constexpr int BK = 32;                     // rows per pipeline stage (= one 128 B K-major row)
 constexpr int TILE_BYTES = 128 * 128;      // one K-major operand tile: 128 X-columns x 32 k x 4 B
 constexpr int GROUP_BYTES = 32 * 128;      // 32 one-hot slots x 128 B
-constexpr int NUM_SCALE_WARPS = 8;
-constexpr int NUM_SCALE_THREADS = NUM_SCALE_WARPS * 32;
-constexpr int NUM_THREADS = 64 + NUM_SCALE_THREADS;  // producer warp + mma warp + scale warps
+// producer warp + mma warp + NSW scale warps (8, or 16: template parameter of the kernel) + SCW
+// scatter warps
+constexpr int tc_threads(int nsw, int scw) { return 64 + 32 * nsw + 32 * scw; }
 constexpr int MAX_STAGES = 16;
 constexpr int MAX_SB = 4;                  // max depth of the operand (S / one-hot / T) ring
 constexpr int SMEM_BUDGET = 220 * 1024;
@@ -378,7 +378,7 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
 // 1024 = 256 columns: the 16 row offsets of the transposing loads fold into the LDS immediates,
 // which takes ~a quarter of the scale warps' instructions away - they are what paces the kernel
 // at p = 256, ncu: issue slots 63 % busy, tensor pipe 47 %), or 0 = use `pitch_rt`
-template <int SUB, int PITCH, int RM>
+template <int SUB, int PITCH, int RM, int NU = 4>
 __device__ __forceinline__ void scale_col4(uint32_t r0, uint32_t pitch_rt, bool ok, uint32_t dsm,
                                            uint32_t Sp, uint32_t t_addr, int c, int kb, int ks,
                                            uint32_t vsm, float& gacc) {
@@ -386,16 +386,16 @@ __device__ __forceinline__ void scale_col4(uint32_t r0, uint32_t pitch_rt, bool 
     // r0: shared address of element (row 0, column c) of the raw stage, pitch: bytes per row;
     // dsm, Sp: shared addresses of the stage's d vector and of the S tile
     constexpr bool s_lo = SUB == 1, t_lo = SUB == 2;   // 3xTF32 sub-pass: which operand is the residual
-    float x[4][4];
+    float x[NU][4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
+    for (int u = 0; u < NU; ++u)
 #pragma unroll
         for (int i = 0; i < 4; ++i)
             x[u][i] = ok ? lds_f32(r0 + (uint32_t)(4 * (kb + u * ks) + i) * pitch) : 0.f;
     const uint32_t tile_off = (uint32_t)(c >> 7) * TILE_BYTES;
     const uint32_t row = (uint32_t)c & 127u;
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < NU; ++u) {
         const int k4 = kb + u * ks;
         const float4 dv = lds_f32x4(dsm + 16u * (uint32_t)k4);
         uint4 a;
@@ -422,20 +422,20 @@ __device__ __forceinline__ void scale_col4(uint32_t r0, uint32_t pitch_rt, bool 
 // 128-byte row of 32 k-values per X column, 16-byte chunks XOR-swizzled by the TMA unit
 // (SWIZZLE_128B) so that the 32 lanes of a warp, one column each, read a chunk without bank
 // conflicts.  No transpose is needed: a lane reads its 4 consecutive k as one LDS.128.
-template <int SUB, int RM>
+template <int SUB, int RM, int NU = 4>
 __device__ __forceinline__ void scale_col4_f(uint32_t R, bool ok, uint32_t dsm, uint32_t Sp,
                                              uint32_t t_addr, int c, int kb, int ks, uint32_t vsm,
                                              float& gacc) {
     constexpr bool s_lo = SUB == 1, t_lo = SUB == 2;
     const uint32_t tile_off = (uint32_t)(c >> 7) * TILE_BYTES;
     const uint32_t row = (uint32_t)c & 127u;
-    float4 x[4];
+    float4 x[NU];
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
+    for (int u = 0; u < NU; ++u)
         x[u] = ok ? lds_f32x4(R + kmajor_chunk_off((uint32_t)c, (uint32_t)(kb + u * ks)))
                   : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < NU; ++u) {
         const int k4 = kb + u * ks;
         const float4 dv = lds_f32x4(dsm + 16u * (uint32_t)k4);
         uint4 a;
@@ -457,12 +457,36 @@ __device__ __forceinline__ void scale_col4_f(uint32_t R, bool ok, uint32_t dsm, 
     }
 }
 
-// one operand slot of a raw stage: sub-pass SUB of the 3xTF32 scheme (0 = the plain TF32 pass)
-template <int SUB, int RM>
+// one operand slot of a raw stage: sub-pass SUB of the 3xTF32 scheme (0 = the plain TF32 pass).
+// Who does what.  8 scale warps: the two warps of a TMEM lane quarter (h = 0, 1) split the 8 row
+// chunks of a column (P <= 128: chunks h, h+2, h+4, h+6) or the two 128-column tiles (P > 128,
+// all 8 chunks).  16 scale warps (h = 0..3): chunks h, h+4 (P <= 128) or tile h >> 1, chunks
+// (h & 1) + 0, 2, 4, 6.
+template <int SUB, int RM, int NSW>
 __device__ __forceinline__ void scale_stage(bool f_order, int mtiles, uint32_t R, uint32_t col_off,
                                             uint32_t pitch, bool ok, uint32_t dsm, uint32_t Sp,
                                             uint32_t t_addr, int my_col, int h, uint32_t vsm,
                                             float& gacc) {
+    if (NSW == 16) {
+        if (f_order) {
+            if (mtiles == 1)
+                scale_col4_f<SUB, RM, 2>(R, ok, dsm, Sp, t_addr, my_col, h, 4, vsm, gacc);
+            else
+                scale_col4_f<SUB, RM, 4>(R, ok, dsm, Sp, t_addr, my_col, h & 1, 2, vsm, gacc);
+        } else if (mtiles == 1) {
+            if (pitch == 512)
+                scale_col4<SUB, 512, RM, 2>(R + col_off, pitch, ok, dsm, Sp, t_addr, my_col, h, 4, vsm, gacc);
+            else
+                scale_col4<SUB, 0, RM, 2>(R + col_off, pitch, ok, dsm, Sp, t_addr, my_col, h, 4, vsm, gacc);
+        } else if (pitch == 1024) {
+            scale_col4<SUB, 1024, RM, 4>(R + col_off, pitch, ok, dsm, Sp, t_addr, my_col, h & 1, 2, vsm, gacc);
+        } else if (pitch == 512) {
+            scale_col4<SUB, 512, RM, 4>(R + col_off, pitch, ok, dsm, Sp, t_addr, my_col, h & 1, 2, vsm, gacc);
+        } else {
+            scale_col4<SUB, 0, RM, 4>(R + col_off, pitch, ok, dsm, Sp, t_addr, my_col, h & 1, 2, vsm, gacc);
+        }
+        return;
+    }
     if (f_order) {
         if (mtiles == 1) {
             scale_col4_f<SUB, RM>(R, ok, dsm, Sp, t_addr, my_col, h, 2, vsm, gacc);
@@ -492,10 +516,10 @@ int g_tc_round = -1;
 static int tc_round_mode() {
     int rm = g_tc_round;
     if (rm < 0) {
-        static const int env = getenv("TABMAT_B200_TC_ROUND") ? atoi(getenv("TABMAT_B200_TC_ROUND")) : 1;
+        static const int env = getenv("TABMAT_B200_TC_ROUND") ? atoi(getenv("TABMAT_B200_TC_ROUND")) : 2;
         rm = env;
     }
-    return rm < 0 || rm > 2 ? 1 : rm;
+    return rm < 0 || rm > 2 ? 2 : rm;
 }
 
 // tensor maps of one launch: the X tile, the weight vector d and the one-hot code vectors
@@ -523,8 +547,8 @@ __device__ __forceinline__ void tl_stamp(const Params& prm, int it, int e) {
 // NSUB = operand slots per raw stage: 1 (TF32) or 3 (3xTF32, tm_set_dense_f32_mode(3)); a
 // template parameter because the scale warps are the throughput-critical part of the pipeline
 // and the plain path must not pay for the residual arithmetic
-template <int MIN_BLOCKS, int SCW, int NSUB>
-__global__ void __launch_bounds__(NUM_THREADS + 32 * SCW, MIN_BLOCKS)
+template <int MIN_BLOCKS, int SCW, int NSUB, int NSW>
+__global__ void __launch_bounds__(tc_threads(NSW, SCW), MIN_BLOCKS)
 k_dense_syrk_tc(const __grid_constant__ TmapSet tmaps, const Params prm) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* base = reinterpret_cast<uint8_t*>(
@@ -555,7 +579,7 @@ k_dense_syrk_tc(const __grid_constant__ TmapSet tmaps, const Params prm) {
     // one-hot tiles are all-zero except for the ones set (and cleared again) per stage
     {
         uint4* z = reinterpret_cast<uint4*>(Oper);
-        for (uint32_t i = threadIdx.x; i < SB * slot_bytes / 16; i += NUM_THREADS + 32 * SCW)
+        for (uint32_t i = threadIdx.x; i < SB * slot_bytes / 16; i += tc_threads(NSW, SCW))
             z[i] = make_uint4(0, 0, 0, 0);
         fence_proxy_async();
     }
@@ -563,10 +587,10 @@ k_dense_syrk_tc(const __grid_constant__ TmapSet tmaps, const Params prm) {
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < SR; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&emptyR[s], NUM_SCALE_WARPS + SCW);
+            mbar_init(&emptyR[s], NSW + SCW);
         }
         for (int b = 0; b < SB; ++b) {
-            mbar_init(&scaled[b], NUM_SCALE_WARPS);  // one arrive per scale warp
+            mbar_init(&scaled[b], NSW);  // one arrive per scale warp
             mbar_init(&emptyB[b], 1);
         }
         mbar_init(done, 1);
@@ -707,7 +731,7 @@ k_dense_syrk_tc(const __grid_constant__ TmapSet tmaps, const Params prm) {
         }
         if (elect_one()) tcgen05_commit(done);
         __syncwarp();
-    } else if (SCW > 0 && warp >= 2 + NUM_SCALE_WARPS) {
+    } else if (SCW > 0 && warp >= 2 + NSW) {
         // ===== scatter warps: vector REDs of the cross blocks that share the dense operand =====
         // Warp ws owns rows [ws * RPW, (ws + 1) * RPW) of every row tile of this CTA.  It copies
         // its rows from the raw stage into registers (one LDS.128 per row: lane l holds columns
@@ -720,7 +744,7 @@ k_dense_syrk_tc(const __grid_constant__ TmapSet tmaps, const Params prm) {
         constexpr int RPW = SCW > 0 ? BK / SCW : 1;       // rows per warp and tile (8 or 4)
         constexpr int NCM = TC_SCATTER_MAX_CATS;
         const unsigned FULL = 0xffffffffu;
-        const int ws = warp - (2 + NUM_SCALE_WARPS);
+        const int ws = warp - (2 + NSW);
         const int r0 = ws * RPW;
         const bool lane_ok = lane * 4 < P;
         const int nc = prm.sc_ncat;
@@ -983,12 +1007,12 @@ k_dense_syrk_tc(const __grid_constant__ TmapSet tmaps, const Params prm) {
         }   // general (sparse + global-load) path
     } else {
         // ===== scale warps, then epilogue =====
-        const int w = warp - 2;                // 0..7
-        const int t = (int)threadIdx.x - 64;   // 0..255
-        // one-hot: thread t encodes row (t >> 3) of categorical block (t & 7)
-        const int oh_r = t >> 3;
+        const int w = warp - 2;                // 0..NSW-1
+        const int t = (int)threadIdx.x - 64;   // 0..32*NSW-1
+        // one-hot: thread t < 256 encodes row (t >> 3) of categorical block (t & 7)
+        const int oh_r = (t >> 3) & 31;
         const int oh_c = t & 7;
-        const bool oh_thread = oh_c < prm.oh_ncat;
+        const bool oh_thread = oh_c < prm.oh_ncat && t < 256;
         const int my_off = oh_thread ? prm.oh_off[oh_c] : 0;
         const int my_K = oh_thread ? prm.oh_K[oh_c] : 0;
         const int my_df = oh_thread ? prm.oh_df[oh_c] : 0;
@@ -999,7 +1023,7 @@ k_dense_syrk_tc(const __grid_constant__ TmapSet tmaps, const Params prm) {
         // 128-column tiles (P > 128)
         const int q = warp & 3;
         const int h = w >> 2;
-        const int my_col = (prm.mtiles == 2 ? h * 128 : 0) + q * 32 + lane;
+        const int my_col = (prm.mtiles == 2 ? (NSW == 16 ? h >> 1 : h) * 128 : 0) + q * 32 + lane;
         const uint32_t oper_sa = smem_u32(Oper), rring_sa = smem_u32(Rring);
         // where this thread's column sits in a raw stage (row-major X)
         uint32_t col_off, col_pitch;
@@ -1063,22 +1087,22 @@ k_dense_syrk_tc(const __grid_constant__ TmapSet tmaps, const Params prm) {
                 const uint32_t vsm = (prm.has_v && sub == 0) ? dsm + 128u * 9u : 0u;
                 if (NSUB == 1) {
                     if (prm.round_mode == 2)
-                        scale_stage<0, 2>(prm.f_order, prm.mtiles, R, col_off, col_pitch, col_ok,
+                        scale_stage<0, 2, NSW>(prm.f_order, prm.mtiles, R, col_off, col_pitch, col_ok,
                                           dsm, Sp, t_addr, my_col, h, vsm, gacc);
                     else if (prm.round_mode == 1)
-                        scale_stage<0, 1>(prm.f_order, prm.mtiles, R, col_off, col_pitch, col_ok,
+                        scale_stage<0, 1, NSW>(prm.f_order, prm.mtiles, R, col_off, col_pitch, col_ok,
                                           dsm, Sp, t_addr, my_col, h, vsm, gacc);
                     else
-                        scale_stage<0, 0>(prm.f_order, prm.mtiles, R, col_off, col_pitch, col_ok,
+                        scale_stage<0, 0, NSW>(prm.f_order, prm.mtiles, R, col_off, col_pitch, col_ok,
                                           dsm, Sp, t_addr, my_col, h, vsm, gacc);
                 } else if (sub == 0)
-                    scale_stage<0, 1>(prm.f_order, prm.mtiles, R, col_off, col_pitch, col_ok, dsm,
+                    scale_stage<0, 1, NSW>(prm.f_order, prm.mtiles, R, col_off, col_pitch, col_ok, dsm,
                                       Sp, t_addr, my_col, h, vsm, gacc);
                 else if (sub == 1)
-                    scale_stage<1, 1>(prm.f_order, prm.mtiles, R, col_off, col_pitch, col_ok, dsm,
+                    scale_stage<1, 1, NSW>(prm.f_order, prm.mtiles, R, col_off, col_pitch, col_ok, dsm,
                                       Sp, t_addr, my_col, h, 0u, gacc);
                 else
-                    scale_stage<2, 1>(prm.f_order, prm.mtiles, R, col_off, col_pitch, col_ok, dsm,
+                    scale_stage<2, 1, NSW>(prm.f_order, prm.mtiles, R, col_off, col_pitch, col_ok, dsm,
                                       Sp, t_addr, my_col, h, 0u, gacc);
             }
             if (t == 0) tl_stamp(prm, it, 6);
@@ -1099,7 +1123,8 @@ k_dense_syrk_tc(const __grid_constant__ TmapSet tmaps, const Params prm) {
         // epilogue: TMEM -> registers -> RED into `out` (transposed: lanes = output columns)
         mbar_wait_t<(SCW > 0)>(done, 0);
         tcgen05_fence_after();
-        const int chalf = (warp - 2) >> 2;    // which half of the column chunks this warp drains
+        const int chalf = (warp - 2) >> 2;    // which share of the column chunks this warp drains
+        constexpr int CPW = 16 / NSW;         // 32-column chunks of a 128-column tile per warp
         if (my_count > 0) {
             // local column -> global column of the result (legacy: identity)
             auto gcol = [&](int c) -> int {
@@ -1114,11 +1139,11 @@ k_dense_syrk_tc(const __grid_constant__ TmapSet tmaps, const Params prm) {
                     if (prm.mtiles == 2 && !((prm.tile_mask >> tile) & 1)) continue;
                     const int C = gcol(mt * 128 + q * 32 + lane);  // output column (= X column of A)
 #pragma unroll 1
-                    for (int cc = 0; cc < (prm.dual_acc ? 4 : 2); ++cc) {
+                    for (int cc = 0; cc < (prm.dual_acc ? 2 : 1) * CPW; ++cc) {
                         // dual_acc: the second accumulator tile (TMEM columns 128..255) holds the
                         // odd k steps of the same output tile
-                        const int dup = cc >> 1;
-                        const int n0 = chalf * 64 + (cc & 1) * 32;
+                        const int dup = cc / CPW;
+                        const int n0 = chalf * (32 * CPW) + (cc % CPW) * 32;
                         uint32_t v[32];
                         uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) +
                                          (uint32_t)((tile + dup) * 128 + n0);
@@ -1141,7 +1166,7 @@ k_dense_syrk_tc(const __grid_constant__ TmapSet tmaps, const Params prm) {
             // one-hot block: D'[col = lane, slot] -> oh_out[slot, col]
             const int C = q * 32 + lane;
 #pragma unroll 1
-            for (int ch = chalf; ch < prm.oh_groups; ch += 2) {
+            for (int ch = chalf; ch < prm.oh_groups; ch += NSW / 4) {
                 uint32_t v[32];
                 uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + oh_col0 + (uint32_t)ch * 32;
                 TM_TMEM_LD_32x32B_X32(taddr, v);
@@ -1255,13 +1280,13 @@ bool dense_tc_scatter_eligible(int64_t p, int n_cat, bool with_sparse) {
     return tc_scatter_warps(with_sparse) > 0 && p <= 128 && n_cat <= TC_SCATTER_MAX_CATS;
 }
 
-template <int MB, int SCW, int NSUB>
+template <int MB, int SCW, int NSUB, int NSW = 8>
 static int launch_tc(const tc::TmapSet& tmaps, const tc::Params& prm, unsigned grid, size_t smem,
                      cudaStream_t st) {
     // per device and cheap: set on every launch rather than cached in a process-wide static
-    TM_CUDA(cudaFuncSetAttribute(tc::k_dense_syrk_tc<MB, SCW, NSUB>,
+    TM_CUDA(cudaFuncSetAttribute(tc::k_dense_syrk_tc<MB, SCW, NSUB, NSW>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    tc::k_dense_syrk_tc<MB, SCW, NSUB><<<grid, tc::NUM_THREADS + 32 * SCW, smem, st>>>(tmaps, prm);
+    tc::k_dense_syrk_tc<MB, SCW, NSUB, NSW><<<grid, tc::tc_threads(NSW, SCW), smem, st>>>(tmaps, prm);
     TM_LAUNCHED();
     return 0;
 }
@@ -1514,6 +1539,8 @@ static int dense_sandwich_tc_launch(const float* X, int64_t n, int64_t p, int c_
 
     if (!ps) TM_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)(p * p), st));
     long long grid = prm.num_row_tiles < sm_count() ? prm.num_row_tiles : sm_count();
+    // TABMAT_B200_TC_NSW = 8 | 16 scale warps
+    static const int nsw = getenv("TABMAT_B200_TC_NSW") ? atoi(getenv("TABMAT_B200_TC_NSW")) : 8;
     int rc;
     if (prm.nsub == 3) {
         if (scw == 8)
@@ -1524,8 +1551,12 @@ static int dense_sandwich_tc_launch(const float* X, int64_t n, int64_t p, int c_
             rc = launch_tc<1, 0, 3>(tmaps, prm, (unsigned)grid, smem, st);
     } else if (scw == 8) {
         rc = launch_tc<1, 8, 1>(tmaps, prm, (unsigned)grid, smem, st);
+    } else if (scw == 4 && nsw == 16) {
+        rc = launch_tc<1, 4, 1, 16>(tmaps, prm, (unsigned)grid, smem, st);
     } else if (scw == 4) {
         rc = launch_tc<1, 4, 1>(tmaps, prm, (unsigned)grid, smem, st);
+    } else if (nsw == 16 && !share_sm) {
+        rc = launch_tc<1, 0, 1, 16>(tmaps, prm, (unsigned)grid, smem, st);
     } else if (share_sm) {
         rc = launch_tc<2, 0, 1>(tmaps, prm, (unsigned)grid, smem, st);
     } else {

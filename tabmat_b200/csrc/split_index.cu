@@ -739,6 +739,14 @@ static int launch_cat_sparse_cols(const F* data, const int32_t* row_idx, const i
                                   int p_s, const CodeSrc& rec, const ColOwnerParams& prm, int grid,
                                   cudaStream_t st) {
     const size_t smem = sizeof(F) * (size_t)prm.slot * (size_t)prm.cols_per_cta;
+    if (smem > 48 * 1024) {
+        if (rec.pk)
+            TM_CUDA(cudaFuncSetAttribute(k_cat_sparse_cols<F, NC, true>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        else
+            TM_CUDA(cudaFuncSetAttribute(k_cat_sparse_cols<F, NC, false>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
     if (rec.pk)
         k_cat_sparse_cols<F, NC, true><<<grid, CO_THREADS, smem > 0 ? smem : 16, st>>>(
             data, row_idx, indptr, p_s, rec, prm);
@@ -761,7 +769,11 @@ static int cat_sparse_cols(const CodeSrc& rec, int n_cat, const int64_t* K, cons
     if (grid > p_s) grid = (int)p_s;
     prm.cols_per_cta = (int)((p_s + grid - 1) / grid);
     grid = (int)((p_s + prm.cols_per_cta - 1) / prm.cols_per_cta);
-    const int64_t budget = (int64_t)(40 * 1024 / sizeof(F)) / prm.cols_per_cta;  // per column
+    // shared-memory column tables: blocks with <= max_k levels while they fit `smem_kb` per CTA
+    // (TABMAT_B200_COLS_SMEM_MAXK / TABMAT_B200_COLS_SMEM_KB)
+    static const int max_k = getenv("TABMAT_B200_COLS_SMEM_MAXK") ? atoi(getenv("TABMAT_B200_COLS_SMEM_MAXK")) : 512;
+    static const int smem_kb = getenv("TABMAT_B200_COLS_SMEM_KB") ? atoi(getenv("TABMAT_B200_COLS_SMEM_KB")) : 40;
+    const int64_t budget = (int64_t)(smem_kb * 1024 / sizeof(F)) / prm.cols_per_cta;  // per column
     int64_t slot = 0;
     bool done[IDX_MAX_CATS] = {false};
     for (int it = 0; it < n_cat; ++it) {  // smallest blocks first
@@ -772,7 +784,7 @@ static int cat_sparse_cols(const CodeSrc& rec, int n_cat, const int64_t* K, cons
         prm.K[best] = (int)K[best];
         prm.runs[best] = runs ? runs[best] : 0;
         prm.rep[best] = 1;
-        if (K[best] <= 512 && slot + K[best] <= budget) {
+        if (K[best] <= max_k && slot + K[best] <= budget) {
             int rep = 1;
             while (rep < 8 && K[best] * rep * 2 <= 256 && slot + K[best] * rep * 2 <= budget) rep *= 2;
             prm.in_smem[best] = 1;
