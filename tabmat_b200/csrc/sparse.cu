@@ -13,7 +13,7 @@ namespace tmb {
 // the lower triangle is touched (the reference does the same with its `i > j: break`,
 // sparse.pyx:64-67) and mirrored afterwards (sparse.pyx:76).
 // ---------------------------------------------------------------------------------------
-template <typename F>
+template <typename F, bool OFFDIAG = false>
 __global__ void k_sparse_sandwich(const F* __restrict__ data, const int32_t* __restrict__ indices,
                                   const int32_t* __restrict__ indptr,
                                   const int32_t* __restrict__ nz_row, int64_t nnz,
@@ -29,7 +29,7 @@ __global__ void k_sparse_sandwich(const F* __restrict__ data, const int32_t* __r
         if (pa < 0) continue;
         F va = data[e] * d[k];
         F* orow = out + (int64_t)pa * m;
-        for (int64_t b = indptr[k]; b <= e; ++b) {
+        for (int64_t b = indptr[k]; b < e + (OFFDIAG ? 0 : 1); ++b) {
             int jb = indices[b];
             int pb = col_pos ? col_pos[jb] : jb;
             if (pb < 0) continue;
@@ -182,13 +182,13 @@ __global__ void k_csc_colreduce(const F* __restrict__ data, const int32_t* __res
 
 // ---- host wrappers ---------------------------------------------------------------------
 template <typename F>
-int sparse_sandwich(const F* data, const int32_t* indices, const int32_t* indptr,
-                    const int32_t* nz_row, int64_t n, int64_t p, int64_t nnz, const F* d,
-                    const int32_t* rows, int64_t n_rows, const int32_t* cols, int64_t m, F* out,
-                    cudaStream_t st) {
+int sparse_sandwich_ex(const F* data, const int32_t* indices, const int32_t* indptr,
+                       const int32_t* nz_row, int64_t n, int64_t p, int64_t nnz, const F* d,
+                       const int32_t* rows, int64_t n_rows, const int32_t* cols, int64_t m, F* out,
+                       cudaStream_t st, bool offdiag_only) {
     if (!cols) m = p;
     if (m <= 0) return 0;
-    TM_CUDA(cudaMemsetAsync(out, 0, sizeof(F) * (size_t)(m * m), st));
+    if (!offdiag_only) TM_CUDA(cudaMemsetAsync(out, 0, sizeof(F) * (size_t)(m * m), st));
     if (nnz <= 0 || (rows && n_rows <= 0)) return 0;
     Scratch rmask(rows ? (size_t)n : 0, st);
     Scratch cpos(cols ? sizeof(int32_t) * (size_t)p : 0, st);
@@ -207,7 +207,7 @@ int sparse_sandwich(const F* data, const int32_t* indices, const int32_t* indptr
     const size_t tri_bytes = sizeof(F) * (size_t)(m * (m + 1) / 2);
     const char* sm_env = getenv("TABMAT_B200_SPARSE_SMEM");
     const int sm_mode = sm_env ? atoi(sm_env) : 1;
-    const bool in_smem = sm_mode != 0 && tri_bytes <= 200 * 1024 &&
+    const bool in_smem = !offdiag_only && sm_mode != 0 && tri_bytes <= 200 * 1024 &&
                          (sm_mode == 2 || nnz > (int64_t)sm_count() * (m * (m + 1) / 2));
     if (in_smem) {
         static bool attr_done[2][16] = {};
@@ -225,13 +225,26 @@ int sparse_sandwich(const F* data, const int32_t* indices, const int32_t* indptr
             cols ? cpos.as<int32_t>() : nullptr, (int)m, out);
     } else {
         int g = grid_for(nnz, 256, sm_count() * 32);
-        k_sparse_sandwich<F><<<g, 256, 0, st>>>(data, indices, indptr, nz_row, nnz, d,
-                                                rows ? rmask.as<uint8_t>() : nullptr,
-                                                cols ? cpos.as<int32_t>() : nullptr, m, out);
+        if (offdiag_only)
+            k_sparse_sandwich<F, true><<<g, 256, 0, st>>>(data, indices, indptr, nz_row, nnz, d,
+                                                          rows ? rmask.as<uint8_t>() : nullptr,
+                                                          cols ? cpos.as<int32_t>() : nullptr, m, out);
+        else
+            k_sparse_sandwich<F><<<g, 256, 0, st>>>(data, indices, indptr, nz_row, nnz, d,
+                                                    rows ? rmask.as<uint8_t>() : nullptr,
+                                                    cols ? cpos.as<int32_t>() : nullptr, m, out);
     }
     TM_LAUNCHED();
     return symmetrize_from_lower<F>(out, m, st);
 }
+
+template int sparse_sandwich_ex<float>(const float*, const int32_t*, const int32_t*, const int32_t*,
+                                       int64_t, int64_t, int64_t, const float*, const int32_t*,
+                                       int64_t, const int32_t*, int64_t, float*, cudaStream_t, bool);
+template int sparse_sandwich_ex<double>(const double*, const int32_t*, const int32_t*,
+                                        const int32_t*, int64_t, int64_t, int64_t, const double*,
+                                        const int32_t*, int64_t, const int32_t*, int64_t, double*,
+                                        cudaStream_t, bool);
 
 template <typename F>
 int csr_dense_sandwich(const F* data, const int32_t* indices, const int32_t* indptr, int64_t n,
@@ -316,8 +329,9 @@ extern "C" {
                                  int64_t p, int64_t nnz, const F* d, const int32_t* rows,         \
                                  int64_t n_rows, const int32_t* cols, int64_t n_cols, F* out,     \
                                  tm_stream_t stream) {                                            \
-        return tmb::sparse_sandwich<F>(csr_data, csr_indices, csr_indptr, csr_row, n, p, nnz, d,   \
-                                      rows, n_rows, cols, n_cols, out, tmb::as_stream(stream));    \
+        return tmb::sparse_sandwich_ex<F>(csr_data, csr_indices, csr_indptr, csr_row, n, p, nnz,   \
+                                          d, rows, n_rows, cols, n_cols, out,                     \
+                                          tmb::as_stream(stream), false);                         \
     }                                                                                             \
     int tm_csr_dense_sandwich_##SUF(const F* csr_data, const int32_t* csr_indices,                \
                                     const int32_t* csr_indptr, int64_t n, int64_t p_sparse,       \

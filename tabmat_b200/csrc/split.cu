@@ -393,7 +393,7 @@ int split_blocks(const tm_block_desc* blk, int nb, int64_t n, const F* d, const 
         // fused index blocks (split_index.cu): all categorical self / pair blocks in one pass
         // over 32-byte row records, categorical x sparse for all categorical blocks from the
         // CSC copy without global atomics
-        bool cats_fused = false, cat_sparse_fused = false;
+        bool cats_fused = false, cat_sparse_fused = false, sparse_diag_done = false;
         {
             int cats[8];
             int nc = 0;
@@ -468,14 +468,24 @@ int split_blocks(const tm_block_desc* blk, int nb, int64_t n, const F* d, const 
                         const int hi = cats[a] < sparse_idx ? sparse_idx : cats[a];
                         outs[a] = ws + cross_off[lo][hi];
                     }
+                    // by-product of the column-owner kernel: the diagonal of the sparse block's
+                    // own sandwich (TABMAT_B200_SPARSE_DIAG=0: the CSR kernel adds it itself)
+                    static const bool diag_off = getenv("TABMAT_B200_SPARSE_DIAG") &&
+                                                 atoi(getenv("TABMAT_B200_SPARSE_DIAG")) == 0;
+                    F* sdiag = nullptr;
+                    if (S.csc_row_blocks > 1 && !diag_off) {
+                        sdiag = ws + self_off[sparse_idx];
+                        TM_CUDA(cudaMemsetAsync(sdiag, 0, sizeof(F) * (size_t)(S.ncols * S.ncols), st));
+                    }
                     rc = index_cat_sparse<F>(use_packed ? nullptr : rec.p, dd,
                                              use_packed ? S.csc_cat_codes : nullptr, nc, Kc, runp,
                                              static_cast<const F*>(S.csc_data), S.csc_indices,
                                              S.csc_indptr, S.ncols,
                                              (int)(S.csc_row_blocks > 1 ? S.csc_row_blocks : 1),
-                                             outs, st);
+                                             outs, sdiag, S.ncols + 1, st);
                     if (rc) return rc;
                     cat_sparse_fused = true;
+                    sparse_diag_done = sdiag != nullptr;
                 }
             }
         }
@@ -490,6 +500,10 @@ int split_blocks(const tm_block_desc* blk, int nb, int64_t n, const F* d, const 
             else if (bi.kind == KIND_DENSE)
                 rc = dense_sandwich(tag, static_cast<const F*>(bi.data), n, bi.ncols, bi.c_order, d,
                                     rows, n_rows, (const int32_t*)nullptr, (int64_t)0, so, stream);
+            else if (bi.kind == KIND_SPARSE && sparse_diag_done && i == sparse_idx)
+                rc = sparse_sandwich_ex<F>(static_cast<const F*>(bi.data), bi.csr_indices,
+                                           bi.csr_indptr, bi.csr_row, n, bi.ncols, bi.nnz, d, rows,
+                                           n_rows, (const int32_t*)nullptr, (int64_t)0, so, st, true);
             else if (bi.kind == KIND_SPARSE)
                 rc = sparse_sandwich(tag, static_cast<const F*>(bi.data), bi.csr_indices,
                                      bi.csr_indptr, bi.csr_row, n, bi.ncols, bi.nnz, d, rows,

@@ -404,6 +404,12 @@ struct ColOwnerParams {
     int slot;                    // shared-memory elements per owned column
     int cols_per_cta;
     int n_row_blocks;
+    // optional by-product: the diagonal of the sparse block's own sandwich,
+    // diag[j * diag_ld] = sum_k d[k] * A[k, j]^2 - this kernel walks every non-zero of column j
+    // with d[k] in hand anyway, and the CSR outer-product kernel then skips its 40 % of REDs
+    // that all land on those p_s addresses
+    void* diag;
+    long long diag_ld;
 };
 
 template <typename F, int NC, bool PK>
@@ -417,12 +423,15 @@ k_cat_sparse_cols(const F* __restrict__ data, const int32_t* __restrict__ row_id
     const int c0 = blockIdx.x * prm.cols_per_cta;
     const int c1 = min(p_s, c0 + prm.cols_per_cta);
     if (c0 >= c1) return;
+    F* dsm = smem + (size_t)prm.cols_per_cta * prm.slot;   // [cols_per_cta] diagonal sums
     for (int i = threadIdx.x; i < (c1 - c0) * prm.slot; i += CO_THREADS) smem[i] = F(0);
+    if (threadIdx.x < prm.cols_per_cta) dsm[threadIdx.x] = F(0);
     __syncthreads();
     for (int blk = 0; blk < prm.n_row_blocks; ++blk) {
         const int64_t base = (int64_t)blk * p_s;
         for (int j = c0; j < c1; ++j) {
             F* tab = smem + (j - c0) * prm.slot;
+            F dacc = F(0);
             const int e0 = indptr[base + j], e1 = indptr[base + j + 1];
             // warp-uniform trip count (run_reduce needs whole warps)
             // two groups of CO_THREADS non-zeros per visit: the loads (and the dependent d
@@ -448,6 +457,7 @@ k_cat_sparse_cols(const F* __restrict__ data, const int32_t* __restrict__ row_id
                 for (int u = 0; u < UC; ++u) {
                     if (eb + u * CO_THREADS >= e1) break;   // warp-uniform
                     const F val0 = dk[u] * a[u];
+                    dacc += val0 * a[u];
 #pragma unroll
                     for (int c = 0; c < NC; ++c) {
                         int key = keys[u][c];
@@ -462,9 +472,16 @@ k_cat_sparse_cols(const F* __restrict__ data, const int32_t* __restrict__ row_id
                     }
                 }
             }
+            if (prm.diag) {   // warp-uniform
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) dacc += __shfl_xor_sync(0xffffffffu, dacc, o);
+                if (lane == 0 && dacc != F(0)) atomicAdd(dsm + (j - c0), dacc);
+            }
         }
     }
     __syncthreads();
+    if (prm.diag && threadIdx.x < c1 - c0)   // this CTA is the only owner of these columns
+        static_cast<F*>(prm.diag)[(int64_t)(c0 + threadIdx.x) * prm.diag_ld] = dsm[threadIdx.x];
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
         if (!prm.in_smem[c]) continue;
@@ -738,7 +755,7 @@ template <typename F, int NC>
 static int launch_cat_sparse_cols(const F* data, const int32_t* row_idx, const int32_t* indptr,
                                   int p_s, const CodeSrc& rec, const ColOwnerParams& prm, int grid,
                                   cudaStream_t st) {
-    const size_t smem = sizeof(F) * (size_t)prm.slot * (size_t)prm.cols_per_cta;
+    const size_t smem = sizeof(F) * ((size_t)prm.slot + 1) * (size_t)prm.cols_per_cta;
     if (smem > 48 * 1024) {
         if (rec.pk)
             TM_CUDA(cudaFuncSetAttribute(k_cat_sparse_cols<F, NC, true>,
@@ -760,10 +777,13 @@ static int launch_cat_sparse_cols(const F* data, const int32_t* row_idx, const i
 template <typename F>
 static int cat_sparse_cols(const CodeSrc& rec, int n_cat, const int64_t* K, const int32_t* runs,
                            const F* csc_data, const int32_t* csc_row, const int32_t* csc_indptr,
-                           int64_t p_s, int n_row_blocks, F* const* outs, cudaStream_t st) {
+                           int64_t p_s, int n_row_blocks, F* const* outs, F* diag, int64_t diag_ld,
+                           cudaStream_t st) {
     ColOwnerParams prm;
     memset(&prm, 0, sizeof(prm));
     prm.n_row_blocks = n_row_blocks;
+    prm.diag = diag;
+    prm.diag_ld = diag_ld;
     // one resident wave: 4 CTAs of 256 threads per SM
     int grid = sm_count() * 4;
     if (grid > p_s) grid = (int)p_s;
@@ -785,8 +805,14 @@ static int cat_sparse_cols(const CodeSrc& rec, int n_cat, const int64_t* K, cons
         prm.runs[best] = runs ? runs[best] : 0;
         prm.rep[best] = 1;
         if (K[best] <= max_k && slot + K[best] <= budget) {
+            // replicas (lane % rep) against the CAS-loop contention of shared-memory float
+            // atomics (TABMAT_B200_COLS_REP_MAX / _ELEMS: most replicas, largest replicated table)
+            static const int rep_max = getenv("TABMAT_B200_COLS_REP_MAX") ? atoi(getenv("TABMAT_B200_COLS_REP_MAX")) : 8;
+            static const int rep_elems = getenv("TABMAT_B200_COLS_REP_ELEMS") ? atoi(getenv("TABMAT_B200_COLS_REP_ELEMS")) : 256;
             int rep = 1;
-            while (rep < 8 && K[best] * rep * 2 <= 256 && slot + K[best] * rep * 2 <= budget) rep *= 2;
+            while (rep < rep_max && rep < 32 && K[best] * rep * 2 <= rep_elems &&
+                   slot + K[best] * rep * 2 <= budget)
+                rep *= 2;
             prm.in_smem[best] = 1;
             prm.rep[best] = rep;
             prm.off[best] = (int)slot;
@@ -831,7 +857,7 @@ template <typename F>
 int index_cat_sparse(const void* rec_v, const F* d, const uint64_t* packed, int n_cat,
                      const int64_t* K, const int32_t* runs, const F* csc_data,
                      const int32_t* csc_row, const int32_t* csc_indptr, int64_t p_s,
-                     int n_row_blocks, F* const* outs, cudaStream_t st) {
+                     int n_row_blocks, F* const* outs, F* diag, int64_t diag_ld, cudaStream_t st) {
     CodeSrc rec;
     memset(&rec, 0, sizeof(rec));
     rec.rec = rec_v;
@@ -850,7 +876,8 @@ int index_cat_sparse(const void* rec_v, const F* d, const uint64_t* packed, int 
     }
     if (n_row_blocks > 1)
         return cat_sparse_cols<F>(rec, n_cat, K, runs, csc_data, csc_row, csc_indptr, p_s,
-                                  n_row_blocks, outs, st);
+                                  n_row_blocks, outs, diag, diag_ld, st);
+    if (diag) return fail("index_cat_sparse: the diagonal by-product needs the row-blocked CSC");
     CatSparseParams prm;
     cat_sparse_layout<F>(n_cat, K, runs, prm);
     for (int c = 0; c < n_cat; ++c) {
@@ -872,10 +899,11 @@ int index_cat_sparse(const void* rec_v, const F* d, const uint64_t* packed, int 
 }
 template int index_cat_sparse<float>(const void*, const float*, const uint64_t*, int,
                                      const int64_t*, const int32_t*, const float*, const int32_t*,
-                                     const int32_t*, int64_t, int, float* const*, cudaStream_t);
+                                     const int32_t*, int64_t, int, float* const*, float*, int64_t,
+                                     cudaStream_t);
 template int index_cat_sparse<double>(const void*, const double*, const uint64_t*, int,
                                       const int64_t*, const int32_t*, const double*,
                                       const int32_t*, const int32_t*, int64_t, int,
-                                      double* const*, cudaStream_t);
+                                      double* const*, double*, int64_t, cudaStream_t);
 
 }  // namespace tmb

@@ -220,6 +220,14 @@ template <typename F>
 int index_cat_sparse(const void* rec, const F* d, const uint64_t* packed, int n_cat,
                      const int64_t* K, const int32_t* runs, const F* csc_data,
                      const int32_t* csc_row, const int32_t* csc_indptr, int64_t p_s,
-                     int n_row_blocks, F* const* outs, cudaStream_t st);
+                     int n_row_blocks, F* const* outs, F* diag, int64_t diag_ld, cudaStream_t st);
+// sparse self sandwich (sparse.cu); offdiag_only: `out` was zero-filled by the caller and its
+// diagonal comes from elsewhere (index_cat_sparse's by-product), the kernel adds the strictly
+// lower triangle and mirrors it
+template <typename F>
+int sparse_sandwich_ex(const F* data, const int32_t* indices, const int32_t* indptr,
+                       const int32_t* nz_row, int64_t n, int64_t p, int64_t nnz, const F* d,
+                       const int32_t* rows, int64_t n_rows, const int32_t* cols, int64_t m, F* out,
+                       cudaStream_t st, bool offdiag_only);
 
 }  // namespace tmb
