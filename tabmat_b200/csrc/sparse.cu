@@ -13,7 +13,11 @@ namespace tmb {
 // the lower triangle is touched (the reference does the same with its `i > j: break`,
 // sparse.pyx:64-67) and mirrored afterwards (sparse.pyx:76).
 // ---------------------------------------------------------------------------------------
-template <typename F, bool OFFDIAG = false>
+// PACKED: `out` is the packed lower triangle (row pa starts at pa (pa + 1) / 2) - half the
+// footprint, so that the table of a wide block stays in the 126 MB L2 instead of doing DRAM
+// read-modify-writes (C4: 5000^2 doubles = 200 MB as a square, 100 MB packed); k_unpack_tri
+// writes the square afterwards.
+template <typename F, bool OFFDIAG = false, bool PACKED = false>
 __global__ void k_sparse_sandwich(const F* __restrict__ data, const int32_t* __restrict__ indices,
                                   const int32_t* __restrict__ indptr,
                                   const int32_t* __restrict__ nz_row, int64_t nnz,
@@ -28,13 +32,25 @@ __global__ void k_sparse_sandwich(const F* __restrict__ data, const int32_t* __r
         int pa = col_pos ? col_pos[ja] : ja;
         if (pa < 0) continue;
         F va = data[e] * d[k];
-        F* orow = out + (int64_t)pa * m;
+        F* orow = out + (PACKED ? (int64_t)pa * (pa + 1) / 2 : (int64_t)pa * m);
         for (int64_t b = indptr[k]; b < e + (OFFDIAG ? 0 : 1); ++b) {
             int jb = indices[b];
             int pb = col_pos ? col_pos[jb] : jb;
             if (pb < 0) continue;
             red_add(&orow[pb], va * data[b]);
         }
+    }
+}
+
+// packed lower triangle -> full symmetric square (every element of `out` is written)
+template <typename F>
+__global__ void k_unpack_tri(const F* __restrict__ tri, int64_t m, F* __restrict__ out) {
+    const int64_t total = m * m;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+        const int64_t i = t / m, j = t - i * m;
+        const int64_t a = i > j ? i : j, b = i > j ? j : i;
+        out[t] = tri[a * (a + 1) / 2 + b];
     }
 }
 
@@ -168,7 +184,24 @@ __global__ void k_csc_colreduce(const F* __restrict__ data, const int32_t* __res
     for (int64_t c = warp; c < n_cols; c += nwarps) {
         int64_t j = cols ? (int64_t)cols[c] : c;
         F s = F(0);
-        for (int e = indptr[j] + lane; e < indptr[j + 1]; e += 32) {
+        const int e_end = indptr[j + 1];
+        int e = indptr[j] + lane;
+        // four index loads, then four dependent gathers of v in flight per lane
+        for (; e + 96 < e_end; e += 128) {
+            int i[4];
+            F x[4], w[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                i[u] = __ldg(indices + e + 32 * u);
+                x[u] = __ldg(data + e + 32 * u);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                w[u] = (row_mask && !row_mask[i[u]]) ? F(0) : __ldg(v + i[u]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) s += (MODE == 0) ? x[u] * w[u] : w[u] * x[u] * x[u];
+        }
+        for (; e < e_end; e += 32) {
             int i = indices[e];
             if (row_mask && !row_mask[i]) continue;
             F x = data[e];
@@ -188,7 +221,20 @@ int sparse_sandwich_ex(const F* data, const int32_t* indices, const int32_t* ind
                        cudaStream_t st, bool offdiag_only) {
     if (!cols) m = p;
     if (m <= 0) return 0;
-    if (!offdiag_only) TM_CUDA(cudaMemsetAsync(out, 0, sizeof(F) * (size_t)(m * m), st));
+    // a square that does not fit the L2 is accumulated as a packed triangle (TABMAT_B200_SPARSE_TRI:
+    // 0 never, 1 when the square is > 96 MB (default), 2 always)
+    const int tri_mode = getenv("TABMAT_B200_SPARSE_TRI") ? atoi(getenv("TABMAT_B200_SPARSE_TRI")) : 1;
+    const size_t sq_bytes = sizeof(F) * (size_t)(m * m);
+    const bool packed = !offdiag_only && nnz > 0 && !(rows && n_rows <= 0) &&
+                        (tri_mode == 2 || (tri_mode == 1 && sq_bytes > ((size_t)96 << 20)));
+    const size_t tri_elems = (size_t)(m * (m + 1) / 2);
+    Scratch tri(packed ? sizeof(F) * tri_elems : 0, st);
+    if (tri.err != cudaSuccess) return fail_cuda(tri.err, "scratch");
+    if (packed) {
+        TM_CUDA(cudaMemsetAsync(tri.p, 0, sizeof(F) * tri_elems, st));
+    } else if (!offdiag_only) {
+        TM_CUDA(cudaMemsetAsync(out, 0, sizeof(F) * (size_t)(m * m), st));
+    }
     if (nnz <= 0 || (rows && n_rows <= 0)) return 0;
     Scratch rmask(rows ? (size_t)n : 0, st);
     Scratch cpos(cols ? sizeof(int32_t) * (size_t)p : 0, st);
@@ -207,7 +253,7 @@ int sparse_sandwich_ex(const F* data, const int32_t* indices, const int32_t* ind
     const size_t tri_bytes = sizeof(F) * (size_t)(m * (m + 1) / 2);
     const char* sm_env = getenv("TABMAT_B200_SPARSE_SMEM");
     const int sm_mode = sm_env ? atoi(sm_env) : 1;
-    const bool in_smem = !offdiag_only && sm_mode != 0 && tri_bytes <= 200 * 1024 &&
+    const bool in_smem = !offdiag_only && !packed && sm_mode != 0 && tri_bytes <= 200 * 1024 &&
                          (sm_mode == 2 || nnz > (int64_t)sm_count() * (m * (m + 1) / 2));
     if (in_smem) {
         static bool attr_done[2][16] = {};
@@ -225,6 +271,15 @@ int sparse_sandwich_ex(const F* data, const int32_t* indices, const int32_t* ind
             cols ? cpos.as<int32_t>() : nullptr, (int)m, out);
     } else {
         int g = grid_for(nnz, 256, sm_count() * 32);
+        if (packed) {
+            k_sparse_sandwich<F, false, true><<<g, 256, 0, st>>>(
+                data, indices, indptr, nz_row, nnz, d, rows ? rmask.as<uint8_t>() : nullptr,
+                cols ? cpos.as<int32_t>() : nullptr, m, tri.as<F>());
+            TM_LAUNCHED();
+            k_unpack_tri<F><<<grid_for(m * m, 256, sm_count() * 16), 256, 0, st>>>(tri.as<F>(), m, out);
+            TM_LAUNCHED();
+            return 0;
+        }
         if (offdiag_only)
             k_sparse_sandwich<F, true><<<g, 256, 0, st>>>(data, indices, indptr, nz_row, nnz, d,
                                                           rows ? rmask.as<uint8_t>() : nullptr,

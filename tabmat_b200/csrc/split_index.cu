@@ -807,8 +807,8 @@ static int cat_sparse_cols(const CodeSrc& rec, int n_cat, const int64_t* K, cons
         if (K[best] <= max_k && slot + K[best] <= budget) {
             // replicas (lane % rep) against the CAS-loop contention of shared-memory float
             // atomics (TABMAT_B200_COLS_REP_MAX / _ELEMS: most replicas, largest replicated table)
-            static const int rep_max = getenv("TABMAT_B200_COLS_REP_MAX") ? atoi(getenv("TABMAT_B200_COLS_REP_MAX")) : 8;
-            static const int rep_elems = getenv("TABMAT_B200_COLS_REP_ELEMS") ? atoi(getenv("TABMAT_B200_COLS_REP_ELEMS")) : 256;
+            static const int rep_max = getenv("TABMAT_B200_COLS_REP_MAX") ? atoi(getenv("TABMAT_B200_COLS_REP_MAX")) : 32;
+            static const int rep_elems = getenv("TABMAT_B200_COLS_REP_ELEMS") ? atoi(getenv("TABMAT_B200_COLS_REP_ELEMS")) : 2048;
             int rep = 1;
             while (rep < rep_max && rep < 32 && K[best] * rep * 2 <= rep_elems &&
                    slot + K[best] * rep * 2 <= budget)

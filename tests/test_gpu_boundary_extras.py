@@ -135,6 +135,11 @@ def test_sparse_self_sandwich_shared_memory_tables(dt, m, monkeypatch):
         got = S.sandwich(d, r, c)
         monkeypatch.setenv("TABMAT_B200_SPARSE_SMEM", "0")
         red = S.sandwich(d, r, c)
+        # packed-triangle accumulation (the form for squares larger than the L2, C4)
+        monkeypatch.setenv("TABMAT_B200_SPARSE_TRI", "2")
+        tri = S.sandwich(d, r, c)
+        monkeypatch.delenv("TABMAT_B200_SPARSE_TRI")
         cases.assert_close(got, ref, dt, "shared-memory tables")
         cases.assert_close(red, ref, dt, "L2 RED form")
-        assert np.array_equal(got, got.T)
+        cases.assert_close(tri, ref, dt, "packed triangle")
+        assert np.array_equal(got, got.T) and np.array_equal(tri, tri.T)
