@@ -394,6 +394,7 @@ int split_blocks(const tm_block_desc* blk, int nb, int64_t n, const F* d, const 
         // over 32-byte row records, categorical x sparse for all categorical blocks from the
         // CSC copy without global atomics
         bool cats_fused = false, cat_sparse_fused = false, sparse_diag_done = false;
+        cudaStream_t sparse_side = nullptr;
         {
             int cats[8];
             int nc = 0;
@@ -456,10 +457,39 @@ int split_blocks(const tm_block_desc* blk, int nb, int64_t n, const F* d, const 
                     for (int b = a + 1; b < nc; ++b)
                         outs_pair[a * nc + b] = ws + cross_off[cats[a]][cats[b]];
                 }
+                // by-product of the column-owner kernel below: the diagonal of the sparse block's
+                // own sandwich (TABMAT_B200_SPARSE_DIAG=0: the CSR kernel adds it itself).  The
+                // CSR kernel then only adds the strictly lower triangle - L2 REDs, few threads
+                // busy - and can run on a side stream under the shared-memory-bound pairs kernel
+                // (TABMAT_B200_INDEX_OVERLAP=1; the pairs kernel is launched first so that its one
+                // CTA per SM is resident before the CSR kernel's CTAs fill the rest).
+                static const bool diag_off = getenv("TABMAT_B200_SPARSE_DIAG") &&
+                                             atoi(getenv("TABMAT_B200_SPARSE_DIAG")) == 0;
+                static const bool overlap_on = getenv("TABMAT_B200_INDEX_OVERLAP") &&
+                                               atoi(getenv("TABMAT_B200_INDEX_OVERLAP")) == 1;
+                F* sdiag = nullptr;
+                if (want_cs && blk[sparse_idx].csc_row_blocks > 1 && !diag_off) {
+                    const tm_block_desc& S = blk[sparse_idx];
+                    sdiag = ws + self_off[sparse_idx];
+                    TM_CUDA(cudaMemsetAsync(sdiag, 0, sizeof(F) * (size_t)(S.ncols * S.ncols), st));
+                    if (overlap_on && g_split_sched == 3 && side_stream(0)) {
+                        sparse_side = side_stream(0);
+                        TM_CUDA(cudaEventRecord(side_event(2), st));
+                        TM_CUDA(cudaStreamWaitEvent(sparse_side, side_event(2), 0));
+                    }
+                }
                 rc = index_cat_pairs<F>(pairs_direct_off ? rec.p : nullptr, dd, cc, dfc, n, nc, Kc,
                                         runc, outs_self, outs_pair, st);
                 if (rc) return rc;
                 cats_fused = true;
+                if (sparse_side) {
+                    const tm_block_desc& S = blk[sparse_idx];
+                    rc = sparse_sandwich_ex<F>(static_cast<const F*>(S.data), S.csr_indices,
+                                               S.csr_indptr, S.csr_row, n, S.ncols, S.nnz, d, rows,
+                                               n_rows, (const int32_t*)nullptr, (int64_t)0, sdiag,
+                                               sparse_side, true);
+                    if (rc) return rc;
+                }
                 if (want_cs) {
                     const tm_block_desc& S = blk[sparse_idx];
                     F* outs[8];
@@ -467,15 +497,6 @@ int split_blocks(const tm_block_desc* blk, int nb, int64_t n, const F* d, const 
                         const int lo = cats[a] < sparse_idx ? cats[a] : sparse_idx;
                         const int hi = cats[a] < sparse_idx ? sparse_idx : cats[a];
                         outs[a] = ws + cross_off[lo][hi];
-                    }
-                    // by-product of the column-owner kernel: the diagonal of the sparse block's
-                    // own sandwich (TABMAT_B200_SPARSE_DIAG=0: the CSR kernel adds it itself)
-                    static const bool diag_off = getenv("TABMAT_B200_SPARSE_DIAG") &&
-                                                 atoi(getenv("TABMAT_B200_SPARSE_DIAG")) == 0;
-                    F* sdiag = nullptr;
-                    if (S.csc_row_blocks > 1 && !diag_off) {
-                        sdiag = ws + self_off[sparse_idx];
-                        TM_CUDA(cudaMemsetAsync(sdiag, 0, sizeof(F) * (size_t)(S.ncols * S.ncols), st));
                     }
                     rc = index_cat_sparse<F>(use_packed ? nullptr : rec.p, dd,
                                              use_packed ? S.csc_cat_codes : nullptr, nc, Kc, runp,
@@ -500,6 +521,8 @@ int split_blocks(const tm_block_desc* blk, int nb, int64_t n, const F* d, const 
             else if (bi.kind == KIND_DENSE)
                 rc = dense_sandwich(tag, static_cast<const F*>(bi.data), n, bi.ncols, bi.c_order, d,
                                     rows, n_rows, (const int32_t*)nullptr, (int64_t)0, so, stream);
+            else if (bi.kind == KIND_SPARSE && sparse_diag_done && i == sparse_idx && sparse_side)
+                rc = 0;   // already running on the side stream
             else if (bi.kind == KIND_SPARSE && sparse_diag_done && i == sparse_idx)
                 rc = sparse_sandwich_ex<F>(static_cast<const F*>(bi.data), bi.csr_indices,
                                            bi.csr_indptr, bi.csr_row, n, bi.ncols, bi.nnz, d, rows,
@@ -552,6 +575,10 @@ int split_blocks(const tm_block_desc* blk, int nb, int64_t n, const F* d, const 
                                 "sparse blocks must be merged first, split_matrix.py:85-141)");
                 if (rc) return rc;
             }
+        }
+        if (sparse_side) {
+            TM_CUDA(cudaEventRecord(side_event(3), sparse_side));
+            TM_CUDA(cudaStreamWaitEvent(st, side_event(3), 0));
         }
         pass_mark(PASS_INDEX, 1, st);
         return 0;
