@@ -240,8 +240,16 @@ class C2(Workload):
     n_default = 10_000_000
     P = 256
 
+    @staticmethod
+    def f_order():
+        # TABMAT_B200_BENCH_C2_ORDER=F: a column-major device tensor (served by the F-order TMA
+        # box of the tcgen05 kernel, no transpose anywhere)
+        return os.environ.get("TABMAT_B200_BENCH_C2_ORDER", "C").upper() == "F"
+
     def describe(self):
-        return f"DenseMatrix.sandwich f32, n={self.n}, p={self.P}, C-order (BASELINE.json configs[1])"
+        order = "F" if self.f_order() else "C"
+        return (f"DenseMatrix.sandwich f32, n={self.n}, p={self.P}, {order}-order "
+                "(BASELINE.json configs[1])")
 
     def device_matrix(self, n, seed, device):
         import torch
@@ -249,7 +257,10 @@ class C2(Workload):
         import tabmat_b200 as tm
 
         g = torch.Generator(device=device).manual_seed(seed)
-        X = torch.randn((n, self.P), device=device, dtype=torch.float32, generator=g)
+        if self.f_order():
+            X = torch.randn((self.P, n), device=device, dtype=torch.float32, generator=g).t()
+        else:
+            X = torch.randn((n, self.P), device=device, dtype=torch.float32, generator=g)
         d = torch.rand(n, device=device, dtype=torch.float32, generator=g)
         return tm.DenseMatrix(X), d, float(n) * self.P * (self.P + 1), {}
 
@@ -906,6 +917,15 @@ def main():
                 "note": "X.sandwich_and_transpose_matvec(d, v): Hessian and score of one IRLS step; the "
                         "dense block's share of X^T v rides in the tcgen05 kernel's scale warps"}
         del vvec, Hf, gf, gs
+        # glum's active-set call: X.sandwich(d, cols=half of the columns) through the selecting
+        # assembly (the passes compute whole blocks; only the placement changes)
+        if world == 1:
+            p_tot = S.shape[1]
+            half = np.sort(np.random.default_rng(11).choice(p_tot, size=p_tot // 2,
+                                                            replace=False)).astype(np.int32)
+            t_half = ev_time(lambda: S.sandwich(d, cols=half))
+            irls["cols_half_ms"] = t_half
+            irls["cols_half_over_full"] = t_half / t_sand
     if shared is not None:
         shared.close(unlink=rank == 0)
     fl = torch.tensor([float(flops_local), float(nnz_local)], device=device, dtype=torch.float64)

@@ -363,7 +363,8 @@ class CategoricalMatrix(MatrixBase):
     def _cross_sandwich(self, other, d, rows=None, L_cols=None, R_cols=None):
         """self[rows, L_cols].T @ diag(d[rows]) @ other[rows, R_cols]."""
         if isinstance(other, DenseMatrix):
-            return self._cross_dense(other._array, d, rows, L_cols, R_cols)
+            return other._trim_cols(self._cross_dense(other._native(), d, rows, L_cols, R_cols),
+                                    R_cols)
         if isinstance(other, SparseMatrix):
             return self._cross_sparse(other, d, rows, L_cols, R_cols)
         if isinstance(other, CategoricalMatrix):

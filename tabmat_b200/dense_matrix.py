@@ -6,6 +6,7 @@ tcgen05 weighted-SYRK kernel (fp32, C order, p <= 256) or the CUDA-core kernel; 
 
 from __future__ import annotations
 
+import os
 import warnings
 from typing import Optional
 
@@ -71,7 +72,23 @@ class DenseMatrix(MatrixBase):
     """Dense block backed by a CUDA tensor; same API as ``tabmat.DenseMatrix``."""
 
     def __init__(self, input_array, column_names=None, term_names=None):
-        self._array = _dense_to_dev(input_array)
+        arr = _dense_to_dev(input_array)
+        # float32, row-major, width not a multiple of 4: the TMA / tcgen05 SYRK, the one-hot MMAs
+        # and the 16-byte vector kernels all need a 16-byte row pitch.  The block is STORED with
+        # its width padded to the next multiple of 4 by zero columns (<= 3 extra columns of HBM);
+        # `_array` is the logical (n x p) view of it, `_store` what the kernels see.  Zero columns
+        # change nothing in X^T D X, X v or X^T v apart from zero rows / entries that are cut off
+        # again.  TABMAT_B200_DENSE_PAD=0 keeps the width (CUDA-core kernels then).
+        self._store = None
+        if (os.environ.get("TABMAT_B200_DENSE_PAD", "1") != "0" and arr.dtype == torch.float32
+                and arr.dim() == 2 and arr.is_contiguous() and arr.shape[0] > 0
+                and arr.shape[1] > 0 and arr.shape[1] % 4):
+            n, p = arr.shape
+            store = torch.zeros((n, (p + 3) // 4 * 4), dtype=arr.dtype, device=arr.device)
+            store[:, :p] = arr
+            self._store = store
+            arr = store[:, :p]
+        self._array = arr
         width = self._array.shape[1]
         if column_names is not None:
             if len(column_names) != width:
@@ -86,10 +103,39 @@ class DenseMatrix(MatrixBase):
         else:
             self._terms = self._colnames
 
+    # ---- padded storage ----------------------------------------------------------------
+    def _native(self) -> torch.Tensor:
+        """The tensor handed to the native kernels: the zero-padded storage when there is one."""
+        return self._array if self._store is None else self._store
+
+    def _pad_vec(self, v_t: torch.Tensor) -> torch.Tensor:
+        """A length-p vector (or p x k matrix) over the columns, extended by zeros to the stored
+        width."""
+        if self._store is None or v_t.shape[0] == self._store.shape[1]:
+            return v_t
+        extra = self._store.shape[1] - v_t.shape[0]
+        return torch.cat([v_t, v_t.new_zeros((extra,) + tuple(v_t.shape[1:]))], dim=0)
+
+    def _trim_cols(self, res, cols):
+        """Cut the padding columns off a result whose LAST axis runs over all stored columns
+        (`cols` is None); results over a `cols` selection never contain them."""
+        if self._store is None or cols is not None:
+            return res
+        p = self._array.shape[1]
+        out = res[..., :p]
+        return out.contiguous() if isinstance(out, torch.Tensor) else np.ascontiguousarray(out)
+
     # ---- array-like surface ----------------------------------------------------------
     def _take_rows_dev(self, rows_t: torch.Tensor) -> "DenseMatrix":
         """X[rows_t, :] for an int64 CUDA index tensor; keeps the C / F storage order."""
         A = self._array
+        if self._store is not None:
+            # gather the padded rows (one contiguous copy) and adopt them as the new storage
+            new = type(self).__new__(type(self))
+            new._store = self._store.index_select(0, rows_t)
+            new._array = new._store[:, :A.shape[1]]
+            new._colnames, new._terms = self._colnames, self._terms
+            return new
         if A.dim() == 2 and not A.is_contiguous() and A.t().is_contiguous():
             sub = A.t().index_select(1, rows_t).t()
         else:
@@ -128,12 +174,14 @@ class DenseMatrix(MatrixBase):
         return _dev.np_dtype(self._array.dtype)
 
     def transpose(self):
-        return type(self)(self._array.t())
+        a = self._array if self._store is None else self._array.contiguous()
+        return type(self)(a.t())
 
     T = property(transpose)
 
     def astype(self, dtype, order="K", casting="unsafe", copy=True):
-        return type(self)(self._array.to(_dev.torch_dtype(dtype)), column_names=self.column_names,
+        a = self._array if self._store is None else self._array.contiguous()
+        return type(self)(a.to(_dev.torch_dtype(dtype)), column_names=self.column_names,
                           term_names=self.term_names)
 
     def getcol(self, i):
@@ -142,6 +190,8 @@ class DenseMatrix(MatrixBase):
 
     def toarray(self):
         a = self._array
+        if self._store is not None:
+            return _dev.to_host(a.contiguous())
         if a.is_contiguous():
             return _dev.to_host(a)
         return _dev.to_host(a.t()).T  # keeps F order on the host
@@ -157,7 +207,11 @@ class DenseMatrix(MatrixBase):
         check_sandwich_compatible(self, d)
         d_t, host = _vec_in(d)
         rows_t, cols_t = setup_restrictions(self.shape, rows, cols)
-        return _dev.ret(dense_sandwich(self._array, d_t, rows_t, cols_t), host)
+        res = dense_sandwich(self._native(), d_t, rows_t, cols_t)
+        if self._store is not None and cols_t is None:
+            p = self._array.shape[1]
+            res = res[:p, :p].contiguous()
+        return _dev.ret(res, host)
 
     def _cross_sandwich(self, other, d, rows=None, L_cols=None, R_cols=None):
         from .categorical_matrix import CategoricalMatrix
@@ -171,7 +225,8 @@ class DenseMatrix(MatrixBase):
     def _get_col_stds(self, weights, col_means):
         w_t, host = _vec_in(weights, self._array.dtype)
         m_t, _ = _vec_in(col_means, self._array.dtype)
-        sqrt_arg = transpose_square_dot_weights(self._array, w_t, m_t)
+        sqrt_arg = transpose_square_dot_weights(self._native(), w_t, self._pad_vec(m_t))
+        sqrt_arg = self._trim_cols(sqrt_arg, None)
         return _dev.ret(torch.sqrt(torch.clamp_min(sqrt_arg, 0)), host)
 
     def _matvec_helper(self, vec, rows, cols, out, transpose: bool):
@@ -186,13 +241,18 @@ class DenseMatrix(MatrixBase):
             cols = None
         rows_t, cols_t = setup_restrictions(self.shape, rows, cols)
         fast = dense_rmatvec if transpose else dense_matvec
+        X = self._native()
+        if not transpose:
+            vec_t = self._pad_vec(vec_t)   # X v: the padding columns meet zeros
         if vec_t.dim() == 1:
-            res = fast(self._array, vec_t, rows_t, cols_t)
+            res = fast(X, vec_t, rows_t, cols_t)
         else:
             flat = vec_t.reshape(vec_t.shape[0], -1)
-            cols_out = [fast(self._array, flat[:, j].contiguous(), rows_t, cols_t)
+            cols_out = [fast(X, flat[:, j].contiguous(), rows_t, cols_t)
                         for j in range(flat.shape[1])]
             res = torch.stack(cols_out, dim=1).reshape((-1,) + tuple(vec_t.shape[1:]))
+        if transpose and self._store is not None and cols_t is None:
+            res = res[:self._array.shape[1]].contiguous()   # X^T v: cut the padding entries off
         if res_dtype != self.dtype and np.issubdtype(res_dtype, np.floating):
             res = res.to(_dev.torch_dtype(res_dtype))
         if out is None:

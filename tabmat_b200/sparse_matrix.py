@@ -278,7 +278,8 @@ class SparseMatrix(MatrixBase):
         from .dense_matrix import DenseMatrix
 
         if isinstance(other, DenseMatrix):
-            return self.sandwich_dense(other._array, d, rows, L_cols, R_cols)
+            return other._trim_cols(self.sandwich_dense(other._native(), d, rows, L_cols, R_cols),
+                                    R_cols)
         if isinstance(other, CategoricalMatrix):
             res = other._cross_sandwich(self, d, rows, R_cols, L_cols)
             return res.T if isinstance(res, np.ndarray) else res.t()

@@ -210,6 +210,15 @@ class SplitMatrix(MatrixBase):
             self._indices_dev = [_dev.to_dev(idx) for idx in self.indices]
         return self._indices_dev
 
+    def _native_indices(self):
+        """Per block: destination column of every STORED column (int64 numpy), -1 for the zero
+        padding columns of a dense block (DenseMatrix._store)."""
+        out = []
+        for mat, idx in zip(self.matrices, self.indices):
+            extra = mat._native().shape[1] - mat.shape[1] if isinstance(mat, DenseMatrix) else 0
+            out.append(np.concatenate([idx, np.full(extra, -1, dtype=np.int64)]) if extra else idx)
+        return out
+
     def _block_order(self):
         """(int32 CUDA tensor: column position of every block column, blocks concatenated;
         block offsets).  One ``tm_permute_gather`` / ``tm_permute_scatter`` with it moves a
@@ -293,9 +302,16 @@ class SplitMatrix(MatrixBase):
             dsc.ncols = mat.shape[1]
             dsc.col_index = idx_t.data_ptr()
             if isinstance(mat, DenseMatrix):
-                X = mat._array
+                X = mat._native()
                 ok = X.dtype == tdtype
                 dsc.kind, dsc.c_order, dsc.data = 0, int(X.is_contiguous()), X.data_ptr()
+                if X.shape[1] != mat.shape[1]:
+                    # zero-padded storage (DenseMatrix.__init__): the block has the stored width,
+                    # its padding columns have no destination (dropped by the assembly)
+                    pad_idx = _dev.to_dev(self._native_indices()[b])
+                    cache[("pad_idx", b)] = pad_idx
+                    dsc.ncols = X.shape[1]
+                    dsc.col_index = pad_idx.data_ptr()
             elif isinstance(mat, SparseMatrix):
                 c = mat._csr
                 ok = c.data.dtype == tdtype
@@ -366,10 +382,10 @@ class SplitMatrix(MatrixBase):
         if mode == "red":
             return 0
         dense = [m for m in self.matrices if isinstance(m, DenseMatrix)]
-        if len(dense) != 1 or dense[0]._array.dtype != tdtype or not dense[0]._array.is_contiguous():
+        if len(dense) != 1 or dense[0]._native().dtype != tdtype or not dense[0]._native().is_contiguous():
             return 0
         fsize = 4 if tdtype == torch.float32 else 8
-        q = dense[0].shape[1]
+        q = dense[0]._native().shape[1]
         width = 16 // fsize
         if q <= 0 or q % width or q > 64 * width:
             return 0
@@ -482,8 +498,12 @@ class SplitMatrix(MatrixBase):
         offs = np.concatenate([[0], np.cumsum([m.shape[1] for m in self.matrices])]).astype(int)
         dense = [b for b, m in enumerate(self.matrices) if isinstance(m, DenseMatrix)]
         dvec = vec[offs[dense[0]]:offs[dense[0] + 1]] if len(dense) == 1 else vec[:0]
-        if len(dense) == 1 and (dvec.data_ptr() % 16):   # keep the RED target vector aligned
-            dvec = torch.empty(dvec.numel(), dtype=d_t.dtype, device=d_t.device)
+        if len(dense) == 1:
+            stored = self.matrices[dense[0]]._native().shape[1]
+            # keep the RED target vector aligned; zero-padded storage: the kernel writes one
+            # entry per STORED column
+            if (dvec.data_ptr() % 16) or stored != dvec.numel():
+                dvec = torch.empty(stored, dtype=d_t.dtype, device=d_t.device)
         check(fn("tm_split_sandwich_rmatvec_blocks", _dev.suffix(d_t.dtype))(
             descs, len(self.matrices), self.shape[0], _dev.ptr(d_t), _dev.ptr(v_t),
             _dev.ptr(rows_t), _dev.length(rows_t), _dev.ptr(ws),
@@ -492,7 +512,7 @@ class SplitMatrix(MatrixBase):
             part = vec[offs[b]:offs[b + 1]]
             if len(dense) == 1 and b == dense[0]:
                 if dvec.data_ptr() != part.data_ptr():
-                    part.copy_(dvec)
+                    part.copy_(dvec[:part.numel()])
                 continue
             part.copy_(m.transpose_matvec(v_t, rows=rows_t))
         return buf, elems
@@ -529,7 +549,8 @@ class SplitMatrix(MatrixBase):
             p = len(cols)
             sel = (BlockDesc * len(self.matrices))()
             keep = []
-            for b, idx in enumerate(self.indices):
+            dest = np.concatenate([dest, [-1]])   # index -1 (padding column) -> no destination
+            for b, idx in enumerate(self._native_indices()):
                 C.memmove(C.byref(sel[b]), C.byref(descs[b]), C.sizeof(BlockDesc))
                 t = _dev.to_dev(dest[idx])
                 keep.append(t)
@@ -771,9 +792,10 @@ class SplitMatrix(MatrixBase):
         if len(dense) != 1:
             return {}
         b = dense[0]
-        X = self.matrices[b]._array
+        X = self.matrices[b]._native()
         width = 4 if X.dtype == torch.float32 else 2
         p = X.shape[1]
+        p_log = self.matrices[b].shape[1]   # < p with zero-padded storage
         if (X.dtype != d_t.dtype or not X.is_contiguous() or p % width or p > 64 * width
                 or X.data_ptr() % 16):
             return {}
@@ -787,6 +809,9 @@ class SplitMatrix(MatrixBase):
         outs, out_s = dense_cross_sandwich(
             X, d_t, rows_t, [(m._codes, m.shape[1], m.drop_first) for _, m in cats],
             sparse[0][1]._csr if sparse else None)
+        if p_log != p:
+            outs = [o[:, :p_log].contiguous() for o in outs]
+            out_s = out_s[:, :p_log].contiguous() if out_s is not None else None
         fused = {(i, b): o for (i, _), o in zip(cats, outs)}
         if sparse and out_s is not None:
             fused[(sparse[0][0], b)] = out_s
