@@ -79,6 +79,14 @@ void tm_set_tc_scatter_warps(int warps);
  * (the tensor core ignores the low 13 bits of a tf32 operand; tested), -1 = default
  * (TABMAT_B200_TC_ROUND, else 2). */
 void tm_set_tc_round_mode(int mode);
+/* Length of an accumulation chain in the tcgen05 kernels, in K = 8 MMA steps.  The tensor core's
+ * fp32 accumulator truncates at every step, so a chain of T steps onto a growing sum loses about
+ * T * 2^-25 of it (measured -9.3e-4 on the diagonal of X^T D X at 4e7 rows on one GPU); a long
+ * input is therefore cut into several launches, each draining its TMEM accumulators into the
+ * result (fp32 REDs) after at most `steps` steps per CTA.
+ * -1 = default (TABMAT_B200_TC_FLUSH_STEPS, else 4096 = a loss of 1.2e-4 .. 2.4e-4), 0 = one
+ * launch whatever the length. */
+void tm_set_tc_flush_steps(int steps);
 
 /* ---- dense block (reference: ext/dense.pyx) --------------------------------------- */
 /* dense_sandwich, dense.pyx:19-44 -> _dense{C,F}_sandwich, dense_helpers-tmpl.cpp:266-308.

@@ -56,7 +56,8 @@ struct Params {
     int P;            // number of columns (<= 256)
     int groups;       // ceil(P/32)
     int mtiles;       // ceil(P/128): 128-wide output tile rows (1 or 2)
-    long long num_row_tiles;
+    long long num_row_tiles;   // row tiles of THIS launch
+    long long tile0;           // first row tile of this launch (long inputs are cut into segments)
     int stagesR;      // depth of the TMA ring (raw X tiles)
     int sb;           // depth of the operand ring (2..MAX_SB): S + one-hot in smem, T in TMEM
     int dual_acc;     // mtiles == 1 without one-hot blocks: two SYRK accumulators (even/odd k steps)
@@ -513,6 +514,8 @@ __device__ __forceinline__ void scale_stage(bool f_order, int mtiles, uint32_t R
 
 // fp32 -> tf32 of the MMA operands (to_tf32<RM>): -1 = TABMAT_B200_TC_ROUND or the default
 int g_tc_round = -1;
+// longest accumulation chain in MMA steps (tm_set_tc_flush_steps): -1 = env / default, 0 = unbounded
+int g_tc_flush_steps = -1;
 static int tc_round_mode() {
     int rm = g_tc_round;
     if (rm < 0) {
@@ -635,7 +638,7 @@ k_dense_syrk_tc(const __grid_constant__ TmapSet tmaps, const Params prm) {
                 }
                 mbar_wait_t<(SCW > 0)>(&emptyR[s], ph ^ 1);
                 tl_stamp(prm, it, 0);
-                const long long k0 = ((long long)blockIdx.x + (long long)it * gridDim.x) * BK;
+                const long long k0 = (prm.tile0 + (long long)blockIdx.x + (long long)it * gridDim.x) * BK;
                 uint8_t* stage = Rring + (size_t)s * prm.r_bytes;
                 const uint32_t aux = smem_u32(stage) + (uint32_t)prm.aux_off;
                 mbar_expect_tx(&full[s], tx);
@@ -887,7 +890,7 @@ k_dense_syrk_tc(const __grid_constant__ TmapSet tmaps, const Params prm) {
         }
         float* const osp = prm.out_sparse + lane * 4;
         auto tile_row0 = [&](int it) -> long long {
-            return ((long long)blockIdx.x + (long long)it * gridDim.x) * BK + r0;
+            return (prm.tile0 + (long long)blockIdx.x + (long long)it * gridDim.x) * BK + r0;
         };
         // indptr of rows k .. k + RPW (lanes 0..RPW), clamped to n (rows past the end are empty)
         auto load_ip = [&](int it) -> int {
@@ -1538,10 +1541,34 @@ static int dense_sandwich_tc_launch(const float* X, int64_t n, int64_t p, int c_
     size_t smem = (size_t)stagesR * prm.r_bytes + fixed;
 
     if (!ps) TM_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)(p * p), st));
-    long long grid = prm.num_row_tiles < sm_count() ? prm.num_row_tiles : sm_count();
     // TABMAT_B200_TC_NSW = 8 | 16 scale warps
     static const int nsw = getenv("TABMAT_B200_TC_NSW") ? atoi(getenv("TABMAT_B200_TC_NSW")) : 8;
-    int rc;
+    // The tensor core's fp32 accumulator TRUNCATES at every K = 8 step: a chain of T steps onto a
+    // growing sum loses ~T * 2^-25 of it (measured: -9.3e-4 on the diagonal of X^T D X at n = 4e7
+    // on one GPU = 34k steps per CTA, against 6.5e-5 for the fp32 CUDA-core kernel).  So a long
+    // input is cut into launches of at most `chain` steps per CTA; each launch drains its TMEM
+    // accumulators into `out` with fp32 REDs (rounded to nearest).  The kernel's loops stay
+    // untouched (cutting the chain inside the kernel cost 0.9-1.7 ms on the 7 ms pass even with
+    // the cut disabled, profiles/bench_r3f..r3i_*); an extra launch costs ~0.03 ms
+    // (4096 steps: 8 launches at n = 4e7, error 1.2e-4; 2048: 16 launches, 5.8e-5, +0.3 ms).
+    const long long total_tiles = prm.num_row_tiles;
+    long long seg_tiles = total_tiles;
+    {
+        static const int env_steps = getenv("TABMAT_B200_TC_FLUSH_STEPS") ? atoi(getenv("TABMAT_B200_TC_FLUSH_STEPS")) : 4096;
+        const long long steps = g_tc_flush_steps >= 0 ? g_tc_flush_steps : env_steps;
+        if (steps > 0) {
+            long long per_cta = steps / ((BK / 8) * prm.nsub);
+            if (per_cta < 1) per_cta = 1;
+            seg_tiles = per_cta * sm_count();
+        }
+    }
+    int rc = 0;
+    for (long long t0 = 0; t0 < total_tiles && rc == 0; t0 += seg_tiles) {
+    prm.tile0 = t0;
+    prm.num_row_tiles = total_tiles - t0 < seg_tiles ? total_tiles - t0 : seg_tiles;
+    // an almost empty last launch is folded into the previous one
+    if (total_tiles - t0 - prm.num_row_tiles < seg_tiles / 4) prm.num_row_tiles = total_tiles - t0;
+    long long grid = prm.num_row_tiles < sm_count() ? prm.num_row_tiles : sm_count();
     if (prm.nsub == 3) {
         if (scw == 8)
             rc = launch_tc<1, 8, 3>(tmaps, prm, (unsigned)grid, smem, st);
@@ -1561,6 +1588,8 @@ static int dense_sandwich_tc_launch(const float* X, int64_t n, int64_t p, int c_
         rc = launch_tc<2, 0, 1>(tmaps, prm, (unsigned)grid, smem, st);
     } else {
         rc = launch_tc<1, 0, 1>(tmaps, prm, (unsigned)grid, smem, st);
+    }
+    if (prm.num_row_tiles == total_tiles - t0) break;
     }
     if (rc) return rc;
     if (ps) return 0;   // the caller mirrors the triangle once, after the last panel pass
@@ -1608,6 +1637,7 @@ int tm_has_tcgen05(void) {
 }
 void tm_set_dense_f32_mode(int mode) { tmb::g_dense_f32_mode = mode; }
 void tm_set_tc_round_mode(int mode) { tmb::tc::g_tc_round = mode; }
+void tm_set_tc_flush_steps(int steps) { tmb::tc::g_tc_flush_steps = steps; }
 void tm_set_tc_scatter_warps(int warps) {
     if (warps == -1 || warps == 0 || warps == 4 || warps == 8) tmb::g_tc_scatter_warps = warps;
 }

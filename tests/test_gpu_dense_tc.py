@@ -297,3 +297,42 @@ def test_tf32_rounding_modes_agree():
     for mode in (0, 1, 2):
         # unbiased rounding: far below the 2^-11 relative bias of a truncating conversion
         assert abs((res[mode] - ref).mean()) / scale < 2e-5, mode
+
+
+@pytest.mark.parametrize("p,order", [(64, "C"), (256, "C"), (128, "F")])
+def test_accumulator_chains_are_cut(p, order):
+    """The tensor core's fp32 accumulator truncates at every K = 8 step: without a limit on the
+    chain length the sandwich of 2e6 rows of all-positive data is ~5e-5 too small (and 1e-3 at
+    4e7 rows).  tm_set_tc_flush_steps bounds the chain: the accumulators are drained into the
+    result every so many steps.  Many drains per CTA must give the same result, more accurately."""
+    import torch
+
+    import tabmat_b200 as tm
+
+    lib = tm._lib.lib
+    if not lib.tm_has_tcgen05():
+        pytest.skip("needs sm_100")
+    n = 2_000_000
+    dev = torch.device("cuda")
+    g = torch.Generator(device=dev).manual_seed(p)
+    X = 1.0 + torch.rand((n, p), device=dev, dtype=torch.float32, generator=g)
+    if order == "F":
+        X = X.t().contiguous().t()
+    d = torch.rand(n, device=dev, dtype=torch.float32, generator=g)
+    ref = torch.zeros((p, p), device=dev, dtype=torch.float64)
+    for lo in range(0, n, 250_000):
+        Xc = X[lo:lo + 250_000].double()
+        ref += Xc.t() @ (Xc * d[lo:lo + 250_000].double()[:, None])
+    D = tm.DenseMatrix(X)
+    err = {}
+    try:
+        for steps in (0, 128, 2048):
+            lib.tm_set_tc_flush_steps(steps)
+            got = D.sandwich(d).double()
+            err[steps] = float(((got - ref).abs().max() / ref.abs().max()).item())
+    finally:
+        lib.tm_set_tc_flush_steps(-1)
+    print(f"\np={p} {order}: normwise error by chain length", {k: f"{v:.2e}" for k, v in err.items()})
+    assert err[0] < 1e-3 and err[128] < 1e-3 and err[2048] < 1e-3
+    assert err[128] < err[0] / 3, err      # ~13 drains per CTA: the truncation loss is gone
+    assert err[2048] <= err[0] * 1.05, err

@@ -6,11 +6,12 @@ error of the diagonal (sums of like-signed terms, where an accumulator bias show
 """
 
 import sys
+from pathlib import Path
 
-import numpy as np
 import torch
 
-import tabmat_b200 as tm
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+import tabmat_b200 as tm  # noqa: E402
 
 
 def main():
