@@ -64,10 +64,12 @@ def test_from_pandas_rejects_and_warns():
     assert isinstance(C, tm.CategoricalMatrix) and C.shape == (5, 4)
 
 
-def test_from_pandas_matrix_takes_the_tensor_path():
+@pytest.mark.parametrize("n_num", [8, 7])
+def test_from_pandas_matrix_takes_the_tensor_path(n_num):
     """A SplitMatrix built the normal tabmat way (pandas -> F-ordered numpy columns) is stored
-    row-major in HBM and its f32 sandwich runs the tcgen05 pass of tm_split_sandwich_blocks
-    (pass timer of the native call > 0), not the CUDA-core fallback."""
+    row-major in HBM - zero-padded to a multiple of 4 columns when it has 7 numeric columns - and
+    its f32 sandwich runs the tcgen05 pass of tm_split_sandwich_blocks (pass timer of the native
+    call > 0), not the CUDA-core fallback."""
     import ctypes
 
     import pandas as pd
@@ -79,14 +81,15 @@ def test_from_pandas_matrix_takes_the_tensor_path():
         pytest.skip("needs sm_100")
     rng = np.random.default_rng(3)
     n = 5000
-    cols = {f"x{i}": rng.standard_normal(n).astype(np.float32) for i in range(8)}
+    cols = {f"x{i}": rng.standard_normal(n).astype(np.float32) for i in range(n_num)}
     cols["big"] = pd.Categorical(rng.integers(0, 300, size=n))
     cols["small"] = pd.Categorical(rng.integers(0, 6, size=n))
     df = pd.DataFrame(cols)
-    assert not df[[f"x{i}" for i in range(8)]].to_numpy().flags["C_CONTIGUOUS"]
+    assert not df[[f"x{i}" for i in range(n_num)]].to_numpy().flags["C_CONTIGUOUS"]
     X = tm.from_pandas(df, dtype=np.float32)
     dense = [m for m in X.matrices if isinstance(m, tm.DenseMatrix)]
-    assert len(dense) == 1 and dense[0]._array.is_contiguous()
+    assert len(dense) == 1 and dense[0]._native().is_contiguous()
+    assert dense[0].shape[1] == n_num and dense[0]._native().shape[1] % 4 == 0
     d = rng.random(n).astype(np.float32)
     lib.tm_split_profile_enable(1)
     got = X.sandwich(d)
@@ -98,4 +101,4 @@ def test_from_pandas_matrix_takes_the_tensor_path():
     cases.assert_close(got, (full * d[:, None].astype(np.float64)).T @ full, np.float32,
                        "from_pandas f32 sandwich")
     C = tm.from_csc(sps.random(400, 16, density=0.5, format="csc", random_state=rng), threshold=0.1)
-    assert all(m._array.is_contiguous() for m in C.matrices if isinstance(m, tm.DenseMatrix))
+    assert all(m._native().is_contiguous() for m in C.matrices if isinstance(m, tm.DenseMatrix))
