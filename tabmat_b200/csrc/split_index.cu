@@ -425,7 +425,7 @@ k_cat_sparse_cols(const F* __restrict__ data, const int32_t* __restrict__ row_id
     if (c0 >= c1) return;
     F* dsm = smem + (size_t)prm.cols_per_cta * prm.slot;   // [cols_per_cta] diagonal sums
     for (int i = threadIdx.x; i < (c1 - c0) * prm.slot; i += CO_THREADS) smem[i] = F(0);
-    if (threadIdx.x < prm.cols_per_cta) dsm[threadIdx.x] = F(0);
+    for (int i = threadIdx.x; i < prm.cols_per_cta; i += CO_THREADS) dsm[i] = F(0);
     __syncthreads();
     for (int blk = 0; blk < prm.n_row_blocks; ++blk) {
         const int64_t base = (int64_t)blk * p_s;
@@ -480,8 +480,9 @@ k_cat_sparse_cols(const F* __restrict__ data, const int32_t* __restrict__ row_id
         }
     }
     __syncthreads();
-    if (prm.diag && threadIdx.x < c1 - c0)   // this CTA is the only owner of these columns
-        static_cast<F*>(prm.diag)[(int64_t)(c0 + threadIdx.x) * prm.diag_ld] = dsm[threadIdx.x];
+    if (prm.diag)   // this CTA is the only owner of these columns
+        for (int i = threadIdx.x; i < c1 - c0; i += CO_THREADS)
+            static_cast<F*>(prm.diag)[(int64_t)(c0 + i) * prm.diag_ld] = dsm[i];
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
         if (!prm.in_smem[c]) continue;
