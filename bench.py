@@ -921,6 +921,23 @@ def main():
                 "note": "X.sandwich_and_transpose_matvec(d, v): Hessian and score of one IRLS step; the "
                         "dense block's share of X^T v rides in the tcgen05 kernel's scale warps"}
         del vvec, Hf, gf, gs
+        if world == 1 and hasattr(Xs, "to_stored_order"):
+            # a whole IRLS step (eta = X beta, logistic weights on the device, Hessian + score):
+            # caller's row order (three n-vector permutations per step) vs stored order
+            yv = (torch.rand(n_local, device=device) < 0.4).to(tdt)
+            ys = Xs.to_stored_order(yv)
+            beta_t = torch.zeros(Xs.shape[1], device=device, dtype=tdt)
+
+            def logistic(resp):
+                def fn(eta):
+                    mu = torch.sigmoid(eta)
+                    return mu * (1 - mu), resp - mu
+                return fn
+
+            irls["irls_step_ms"] = ev_time(lambda: tm.irls_step(Xs, beta_t, logistic(yv)))
+            irls["irls_step_stored_order_ms"] = ev_time(
+                lambda: tm.irls_step(Xs, beta_t, logistic(ys), stored_order=True))
+            del yv, ys
         # glum's active-set call: X.sandwich(d, cols=half of the columns) through the selecting
         # assembly (the passes compute whole blocks; only the placement changes)
         if world == 1:

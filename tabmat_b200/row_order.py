@@ -140,6 +140,19 @@ class RowSortedMatrix(MatrixBase):
             _dev.stream_ptr()))
         return out
 
+    def to_stored_order(self, v) -> torch.Tensor:
+        """A length-n vector from the caller's row order into the stored one (CUDA tensor).  For
+        per-row data that an iteration keeps on the device (the response, offsets, prior
+        weights): permuted ONCE, so that ``irls_step(..., stored_order=True)`` needs no
+        permutation per iteration."""
+        v_t, _ = _vec_in(v if _dev.is_dev(v) else np.asarray(v))
+        return self._gather(v_t)
+
+    def from_stored_order(self, y) -> torch.Tensor:
+        """The inverse of :meth:`to_stored_order`."""
+        y_t, _ = _vec_in(y if _dev.is_dev(y) else np.asarray(y))
+        return self._scatter(y_t)
+
     def _rows_in(self, rows) -> Optional[torch.Tensor]:
         """Original row ids -> stored positions, ascending (so that runs stay runs)."""
         r = _dev.idx32(rows)
