@@ -65,6 +65,9 @@ void tm_set_cross_runs_mode(int mode);
  * collective running on another stream (the allreduce of the blocks that are already finished,
  * tabmat_b200/distributed.py) has somewhere to run.  0 = none (default). */
 void tm_set_sm_reserve(int sms);
+/* The same for the persistent tcgen05 kernel: it runs on (SMs - sms) CTAs, so that a collective
+ * started before it has SMs (and their shared memory) to run on.  0 = none (default). */
+void tm_set_tc_sm_reserve(int sms);
 /* SplitMatrix sandwich, f32: number of scatter warps appended to the tcgen05 kernel, which then
  * also computes the dense x many-level categorical blocks (run sums + vector REDs) - and, when
  * forced, the per-non-zero REDs of the dense x sparse block - from the TMA-staged tile.

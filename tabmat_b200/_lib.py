@@ -85,6 +85,7 @@ _SIGS = {
 EXPORTED = ["tm_version", "tm_last_error", "tm_launch_count", "tm_reset_launch_count",
             "tm_has_tcgen05", "tm_set_dense_f32_mode", "tm_set_cross_runs_mode",
             "tm_set_tc_scatter_warps", "tm_set_tc_round_mode", "tm_set_tc_flush_steps", "tm_set_sm_reserve",
+            "tm_set_tc_sm_reserve",
             "tm_split_workspace_elems", "tm_split_workspace_head_elems", "tm_memcpy2d_to_host",
             "tm_dense_onehot_sandwich_f32", "tm_split_profile_enable", "tm_split_profile_read", "tm_sizeof_block_desc",
             "tm_split_last_plan"]
@@ -139,6 +140,8 @@ lib.tm_memcpy2d_to_host.argtypes = [P, I, P, I, I, I, P]
 lib.tm_memcpy2d_to_host.restype = c_int
 lib.tm_set_sm_reserve.argtypes = [c_int]
 lib.tm_set_sm_reserve.restype = None
+lib.tm_set_tc_sm_reserve.argtypes = [c_int]
+lib.tm_set_tc_sm_reserve.restype = None
 lib.tm_set_tc_scatter_warps.argtypes = [c_int]
 lib.tm_set_tc_scatter_warps.restype = None
 lib.tm_set_tc_round_mode.argtypes = [c_int]

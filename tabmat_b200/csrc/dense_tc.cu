@@ -516,6 +516,8 @@ __device__ __forceinline__ void scale_stage(bool f_order, int mtiles, uint32_t R
 int g_tc_round = -1;
 // longest accumulation chain in MMA steps (tm_set_tc_flush_steps): -1 = env / default, 0 = unbounded
 int g_tc_flush_steps = -1;
+// SMs the persistent kernel does not occupy (tm_set_tc_sm_reserve)
+int g_tc_sm_reserve = 0;
 static int tc_round_mode() {
     int rm = g_tc_round;
     if (rm < 0) {
@@ -1568,7 +1570,9 @@ static int dense_sandwich_tc_launch(const float* X, int64_t n, int64_t p, int c_
     prm.num_row_tiles = total_tiles - t0 < seg_tiles ? total_tiles - t0 : seg_tiles;
     // an almost empty last launch is folded into the previous one
     if (total_tiles - t0 - prm.num_row_tiles < seg_tiles / 4) prm.num_row_tiles = total_tiles - t0;
-    long long grid = prm.num_row_tiles < sm_count() ? prm.num_row_tiles : sm_count();
+    // SMs left to a collective that runs beside this kernel (tm_set_tc_sm_reserve)
+    const long long sms = sm_count() - g_tc_sm_reserve > 8 ? sm_count() - g_tc_sm_reserve : 8;
+    long long grid = prm.num_row_tiles < sms ? prm.num_row_tiles : sms;
     if (prm.nsub == 3) {
         if (scw == 8)
             rc = launch_tc<1, 8, 3>(tmaps, prm, (unsigned)grid, smem, st);
@@ -1638,6 +1642,7 @@ int tm_has_tcgen05(void) {
 void tm_set_dense_f32_mode(int mode) { tmb::g_dense_f32_mode = mode; }
 void tm_set_tc_round_mode(int mode) { tmb::tc::g_tc_round = mode; }
 void tm_set_tc_flush_steps(int steps) { tmb::tc::g_tc_flush_steps = steps; }
+void tm_set_tc_sm_reserve(int sms) { tmb::tc::g_tc_sm_reserve = sms < 0 ? 0 : (sms > 64 ? 64 : sms); }
 void tm_set_tc_scatter_warps(int warps) {
     if (warps == -1 || warps == 0 || warps == 4 || warps == 8) tmb::g_tc_scatter_warps = warps;
 }

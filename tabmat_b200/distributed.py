@@ -148,7 +148,10 @@ class RowShardedMatrix:
         # shares L2 and SMs with the L2-bound gather kernel, which goes from 3.8 to 5.0 ms
         import os
 
-        self.overlap = os.environ.get("TABMAT_B200_DIST_OVERLAP", "0") == "1"
+        # =2: the same with the SMs taken from the tcgen05 kernel (which runs first) instead of
+        # the gather kernel
+        self.overlap_mode = int(os.environ.get("TABMAT_B200_DIST_OVERLAP", "0") or 0)
+        self.overlap = self.overlap_mode in (1, 2)
         self.sm_reserve = int(os.environ.get("TABMAT_B200_DIST_SM_RESERVE", "8"))
 
     # -- collectives ---------------------------------------------------------------------
@@ -180,7 +183,10 @@ class RowShardedMatrix:
                 # dense-operand passes compute; a few SMs are left to the collective
                 from ._lib import lib
 
-                lib.tm_set_sm_reserve(self.sm_reserve)
+                if self.overlap_mode == 2:
+                    lib.tm_set_tc_sm_reserve(self.sm_reserve)
+                else:
+                    lib.tm_set_sm_reserve(self.sm_reserve)
                 try:
                     ws = self.local._sandwich_blocks_overlapped_dev(
                         d_local, _dev.idx32(local_rows),
@@ -189,6 +195,7 @@ class RowShardedMatrix:
                         self._allreduce)
                 finally:
                     lib.tm_set_sm_reserve(0)
+                    lib.tm_set_tc_sm_reserve(0)
                 if ws is not None:
                     return self.local._assemble_dev(ws, cols)
             ws = self.local._sandwich_blocks_dev(d_local, _dev.idx32(local_rows))
